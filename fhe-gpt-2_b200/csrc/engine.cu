@@ -1,0 +1,1408 @@
+// engine.cu - context, containers and the Evaluator half of the C ABI (include/b200ckks.h).
+//
+// Host orchestration of the sm_100a kernels in ntt.cuh / kernels.cuh.  Each entry point
+// replaces one member of the reference's seal::Evaluator (evaluator.cpp, cited per function);
+// argument checks and their messages follow the reference so the C++ facade can rethrow the
+// same exception types.  There is no CPU arithmetic path: without a CUDA device
+// bk_context_create fails with BK_NO_DEVICE.
+#include "engine.h"
+#include <cmath>
+#include <algorithm>
+#include <cstring>
+#include <limits>
+
+namespace bk
+{
+    static thread_local std::string g_err;
+
+    void set_error(const char *msg)
+    {
+        g_err = msg;
+    }
+
+    bk_status fence(const std::exception_ptr &e)
+    {
+        try
+        {
+            std::rethrow_exception(e);
+        }
+        catch (const NoDevice &x)
+        {
+            g_err = x.what();
+            return BK_NO_DEVICE;
+        }
+        catch (const CudaError &x)
+        {
+            g_err = x.what();
+            return BK_CUDA_ERROR;
+        }
+        catch (const std::invalid_argument &x)
+        {
+            g_err = x.what();
+            return BK_INVALID_ARGUMENT;
+        }
+        catch (const std::out_of_range &x)
+        {
+            g_err = x.what();
+            return BK_OUT_OF_RANGE;
+        }
+        catch (const std::logic_error &x)
+        {
+            g_err = x.what();
+            return BK_LOGIC_ERROR;
+        }
+        catch (const std::exception &x)
+        {
+            g_err = x.what();
+            return BK_LOGIC_ERROR;
+        }
+        catch (...)
+        {
+            g_err = "unknown error";
+            return BK_LOGIC_ERROR;
+        }
+    }
+
+    static int bit_count_u64(uint64_t v)
+    {
+        int b = 0;
+        while (v)
+        {
+            b++;
+            v >>= 1;
+        }
+        return b;
+    }
+
+    // ---------------------------------------------------------------------------------- Context
+    Context::Context(int log_n_, const uint64_t *primes_, int n_primes_, int device_)
+        : log_n(log_n_), n(size_t(1) << log_n_), n_primes(n_primes_), device(device_)
+    {
+        if (log_n < 12 || log_n > 16)
+            throw std::invalid_argument("poly_modulus_degree must be 2^12 .. 2^16");
+        if (n_primes < 2 || n_primes > 62)
+            throw std::invalid_argument("coeff_modulus size is invalid");
+        int dev_count = 0;
+        if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
+            throw NoDevice("no CUDA device: this engine has no CPU path");
+        if (device < 0 || device >= dev_count)
+            throw std::invalid_argument("device ordinal out of range");
+        BK_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        BK_CUDA(cudaGetDeviceProperties(&prop, device));
+        sm_count = prop.multiProcessorCount;
+
+        primes.assign(primes_, primes_ + n_primes);
+        for (int i = 0; i < n_primes; i++)
+        {
+            uint64_t q = primes[i];
+            if (q >> 61 || !is_prime_u64(q) || (q - 1) % (2 * n) != 0)
+                throw std::invalid_argument("coeff_modulus is not valid (need NTT-friendly primes < 2^61)");
+            for (int j = 0; j < i; j++)
+                if (primes[j] == q)
+                    throw std::invalid_argument("coeff_modulus primes must be distinct");
+        }
+        // total_coeff_modulus_bit_count per level (context.cpp:455-523): exact product bit length
+        total_bits.assign(n_primes + 1, 0);
+        {
+            std::vector<uint64_t> prod(1, 1); // little-endian multiword product
+            for (int l = 1; l <= n_primes; l++)
+            {
+                uint64_t carry = 0;
+                for (auto &w : prod)
+                {
+                    u128 t = (u128)w * primes[l - 1] + carry;
+                    w = (uint64_t)t;
+                    carry = (uint64_t)(t >> 64);
+                }
+                if (carry)
+                    prod.push_back(carry);
+                total_bits[l] = (int)(prod.size() - 1) * 64 + bit_count_u64(prod.back());
+            }
+        }
+
+        // memory pool: never hand memory back to the driver between ops
+        cudaMemPool_t pool;
+        BK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t thresh = UINT64_MAX;
+        BK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+
+        // per-prime constants + twiddle tables
+        h_primes.resize(n_primes);
+        std::vector<ulonglong2> tw((size_t)n_primes * n), itw((size_t)n_primes * n);
+        for (int i = 0; i < n_primes; i++)
+        {
+            uint64_t q = primes[i];
+            std::vector<uint64_t> w, iw;
+            ntt_tables(log_n, q, w, iw);
+            for (size_t k = 0; k < n; k++)
+            {
+                tw[(size_t)i * n + k] = make_ulonglong2(w[k], shoup(w[k], q));
+                itw[(size_t)i * n + k] = make_ulonglong2(iw[k], shoup(iw[k], q));
+            }
+            PrimeDev &pd = h_primes[i];
+            pd.q = q;
+            pd.two_q = 2 * q;
+            // floor(2^128 / q) as two words (Modulus::const_ratio, modulus.cpp)
+            u128 hi = (~(u128)0) / q; // floor((2^128-1)/q) == floor(2^128/q) because q is odd > 1
+            pd.r0 = (uint64_t)hi;
+            pd.r1 = (uint64_t)(hi >> 64);
+            uint64_t ninv = invmod((uint64_t)n % q, q);
+            pd.ninv = ninv;
+            pd.ninv_s = shoup(ninv, q);
+            uint64_t nw = mulmod(ninv, iw[1], q);
+            pd.ninvw = nw;
+            pd.ninvw_s = shoup(nw, q);
+        }
+        std::vector<ulonglong2> inv((size_t)n_primes * n_primes);
+        for (int last = 0; last < n_primes; last++)
+            for (int i = 0; i < n_primes; i++)
+            {
+                if (i == last)
+                {
+                    inv[(size_t)last * n_primes + i] = make_ulonglong2(0, 0);
+                    continue;
+                }
+                uint64_t v = invmod(primes[last] % primes[i], primes[i]);
+                inv[(size_t)last * n_primes + i] = make_ulonglong2(v, shoup(v, primes[i]));
+            }
+        BK_CUDA(cudaMalloc((void **)&d_primes, sizeof(PrimeDev) * n_primes));
+        BK_CUDA(cudaMalloc((void **)&d_tw, sizeof(ulonglong2) * tw.size()));
+        BK_CUDA(cudaMalloc((void **)&d_itw, sizeof(ulonglong2) * itw.size()));
+        BK_CUDA(cudaMalloc((void **)&d_inv, sizeof(ulonglong2) * inv.size()));
+        BK_CUDA(cudaMemcpy(d_primes, h_primes.data(), sizeof(PrimeDev) * n_primes, cudaMemcpyHostToDevice));
+        BK_CUDA(cudaMemcpy(d_tw, tw.data(), sizeof(ulonglong2) * tw.size(), cudaMemcpyHostToDevice));
+        BK_CUDA(cudaMemcpy(d_itw, itw.data(), sizeof(ulonglong2) * itw.size(), cudaMemcpyHostToDevice));
+        BK_CUDA(cudaMemcpy(d_inv, inv.data(), sizeof(ulonglong2) * inv.size(), cudaMemcpyHostToDevice));
+        tables.tw = d_tw;
+        tables.itw = d_itw;
+        tables.primes = d_primes;
+        tables.log_n = log_n;
+    }
+
+    Context::~Context()
+    {
+        cudaSetDevice(device);
+        cudaDeviceSynchronize();
+        destroy_encoder(*this);
+        for (auto &kv : streams)
+            cudaStreamDestroy(kv.second);
+        for (auto &kv : galois_tables)
+            cudaFree(kv.second);
+        cudaFree(d_primes);
+        cudaFree(d_tw);
+        cudaFree(d_itw);
+        cudaFree(d_inv);
+    }
+
+    void Context::activate() const
+    {
+        int cur = -1;
+        cudaGetDevice(&cur);
+        if (cur != device)
+            BK_CUDA(cudaSetDevice(device));
+    }
+
+    cudaStream_t Context::stream()
+    {
+        activate();
+        std::lock_guard<std::mutex> g(mu);
+        auto id = std::this_thread::get_id();
+        auto it = streams.find(id);
+        if (it != streams.end())
+            return it->second;
+        cudaStream_t s;
+        BK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+        streams[id] = s;
+        return s;
+    }
+
+    const uint32_t *Context::galois_table(uint32_t elt)
+    {
+        // GaloisTool caches one permutation table per element (galois.cpp:26-50)
+        std::lock_guard<std::mutex> g(mu);
+        auto it = galois_tables.find(elt);
+        if (it != galois_tables.end())
+            return it->second;
+        std::vector<uint32_t> t(n);
+        galois_table_ntt(log_n, elt, t.data());
+        uint32_t *d;
+        BK_CUDA(cudaMalloc((void **)&d, n * sizeof(uint32_t)));
+        BK_CUDA(cudaMemcpy(d, t.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        galois_tables[elt] = d;
+        return d;
+    }
+
+    bool Context::scale_in_bounds(double scale, int limbs) const
+    {
+        // is_scale_within_bounds (evaluator.cpp:29-50), CKKS branch
+        return !(scale <= 0 || ((int)std::log2(scale) >= total_bits[limbs]));
+    }
+
+    int Context::ew_grid(size_t work_items) const
+    {
+        size_t blocks = (work_items + 255) / 256;
+        size_t cap = (size_t)sm_count * 8;
+        return (int)std::max<size_t>(1, std::min(blocks, cap));
+    }
+
+    JobMap limb_map(int limbs)
+    {
+        JobMap m;
+        m.limbs = limbs;
+        m.special_pos = -1;
+        m.special_prime = 0;
+        m.explicit_primes = nullptr;
+        return m;
+    }
+
+    // ------------------------------------------------------------------------------ NTT drivers
+#define BK_DISPATCH_LOGR(logn, ...)                                                                                  \
+    switch (logn)                                                                                                      \
+    {                                                                                                                  \
+    case 12: { constexpr int LOGR = 4; __VA_ARGS__; } break;                                                                  \
+    case 13: { constexpr int LOGR = 5; __VA_ARGS__; } break;                                                                  \
+    case 14: { constexpr int LOGR = 6; __VA_ARGS__; } break;                                                                  \
+    case 15: { constexpr int LOGR = 7; __VA_ARGS__; } break;                                                                  \
+    default: { constexpr int LOGR = 8; __VA_ARGS__; } break;                                                                  \
+    }
+
+    template <class Load>
+    static void launch_fwd_cols(Context &c, cudaStream_t s, const Load &ld, u64 *out, int jobs)
+    {
+        if (jobs <= 0)
+            return;
+        dim3 grid(16, jobs);
+        BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+        c.count();
+    }
+    template <class Store>
+    static void launch_fwd_blocks(Context &c, cudaStream_t s, const u64 *in, const Store &st, int jobs)
+    {
+        if (jobs <= 0)
+            return;
+        dim3 grid((unsigned)(c.n >> 12), jobs);
+        k_fwd_blocks<Store><<<grid, 256, 0, s>>>(in, st, c.tables);
+        c.count();
+    }
+    template <class Load>
+    static void launch_inv_blocks(Context &c, cudaStream_t s, const Load &ld, u64 *out, int jobs)
+    {
+        if (jobs <= 0)
+            return;
+        dim3 grid((unsigned)(c.n >> 12), jobs);
+        k_inv_blocks<Load><<<grid, 256, 0, s>>>(ld, out, c.tables);
+        c.count();
+    }
+    template <class Store>
+    static void launch_inv_cols(Context &c, cudaStream_t s, const u64 *in, const Store &st, int jobs)
+    {
+        if (jobs <= 0)
+            return;
+        dim3 grid(16, jobs);
+        BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
+        c.count();
+    }
+
+    void ntt_fwd(Context &c, cudaStream_t s, u64 *data, int jobs, JobMap map)
+    {
+        Scratch tmp(s, (size_t)jobs * c.n);
+        LdPlain ld{ data, map, c.n };
+        launch_fwd_cols(c, s, ld, tmp.p, jobs);
+        StPlain st{ data, map, c.n };
+        launch_fwd_blocks(c, s, tmp.p, st, jobs);
+    }
+
+    void ntt_inv(Context &c, cudaStream_t s, u64 *data, int jobs, JobMap map)
+    {
+        Scratch tmp(s, (size_t)jobs * c.n);
+        LdInvPlain ld{ data, map, c.n, nullptr };
+        launch_inv_blocks(c, s, ld, tmp.p, jobs);
+        StInvPlain st{ data, map, c.n };
+        launch_inv_cols(c, s, tmp.p, st, jobs);
+    }
+
+    // ------------------------------------------------------------------------------- containers
+    static void realloc_words(Context &c, u64 *&d, size_t &cap, size_t words, bool keep, size_t keep_words)
+    {
+        if (words <= cap)
+            return;
+        cudaStream_t s = c.stream();
+        u64 *nd;
+        BK_CUDA(cudaMallocAsync((void **)&nd, words * sizeof(u64), s));
+        if (d)
+        {
+            if (keep && keep_words)
+                BK_CUDA(cudaMemcpyAsync(nd, d, keep_words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            BK_CUDA(cudaFreeAsync(d, s));
+        }
+        d = nd;
+        cap = words;
+    }
+
+    void ensure_ct(bk_ct_t ct, int size, int limbs, bool keep)
+    {
+        Context &c = *ct->ctx;
+        size_t words = (size_t)size * limbs * c.n;
+        realloc_words(c, ct->d, ct->cap, words, keep, (size_t)ct->size * ct->limbs * c.n);
+        ct->size = size;
+        ct->limbs = limbs;
+    }
+
+    void ensure_pt(bk_pt_t pt, int limbs)
+    {
+        Context &c = *pt->ctx;
+        realloc_words(c, pt->d, pt->cap, (size_t)limbs * c.n, false, 0);
+        pt->limbs = limbs;
+    }
+
+    // replace ct's buffer by a freshly produced one
+    static void adopt(bk_ct_t ct, u64 *nd, size_t cap, int size, int limbs)
+    {
+        cudaStream_t s = ct->ctx->stream();
+        if (ct->d)
+            BK_CUDA(cudaFreeAsync(ct->d, s));
+        ct->d = nd;
+        ct->cap = cap;
+        ct->size = size;
+        ct->limbs = limbs;
+    }
+
+    static u64 *alloc_words(Context &c, size_t words)
+    {
+        u64 *p;
+        BK_CUDA(cudaMallocAsync((void **)&p, words * sizeof(u64), c.stream()));
+        return p;
+    }
+
+    static void check_ct(const Context *ctx, bk_ct_t a, const char *name)
+    {
+        if (!a || a->ctx != ctx || !a->d || a->size < 2 || a->limbs < 1 || a->limbs > ctx->top_limbs())
+            throw std::invalid_argument(std::string(name) + " is not valid for encryption parameters");
+    }
+
+    static bool close_scale(double a, double b)
+    {
+        // util::are_close<double> (util/common.h:569-573)
+        double f = std::max({ std::fabs(a), std::fabs(b), 1.0 });
+        return std::fabs(a - b) < std::numeric_limits<double>::epsilon() * f;
+    }
+
+    // ------------------------------------------------------------------------------- key switch
+    // Evaluator::switch_key_inplace (evaluator.cpp:2281-2525) with the Galois permutation of
+    // apply_galois_inplace (:2191-2207) fused in.  target: [l][N] NTT form.  If perm != null the
+    // target is gathered through it and base0 (= c0) likewise (rotation); out[2][l][N] receives
+    //   out0 = perm(base0) + ModDown(sum_J d_J * key[J][0]),  out1 = base1 + ModDown(... key[J][1]).
+    static void key_switch(Context &c, cudaStream_t s, const u64 *target, const uint32_t *perm, const u64 *base0,
+                           const u64 *base1, u64 *out, int l, bk_kskey_t key)
+    {
+        if (key->digits < l || key->klimbs < l)
+            throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (key pruned below "
+                                        "this level)");
+        const size_t n = c.n;
+        const int sp = c.n_primes - 1;
+        const int chunk = std::max(1, std::min(c.ks_chunk, l + 1));
+        Scratch ttarget(s, (size_t)l * n);
+        Scratch inter(s, (size_t)std::max(chunk * l, 2 * l) * n);
+        Scratch acc(s, (size_t)2 * (l + 1) * n);
+        Scratch tlast(s, 2 * n);
+
+        // A. t_target = INTT(perm(target))   (:2358-2365)
+        {
+            LdInvPlain ld{ target, limb_map(l), n, perm };
+            launch_inv_blocks(c, s, ld, inter.p, l);
+            StInvPlain st{ ttarget.p, limb_map(l), n };
+            launch_inv_cols(c, s, inter.p, st, l);
+        }
+        // B. per output modulus: decompose, NTT, multiply-accumulate with the key (:2368-2463)
+        for (int I0 = 0; I0 <= l; I0 += chunk)
+        {
+            int nI = std::min(chunk, l + 1 - I0);
+            LdKsDigit ld{ ttarget.p, c.d_primes, n, l, I0, sp };
+            launch_fwd_cols(c, s, ld, inter.p, nI * l);
+            KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs };
+            dim3 grid((unsigned)(n >> 12), nI);
+            k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
+            c.count();
+        }
+        // C. ModDown by the special prime (:2465-2523)
+        {
+            LdInvLimbOfT ld{ acc.p, n, l + 1, l, sp };
+            launch_inv_blocks(c, s, ld, inter.p, 2);
+            StInvAddHalf st{ tlast.p, n, sp };
+            launch_inv_cols(c, s, inter.p, st, 2);
+            LdDivRound ld2{ tlast.p, n, l, c.primes[sp] };
+            launch_fwd_cols(c, s, ld2, inter.p, 2 * l);
+            StModDown st2{ acc.p, out, base0, base1, perm, c.inv_last(sp), n, l };
+            launch_fwd_blocks(c, s, inter.p, st2, 2 * l);
+        }
+    }
+
+    static bk_kskey_t find_gkey(bk_gkeys_t gk, uint32_t elt)
+    {
+        std::lock_guard<std::mutex> g(gk->mu);
+        auto it = gk->keys.find(elt);
+        return it == gk->keys.end() ? nullptr : it->second;
+    }
+
+    static void apply_galois(Context &c, bk_ct_t a, uint32_t elt, bk_gkeys_t gk)
+    {
+        check_ct(&c, a, "encrypted");
+        if (!gk || gk->ctx != &c)
+            throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        bk_kskey_t key = find_gkey(gk, elt);
+        if (!key)
+            throw std::invalid_argument("Galois key not present");
+        if (!(elt & 1) || elt >= 2 * c.n)
+            throw std::invalid_argument("Galois element is not valid");
+        if (a->size > 2)
+            throw std::invalid_argument("encrypted size must be 2");
+        if (!a->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        cudaStream_t s = c.stream();
+        const uint32_t *perm = c.galois_table(elt);
+        const int l = a->limbs;
+        size_t words = (size_t)2 * l * c.n;
+        u64 *out = alloc_words(c, words);
+        key_switch(c, s, a->d + (size_t)l * c.n, perm, a->d, nullptr, out, l, key);
+        adopt(a, out, words, 2, l);
+    }
+
+    static void rotate_internal(Context &c, bk_ct_t a, int steps, bk_gkeys_t gk)
+    {
+        // evaluator.cpp:2224-2279
+        check_ct(&c, a, "encrypted");
+        if (!gk || gk->ctx != &c)
+            throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        if (steps == 0)
+            return;
+        uint32_t elt = galois_elt_from_step(c.log_n, steps);
+        if (find_gkey(gk, elt))
+        {
+            apply_galois(c, a, elt, gk);
+            return;
+        }
+        // NAF fallback (util/numth.h:22-42)
+        std::vector<int> naf;
+        {
+            bool sign = steps < 0;
+            int v = std::abs(steps);
+            for (int i = 0; v; i++)
+            {
+                int zi = (v & 1) ? 2 - (v & 3) : 0;
+                v = (v - zi) >> 1;
+                if (zi)
+                    naf.push_back((sign ? -zi : zi) * (1 << i));
+            }
+        }
+        if (naf.size() == 1)
+            throw std::invalid_argument("Galois key not present");
+        for (int st : naf)
+            if ((size_t)std::abs(st) != (c.n >> 1))
+                rotate_internal(c, a, st, gk);
+    }
+
+    // -------------------------------------------------------------------------- scalar encoding
+    // CKKSEncoder::encode_internal(double, ...) (ckks.cpp:77-216): residues of round(value*scale)
+    // for the first `limbs` primes.  The reference encodes at the top level and drops limbs;
+    // the range checks therefore use the top-level bit count.
+    static void scalar_residues(const Context &c, double value, double scale, int limbs, ulonglong2 *out)
+    {
+        int top = c.top_limbs();
+        if (scale <= 0 || ((int)std::log2(scale) >= c.total_bits[top]))
+            throw std::invalid_argument("scale out of bounds");
+        value *= scale;
+        int coeff_bit_count = (int)std::log2(std::fabs(value)) + 2;
+        if (coeff_bit_count >= c.total_bits[top])
+            throw std::invalid_argument("encoded value is too large");
+        double coeffd = std::round(value);
+        bool neg = std::signbit(coeffd);
+        coeffd = std::fabs(coeffd);
+        // coeffd is an exact integer m * 2^e; reduce it exactly
+        int e = 0;
+        uint64_t m = 0;
+        if (coeffd != 0)
+        {
+            double fr = std::frexp(coeffd, &e); // coeffd = fr * 2^e, fr in [0.5,1)
+            m = (uint64_t)std::ldexp(fr, 53);
+            e -= 53;
+        }
+        for (int j = 0; j < limbs; j++)
+        {
+            uint64_t q = c.primes[j];
+            uint64_t r;
+            if (e >= 0)
+                r = mulmod(m % q, powmod(2, (uint64_t)e, q), q);
+            else
+                r = (e <= -64 ? 0 : (m >> (-e))) % q;
+            if (neg && r)
+                r = q - r;
+            out[j] = make_ulonglong2(r, shoup(r, q));
+        }
+    }
+} // namespace bk
+
+namespace bk
+{
+    // divide_and_round_q_last_ntt_inplace (util/rns.cpp:737-808) on every polynomial of `a`;
+    // the last limb's prime index is a->limbs - 1 (at the key level that is the special prime).
+    void rescale_core(Context &c, bk_ct_t a)
+    {
+        cudaStream_t s = c.stream();
+        const int l = a->limbs, lo = l - 1, k = a->size;
+        const size_t n = c.n;
+        Scratch tmp(s, (size_t)k * std::max(lo, 1) * n);
+        Scratch tlast(s, (size_t)k * n);
+        LdInvLimbOf ld{ a->d, n, l, lo, lo };
+        launch_inv_blocks(c, s, ld, tmp.p, k);
+        StInvAddHalf st{ tlast.p, n, lo };
+        launch_inv_cols(c, s, tmp.p, st, k);
+        LdDivRound ld2{ tlast.p, n, lo, c.primes[lo] };
+        launch_fwd_cols(c, s, ld2, tmp.p, k * lo);
+        size_t words = (size_t)k * lo * n;
+        u64 *out = alloc_words(c, words);
+        StRescale st2{ a->d, out, c.inv_last(lo), n, l, lo };
+        launch_fwd_blocks(c, s, tmp.p, st2, k * lo);
+        adopt(a, out, words, k, lo);
+        a->scale = a->scale / (double)c.primes[lo];
+    }
+
+} // namespace bk
+
+using namespace bk;
+
+struct ScalarPack
+{
+    ulonglong2 c[62];
+};
+
+template <bool MUL>
+__global__ void __launch_bounds__(256) k_scalar_pack(u64 *__restrict__ a, ScalarPack sp, const PrimeDev *primes,
+                                                     int log_n, int limbs, int polys)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = (size_t)polys * per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2;
+        int limb = (int)((e % per_poly) >> log_n);
+        const u64 q = primes[limb].q;
+        ulonglong2 f = sp.c[limb];
+        ulonglong2 va = *reinterpret_cast<ulonglong2 *>(a + e);
+        if (MUL)
+        {
+            va.x = csub(mul_shoup_lazy(va.x, f.x, f.y, q), q);
+            va.y = csub(mul_shoup_lazy(va.y, f.x, f.y, q), q);
+        }
+        else
+        {
+            va.x = addmod(va.x, f.x, q);
+            va.y = addmod(va.y, f.x, q);
+        }
+        *reinterpret_cast<ulonglong2 *>(a + e) = va;
+    }
+}
+
+extern "C"
+{
+    const char *bk_last_error(void)
+    {
+        return g_err.c_str();
+    }
+    const char *bk_version(void)
+    {
+        return "b200ckks 0.1 (sm_100a)";
+    }
+
+    // ---- host-only helpers ---------------------------------------------------------------------
+    bk_status bk_coeff_modulus_create(int log_n, const int *bit_sizes, int count, uint64_t *primes_out)
+    {
+        BK_TRY
+        if (!bit_sizes || !primes_out || count < 1)
+            throw std::invalid_argument("bit_sizes is invalid");
+        auto p = coeff_modulus_create(log_n, std::vector<int>(bit_sizes, bit_sizes + count));
+        std::memcpy(primes_out, p.data(), sizeof(uint64_t) * p.size());
+        BK_END
+    }
+    bk_status bk_minimal_primitive_root(int log_n, uint64_t q, uint64_t *root_out)
+    {
+        BK_TRY
+        *root_out = minimal_primitive_root(uint64_t(2) << log_n, q);
+        BK_END
+    }
+    bk_status bk_galois_elt_from_step(int log_n, int step, uint32_t *elt_out)
+    {
+        BK_TRY
+        *elt_out = galois_elt_from_step(log_n, step);
+        BK_END
+    }
+    bk_status bk_galois_table_ntt(int log_n, uint32_t galois_elt, uint32_t *table_out)
+    {
+        BK_TRY
+        galois_table_ntt(log_n, galois_elt, table_out);
+        BK_END
+    }
+    bk_status bk_ntt_root_powers(int log_n, uint64_t q, int inverse, uint64_t *out)
+    {
+        BK_TRY
+        if (inverse)
+        {
+            auto v = seal_inv_root_powers(log_n, q);
+            std::memcpy(out, v.data(), v.size() * sizeof(uint64_t));
+        }
+        else
+        {
+            std::vector<uint64_t> w, iw;
+            ntt_tables(log_n, q, w, iw);
+            std::memcpy(out, w.data(), w.size() * sizeof(uint64_t));
+        }
+        BK_END
+    }
+
+    // ---- context -------------------------------------------------------------------------------
+    bk_status bk_context_create(int log_n, const uint64_t *primes, int n_primes, int device, bk_context_t *out)
+    {
+        BK_TRY
+        if (!primes || !out)
+            throw std::invalid_argument("null argument");
+        *out = new bk_context_s(log_n, primes, n_primes, device);
+        BK_END
+    }
+    bk_status bk_context_destroy(bk_context_t ctx)
+    {
+        BK_TRY
+        delete ctx;
+        BK_END
+    }
+    bk_status bk_context_info(bk_context_t ctx, int *log_n, int *n_primes, int *device)
+    {
+        BK_TRY
+        if (log_n)
+            *log_n = ctx->log_n;
+        if (n_primes)
+            *n_primes = ctx->n_primes;
+        if (device)
+            *device = ctx->device;
+        BK_END
+    }
+    bk_status bk_context_get_primes(bk_context_t ctx, uint64_t *primes_out)
+    {
+        BK_TRY
+        std::memcpy(primes_out, ctx->primes.data(), sizeof(uint64_t) * ctx->n_primes);
+        BK_END
+    }
+    bk_status bk_context_set_ks_chunk(bk_context_t ctx, int chunk)
+    {
+        BK_TRY
+        if (chunk < 1)
+            throw std::invalid_argument("chunk must be positive");
+        ctx->ks_chunk = chunk;
+        BK_END
+    }
+    bk_status bk_sync(bk_context_t ctx)
+    {
+        BK_TRY
+        BK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        BK_END
+    }
+    bk_status bk_stream(bk_context_t ctx, void **stream_out)
+    {
+        BK_TRY
+        *stream_out = (void *)ctx->stream();
+        BK_END
+    }
+    bk_status bk_launch_count(bk_context_t ctx, uint64_t *count_out)
+    {
+        BK_TRY
+        *count_out = ctx->launches.load();
+        BK_END
+    }
+
+    // ---- ciphertext ----------------------------------------------------------------------------
+    bk_status bk_ct_create(bk_context_t ctx, bk_ct_t *out)
+    {
+        BK_TRY
+        auto ct = new bk_ct_s();
+        ct->ctx = ctx;
+        *out = ct;
+        BK_END
+    }
+    bk_status bk_ct_destroy(bk_ct_t ct)
+    {
+        BK_TRY
+        if (ct)
+        {
+            if (ct->d)
+                cudaFreeAsync(ct->d, ct->ctx->stream());
+            delete ct;
+        }
+        BK_END
+    }
+    bk_status bk_ct_copy(bk_ct_t dst, bk_ct_t src)
+    {
+        BK_TRY
+        if (dst == src)
+            return BK_OK;
+        if (dst->ctx != src->ctx)
+            throw std::invalid_argument("context mismatch");
+        Context &c = *src->ctx;
+        ensure_ct(dst, src->size, src->limbs, false);
+        size_t words = (size_t)src->size * src->limbs * c.n;
+        if (words)
+            BK_CUDA(cudaMemcpyAsync(dst->d, src->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream()));
+        dst->scale = src->scale;
+        dst->ntt = src->ntt;
+        BK_END
+    }
+    bk_status bk_ct_resize(bk_ct_t ct, int size, int limbs)
+    {
+        BK_TRY
+        Context &c = *ct->ctx;
+        if (size < 2 || limbs < 1 || limbs > c.n_primes)
+            throw std::invalid_argument("invalid size");
+        // Ciphertext::resize keeps the leading words of the flat buffer (dynarray.h) - same here
+        int old_size = ct->size, old_limbs = ct->limbs;
+        size_t old_words = (size_t)old_size * old_limbs * c.n;
+        size_t words = (size_t)size * limbs * c.n;
+        ensure_ct(ct, size, limbs, true);
+        if (words > old_words)
+            BK_CUDA(cudaMemsetAsync(ct->d + old_words, 0, (words - old_words) * sizeof(u64), c.stream()));
+        BK_END
+    }
+    bk_status bk_ct_info(bk_ct_t ct, int *size, int *limbs, double *scale, int *is_ntt)
+    {
+        BK_TRY
+        if (size)
+            *size = ct->size;
+        if (limbs)
+            *limbs = ct->limbs;
+        if (scale)
+            *scale = ct->scale;
+        if (is_ntt)
+            *is_ntt = ct->ntt ? 1 : 0;
+        BK_END
+    }
+    bk_status bk_ct_set_scale(bk_ct_t ct, double scale)
+    {
+        BK_TRY
+        ct->scale = scale;
+        BK_END
+    }
+    bk_status bk_ct_set_ntt_form(bk_ct_t ct, int is_ntt)
+    {
+        BK_TRY
+        ct->ntt = is_ntt != 0;
+        BK_END
+    }
+    bk_status bk_ct_upload(bk_ct_t ct, const uint64_t *host, int size, int limbs, double scale, int is_ntt)
+    {
+        BK_TRY
+        Context &c = *ct->ctx;
+        if (size < 1 || limbs < 1 || limbs > c.n_primes)
+            throw std::invalid_argument("invalid size");
+        ensure_ct(ct, size, limbs, false);
+        cudaStream_t s = c.stream();
+        BK_CUDA(cudaMemcpyAsync(ct->d, host, (size_t)size * limbs * c.n * sizeof(u64), cudaMemcpyHostToDevice, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        ct->scale = scale;
+        ct->ntt = is_ntt != 0;
+        BK_END
+    }
+    bk_status bk_ct_download(bk_ct_t ct, uint64_t *host_out)
+    {
+        BK_TRY
+        Context &c = *ct->ctx;
+        cudaStream_t s = c.stream();
+        BK_CUDA(cudaMemcpyAsync(host_out, ct->d, (size_t)ct->size * ct->limbs * c.n * sizeof(u64),
+                                cudaMemcpyDeviceToHost, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        BK_END
+    }
+    bk_status bk_ct_device_ptr(bk_ct_t ct, void **dev_ptr_out)
+    {
+        BK_TRY
+        *dev_ptr_out = ct->d;
+        BK_END
+    }
+
+    // ---- plaintext -----------------------------------------------------------------------------
+    bk_status bk_pt_create(bk_context_t ctx, bk_pt_t *out)
+    {
+        BK_TRY
+        auto pt = new bk_pt_s();
+        pt->ctx = ctx;
+        *out = pt;
+        BK_END
+    }
+    bk_status bk_pt_destroy(bk_pt_t pt)
+    {
+        BK_TRY
+        if (pt)
+        {
+            if (pt->d)
+                cudaFreeAsync(pt->d, pt->ctx->stream());
+            delete pt;
+        }
+        BK_END
+    }
+    bk_status bk_pt_copy(bk_pt_t dst, bk_pt_t src)
+    {
+        BK_TRY
+        if (dst == src)
+            return BK_OK;
+        Context &c = *src->ctx;
+        ensure_pt(dst, src->limbs);
+        BK_CUDA(cudaMemcpyAsync(dst->d, src->d, (size_t)src->limbs * c.n * sizeof(u64), cudaMemcpyDeviceToDevice,
+                                c.stream()));
+        dst->scale = src->scale;
+        BK_END
+    }
+    bk_status bk_pt_info(bk_pt_t pt, int *limbs, double *scale)
+    {
+        BK_TRY
+        if (limbs)
+            *limbs = pt->limbs;
+        if (scale)
+            *scale = pt->scale;
+        BK_END
+    }
+    bk_status bk_pt_set_scale(bk_pt_t pt, double scale)
+    {
+        BK_TRY
+        pt->scale = scale;
+        BK_END
+    }
+    bk_status bk_pt_upload(bk_pt_t pt, const uint64_t *host, int limbs, double scale)
+    {
+        BK_TRY
+        Context &c = *pt->ctx;
+        if (limbs < 1 || limbs > c.n_primes)
+            throw std::invalid_argument("invalid size");
+        ensure_pt(pt, limbs);
+        cudaStream_t s = c.stream();
+        BK_CUDA(cudaMemcpyAsync(pt->d, host, (size_t)limbs * c.n * sizeof(u64), cudaMemcpyHostToDevice, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        pt->scale = scale;
+        BK_END
+    }
+    bk_status bk_pt_download(bk_pt_t pt, uint64_t *host_out)
+    {
+        BK_TRY
+        Context &c = *pt->ctx;
+        cudaStream_t s = c.stream();
+        BK_CUDA(cudaMemcpyAsync(host_out, pt->d, (size_t)pt->limbs * c.n * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        BK_END
+    }
+    bk_status bk_pt_mod_switch_to(bk_pt_t pt, int limbs)
+    {
+        BK_TRY
+        // mod_switch_drop_to_next(Plaintext) (evaluator.cpp:1248-1281): limbs are contiguous, the
+        // drop is a truncation
+        if (limbs < 1 || limbs > pt->limbs)
+            throw std::invalid_argument("cannot switch to higher level modulus");
+        pt->limbs = limbs;
+        BK_END
+    }
+
+    // ---- keys ----------------------------------------------------------------------------------
+    bk_status bk_kskey_upload(bk_context_t ctx, const uint64_t *host, int digits, int max_limbs, bk_kskey_t *out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        const int top = c.top_limbs();
+        if (digits < 1 || digits > top)
+            throw std::invalid_argument("kswitch key digit count is invalid");
+        int kl = (max_limbs > 0 && max_limbs < top) ? max_limbs : top;
+        int kd = std::min(digits, kl);
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        auto key = new bk_kskey_s();
+        key->ctx = ctx;
+        key->digits = kd;
+        key->klimbs = kl;
+        key->words = (size_t)kd * 2 * (kl + 1) * n;
+        BK_CUDA(cudaMalloc((void **)&key->d, key->words * sizeof(u64)));
+        // stage one (digit, poly) at a time: [kl+1][N] natural -> transposed-block layout
+        Scratch stage(s, (size_t)(kl + 1) * n);
+        for (int j = 0; j < kd; j++)
+            for (int p = 0; p < 2; p++)
+            {
+                const uint64_t *src = host + ((size_t)j * 2 + p) * c.n_primes * n;
+                BK_CUDA(cudaMemcpyAsync(stage.p, src, (size_t)kl * n * sizeof(u64), cudaMemcpyHostToDevice, s));
+                BK_CUDA(cudaMemcpyAsync(stage.p + (size_t)kl * n, src + (size_t)(c.n_primes - 1) * n, n * sizeof(u64),
+                                        cudaMemcpyHostToDevice, s));
+                size_t total = (size_t)(kl + 1) * n;
+                k_transpose_blocks<<<c.ew_grid(total), 256, 0, s>>>(
+                    stage.p, key->d + ((size_t)j * 2 + p) * (kl + 1) * n, total);
+                c.count();
+                BK_CUDA(cudaStreamSynchronize(s)); // host buffer is pageable; keep staging ordered
+            }
+        *out = key;
+        BK_END
+    }
+    bk_status bk_kskey_destroy(bk_kskey_t key)
+    {
+        BK_TRY
+        if (key)
+        {
+            key->ctx->activate();
+            cudaStreamSynchronize(key->ctx->stream());
+            cudaFree(key->d);
+            delete key;
+        }
+        BK_END
+    }
+    bk_status bk_kskey_info(bk_kskey_t key, int *digits, int *limbs, uint64_t *device_bytes)
+    {
+        BK_TRY
+        if (digits)
+            *digits = key->digits;
+        if (limbs)
+            *limbs = key->klimbs;
+        if (device_bytes)
+            *device_bytes = key->words * sizeof(u64);
+        BK_END
+    }
+    bk_status bk_kskey_download(bk_kskey_t key, uint64_t *host_out)
+    {
+        // SEAL layout restricted to the resident part: [digits][2][klimbs+1][N], special last
+        BK_TRY
+        Context &c = *key->ctx;
+        cudaStream_t s = c.stream();
+        Scratch tmp(s, key->words);
+        // the transposition is an involution on each 256-block
+        k_transpose_blocks<<<c.ew_grid(key->words), 256, 0, s>>>(key->d, tmp.p, key->words);
+        c.count();
+        BK_CUDA(cudaMemcpyAsync(host_out, tmp.p, key->words * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        BK_END
+    }
+    bk_status bk_gkeys_create(bk_context_t ctx, bk_gkeys_t *out)
+    {
+        BK_TRY
+        auto g = new bk_gkeys_s();
+        g->ctx = ctx;
+        *out = g;
+        BK_END
+    }
+    bk_status bk_gkeys_destroy(bk_gkeys_t gk)
+    {
+        BK_TRY
+        if (gk)
+        {
+            for (auto &kv : gk->keys)
+                bk_kskey_destroy(kv.second);
+            delete gk;
+        }
+        BK_END
+    }
+    bk_status bk_gkeys_set(bk_gkeys_t gk, uint32_t galois_elt, bk_kskey_t key)
+    {
+        BK_TRY
+        std::lock_guard<std::mutex> g(gk->mu);
+        auto it = gk->keys.find(galois_elt);
+        if (it != gk->keys.end())
+        {
+            bk_kskey_destroy(it->second);
+            it->second = key;
+        }
+        else
+            gk->keys[galois_elt] = key;
+        BK_END
+    }
+    bk_status bk_gkeys_has(bk_gkeys_t gk, uint32_t galois_elt, int *has_out)
+    {
+        BK_TRY
+        *has_out = find_gkey(gk, galois_elt) ? 1 : 0;
+        BK_END
+    }
+
+    // ---- Evaluator -----------------------------------------------------------------------------
+    static void add_sub(bk_context_t ctx, bk_ct_t a, bk_ct_t b, bool sub)
+    {
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted1");
+        check_ct(ctx, b, "encrypted2");
+        if (a->limbs != b->limbs)
+            throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        if (a->ntt != b->ntt)
+            throw std::invalid_argument("NTT form mismatch");
+        if (!close_scale(a->scale, b->scale))
+            throw std::invalid_argument("scale mismatch");
+        cudaStream_t s = c.stream();
+        const int l = a->limbs;
+        int mn = std::min(a->size, b->size), mx = std::max(a->size, b->size);
+        int a_size = a->size;
+        if (mx > a->size)
+            ensure_ct(a, mx, l, true);
+        size_t per_poly = (size_t)l * c.n;
+        int grid = c.ew_grid((size_t)mn * per_poly / 2);
+        if (sub)
+            k_ew<EW_SUB><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+        else
+            k_ew<EW_ADD><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+        c.count();
+        if (a_size < b->size)
+        {
+            size_t words = (size_t)(b->size - a_size) * per_poly;
+            BK_CUDA(cudaMemcpyAsync(a->d + (size_t)a_size * per_poly, b->d + (size_t)a_size * per_poly,
+                                    words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            if (sub)
+            {
+                k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, s>>>(a->d + (size_t)a_size * per_poly, nullptr,
+                                                                  c.d_primes, c.log_n, l, b->size - a_size, 0);
+                c.count();
+            }
+        }
+    }
+
+    bk_status bk_add_inplace(bk_context_t ctx, bk_ct_t a, bk_ct_t b)
+    {
+        BK_TRY
+        add_sub(ctx, a, b, false);
+        BK_END
+    }
+    bk_status bk_sub_inplace(bk_context_t ctx, bk_ct_t a, bk_ct_t b)
+    {
+        BK_TRY
+        add_sub(ctx, a, b, true);
+        BK_END
+    }
+    bk_status bk_negate_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        size_t words = (size_t)a->size * a->limbs * c.n;
+        k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, nullptr, c.d_primes, c.log_n, a->limbs,
+                                                                   a->size, 0);
+        c.count();
+        BK_END
+    }
+
+    bk_status bk_multiply_inplace(bk_context_t ctx, bk_ct_t a, bk_ct_t b)
+    {
+        BK_TRY
+        // ckks_multiply (evaluator.cpp:673-814), size 2 x size 2 -> size 3
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted1");
+        check_ct(ctx, b, "encrypted2");
+        if (a->limbs != b->limbs)
+            throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        if (!a->ntt || !b->ntt)
+            throw std::invalid_argument("encrypted1 or encrypted2 must be in NTT form");
+        if (a->size != 2 || b->size != 2)
+            throw std::invalid_argument("only size-2 ciphertexts are supported by multiply");
+        double new_scale = a->scale * b->scale;
+        if (!c.scale_in_bounds(new_scale, a->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        const int l = a->limbs;
+        size_t words = (size_t)3 * l * c.n;
+        u64 *out = alloc_words(c, words);
+        if (a == b)
+            k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
+        else
+            k_tensor<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, b->d, out, c.d_primes, c.log_n, l);
+        c.count();
+        adopt(a, out, words, 3, l);
+        a->scale = new_scale;
+        BK_END
+    }
+    bk_status bk_square_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        // ckks_square (evaluator.cpp:1000-1059)
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (!a->ntt)
+            throw std::invalid_argument("encrypted must be in NTT form");
+        if (a->size != 2)
+            throw std::invalid_argument("only size-2 ciphertexts are supported by square");
+        double new_scale = a->scale * a->scale;
+        if (!c.scale_in_bounds(new_scale, a->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        const int l = a->limbs;
+        size_t words = (size_t)3 * l * c.n;
+        u64 *out = alloc_words(c, words);
+        k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
+        c.count();
+        adopt(a, out, words, 3, l);
+        a->scale = new_scale;
+        BK_END
+    }
+
+    bk_status bk_relinearize_inplace(bk_context_t ctx, bk_ct_t a, bk_kskey_t relin_key)
+    {
+        BK_TRY
+        // relinearize_internal (evaluator.cpp:1061-1116) for size 3 -> 2
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (!relin_key || relin_key->ctx != ctx)
+            throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+        if (a->size == 2)
+            return BK_OK;
+        if (a->size != 3)
+            throw std::invalid_argument("not enough relinearization keys");
+        if (!a->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        const int l = a->limbs;
+        size_t per_poly = (size_t)l * c.n;
+        size_t words = 2 * per_poly;
+        u64 *out = alloc_words(c, words);
+        key_switch(c, c.stream(), a->d + 2 * per_poly, nullptr, a->d, a->d + per_poly, out, l, relin_key);
+        adopt(a, out, words, 2, l);
+        BK_END
+    }
+
+    bk_status bk_rescale_to_next_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        // rescale_to_next (evaluator.cpp:1378-1414) -> mod_switch_scale_to_next (:1118-1181)
+        check_ct(ctx, a, "encrypted");
+        if (a->limbs < 2)
+            throw std::invalid_argument("end of modulus switching chain reached");
+        if (!a->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        rescale_core(*ctx, a);
+        BK_END
+    }
+
+    static void drop_to(Context &c, bk_ct_t a, int limbs)
+    {
+        if (limbs == a->limbs)
+            return;
+        size_t words = (size_t)a->size * limbs * c.n;
+        u64 *out = alloc_words(c, words);
+        k_drop_limbs<<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, out, c.log_n, a->limbs, limbs, a->size);
+        c.count();
+        adopt(a, out, words, a->size, limbs);
+    }
+
+    bk_status bk_mod_switch_to_next_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        // mod_switch_drop_to_next (evaluator.cpp:1183-1246)
+        check_ct(ctx, a, "encrypted");
+        if (a->limbs < 2)
+            throw std::invalid_argument("end of modulus switching chain reached");
+        if (!a->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (!ctx->scale_in_bounds(a->scale, a->limbs - 1))
+            throw std::invalid_argument("scale out of bounds");
+        drop_to(*ctx, a, a->limbs - 1);
+        BK_END
+    }
+    bk_status bk_mod_switch_to_inplace(bk_context_t ctx, bk_ct_t a, int limbs)
+    {
+        BK_TRY
+        // mod_switch_to_inplace (evaluator.cpp:1326-1348): repeated drop == one strided copy
+        check_ct(ctx, a, "encrypted");
+        if (limbs < 1 || limbs > ctx->top_limbs())
+            throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        if (limbs > a->limbs)
+            throw std::invalid_argument("cannot switch to higher level modulus");
+        if (limbs < a->limbs)
+        {
+            if (!a->ntt)
+                throw std::invalid_argument("CKKS encrypted must be in NTT form");
+            if (!ctx->scale_in_bounds(a->scale, limbs))
+                throw std::invalid_argument("scale out of bounds");
+        }
+        drop_to(*ctx, a, limbs);
+        BK_END
+    }
+
+    bk_status bk_apply_galois_inplace(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk)
+    {
+        BK_TRY
+        apply_galois(*ctx, a, galois_elt, gk);
+        BK_END
+    }
+    bk_status bk_rotate_vector_inplace(bk_context_t ctx, bk_ct_t a, int steps, bk_gkeys_t gk)
+    {
+        BK_TRY
+        rotate_internal(*ctx, a, steps, gk);
+        BK_END
+    }
+    bk_status bk_complex_conjugate_inplace(bk_context_t ctx, bk_ct_t a, bk_gkeys_t gk)
+    {
+        BK_TRY
+        apply_galois(*ctx, a, (uint32_t)(2 * ctx->n - 1), gk);
+        BK_END
+    }
+
+    static void plain_check(bk_context_t ctx, bk_ct_t a, bk_pt_t p)
+    {
+        check_ct(ctx, a, "encrypted");
+        if (!p || p->ctx != ctx || !p->d)
+            throw std::invalid_argument("plain is not valid for encryption parameters");
+        if (!a->ntt)
+            throw std::invalid_argument("encrypted is not in NTT form");
+        if (a->limbs != p->limbs)
+            throw std::invalid_argument("encrypted and plain parameter mismatch");
+    }
+    bk_status bk_add_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        plain_check(ctx, a, p);
+        if (!close_scale(a->scale, p->scale))
+            throw std::invalid_argument("scale mismatch");
+        k_ew<EW_ADD><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
+                                                                                    a->limbs, 1, 1);
+        c.count();
+        BK_END
+    }
+    bk_status bk_sub_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        plain_check(ctx, a, p);
+        if (!close_scale(a->scale, p->scale))
+            throw std::invalid_argument("scale mismatch");
+        k_ew<EW_SUB><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
+                                                                                    a->limbs, 1, 1);
+        c.count();
+        BK_END
+    }
+    bk_status bk_multiply_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        plain_check(ctx, a, p);
+        double new_scale = a->scale * p->scale;
+        if (!c.scale_in_bounds(new_scale, a->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        k_ew<EW_MUL><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
+            a->d, p->d, c.d_primes, c.log_n, a->limbs, a->size, 1);
+        c.count();
+        a->scale = new_scale;
+        BK_END
+    }
+
+    bk_status bk_transform_to_ntt_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        check_ct(ctx, a, "encrypted");
+        if (a->ntt)
+            throw std::invalid_argument("encrypted is already in NTT form");
+        ntt_fwd(*ctx, ctx->stream(), a->d, a->size * a->limbs, limb_map(a->limbs));
+        a->ntt = true;
+        BK_END
+    }
+    bk_status bk_transform_from_ntt_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        check_ct(ctx, a, "encrypted");
+        if (!a->ntt)
+            throw std::invalid_argument("encrypted is not in NTT form");
+        ntt_inv(*ctx, ctx->stream(), a->d, a->size * a->limbs, limb_map(a->limbs));
+        a->ntt = false;
+        BK_END
+    }
+
+    bk_status bk_add_const_inplace(bk_context_t ctx, bk_ct_t a, double value)
+    {
+        BK_TRY
+        // add_const_inplace (evaluator.cpp:287-293): scalar encode at scale = ct.scale, add to c0
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (!a->ntt)
+            throw std::invalid_argument("encrypted is not in NTT form");
+        ScalarPack sp;
+        scalar_residues(c, value, a->scale, a->limbs, sp.c);
+        k_scalar_pack<false><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, sp, c.d_primes,
+                                                                                            c.log_n, a->limbs, 1);
+        c.count();
+        BK_END
+    }
+    bk_status bk_multiply_const_inplace(bk_context_t ctx, bk_ct_t a, double value)
+    {
+        BK_TRY
+        // multiply_const_inplace (evaluator.cpp:295-301): scalar encode at scale = ct.scale
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (!a->ntt)
+            throw std::invalid_argument("encrypted is not in NTT form");
+        ScalarPack sp;
+        scalar_residues(c, value, a->scale, a->limbs, sp.c);
+        double new_scale = a->scale * a->scale;
+        if (!c.scale_in_bounds(new_scale, a->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        k_scalar_pack<true><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
+            a->d, sp, c.d_primes, c.log_n, a->limbs, a->size);
+        c.count();
+        a->scale = new_scale;
+        BK_END
+    }
+
+    bk_status bk_modraise_inplace(bk_context_t ctx, bk_ct_t a)
+    {
+        BK_TRY
+        // Bootstrapper::modraise_inplace (ckks_bootstrapping/Bootstrapper.cpp:2894-2948)
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (a->size != 2)
+            throw std::invalid_argument("Ciphertexts of size 2 are supported only!");
+        if (a->limbs != 1)
+            throw std::invalid_argument("Ciphertexts in the lowest level are supported only!");
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        const int L = c.top_limbs();
+        if (a->ntt)
+        {
+            ntt_inv(c, s, a->d, 2, limb_map(1));
+            a->ntt = false;
+        }
+        size_t words = (size_t)2 * L * n;
+        Scratch tmp(s, words);
+        u64 *out = alloc_words(c, words);
+        LdModRaise ld{ a->d, n, L, c.primes[0] };
+        launch_fwd_cols(c, s, ld, tmp.p, 2 * L);
+        StPlain st{ out, limb_map(L), n };
+        launch_fwd_blocks(c, s, tmp.p, st, 2 * L);
+        adopt(a, out, words, 2, L);
+        a->ntt = true;
+        BK_END
+    }
+
+    // ---- raw NTT -------------------------------------------------------------------------------
+    bk_status bk_ntt_limbs(bk_context_t ctx, uint64_t *dev_data, const int *prime_idx, int count, int inverse)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (count < 1)
+            return BK_OK;
+        for (int i = 0; i < count; i++)
+            if (prime_idx[i] < 0 || prime_idx[i] >= c.n_primes)
+                throw std::invalid_argument("prime index out of range");
+        cudaStream_t s = c.stream();
+        int *d_idx;
+        BK_CUDA(cudaMallocAsync((void **)&d_idx, sizeof(int) * count, s));
+        BK_CUDA(cudaMemcpyAsync(d_idx, prime_idx, sizeof(int) * count, cudaMemcpyHostToDevice, s));
+        JobMap m = limb_map(count);
+        m.explicit_primes = d_idx;
+        if (inverse)
+            ntt_inv(c, s, (u64 *)dev_data, count, m);
+        else
+            ntt_fwd(c, s, (u64 *)dev_data, count, m);
+        BK_CUDA(cudaFreeAsync(d_idx, s));
+        BK_END
+    }
+    bk_status bk_ntt_limbs_host(bk_context_t ctx, uint64_t *host_data, const int *prime_idx, int count, int inverse)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        cudaStream_t s = c.stream();
+        Scratch buf(s, (size_t)count * c.n);
+        BK_CUDA(cudaMemcpyAsync(buf.p, host_data, (size_t)count * c.n * sizeof(u64), cudaMemcpyHostToDevice, s));
+        bk_status st = bk_ntt_limbs(ctx, (uint64_t *)buf.p, prime_idx, count, inverse);
+        if (st != BK_OK)
+            return st;
+        BK_CUDA(cudaMemcpyAsync(host_data, buf.p, (size_t)count * c.n * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        BK_CUDA(cudaStreamSynchronize(s));
+        BK_END
+    }
+}

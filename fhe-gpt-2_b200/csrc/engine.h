@@ -1,0 +1,173 @@
+// engine.h - host-side objects behind the C ABI (include/b200ckks.h).
+#pragma once
+#include "../../include/b200ckks.h"
+#include "hostmath.h"
+#include "kernels.cuh"
+#include <atomic>
+#include <cuda_runtime.h>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace bk
+{
+    struct CudaError : std::runtime_error
+    {
+        using std::runtime_error::runtime_error;
+    };
+    struct NoDevice : std::runtime_error
+    {
+        using std::runtime_error::runtime_error;
+    };
+
+#define BK_CUDA(expr)                                                                                                  \
+    do                                                                                                                 \
+    {                                                                                                                  \
+        cudaError_t _e = (expr);                                                                                       \
+        if (_e != cudaSuccess)                                                                                         \
+            throw bk::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));                                   \
+    } while (0)
+
+    // stream-ordered scratch buffer (cudaMallocAsync pool; the pool's release threshold is
+    // raised at context creation so steady-state allocation never reaches the driver)
+    struct Scratch
+    {
+        u64 *p = nullptr;
+        cudaStream_t s;
+        Scratch(cudaStream_t stream, size_t words) : s(stream)
+        {
+            BK_CUDA(cudaMallocAsync((void **)&p, words * sizeof(u64), s));
+        }
+        ~Scratch()
+        {
+            if (p)
+                cudaFreeAsync(p, s);
+        }
+        Scratch(const Scratch &) = delete;
+        Scratch &operator=(const Scratch &) = delete;
+    };
+
+    struct EncoderState; // encoder.cu
+
+    struct Context
+    {
+        int log_n = 0;
+        size_t n = 0;
+        int n_primes = 0; // key-level chain, special prime last
+        int device = 0;
+        int sm_count = 148;
+        std::vector<uint64_t> primes;
+        std::vector<int> total_bits; // total_bits[l] = bit count of q_0 * ... * q_{l-1}
+        PrimeDev *d_primes = nullptr;
+        std::vector<PrimeDev> h_primes;
+        ulonglong2 *d_tw = nullptr, *d_itw = nullptr;
+        ulonglong2 *d_inv = nullptr; // [n_primes(last)][n_primes(i)] {q_last^-1 mod q_i, shoup}
+        NttTables tables{};
+        int ks_chunk = 4;
+        int sparse_slots = 0;
+        std::atomic<uint64_t> launches{ 0 };
+
+        std::mutex mu;
+        std::unordered_map<std::thread::id, cudaStream_t> streams;
+        std::unordered_map<uint32_t, uint32_t *> galois_tables; // device tables
+
+        EncoderState *enc = nullptr; // built lazily on first encode/decode (encoder.cu)
+        std::mutex enc_mu;
+
+        Context(int log_n, const uint64_t *primes, int n_primes, int device);
+        ~Context();
+        cudaStream_t stream();
+        const uint32_t *galois_table(uint32_t elt);
+        void count(int k = 1)
+        {
+            launches.fetch_add((uint64_t)k, std::memory_order_relaxed);
+        }
+        int top_limbs() const
+        {
+            return n_primes - 1;
+        }
+        bool scale_in_bounds(double scale, int limbs) const;
+        const ulonglong2 *inv_last(int last_prime) const
+        {
+            return d_inv + (size_t)last_prime * n_primes;
+        }
+        int ew_grid(size_t work_items) const;
+        void activate() const;
+    };
+
+    // ---- internal entry points shared between the .cu files ------------------------------------
+    // NTT of `jobs` limb-polynomials (natural layout) in place; prime of job j = map.prime(j)
+    void ntt_fwd(Context &c, cudaStream_t s, u64 *data, int jobs, JobMap map);
+    void ntt_inv(Context &c, cudaStream_t s, u64 *data, int jobs, JobMap map);
+    JobMap limb_map(int limbs);
+    JobMap key_map(const Context &c); // limbs 0..n_primes-1 incl. special
+    void ensure_ct(bk_ct_t ct, int size, int limbs, bool keep);
+    void ensure_pt(bk_pt_t pt, int limbs);
+    void destroy_encoder(Context &c);
+    void rescale_core(Context &c, bk_ct_t a);
+} // namespace bk
+
+struct bk_context_s : bk::Context
+{
+    using bk::Context::Context;
+};
+
+struct bk_ct_s
+{
+    bk::Context *ctx;
+    u64 *d = nullptr;
+    size_t cap = 0; // words
+    int size = 0, limbs = 0;
+    double scale = 1.0;
+    bool ntt = true;
+};
+
+struct bk_pt_s
+{
+    bk::Context *ctx;
+    u64 *d = nullptr;
+    size_t cap = 0;
+    int limbs = 0;
+    double scale = 1.0;
+};
+
+struct bk_kskey_s
+{
+    bk::Context *ctx;
+    u64 *d = nullptr; // [digits][2][klimbs+1][N], transposed-block layout, special prime at klimbs
+    int digits = 0, klimbs = 0;
+    size_t words = 0;
+};
+
+struct bk_gkeys_s
+{
+    bk::Context *ctx;
+    std::mutex mu;
+    std::map<uint32_t, bk_kskey_t> keys;
+};
+
+struct bk_sk_s
+{
+    bk::Context *ctx;
+    u64 *d = nullptr; // [n_primes][N] NTT form
+};
+
+// ---- C-ABI exception fence ---------------------------------------------------------------------
+namespace bk
+{
+    void set_error(const char *msg);
+    bk_status fence(const std::exception_ptr &e);
+}
+#define BK_TRY try {
+#define BK_END                                                                                                         \
+    }                                                                                                                  \
+    catch (...)                                                                                                        \
+    {                                                                                                                  \
+        return bk::fence(std::current_exception());                                                                    \
+    }                                                                                                                  \
+    return BK_OK;

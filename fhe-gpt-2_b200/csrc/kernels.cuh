@@ -1,0 +1,524 @@
+// kernels.cuh - load/store functors fused into the NTT passes, the key-switch inner-product
+// kernel and the element-wise limb kernels.  Reference loops replaced (all under
+// seal-modified-3.6.6/native/src/seal/):
+//   util/polyarithsmallmod.cpp:18-169   add/sub/negate/dyadic_product/multiply_poly_scalar
+//   util/rns.cpp:737-808                divide_and_round_q_last_ntt_inplace (rescale)
+//   evaluator.cpp:2281-2525             switch_key_inplace (decompose, NTT, MAC, ModDown)
+//   util/galois.cpp:192-218             apply_galois_ntt (gather)
+#pragma once
+#include "ntt.cuh"
+
+// job -> prime index.  A "job" is one limb-polynomial; job % limbs is the limb index which is
+// also the prime index, except for one optional position mapped to the special prime.
+struct JobMap
+{
+    int limbs;
+    int special_pos;   // limb index that maps to special_prime, or -1
+    int special_prime;
+    const int *explicit_primes; // optional [jobs] table (raw NTT API)
+    __device__ __forceinline__ int prime(int job) const
+    {
+        if (explicit_primes)
+            return explicit_primes[job];
+        int l = job % limbs;
+        return l == special_pos ? special_prime : l;
+    }
+};
+
+__device__ __forceinline__ u64 reduce4q(u64 v, const PrimeDev &pd)
+{
+    v = csub(v, pd.two_q);
+    return csub(v, pd.q);
+}
+
+// ---------------------------------------------------------------- forward column-pass loaders
+struct LdPlain
+{
+    const u64 *src;
+    JobMap map;
+    size_t n;
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    __device__ __forceinline__ int prime(int job) const { return map.prime(job); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const
+    {
+        return src[(size_t)job * n + idx];
+    }
+};
+
+// Key-switch digit decomposition (evaluator.cpp:2386-2408): job = iloc * l + J; output modulus
+// I = I0 + iloc (I == l -> special prime); digit J of the INTT'd target is reduced mod q_I only
+// when q_J > q_I; the I == J product uses the NTT-form input directly, so that job is skipped.
+struct LdKsDigit
+{
+    const u64 *ttarget; // [l][N] coefficient form, canonical
+    const PrimeDev *primes;
+    size_t n;
+    int l, I0, special_prime;
+    __device__ __forceinline__ bool skip(int job) const { return (I0 + job / l) == (job % l); }
+    __device__ __forceinline__ int prime(int job) const
+    {
+        int I = I0 + job / l;
+        return I == l ? special_prime : I;
+    }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        int J = job % l;
+        u64 v = ttarget[(size_t)J * n + idx];
+        if (primes[J].q > pd.q)
+            v = barrett64(v, pd);
+        return v;
+    }
+};
+
+// Divide-and-round source (rns.cpp:766-784, evaluator.cpp:2480-2497): job = p * limbs_out + i;
+// value = (tlast[p] mod q_i) + (q_i - (half mod q_i)), half = q_last >> 1.
+struct LdDivRound
+{
+    const u64 *tlast; // [polys][N] coefficient form, canonical mod q_last, half already added
+    size_t n;
+    int limbs_out;
+    u64 qlast;
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    __device__ __forceinline__ int prime(int job) const { return job % limbs_out; }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        int p = job / limbs_out;
+        u64 v = tlast[(size_t)p * n + idx];
+        if (qlast > pd.q)
+            v = barrett64(v, pd);
+        u64 fix = pd.q - barrett64(qlast >> 1, pd);
+        return v + fix;
+    }
+};
+
+// ModRaise (Bootstrapper.cpp:2894-2948): job = p * limbs_out + i; source = coefficient-form
+// 1-limb ciphertext; centred lift of the q0 residue to q_i.
+struct LdModRaise
+{
+    const u64 *c; // [polys][N] coefficient form mod q0
+    size_t n;
+    int limbs_out;
+    u64 q0;
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    __device__ __forceinline__ int prime(int job) const { return job % limbs_out; }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        int p = job / limbs_out;
+        u64 v = c[(size_t)p * n + idx];
+        // value in (-q0/2, q0/2]: v > q0/2 represents v - q0
+        if (v > (q0 >> 1))
+        {
+            u64 neg = q0 - v; // magnitude
+            u64 r = barrett64(neg, pd);
+            return r ? pd.q - r : 0ull;
+        }
+        return barrett64(v, pd);
+    }
+};
+
+// ---------------------------------------------------------------- forward block-pass stores
+struct StPlain
+{
+    u64 *dst;
+    JobMap map;
+    size_t n;
+    __device__ __forceinline__ int prime(int job) const { return map.prime(job); }
+    __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
+    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        dst[(size_t)job * n + idx] = reduce4q(v, pd);
+    }
+};
+
+// Rescale tail (rns.cpp:786-806): dst[p][i] = (x[p][i] - NTT_i(t)) * q_last^-1 mod q_i.
+struct StRescale
+{
+    const u64 *x;  // [polys][limbs_in][N]
+    u64 *dst;      // [polys][limbs_out][N]
+    const ulonglong2 *inv; // [n_primes] {q_last^-1 mod q_i, shoup}
+    size_t n;
+    int limbs_in, limbs_out;
+    __device__ __forceinline__ int prime(int job) const { return job % limbs_out; }
+    __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
+    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        int p = job / limbs_out, i = job % limbs_out;
+        u64 r = x[((size_t)p * limbs_in + i) * n + idx];
+        u64 d = r + 2 * pd.two_q - v; // v in [0,4q)
+        ulonglong2 f = inv[i];
+        dst[(size_t)job * n + idx] = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+    }
+};
+
+// ModDown tail of the key switch (evaluator.cpp:2499-2522):
+//   dst[p][i] = base_p[i] + (acc[p][i] - NTT_i(t_p)) * P^-1 mod q_i
+// acc is in the transposed block layout written by k_ks_mac (pos = k*16 + t <-> e = 16t + k);
+// base_0 = c0 (optionally gathered through the Galois table), base_1 = c1 or nothing.
+struct StModDown
+{
+    const u64 *acc;  // [2][l+1][N] transposed-block layout
+    u64 *dst;        // [2][l][N]
+    const u64 *base0; // [l][N] or null
+    const u64 *base1; // [l][N] or null
+    const uint32_t *perm; // Galois table or null (applies to base0 only)
+    const ulonglong2 *inv; // [n_primes] {P^-1 mod q_i, shoup}
+    size_t n;
+    int l;
+    __device__ __forceinline__ int prime(int job) const { return job % l; }
+    __device__ __forceinline__ u64 pre(int job, int blk, int t, int k, u64 v, const PrimeDev &pd) const
+    {
+        int p = job / l, i = job % l;
+        u64 r = acc[((size_t)p * (l + 1) + i) * n + (size_t)blk * 256 + k * 16 + t];
+        u64 d = r + 2 * pd.two_q - v;
+        ulonglong2 f = inv[i];
+        return csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+    }
+    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        int p = job / l, i = job % l;
+        const u64 *b = p == 0 ? base0 : base1;
+        if (b)
+        {
+            int src = (p == 0 && perm) ? (int)perm[idx] : idx;
+            v = addmod(v, b[(size_t)i * n + src], pd.q);
+        }
+        dst[(size_t)job * n + idx] = v;
+    }
+};
+
+// ---------------------------------------------------------------- inverse block-pass loaders
+struct LdInvPlain
+{
+    static constexpr bool TLAYOUT = false;
+    const u64 *src;
+    JobMap map;
+    size_t n;
+    const uint32_t *perm; // optional Galois gather (apply_galois_ntt fused into the INTT load)
+    __device__ __forceinline__ int prime(int job) const { return map.prime(job); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const
+    {
+        int s = perm ? (int)perm[idx] : idx;
+        return src[(size_t)job * n + s];
+    }
+    __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
+};
+
+// strided source: job p reads limb `limb` of poly p in a [polys][limbs][N] array
+struct LdInvLimbOf
+{
+    static constexpr bool TLAYOUT = false;
+    const u64 *src;
+    size_t n;
+    int limbs, limb, prime_idx;
+    __device__ __forceinline__ int prime(int) const { return prime_idx; }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const
+    {
+        return src[((size_t)job * limbs + limb) * n + idx];
+    }
+    __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
+};
+
+// same, but the source is in the transposed block layout (k_ks_mac accumulators)
+struct LdInvLimbOfT
+{
+    static constexpr bool TLAYOUT = true;
+    const u64 *src;
+    size_t n;
+    int limbs, limb, prime_idx;
+    __device__ __forceinline__ int prime(int) const { return prime_idx; }
+    __device__ __forceinline__ u64 load(int, int, const PrimeDev &) const { return 0; }
+    __device__ __forceinline__ u64 load_t(int job, int blk, int pos) const
+    {
+        return src[((size_t)job * limbs + limb) * n + (size_t)blk * 256 + pos];
+    }
+};
+
+// ---------------------------------------------------------------- inverse column-pass stores
+struct StInvPlain
+{
+    u64 *dst;
+    JobMap map;
+    size_t n;
+    __device__ __forceinline__ int prime(int job) const { return map.prime(job); }
+    __device__ __forceinline__ void store(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        dst[(size_t)job * n + idx] = csub(v, pd.q);
+    }
+};
+
+// canonical INTT output + floor(q/2), reduced (rns.cpp:759-764, evaluator.cpp:2471-2478)
+struct StInvAddHalf
+{
+    u64 *dst;
+    size_t n;
+    int prime_idx;
+    __device__ __forceinline__ int prime(int) const { return prime_idx; }
+    __device__ __forceinline__ void store(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        v = csub(v, pd.q);
+        dst[(size_t)job * n + idx] = csub(v + (pd.q >> 1), pd.q);
+    }
+};
+
+// ============================================================================================
+// Key-switch inner product (evaluator.cpp:2368-2463), fused with the block pass of the digit
+// NTTs.  grid = (N/4096, nI), block = 256.  CTA (tile, iloc) owns 16 blocks of output modulus
+// I = I0 + iloc and loops over the l digits J:
+//    operand  = I == J ? target_ntt[J] (gathered through the Galois table if any)
+//                      : block pass of inter[iloc][J] (column pass output of LdKsDigit)
+//    acc_p   += operand * key[J][p][I]          (128-bit accumulators in registers)
+// One final barrett_reduce_128; result written in the transposed block layout.
+// Key limbs are stored pre-transposed (pos = k*16 + t) so the dominant HBM stream - the key -
+// is read as full 128-byte lines.
+// ============================================================================================
+struct KsMacArgs
+{
+    const u64 *inter;      // [nI][l][N] column-pass output, lazy [0,4q)
+    const u64 *target_ntt; // [l][N] NTT form (natural layout)
+    const uint32_t *perm;  // Galois table or null
+    const u64 *key;        // [digits][2][klimbs+1][N] transposed-block layout
+    u64 *acc;              // [2][l+1][N] transposed-block layout
+    size_t n;
+    int l, I0, special_prime, klimbs; // key stores limbs 0..klimbs-1 and the special at klimbs
+};
+
+static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
+{
+    __shared__ u64 sm[4096];
+    const int iloc = blockIdx.y;
+    const int I = a.I0 + iloc;
+    const int t = threadIdx.x & 15;
+    const int lb = threadIdx.x >> 4;
+    const int blk = blockIdx.x * 16 + lb;
+    const int pi = I == a.l ? a.special_prime : I;
+    const int kl = I == a.l ? a.klimbs : I;
+    const PrimeDev pd = T.primes[pi];
+    const size_t n = a.n;
+    const unsigned B = (unsigned)(n >> 8) + (unsigned)blk;
+    const ulonglong2 *tw = T.tw + (size_t)pi * n;
+    u64 *s = sm + lb * 256;
+    const size_t boff = (size_t)blk * 256;
+    const size_t kstride = (size_t)(a.klimbs + 1) * n; // one key poly
+
+    u64 lo0[16], hi0[16], lo1[16], hi1[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+        lo0[k] = hi0[k] = lo1[k] = hi1[k] = 0ull;
+
+    for (int J = 0; J < a.l; J++)
+    {
+        u64 x[16];
+        if (J == I)
+        {
+            const u64 *src = a.target_ntt + (size_t)J * n;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+            {
+                int idx = (int)boff + 16 * t + k;
+                x[k] = src[a.perm ? (int)a.perm[idx] : idx];
+            }
+        }
+        else
+        {
+            const u64 *src = a.inter + ((size_t)iloc * a.l + J) * n + boff;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                x[k] = src[t + 16 * k];
+            fwd_radix<4>(x, tw, B, pd.q, pd.two_q);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                s[swz(t + 16 * k)] = x[k];
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                x[k] = s[swz(16 * t + k)];
+            fwd_radix<4>(x, tw, 16u * B + (unsigned)t, pd.q, pd.two_q);
+            // operands stay lazy in [0,4q) as in the reference (:2407): l * 4q * q < 2^128
+        }
+        const u64 *k0 = a.key + ((size_t)J * 2) * kstride + (size_t)kl * n + boff;
+        const u64 *k1 = k0 + kstride;
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            u64 w0 = __ldg(k0 + k * 16 + t);
+            u64 w1 = __ldg(k1 + k * 16 + t);
+            mac128(lo0[k], hi0[k], x[k], w0);
+            mac128(lo1[k], hi1[k], x[k], w1);
+        }
+    }
+    u64 *o0 = a.acc + (size_t)I * n + boff;
+    u64 *o1 = a.acc + ((size_t)(a.l + 1) + I) * n + boff;
+#pragma unroll
+    for (int k = 0; k < 16; k++)
+    {
+        o0[k * 16 + t] = barrett128(lo0[k], hi0[k], pd);
+        o1[k * 16 + t] = barrett128(lo1[k], hi1[k], pd);
+    }
+}
+
+// ============================================================================================
+// Element-wise limb kernels.  Data = [polys][limbs][N]; grid-stride over polys*limbs*N with the
+// prime taken from the limb index.  2 coefficients (16 bytes) per thread per step.
+// ============================================================================================
+enum EwOp
+{
+    EW_ADD = 0,
+    EW_SUB = 1,
+    EW_NEG = 2,
+    EW_MUL = 3,       // a * b (b broadcast over polys if b_polys == 1: plaintext operand)
+    EW_ADD_P0 = 4,    // a[0] += b (plaintext add touches poly 0 only)
+    EW_SUB_P0 = 5,
+    EW_MULADD = 6     // a += b * c
+};
+
+template <int OP>
+__global__ void __launch_bounds__(256) k_ew(u64 *__restrict__ a, const u64 *__restrict__ b, const PrimeDev *primes,
+                                            int log_n, int limbs, int a_polys, int b_polys)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = (size_t)a_polys * per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2;
+        int limb = (int)((e % per_poly) >> log_n);
+        const PrimeDev pd = primes[limb];
+        ulonglong2 va = *reinterpret_cast<ulonglong2 *>(a + e);
+        ulonglong2 vb = make_ulonglong2(0, 0);
+        if (OP != EW_NEG)
+        {
+            size_t eb = b_polys == 1 ? e % per_poly : e;
+            vb = *reinterpret_cast<const ulonglong2 *>(b + eb);
+        }
+        if (OP == EW_ADD || OP == EW_ADD_P0)
+        {
+            va.x = addmod(va.x, vb.x, pd.q);
+            va.y = addmod(va.y, vb.y, pd.q);
+        }
+        else if (OP == EW_SUB || OP == EW_SUB_P0)
+        {
+            va.x = submod(va.x, vb.x, pd.q);
+            va.y = submod(va.y, vb.y, pd.q);
+        }
+        else if (OP == EW_NEG)
+        {
+            va.x = va.x ? pd.q - va.x : 0ull;
+            va.y = va.y ? pd.q - va.y : 0ull;
+        }
+        else if (OP == EW_MUL)
+        {
+            va.x = mulmod(va.x, vb.x, pd);
+            va.y = mulmod(va.y, vb.y, pd);
+        }
+        *reinterpret_cast<ulonglong2 *>(a + e) = va;
+    }
+}
+
+// ct x ct tensor product (ckks_multiply, evaluator.cpp:744-772): (a0,a1) x (b0,b1) ->
+// (a0 b0, a0 b1 + a1 b0, a1 b1).  out may alias neither input.
+static __global__ void __launch_bounds__(256) k_tensor(const u64 *__restrict__ a, const u64 *__restrict__ b,
+                                                u64 *__restrict__ out, const PrimeDev *primes, int log_n, int limbs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2;
+        const PrimeDev pd = primes[(int)(e >> log_n)];
+        ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(a + e);
+        ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(a + per_poly + e);
+        ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(b + e);
+        ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(b + per_poly + e);
+        ulonglong2 d0, d1, d2;
+        d0.x = mulmod(a0.x, b0.x, pd);
+        d0.y = mulmod(a0.y, b0.y, pd);
+        d2.x = mulmod(a1.x, b1.x, pd);
+        d2.y = mulmod(a1.y, b1.y, pd);
+        {
+            u64 lo = 0, hi = 0;
+            mac128(lo, hi, a0.x, b1.x);
+            mac128(lo, hi, a1.x, b0.x);
+            d1.x = barrett128(lo, hi, pd);
+            lo = hi = 0;
+            mac128(lo, hi, a0.y, b1.y);
+            mac128(lo, hi, a1.y, b0.y);
+            d1.y = barrett128(lo, hi, pd);
+        }
+        *reinterpret_cast<ulonglong2 *>(out + e) = d0;
+        *reinterpret_cast<ulonglong2 *>(out + per_poly + e) = d1;
+        *reinterpret_cast<ulonglong2 *>(out + 2 * per_poly + e) = d2;
+    }
+}
+
+// ckks_square (evaluator.cpp:1000-1059): (a0,a1) -> (a0^2, 2 a0 a1, a1^2)
+static __global__ void __launch_bounds__(256) k_square(const u64 *__restrict__ a, u64 *__restrict__ out,
+                                                const PrimeDev *primes, int log_n, int limbs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2;
+        const PrimeDev pd = primes[(int)(e >> log_n)];
+        ulonglong2 a0 = *reinterpret_cast<const ulonglong2 *>(a + e);
+        ulonglong2 a1 = *reinterpret_cast<const ulonglong2 *>(a + per_poly + e);
+        ulonglong2 d0, d1, d2;
+        d0.x = mulmod(a0.x, a0.x, pd);
+        d0.y = mulmod(a0.y, a0.y, pd);
+        d2.x = mulmod(a1.x, a1.x, pd);
+        d2.y = mulmod(a1.y, a1.y, pd);
+        u64 m = mulmod(a0.x, a1.x, pd);
+        d1.x = addmod(m, m, pd.q);
+        m = mulmod(a0.y, a1.y, pd);
+        d1.y = addmod(m, m, pd.q);
+        *reinterpret_cast<ulonglong2 *>(out + e) = d0;
+        *reinterpret_cast<ulonglong2 *>(out + per_poly + e) = d1;
+        *reinterpret_cast<ulonglong2 *>(out + 2 * per_poly + e) = d2;
+    }
+}
+
+// Galois gather on NTT-form limbs (galois.cpp:192-218): dst[j][i] = src[j][perm[i]].
+static __global__ void __launch_bounds__(256) k_permute(const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                 const uint32_t *__restrict__ perm, int log_n, int jobs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t total = (size_t)jobs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t j = i >> log_n, k = i & (n - 1);
+        dst[i] = src[(j << log_n) + perm[k]];
+    }
+}
+
+// strided limb copy: dst[p][i][.] = src[p][i][.] for i < limbs_out (mod_switch_drop_to_next,
+// evaluator.cpp:1183-1246) - a pure re-pack, no arithmetic.
+static __global__ void __launch_bounds__(256) k_drop_limbs(const u64 *__restrict__ src, u64 *__restrict__ dst, int log_n,
+                                                    int limbs_in, int limbs_out, int polys)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_out = (size_t)limbs_out * n;
+    const size_t total = (size_t)polys * per_out / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2;
+        size_t p = e / per_out, r = e % per_out;
+        *reinterpret_cast<ulonglong2 *>(dst + e) =
+            *reinterpret_cast<const ulonglong2 *>(src + p * (size_t)limbs_in * n + r);
+    }
+}
+
+// natural <-> transposed-block layout for key limbs (pos = k*16 + t holds e = 16t + k).
+static __global__ void __launch_bounds__(256) k_transpose_blocks(const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                          size_t total)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t blk = i >> 8;
+        int pos = (int)(i & 255);
+        int k = pos >> 4, t = pos & 15;
+        dst[i] = src[(blk << 8) + 16 * t + k];
+    }
+}

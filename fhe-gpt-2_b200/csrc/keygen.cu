@@ -1,0 +1,505 @@
+// keygen.cu - KeyGenerator / Encryptor / Decryptor on the device.
+//
+// Replaces, in the reference's modified SEAL 3.6.6:
+//   keygenerator.cpp:50-97    secret key (fork: Hamming-weight secret :64-76)
+//   keygenerator.cpp:99-131   public key = encrypt_zero_symmetric at the key level
+//   keygenerator.cpp:133-162  relin keys (new key = s^2), :164-233 Galois keys (new key = s∘galois)
+//   keygenerator.cpp:384-417  generate_one_kswitch_key: per digit j a fresh symmetric encryption
+//                             of zero at the key level with (P mod q_j) * new_key added to limb j
+//   util/rlwe.cpp:21-70       ternary / sparse-ternary samplers, :96-135 centred binomial noise
+//   util/rlwe.cpp:221-292     encrypt_zero_asymmetric, :294-409 encrypt_zero_symmetric
+//   encryptor.cpp:88-239      public-key encryption = encrypt zero one level up, divide by the last prime
+//   decryptor.cpp:150-183     ckks_decrypt = dot product of the ciphertext with powers of s
+//
+// The arithmetic (NTT, products, rounding division) is identical to the reference's.  The
+// RANDOMNESS is not: the reference draws from a Blake2xb stream on the CPU, this engine draws
+// from a counter-based Philox4x32-10 generator on the GPU (275 GiB of key material cannot be
+// sampled on the host in reasonable time), so freshly generated keys / ciphertexts have the
+// same distribution but different bits.  Bit-exact parity tests therefore upload the
+// reference's keys and ciphertexts (bk_kskey_upload / bk_ct_upload) instead.
+#include "engine.h"
+#include <algorithm>
+#include <cstring>
+#include <random>
+
+namespace bk
+{
+    void ntt_fwd_small(Context &c, cudaStream_t s, const int *small, u64 *out, int polys, int limbs, JobMap map);
+}
+using namespace bk;
+
+// ---- Philox4x32-10 -----------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key)
+{
+#pragma unroll
+    for (int r = 0; r < 10; r++)
+    {
+        unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+
+// uniform residue in [0,q) by rejection (sample_poly_uniform, util/rlwe.cpp:137-178)
+__device__ __forceinline__ u64 uniform_mod(u64 seed, unsigned stream, u64 index, const PrimeDev &pd)
+{
+    const u64 max_multiple = 0xFFFFFFFFFFFFFFFFull - barrett64(0xFFFFFFFFFFFFFFFFull, pd) - 1;
+    uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    for (unsigned attempt = 0;; attempt++)
+    {
+        uint4 r = philox(make_uint4((unsigned)index, (unsigned)(index >> 32), stream, attempt), key);
+        u64 v = ((u64)r.x << 32) | r.y;
+        if (v < max_multiple)
+            return barrett64(v, pd);
+        v = ((u64)r.z << 32) | r.w;
+        if (v < max_multiple)
+            return barrett64(v, pd);
+    }
+}
+
+// small signed polynomials: mode 0 = uniform ternary (sample_poly_ternary), 1 = centred binomial
+// with sigma 3.2 (sample_poly_cbd: 21 bits minus 21 bits)
+__global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, size_t count, u64 seed, unsigned stream,
+                                                      int mode)
+{
+    size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i >= count)
+        return;
+    uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
+    if (mode == 0)
+    {
+        for (unsigned attempt = 0;; attempt++)
+        {
+            uint4 r = philox(make_uint4((unsigned)i, (unsigned)(i >> 32), stream, attempt), key);
+            // uniform in {0,1,2} by rejection on 32-bit words
+            unsigned w[4] = { r.x, r.y, r.z, r.w };
+            bool done = false;
+            for (int k = 0; k < 4 && !done; k++)
+                if (w[k] < 0xFFFFFFFFu - (0xFFFFFFFFu % 3u) - 0u)
+                {
+                    out[i] = (int)(w[k] % 3u) - 1;
+                    done = true;
+                }
+            if (done)
+                return;
+        }
+    }
+    else
+    {
+        uint4 r = philox(make_uint4((unsigned)i, (unsigned)(i >> 32), stream, 0u), key);
+        out[i] = __popc(r.x & 0x1FFFFFu) - __popc(r.y & 0x1FFFFFu);
+    }
+}
+
+// forward column-pass loader for small signed polynomials: job = p * limbs + l
+struct LdSmall
+{
+    const int *src; // [polys][N]
+    JobMap map;
+    size_t n;
+    int limbs;
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    __device__ __forceinline__ int prime(int job) const { return map.prime(job); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        int v = src[(size_t)(job / limbs) * n + idx];
+        return v < 0 ? pd.q - (u64)(-v) : (u64)v;
+    }
+};
+
+namespace bk
+{
+    // out[p][l][.] = NTT_{prime(l)}(small[p])
+    void ntt_fwd_small(Context &c, cudaStream_t s, const int *small, u64 *out, int polys, int limbs, JobMap map)
+    {
+        const int jobs = polys * limbs;
+        Scratch tmp(s, (size_t)jobs * c.n);
+        LdSmall ld{ small, map, c.n, limbs };
+        dim3 grid(16, jobs);
+        switch (c.log_n)
+        {
+        case 12: k_fwd_cols<4, LdSmall><<<grid, 16, 0, s>>>(ld, tmp.p, c.tables); break;
+        case 13: k_fwd_cols<5, LdSmall><<<grid, 32, 0, s>>>(ld, tmp.p, c.tables); break;
+        case 14: k_fwd_cols<6, LdSmall><<<grid, 64, 0, s>>>(ld, tmp.p, c.tables); break;
+        case 15: k_fwd_cols<7, LdSmall><<<grid, 128, 0, s>>>(ld, tmp.p, c.tables); break;
+        default: k_fwd_cols<8, LdSmall><<<grid, 256, 0, s>>>(ld, tmp.p, c.tables); break;
+        }
+        c.count();
+        StPlain st{ out, map, c.n };
+        dim3 grid2((unsigned)(c.n >> 12), jobs);
+        k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
+        c.count();
+    }
+}
+
+// symmetric encryption of zero, NTT form, over `limbs` limbs whose prime is map.prime(l):
+//   c1 = a (uniform, sampled directly in NTT form), c0 = -(a*s + e)      (rlwe.cpp:340-371)
+// optional: c0[limb == add_limb] += factor * newkey      (keygenerator.cpp:406-416)
+// TRANSPOSED: write in the key's transposed-block layout.
+template <bool TRANSPOSED>
+__global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__restrict__ c1,
+                                                  const u64 *__restrict__ sk /*[n_primes][N]*/,
+                                                  const u64 *__restrict__ e_ntt /*[limbs][N]*/,
+                                                  const u64 *__restrict__ newkey /*[n_primes][N] or null*/,
+                                                  int add_limb, u64 factor, JobMap map, const PrimeDev *primes,
+                                                  int log_n, int limbs, u64 seed, unsigned stream)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t total = (size_t)limbs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        int l = (int)(i >> log_n);
+        size_t idx = i & (n - 1);
+        int pi = map.prime(l);
+        const PrimeDev pd = primes[pi];
+        u64 a = uniform_mod(seed, stream, i, pd);
+        u64 s = sk[(size_t)pi * n + idx];
+        u64 v = addmod(mulmod(a, s, pd), e_ntt[i], pd.q);
+        v = v ? pd.q - v : 0ull;
+        if (newkey && l == add_limb)
+            v = addmod(v, mulmod(factor, newkey[(size_t)pi * n + idx], pd), pd.q);
+        size_t o = i;
+        if (TRANSPOSED)
+        {
+            size_t blk = idx >> 8;
+            int e = (int)(idx & 255);
+            int t = e >> 4, k = e & 15;
+            o = ((size_t)l << log_n) + (blk << 8) + (size_t)(k * 16 + t);
+        }
+        c0[o] = v;
+        c1[o] = a;
+    }
+}
+
+// c_j = pk_j * u + e_j over limbs 0..limbs-1 (rlwe.cpp:253-291); pk is [2][n_primes][N]
+__global__ void __launch_bounds__(256) k_asym_zero(u64 *__restrict__ out /*[2][limbs][N]*/,
+                                                   const u64 *__restrict__ pk, const u64 *__restrict__ u_ntt,
+                                                   const u64 *__restrict__ e_ntt /*[2][limbs][N]*/,
+                                                   const PrimeDev *primes, int log_n, int limbs, int n_primes)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per = (size_t)limbs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * per; i += (size_t)gridDim.x * blockDim.x)
+    {
+        int p = (int)(i / per);
+        size_t r = i % per;
+        int l = (int)(r >> log_n);
+        size_t idx = r & (n - 1);
+        const PrimeDev pd = primes[l];
+        u64 k = pk[((size_t)p * n_primes + l) * n + idx];
+        out[i] = addmod(mulmod(k, u_ntt[r], pd), e_ntt[i], pd.q);
+    }
+}
+
+// dot_product_ct_sk_array (decryptor.cpp:185-260): m = c0 + c1 s + c2 s^2 ...
+__global__ void __launch_bounds__(256) k_decrypt(const u64 *__restrict__ ct, const u64 *__restrict__ sk,
+                                                 u64 *__restrict__ out, const PrimeDev *primes, int log_n, int limbs,
+                                                 int size)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per = (size_t)limbs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x)
+    {
+        int l = (int)(i >> log_n);
+        const PrimeDev pd = primes[l];
+        u64 s = sk[i];
+        u64 acc = ct[(size_t)(size - 1) * per + i];
+        for (int p = size - 2; p >= 0; p--)
+            acc = addmod(mulmod(acc, s, pd), ct[(size_t)p * per + i], pd.q);
+        out[i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_permute_limbs(const u64 *__restrict__ src, u64 *__restrict__ dst,
+                                                       const uint32_t *__restrict__ perm, int log_n, int jobs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t total = (size_t)jobs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t j = i >> log_n, k = i & (n - 1);
+        dst[i] = src[(j << log_n) + perm[k]];
+    }
+}
+
+namespace bk
+{
+    static std::atomic<unsigned> g_stream_counter{ 1 };
+
+    // one kswitch key for `newkey` ([n_primes][N] NTT form), pruned to max_limbs
+    static bk_kskey_t make_kskey(Context &c, bk_sk_t sk, const u64 *newkey, u64 seed, int max_limbs)
+    {
+        const int top = c.top_limbs();
+        const int sp = c.n_primes - 1;
+        int kl = (max_limbs > 0 && max_limbs < top) ? max_limbs : top;
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        auto key = new bk_kskey_s();
+        key->ctx = static_cast<bk_context_t>(&c);
+        key->digits = kl;
+        key->klimbs = kl;
+        key->words = (size_t)kl * 2 * (kl + 1) * n;
+        BK_CUDA(cudaMalloc((void **)&key->d, key->words * sizeof(u64)));
+        JobMap map = limb_map(kl + 1);
+        map.special_pos = kl;
+        map.special_prime = sp;
+        Scratch small(s, (n + 1) / 2);
+        Scratch e_ntt(s, (size_t)(kl + 1) * n);
+        for (int j = 0; j < kl; j++)
+        {
+            unsigned st_e = g_stream_counter.fetch_add(2);
+            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st_e, 1);
+            c.count();
+            ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, kl + 1, map);
+            u64 factor = c.primes[sp] % c.primes[j];
+            u64 *c0 = key->d + ((size_t)j * 2) * (kl + 1) * n;
+            u64 *c1 = c0 + (size_t)(kl + 1) * n;
+            k_sym_zero<true><<<c.ew_grid((size_t)(kl + 1) * n), 256, 0, s>>>(c0, c1, sk->d, e_ntt.p, newkey, j, factor,
+                                                                            map, c.d_primes, c.log_n, kl + 1, seed,
+                                                                            st_e + 1);
+            c.count();
+        }
+        BK_CUDA(cudaStreamSynchronize(s));
+        return key;
+    }
+}
+
+extern "C"
+{
+    bk_status bk_sk_generate(bk_context_t ctx, int hamming_weight, uint64_t seed, bk_sk_t *out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        const size_t n = c.n;
+        if (hamming_weight < 0 || (size_t)hamming_weight > n)
+            throw std::invalid_argument("hamming_weight is invalid");
+        std::vector<int> small(n, 0);
+        std::mt19937_64 rng(seed ? seed : std::random_device{}());
+        if (hamming_weight == 0)
+        {
+            std::uniform_int_distribution<int> d(0, 2);
+            for (auto &v : small)
+                v = d(rng) - 1;
+        }
+        else
+        {
+            // sample_poly_sparse_ternary (rlwe.cpp:40-70): h distinct positions, each +-1
+            std::uniform_int_distribution<size_t> pos(0, n - 1);
+            std::uniform_int_distribution<int> sign(0, 1);
+            int w = 0;
+            while (w < hamming_weight)
+            {
+                size_t i = pos(rng);
+                if (small[i])
+                    continue;
+                small[i] = sign(rng) ? 1 : -1;
+                w++;
+            }
+        }
+        cudaStream_t s = c.stream();
+        Scratch d_small(s, (n + 1) / 2);
+        BK_CUDA(cudaMemcpyAsync(d_small.p, small.data(), n * sizeof(int), cudaMemcpyHostToDevice, s));
+        auto sk = new bk_sk_s();
+        sk->ctx = ctx;
+        BK_CUDA(cudaMalloc((void **)&sk->d, (size_t)c.n_primes * n * sizeof(u64)));
+        ntt_fwd_small(c, s, (const int *)d_small.p, sk->d, 1, c.n_primes, limb_map(c.n_primes));
+        BK_CUDA(cudaStreamSynchronize(s));
+        *out = sk;
+        BK_END
+    }
+    bk_status bk_sk_upload(bk_context_t ctx, const uint64_t *host, bk_sk_t *out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        c.activate();
+        auto sk = new bk_sk_s();
+        sk->ctx = ctx;
+        BK_CUDA(cudaMalloc((void **)&sk->d, (size_t)c.n_primes * c.n * sizeof(u64)));
+        BK_CUDA(cudaMemcpy(sk->d, host, (size_t)c.n_primes * c.n * sizeof(u64), cudaMemcpyHostToDevice));
+        *out = sk;
+        BK_END
+    }
+    bk_status bk_sk_download(bk_sk_t sk, uint64_t *host_out)
+    {
+        BK_TRY
+        Context &c = *sk->ctx;
+        BK_CUDA(cudaStreamSynchronize(c.stream()));
+        BK_CUDA(cudaMemcpy(host_out, sk->d, (size_t)c.n_primes * c.n * sizeof(u64), cudaMemcpyDeviceToHost));
+        BK_END
+    }
+    bk_status bk_sk_destroy(bk_sk_t sk)
+    {
+        BK_TRY
+        if (sk)
+        {
+            sk->ctx->activate();
+            cudaStreamSynchronize(sk->ctx->stream());
+            cudaFree(sk->d);
+            delete sk;
+        }
+        BK_END
+    }
+
+    bk_status bk_pk_generate(bk_context_t ctx, bk_sk_t sk, uint64_t seed, bk_ct_t pk_out)
+    {
+        BK_TRY
+        // keygenerator.cpp:99-131: encrypt_zero_symmetric at the key level, NTT form
+        Context &c = *ctx;
+        if (!sk || sk->ctx != ctx)
+            throw std::logic_error("cannot generate public key for unspecified secret key");
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        const int L = c.n_primes;
+        ensure_ct(pk_out, 2, L, false);
+        Scratch small(s, (n + 1) / 2);
+        Scratch e_ntt(s, (size_t)L * n);
+        unsigned st = g_stream_counter.fetch_add(2);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st, 1);
+        c.count();
+        ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, L, limb_map(L));
+        k_sym_zero<false><<<c.ew_grid((size_t)L * n), 256, 0, s>>>(pk_out->d, pk_out->d + (size_t)L * n, sk->d,
+                                                                   e_ntt.p, nullptr, -1, 0, limb_map(L), c.d_primes,
+                                                                   c.log_n, L, seed, st + 1);
+        c.count();
+        pk_out->scale = 1.0;
+        pk_out->ntt = true;
+        BK_END
+    }
+
+    bk_status bk_relin_key_generate(bk_context_t ctx, bk_sk_t sk, uint64_t seed, int max_limbs, bk_kskey_t *out)
+    {
+        BK_TRY
+        // keygenerator.cpp:133-162: new key = s^2 (compute_secret_key_array)
+        Context &c = *ctx;
+        if (!sk || sk->ctx != ctx)
+            throw std::logic_error("cannot generate relinearization keys for unspecified secret key");
+        cudaStream_t s = c.stream();
+        size_t words = (size_t)c.n_primes * c.n;
+        Scratch sq(s, words);
+        BK_CUDA(cudaMemcpyAsync(sq.p, sk->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+        k_ew<EW_MUL><<<c.ew_grid(words / 2), 256, 0, s>>>(sq.p, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
+        c.count();
+        *out = make_kskey(c, sk, sq.p, seed, max_limbs);
+        BK_END
+    }
+
+    bk_status bk_galois_key_generate(bk_context_t ctx, bk_sk_t sk, uint32_t galois_elt, uint64_t seed, int max_limbs,
+                                     bk_kskey_t *out)
+    {
+        BK_TRY
+        // keygenerator.cpp:199-227: new key = apply_galois_ntt(s, elt)
+        Context &c = *ctx;
+        if (!sk || sk->ctx != ctx)
+            throw std::logic_error("cannot generate Galois keys for unspecified secret key");
+        if (!(galois_elt & 1) || galois_elt >= 2 * c.n)
+            throw std::invalid_argument("Galois element is not valid");
+        cudaStream_t s = c.stream();
+        size_t words = (size_t)c.n_primes * c.n;
+        Scratch rot(s, words);
+        const uint32_t *perm = c.galois_table(galois_elt);
+        k_permute_limbs<<<c.ew_grid(words), 256, 0, s>>>(sk->d, rot.p, perm, c.log_n, c.n_primes);
+        c.count();
+        *out = make_kskey(c, sk, rot.p, seed, max_limbs);
+        BK_END
+    }
+
+    bk_status bk_encrypt(bk_context_t ctx, bk_ct_t pk, bk_pt_t pt, uint64_t seed, bk_ct_t out)
+    {
+        BK_TRY
+        // Encryptor::encrypt_internal (encryptor.cpp:165-239) -> encrypt_zero_internal (:88-163):
+        // encrypt zero with l+1 limbs (the next prime up, or the special prime at the top level),
+        // divide by that prime with rounding, add the plaintext to c0.
+        Context &c = *ctx;
+        if (!pk || pk->ctx != ctx || pk->size != 2 || pk->limbs != c.n_primes)
+            throw std::logic_error("public key is not set");
+        if (!pt || pt->ctx != ctx || !pt->d)
+            throw std::invalid_argument("plain is not valid for encryption parameters");
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        const int l = pt->limbs, l1 = l + 1;
+        if (l > c.top_limbs())
+            throw std::invalid_argument("plain is not valid for encryption parameters");
+        Scratch small(s, (3 * n + 1) / 2);
+        int *d_small = (int *)small.p;
+        unsigned st = g_stream_counter.fetch_add(2);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_small, n, seed, st, 0);
+        k_sample_small<<<(unsigned)((2 * n + 255) / 256), 256, 0, s>>>(d_small + n, 2 * n, seed, st + 1, 1);
+        c.count(2);
+        Scratch u_ntt(s, (size_t)l1 * n);
+        Scratch e_ntt(s, (size_t)2 * l1 * n);
+        ntt_fwd_small(c, s, d_small, u_ntt.p, 1, l1, limb_map(l1));
+        ntt_fwd_small(c, s, d_small + n, e_ntt.p, 2, l1, limb_map(l1));
+        bk_ct_s tmp;
+        tmp.ctx = ctx;
+        ensure_ct(&tmp, 2, l1, false);
+        k_asym_zero<<<c.ew_grid((size_t)2 * l1 * n), 256, 0, s>>>(tmp.d, pk->d, u_ntt.p, e_ntt.p, c.d_primes, c.log_n, l1,
+                                                                  c.n_primes);
+        c.count();
+        tmp.ntt = true;
+        tmp.scale = 1.0;
+        // divide_and_round_q_last_ntt_inplace by prime index l (the special prime when l is the top level:
+        // there prime index l == n_primes - 1)
+        rescale_core(c, &tmp);
+        k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(tmp.d, pt->d, c.d_primes, c.log_n, l, 1, 1);
+        c.count();
+        if (out->d)
+            BK_CUDA(cudaFreeAsync(out->d, s));
+        out->d = tmp.d;
+        out->cap = tmp.cap;
+        out->size = 2;
+        out->limbs = l;
+        out->scale = pt->scale;
+        out->ntt = true;
+        BK_END
+    }
+
+    bk_status bk_encrypt_symmetric(bk_context_t ctx, bk_sk_t sk, bk_pt_t pt, uint64_t seed, bk_ct_t out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (!sk || sk->ctx != ctx)
+            throw std::logic_error("secret key is not set");
+        if (!pt || pt->ctx != ctx || !pt->d)
+            throw std::invalid_argument("plain is not valid for encryption parameters");
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        const int l = pt->limbs;
+        ensure_ct(out, 2, l, false);
+        Scratch small(s, (n + 1) / 2);
+        Scratch e_ntt(s, (size_t)l * n);
+        unsigned st = g_stream_counter.fetch_add(2);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st, 1);
+        c.count();
+        ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, l, limb_map(l));
+        k_sym_zero<false><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(out->d, out->d + (size_t)l * n, sk->d, e_ntt.p,
+                                                                   nullptr, -1, 0, limb_map(l), c.d_primes, c.log_n, l,
+                                                                   seed, st + 1);
+        k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(out->d, pt->d, c.d_primes, c.log_n, l, 1, 1);
+        c.count(2);
+        out->scale = pt->scale;
+        out->ntt = true;
+        BK_END
+    }
+
+    bk_status bk_decrypt(bk_context_t ctx, bk_sk_t sk, bk_ct_t ct, bk_pt_t out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (!sk || sk->ctx != ctx)
+            throw std::invalid_argument("secret key is not valid for encryption parameters");
+        if (!ct || ct->ctx != ctx || !ct->d || ct->size < 2)
+            throw std::invalid_argument("encrypted is not valid for encryption parameters");
+        if (!ct->ntt)
+            throw std::invalid_argument("encrypted must be in NTT form");
+        const int l = ct->limbs;
+        ensure_pt(out, l);
+        k_decrypt<<<c.ew_grid((size_t)l * c.n), 256, 0, c.stream()>>>(ct->d, sk->d, out->d, c.d_primes, c.log_n, l,
+                                                                      ct->size);
+        c.count();
+        out->scale = ct->scale;
+        BK_END
+    }
+}
