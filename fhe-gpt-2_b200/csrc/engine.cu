@@ -273,6 +273,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid(16, jobs);
+        ProfScope ps(c, s, TAG_FWD_COLS);
         BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
         c.count();
     }
@@ -282,6 +283,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid((unsigned)(c.n >> 12), jobs);
+        ProfScope ps(c, s, TAG_FWD_BLOCKS);
         k_fwd_blocks<Store><<<grid, 256, 0, s>>>(in, st, c.tables);
         c.count();
     }
@@ -291,6 +293,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid((unsigned)(c.n >> 12), jobs);
+        ProfScope ps(c, s, TAG_INV_BLOCKS);
         k_inv_blocks<Load><<<grid, 256, 0, s>>>(ld, out, c.tables);
         c.count();
     }
@@ -300,6 +303,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid(16, jobs);
+        ProfScope ps(c, s, TAG_INV_COLS);
         BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
         c.count();
     }
@@ -422,7 +426,10 @@ namespace bk
             launch_fwd_cols(c, s, ld, inter.p, nI * l);
             KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs };
             dim3 grid((unsigned)(n >> 12), nI);
-            k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
+            {
+                ProfScope ps(c, s, TAG_KS_MAC);
+                k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
+            }
             c.count();
         }
         // C. ModDown by the special prime (:2465-2523)
@@ -719,6 +726,74 @@ extern "C"
         BK_END
     }
 
+    // ---- timing helpers (CUDA events on the calling thread's stream) ------------------------------
+    bk_status bk_timer_begin(bk_context_t ctx)
+    {
+        BK_TRY
+        cudaStream_t s = ctx->stream();
+        cudaEvent_t e;
+        BK_CUDA(cudaEventCreate(&e));
+        BK_CUDA(cudaEventRecord(e, s));
+        ctx->timer_stack.push_back(e);
+        BK_END
+    }
+    bk_status bk_timer_end(bk_context_t ctx, double *ms_out)
+    {
+        BK_TRY
+        if (ctx->timer_stack.empty())
+            throw std::logic_error("bk_timer_end without bk_timer_begin");
+        cudaStream_t s = ctx->stream();
+        cudaEvent_t e0 = ctx->timer_stack.back(), e1;
+        ctx->timer_stack.pop_back();
+        BK_CUDA(cudaEventCreate(&e1));
+        BK_CUDA(cudaEventRecord(e1, s));
+        BK_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        BK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        *ms_out = ms;
+        BK_END
+    }
+    bk_status bk_profile_begin(bk_context_t ctx, int kernel_tag)
+    {
+        BK_TRY
+        if (kernel_tag < 0 || kernel_tag >= TAG_COUNT)
+            throw std::invalid_argument("unknown kernel tag");
+        BK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        ctx->prof_events.clear();
+        ctx->prof_tag = kernel_tag;
+        BK_END
+    }
+    bk_status bk_profile_end(bk_context_t ctx, uint64_t *launches_out, double *total_ms_out)
+    {
+        BK_TRY
+        ctx->prof_tag = -1;
+        BK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        double total = 0;
+        for (auto &pr : ctx->prof_events)
+        {
+            float ms = 0;
+            BK_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            total += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        *launches_out = ctx->prof_events.size();
+        *total_ms_out = total;
+        ctx->prof_events.clear();
+        BK_END
+    }
+    // write `bytes` bytes of junk (> L2) so the next timed region starts with a cold L2
+    bk_status bk_flush_l2(bk_context_t ctx)
+    {
+        BK_TRY
+        static const size_t words = (size_t)192 << 17; // 192 MiB
+        Scratch junk(ctx->stream(), words);
+        BK_CUDA(cudaMemsetAsync(junk.p, 0x5a, words * sizeof(u64), ctx->stream()));
+        BK_END
+    }
+
     // ---- ciphertext ----------------------------------------------------------------------------
     bk_status bk_ct_create(bk_context_t ctx, bk_ct_t *out)
     {
@@ -977,6 +1052,32 @@ extern "C"
         c.count();
         BK_CUDA(cudaMemcpyAsync(host_out, tmp.p, key->words * sizeof(u64), cudaMemcpyDeviceToHost, s));
         BK_CUDA(cudaStreamSynchronize(s));
+        BK_END
+    }
+    bk_status bk_kskey_export_device(bk_kskey_t key, void *dev_dst)
+    {
+        BK_TRY
+        Context &c = *key->ctx;
+        BK_CUDA(cudaMemcpyAsync(dev_dst, key->d, key->words * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream()));
+        BK_CUDA(cudaStreamSynchronize(c.stream()));
+        BK_END
+    }
+    bk_status bk_kskey_import_device(bk_context_t ctx, const void *dev_src, int digits, int limbs, bk_kskey_t *out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (digits < 1 || limbs < digits || limbs > c.top_limbs())
+            throw std::invalid_argument("kswitch key shape is invalid");
+        auto key = new bk_kskey_s();
+        key->ctx = ctx;
+        key->digits = digits;
+        key->klimbs = limbs;
+        key->words = (size_t)digits * 2 * (limbs + 1) * c.n;
+        c.activate();
+        BK_CUDA(cudaMalloc((void **)&key->d, key->words * sizeof(u64)));
+        BK_CUDA(cudaMemcpyAsync(key->d, dev_src, key->words * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream()));
+        BK_CUDA(cudaStreamSynchronize(c.stream()));
+        *out = key;
         BK_END
     }
     bk_status bk_gkeys_create(bk_context_t ctx, bk_gkeys_t *out)

@@ -71,6 +71,10 @@ namespace bk
         int ks_chunk = 4;
         int sparse_slots = 0;
         std::atomic<uint64_t> launches{ 0 };
+        // per-kernel live timing (bk_profile_begin/end): events around every launch of one tag
+        int prof_tag = -1;
+        std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+        std::vector<cudaEvent_t> timer_stack;
 
         std::mutex mu;
         std::unordered_map<std::thread::id, cudaStream_t> streams;
@@ -98,6 +102,39 @@ namespace bk
         }
         int ew_grid(size_t work_items) const;
         void activate() const;
+    };
+
+    enum KernelTag
+    {
+        TAG_FWD_COLS = 0,
+        TAG_FWD_BLOCKS = 1,
+        TAG_INV_BLOCKS = 2,
+        TAG_INV_COLS = 3,
+        TAG_KS_MAC = 4,
+        TAG_ELEMENTWISE = 5,
+        TAG_COUNT = 6
+    };
+    // RAII: records an event pair around one launch when its tag is being profiled
+    struct ProfScope
+    {
+        Context &c;
+        cudaStream_t s;
+        cudaEvent_t stop = nullptr;
+        ProfScope(Context &ctx, cudaStream_t stream, int tag) : c(ctx), s(stream)
+        {
+            if (c.prof_tag != tag)
+                return;
+            cudaEvent_t start;
+            cudaEventCreate(&start);
+            cudaEventCreate(&stop);
+            cudaEventRecord(start, s);
+            c.prof_events.emplace_back(start, stop);
+        }
+        ~ProfScope()
+        {
+            if (stop)
+                cudaEventRecord(stop, s);
+        }
     };
 
     // ---- internal entry points shared between the .cu files ------------------------------------

@@ -63,6 +63,9 @@ def version():
     return _L.bk_version().decode()
 
 
+KERNEL_TAGS = dict(fwd_cols=0, fwd_blocks=1, inv_blocks=2, inv_cols=3, ks_mac=4, elementwise=5)
+
+
 # ---- host-only helpers -------------------------------------------------------------------------
 def coeff_modulus_create(log_n, bits):
     arr = (C.c_int * len(bits))(*bits)
@@ -131,6 +134,14 @@ class Ciphertext:
         assert n == self.ctx.n
         _ck(_L.bk_ct_upload(self.h, _ptr(d), size, limbs, C.c_double(scale), int(is_ntt)))
         return self
+
+    def upload_ptr(self, host_ptr, size, limbs, scale, is_ntt=True):
+        """upload from a raw (e.g. pinned) host pointer"""
+        _ck(_L.bk_ct_upload(self.h, C.c_void_p(host_ptr), size, limbs, C.c_double(scale), int(is_ntt)))
+        return self
+
+    def download_ptr(self, host_ptr):
+        _ck(_L.bk_ct_download(self.h, C.c_void_p(host_ptr)))
 
     def download(self):
         size, limbs, _, _ = self.info()
@@ -216,6 +227,9 @@ class KSwitchKey:
         _ck(_L.bk_kskey_info(self.h, C.byref(d), C.byref(l), C.byref(b)))
         return d.value, l.value, b.value
 
+    def export_device(self, dev_ptr):
+        _ck(_L.bk_kskey_export_device(self.h, C.c_void_p(dev_ptr)))
+
     def download(self):
         d, l, _ = self.info()
         out = np.zeros((d, 2, l + 1, self.ctx.n), dtype=np.uint64)
@@ -289,6 +303,30 @@ class Context:
         n = C.c_uint64()
         _ck(_L.bk_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def timer_begin(self):
+        _ck(_L.bk_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        _ck(_L.bk_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_begin(self, tag):
+        _ck(_L.bk_profile_begin(self.h, KERNEL_TAGS[tag] if isinstance(tag, str) else tag))
+
+    def profile_end(self):
+        n, ms = C.c_uint64(), C.c_double()
+        _ck(_L.bk_profile_end(self.h, C.byref(n), C.byref(ms)))
+        return n.value, ms.value
+
+    def flush_l2(self):
+        _ck(_L.bk_flush_l2(self.h))
+
+    def import_kskey_device(self, dev_ptr, digits, limbs):
+        h = C.c_void_p()
+        _ck(_L.bk_kskey_import_device(self.h, C.c_void_p(dev_ptr), digits, limbs, C.byref(h)))
+        return KSwitchKey(self, h)
 
     def set_ks_chunk(self, chunk):
         _ck(_L.bk_context_set_ks_chunk(self.h, chunk))

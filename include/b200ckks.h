@@ -78,6 +78,18 @@ bk_status bk_stream(bk_context_t ctx, void **stream_out);
 /* number of kernels this context has launched so far (all threads). */
 bk_status bk_launch_count(bk_context_t ctx, uint64_t *count_out);
 
+/* ---- measurement helpers ------------------------------------------------------------------ */
+/* CUDA-event stopwatch on the calling thread's stream (nestable); bk_timer_end synchronises. */
+bk_status bk_timer_begin(bk_context_t ctx);
+bk_status bk_timer_end(bk_context_t ctx, double *ms_out);
+/* live per-kernel timing: event pairs around every launch of one kernel family until
+ * bk_profile_end.  Tags: 0 fwd column pass, 1 fwd block pass, 2 inv block pass, 3 inv column
+ * pass, 4 key-switch inner product (k_ks_mac), 5 element-wise. */
+bk_status bk_profile_begin(bk_context_t ctx, int kernel_tag);
+bk_status bk_profile_end(bk_context_t ctx, uint64_t *launches_out, double *total_ms_out);
+/* overwrite a 192 MiB scratch buffer (> the 126 MB L2) on the caller's stream. */
+bk_status bk_flush_l2(bk_context_t ctx);
+
 /* ---- ciphertext container (ciphertext.h) -------------------------------------------------- */
 bk_status bk_ct_create(bk_context_t ctx, bk_ct_t *out);
 bk_status bk_ct_destroy(bk_ct_t ct);
@@ -111,6 +123,10 @@ bk_status bk_kskey_destroy(bk_kskey_t key);
 bk_status bk_kskey_info(bk_kskey_t key, int *digits, int *limbs, uint64_t *device_bytes);
 /* resident part in SEAL's order: [digits][2][limbs+1][N], the special prime's limb last. */
 bk_status bk_kskey_download(bk_kskey_t key, uint64_t *host_out);
+/* device-to-device export/import of the resident key ([digits][2][limbs+1][N] words, engine
+ * layout) - the buffer an NCCL broadcast moves between GPUs (keys are generated once). */
+bk_status bk_kskey_export_device(bk_kskey_t key, void *dev_dst);
+bk_status bk_kskey_import_device(bk_context_t ctx, const void *dev_src, int digits, int limbs, bk_kskey_t *out);
 bk_status bk_gkeys_create(bk_context_t ctx, bk_gkeys_t *out);
 bk_status bk_gkeys_destroy(bk_gkeys_t gk);                      /* destroys the keys it owns */
 bk_status bk_gkeys_set(bk_gkeys_t gk, uint32_t galois_elt, bk_kskey_t key); /* takes ownership */
