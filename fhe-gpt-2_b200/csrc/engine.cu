@@ -418,14 +418,17 @@ namespace bk
             StInvPlain st{ ttarget.p, limb_map(l), n };
             launch_inv_cols(c, s, inter.p, st, l);
         }
-        // B. per output modulus: decompose, NTT, multiply-accumulate with the key (:2368-2463)
+        // B. per output modulus: decompose + NTT every digit (two passes, intermediates stay in L2),
+        //    then stream the key through the multiply-accumulate (:2368-2463)
         for (int I0 = 0; I0 <= l; I0 += chunk)
         {
             int nI = std::min(chunk, l + 1 - I0);
             LdKsDigit ld{ ttarget.p, c.d_primes, n, l, I0, sp };
             launch_fwd_cols(c, s, ld, inter.p, nI * l);
+            StKsDigit st{ inter.p, n, l, I0, sp };
+            launch_fwd_blocks(c, s, inter.p, st, nI * l);
             KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs };
-            dim3 grid((unsigned)(n >> 12), nI);
+            dim3 grid((unsigned)((n / 2 + 255) / 256), nI);
             {
                 ProfScope ps(c, s, TAG_KS_MAC);
                 k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
@@ -434,7 +437,7 @@ namespace bk
         }
         // C. ModDown by the special prime (:2465-2523)
         {
-            LdInvLimbOfT ld{ acc.p, n, l + 1, l, sp };
+            LdInvLimbOf ld{ acc.p, n, l + 1, l, sp };
             launch_inv_blocks(c, s, ld, inter.p, 2);
             StInvAddHalf st{ tlast.p, n, sp };
             launch_inv_cols(c, s, inter.p, st, 2);
@@ -999,21 +1002,17 @@ extern "C"
         key->klimbs = kl;
         key->words = (size_t)kd * 2 * (kl + 1) * n;
         BK_CUDA(cudaMalloc((void **)&key->d, key->words * sizeof(u64)));
-        // stage one (digit, poly) at a time: [kl+1][N] natural -> transposed-block layout
-        Scratch stage(s, (size_t)(kl + 1) * n);
+        // one (digit, poly) at a time: limbs 0..kl-1, then the special prime's limb
         for (int j = 0; j < kd; j++)
             for (int p = 0; p < 2; p++)
             {
                 const uint64_t *src = host + ((size_t)j * 2 + p) * c.n_primes * n;
-                BK_CUDA(cudaMemcpyAsync(stage.p, src, (size_t)kl * n * sizeof(u64), cudaMemcpyHostToDevice, s));
-                BK_CUDA(cudaMemcpyAsync(stage.p + (size_t)kl * n, src + (size_t)(c.n_primes - 1) * n, n * sizeof(u64),
+                u64 *dst = key->d + ((size_t)j * 2 + p) * (kl + 1) * n;
+                BK_CUDA(cudaMemcpyAsync(dst, src, (size_t)kl * n * sizeof(u64), cudaMemcpyHostToDevice, s));
+                BK_CUDA(cudaMemcpyAsync(dst + (size_t)kl * n, src + (size_t)(c.n_primes - 1) * n, n * sizeof(u64),
                                         cudaMemcpyHostToDevice, s));
-                size_t total = (size_t)(kl + 1) * n;
-                k_transpose_blocks<<<c.ew_grid(total), 256, 0, s>>>(
-                    stage.p, key->d + ((size_t)j * 2 + p) * (kl + 1) * n, total);
-                c.count();
-                BK_CUDA(cudaStreamSynchronize(s)); // host buffer is pageable; keep staging ordered
             }
+        BK_CUDA(cudaStreamSynchronize(s));
         *out = key;
         BK_END
     }
@@ -1046,11 +1045,7 @@ extern "C"
         BK_TRY
         Context &c = *key->ctx;
         cudaStream_t s = c.stream();
-        Scratch tmp(s, key->words);
-        // the transposition is an involution on each 256-block
-        k_transpose_blocks<<<c.ew_grid(key->words), 256, 0, s>>>(key->d, tmp.p, key->words);
-        c.count();
-        BK_CUDA(cudaMemcpyAsync(host_out, tmp.p, key->words * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        BK_CUDA(cudaMemcpyAsync(host_out, key->d, key->words * sizeof(u64), cudaMemcpyDeviceToHost, s));
         BK_CUDA(cudaStreamSynchronize(s));
         BK_END
     }

@@ -176,7 +176,7 @@ struct bk_pt_s
 struct bk_kskey_s
 {
     bk::Context *ctx;
-    u64 *d = nullptr; // [digits][2][klimbs+1][N], transposed-block layout, special prime at klimbs
+    u64 *d = nullptr; // [digits][2][klimbs+1][N], the special prime's limb at index klimbs
     int digits = 0, klimbs = 0;
     size_t words = 0;
 };

@@ -119,6 +119,7 @@ struct LdModRaise
 // ---------------------------------------------------------------- forward block-pass stores
 struct StPlain
 {
+    __device__ __forceinline__ bool skip(int) const { return false; }
     u64 *dst;
     JobMap map;
     size_t n;
@@ -130,9 +131,31 @@ struct StPlain
     }
 };
 
+// Key-switch digits: keep the lazy NTT output in [0,4q) in place (the reference multiplies
+// the lazy values straight into the key, evaluator.cpp:2407-2436).  job = iloc * l + J as in
+// LdKsDigit; the I == J job is skipped (its operand is the NTT-form input itself).
+struct StKsDigit
+{
+    u64 *dst;
+    size_t n;
+    int l, I0, special_prime;
+    __device__ __forceinline__ bool skip(int job) const { return (I0 + job / l) == (job % l); }
+    __device__ __forceinline__ int prime(int job) const
+    {
+        int I = I0 + job / l;
+        return I == l ? special_prime : I;
+    }
+    __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
+    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &) const
+    {
+        dst[(size_t)job * n + idx] = v;
+    }
+};
+
 // Rescale tail (rns.cpp:786-806): dst[p][i] = (x[p][i] - NTT_i(t)) * q_last^-1 mod q_i.
 struct StRescale
 {
+    __device__ __forceinline__ bool skip(int) const { return false; }
     const u64 *x;  // [polys][limbs_in][N]
     u64 *dst;      // [polys][limbs_out][N]
     const ulonglong2 *inv; // [n_primes] {q_last^-1 mod q_i, shoup}
@@ -152,11 +175,13 @@ struct StRescale
 
 // ModDown tail of the key switch (evaluator.cpp:2499-2522):
 //   dst[p][i] = base_p[i] + (acc[p][i] - NTT_i(t_p)) * P^-1 mod q_i
-// acc is in the transposed block layout written by k_ks_mac (pos = k*16 + t <-> e = 16t + k);
-// base_0 = c0 (optionally gathered through the Galois table), base_1 = c1 or nothing.
+// acc is in natural layout (written by k_ks_mac); register element (t,k) of a block is
+// coefficient 16t + k.  base_0 = c0 (optionally gathered through the Galois table), base_1 = c1
+// or nothing.
 struct StModDown
 {
-    const u64 *acc;  // [2][l+1][N] transposed-block layout
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    const u64 *acc;  // [2][l+1][N]
     u64 *dst;        // [2][l][N]
     const u64 *base0; // [l][N] or null
     const u64 *base1; // [l][N] or null
@@ -168,7 +193,7 @@ struct StModDown
     __device__ __forceinline__ u64 pre(int job, int blk, int t, int k, u64 v, const PrimeDev &pd) const
     {
         int p = job / l, i = job % l;
-        u64 r = acc[((size_t)p * (l + 1) + i) * n + (size_t)blk * 256 + k * 16 + t];
+        u64 r = acc[((size_t)p * (l + 1) + i) * n + (size_t)blk * 256 + 16 * t + k];
         u64 d = r + 2 * pd.two_q - v;
         ulonglong2 f = inv[i];
         return csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
@@ -218,21 +243,6 @@ struct LdInvLimbOf
     __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
 };
 
-// same, but the source is in the transposed block layout (k_ks_mac accumulators)
-struct LdInvLimbOfT
-{
-    static constexpr bool TLAYOUT = true;
-    const u64 *src;
-    size_t n;
-    int limbs, limb, prime_idx;
-    __device__ __forceinline__ int prime(int) const { return prime_idx; }
-    __device__ __forceinline__ u64 load(int, int, const PrimeDev &) const { return 0; }
-    __device__ __forceinline__ u64 load_t(int job, int blk, int pos) const
-    {
-        return src[((size_t)job * limbs + limb) * n + (size_t)blk * 256 + pos];
-    }
-};
-
 // ---------------------------------------------------------------- inverse column-pass stores
 struct StInvPlain
 {
@@ -261,100 +271,80 @@ struct StInvAddHalf
 };
 
 // ============================================================================================
-// Key-switch inner product (evaluator.cpp:2368-2463), fused with the block pass of the digit
-// NTTs.  grid = (N/4096, nI), block = 256.  CTA (tile, iloc) owns 16 blocks of output modulus
-// I = I0 + iloc and loops over the l digits J:
-//    operand  = I == J ? target_ntt[J] (gathered through the Galois table if any)
-//                      : block pass of inter[iloc][J] (column pass output of LdKsDigit)
-//    acc_p   += operand * key[J][p][I]          (128-bit accumulators in registers)
-// One final barrett_reduce_128; result written in the transposed block layout.
-// Key limbs are stored pre-transposed (pos = k*16 + t) so the dominant HBM stream - the key -
-// is read as full 128-byte lines.
+// Key-switch inner product (evaluator.cpp:2368-2463).  The digit NTTs are complete when this
+// runs (column pass LdKsDigit + block pass StKsDigit, lazy values in [0,4q)); this kernel is the
+// pure stream  acc_p[I][i] = sum_J digit[I][J][i] * key[J][p][I][i]  with 128-bit accumulators
+// and one final barrett_reduce_128.  The key (2 l (l+1) limb-polys, up to 1 GiB) is the
+// dominant HBM stream of the whole key switch: 16-byte loads, two coefficients per thread,
+// J loop unrolled so several independent 128-byte lines are in flight per warp.
+//   operand for J == I: target_ntt[J] gathered through the Galois table (if any).
+// grid = (ceil(N/2/256), nI), block = 256.
 // ============================================================================================
 struct KsMacArgs
 {
-    const u64 *inter;      // [nI][l][N] column-pass output, lazy [0,4q)
-    const u64 *target_ntt; // [l][N] NTT form (natural layout)
+    const u64 *digits;     // [nI][l][N] NTT form, lazy [0,4q); slot J == I unused
+    const u64 *target_ntt; // [l][N] NTT form
     const uint32_t *perm;  // Galois table or null
-    const u64 *key;        // [digits][2][klimbs+1][N] transposed-block layout
-    u64 *acc;              // [2][l+1][N] transposed-block layout
+    const u64 *key;        // [digits][2][klimbs+1][N], special prime's limb at index klimbs
+    u64 *acc;              // [2][l+1][N]
     size_t n;
-    int l, I0, special_prime, klimbs; // key stores limbs 0..klimbs-1 and the special at klimbs
+    int l, I0, special_prime, klimbs;
 };
+
+__device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
+    return v;
+}
 
 static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
 {
-    __shared__ u64 sm[4096];
     const int iloc = blockIdx.y;
     const int I = a.I0 + iloc;
-    const int t = threadIdx.x & 15;
-    const int lb = threadIdx.x >> 4;
-    const int blk = blockIdx.x * 16 + lb;
     const int pi = I == a.l ? a.special_prime : I;
     const int kl = I == a.l ? a.klimbs : I;
-    const PrimeDev pd = T.primes[pi];
     const size_t n = a.n;
-    const unsigned B = (unsigned)(n >> 8) + (unsigned)blk;
-    const ulonglong2 *tw = T.tw + (size_t)pi * n;
-    u64 *s = sm + lb * 256;
-    const size_t boff = (size_t)blk * 256;
+    const size_t e = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (e >= n)
+        return;
+    const PrimeDev pd = T.primes[pi];
     const size_t kstride = (size_t)(a.klimbs + 1) * n; // one key poly
+    const u64 *dig = a.digits + (size_t)iloc * a.l * n + e;
+    const u64 *k0 = a.key + (size_t)kl * n + e;
 
-    u64 lo0[16], hi0[16], lo1[16], hi1[16];
-#pragma unroll
-    for (int k = 0; k < 16; k++)
-        lo0[k] = hi0[k] = lo1[k] = hi1[k] = 0ull;
-
+    u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+#pragma unroll 4
     for (int J = 0; J < a.l; J++)
     {
-        u64 x[16];
+        ulonglong2 x;
         if (J == I)
         {
             const u64 *src = a.target_ntt + (size_t)J * n;
-#pragma unroll
-            for (int k = 0; k < 16; k++)
+            if (a.perm)
             {
-                int idx = (int)boff + 16 * t + k;
-                x[k] = src[a.perm ? (int)a.perm[idx] : idx];
+                x.x = src[a.perm[e]];
+                x.y = src[a.perm[e + 1]];
             }
+            else
+                x = *reinterpret_cast<const ulonglong2 *>(src + e);
         }
         else
-        {
-            const u64 *src = a.inter + ((size_t)iloc * a.l + J) * n + boff;
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                x[k] = src[t + 16 * k];
-            fwd_radix<4>(x, tw, B, pd.q, pd.two_q);
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                s[swz(t + 16 * k)] = x[k];
-            __syncwarp();
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                x[k] = s[swz(16 * t + k)];
-            fwd_radix<4>(x, tw, 16u * B + (unsigned)t, pd.q, pd.two_q);
-            // operands stay lazy in [0,4q) as in the reference (:2407): l * 4q * q < 2^128
-        }
-        const u64 *k0 = a.key + ((size_t)J * 2) * kstride + (size_t)kl * n + boff;
-        const u64 *k1 = k0 + kstride;
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-        {
-            u64 w0 = __ldg(k0 + k * 16 + t);
-            u64 w1 = __ldg(k1 + k * 16 + t);
-            mac128(lo0[k], hi0[k], x[k], w0);
-            mac128(lo1[k], hi1[k], x[k], w1);
-        }
+            x = *reinterpret_cast<const ulonglong2 *>(dig + (size_t)J * n);
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)J * 2 * kstride);
+        ulonglong2 w1 = ldg_stream2(k0 + (size_t)J * 2 * kstride + kstride);
+        mac128(l0x, h0x, x.x, w0.x);
+        mac128(l0y, h0y, x.y, w0.y);
+        mac128(l1x, h1x, x.x, w1.x);
+        mac128(l1y, h1y, x.y, w1.y);
     }
-    u64 *o0 = a.acc + (size_t)I * n + boff;
-    u64 *o1 = a.acc + ((size_t)(a.l + 1) + I) * n + boff;
-#pragma unroll
-    for (int k = 0; k < 16; k++)
-    {
-        o0[k * 16 + t] = barrett128(lo0[k], hi0[k], pd);
-        o1[k * 16 + t] = barrett128(lo1[k], hi1[k], pd);
-    }
+    ulonglong2 r0, r1;
+    r0.x = barrett128(l0x, h0x, pd);
+    r0.y = barrett128(l0y, h0y, pd);
+    r1.x = barrett128(l1x, h1x, pd);
+    r1.y = barrett128(l1y, h1y, pd);
+    *reinterpret_cast<ulonglong2 *>(a.acc + (size_t)I * n + e) = r0;
+    *reinterpret_cast<ulonglong2 *>(a.acc + ((size_t)(a.l + 1) + I) * n + e) = r1;
 }
 
 // ============================================================================================
@@ -507,18 +497,5 @@ static __global__ void __launch_bounds__(256) k_drop_limbs(const u64 *__restrict
         size_t p = e / per_out, r = e % per_out;
         *reinterpret_cast<ulonglong2 *>(dst + e) =
             *reinterpret_cast<const ulonglong2 *>(src + p * (size_t)limbs_in * n + r);
-    }
-}
-
-// natural <-> transposed-block layout for key limbs (pos = k*16 + t holds e = 16t + k).
-static __global__ void __launch_bounds__(256) k_transpose_blocks(const u64 *__restrict__ src, u64 *__restrict__ dst,
-                                                          size_t total)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
-    {
-        size_t blk = i >> 8;
-        int pos = (int)(i & 255);
-        int k = pos >> 4, t = pos & 15;
-        dst[i] = src[(blk << 8) + 16 * t + k];
     }
 }

@@ -257,7 +257,7 @@ namespace bk
             u64 factor = c.primes[sp] % c.primes[j];
             u64 *c0 = key->d + ((size_t)j * 2) * (kl + 1) * n;
             u64 *c1 = c0 + (size_t)(kl + 1) * n;
-            k_sym_zero<true><<<c.ew_grid((size_t)(kl + 1) * n), 256, 0, s>>>(c0, c1, sk->d, e_ntt.p, newkey, j, factor,
+            k_sym_zero<false><<<c.ew_grid((size_t)(kl + 1) * n), 256, 0, s>>>(c0, c1, sk->d, e_ntt.p, newkey, j, factor,
                                                                             map, c.d_primes, c.log_n, kl + 1, seed,
                                                                             st_e + 1);
             c.count();

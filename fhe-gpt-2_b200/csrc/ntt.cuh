@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 // ============================================================================================
 // Block pass, forward (last 8 stages).  grid = (N/4096, jobs), block = 256 threads:
 // 16 blocks of 256 coefficients per CTA, one half-warp per block (only __syncwarp needed).
-//   Store: int prime(int job);
+//   Store: int prime(int job);  bool skip(int job);
 //          u64  pre (int job, int blk, int t, int k, u64 v, const PrimeDev&)   - register layout
 //               e = 16t + k, v in [0,4q); returns the value to be staged;
 //          void post(int job, int idx, u64 v, const PrimeDev&)                  - coalesced order.
@@ -194,6 +194,8 @@ __global__ void __launch_bounds__(256) k_fwd_blocks(const u64 *__restrict__ in, 
 {
     __shared__ u64 sm[4096];
     const int job = blockIdx.y;
+    if (st.skip(job))
+        return;
     const int t = threadIdx.x & 15;
     const int lb = threadIdx.x >> 4;         // local block 0..15
     const int blk = blockIdx.x * 16 + lb;    // 256-block index within the limb
