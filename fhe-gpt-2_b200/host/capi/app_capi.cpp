@@ -1,0 +1,612 @@
+// capi/app_capi.cpp - the C ABI of include/b200ckks_app.h over the C++ application classes.
+//
+// The same file is compiled twice: against fhe-gpt-2_b200/host/seal/seal.h (the engine; product) and, as test
+// infrastructure only, against the reference's own SEAL headers (oracle/Makefile, target `app_ref`), which yields a
+// CPU oracle for the application layers that runs the identical host code on the reference library.
+#include "../../../include/b200ckks_app.h"
+#include "cnn/infer_seal.h"
+#include <algorithm>
+#include <cstring>
+#include <memory>
+#include <string>
+
+using namespace seal;
+using std::vector;
+
+namespace
+{
+    thread_local std::string g_err;
+
+    int fail(const std::exception &e, int code)
+    {
+        g_err = e.what();
+        return code;
+    }
+#define BKA_TRY try {
+#define BKA_END                                                                                                        \
+    }                                                                                                                  \
+    catch (const std::invalid_argument &e) { return fail(e, 1); }                                                      \
+    catch (const std::out_of_range &e) { return fail(e, 3); }                                                          \
+    catch (const std::logic_error &e) { return fail(e, 2); }                                                           \
+    catch (const std::exception &e) { return fail(e, 4); }                                                             \
+    return 0;
+} // namespace
+
+struct bka_ct_s
+{
+    Ciphertext ct;
+};
+
+struct bka_session_s
+{
+    int log_n = 0;
+    vector<int> bits;
+    EncryptionParameters parms{ scheme_type::ckks };
+    std::unique_ptr<SEALContext> context;
+    std::unique_ptr<KeyGenerator> keygen;
+    PublicKey public_key;
+    SecretKey secret_key;
+    RelinKeys relin_keys;
+    GaloisKeys gal_keys;
+    std::unique_ptr<CKKSEncoder> encoder;
+    std::unique_ptr<Encryptor> encryptor;
+    std::unique_ptr<Evaluator> evaluator;
+    std::unique_ptr<Decryptor> decryptor;
+    vector<int> steps;
+    bool keys_ready = false;
+    vector<minicomp::Tree> relu_tree;
+
+    void add_steps(const int *s, int n)
+    {
+        for (int i = 0; i < n; i++)
+            if (std::find(steps.begin(), steps.end(), s[i]) == steps.end())
+            {
+                steps.push_back(s[i]);
+                keys_ready = false;
+            }
+    }
+    // KeyGenerator::create_galois_keys on the collected step list (infer_seal.cpp:379)
+    void ensure_keys()
+    {
+        if (keys_ready)
+            return;
+        keygen->create_galois_keys(steps, gal_keys);
+        keys_ready = true;
+    }
+};
+
+struct bka_bootstrapper_s
+{
+    bka_session_t s;
+    std::unique_ptr<Bootstrapper> b;
+    bool coeffs = false;
+    void ready()
+    {
+        s->ensure_keys();
+        if (!coeffs)
+        {
+            b->slot_vec.push_back(b->logn);
+            b->generate_LT_coefficient_3();
+            coeffs = true;
+        }
+    }
+};
+
+struct bka_resnet_s
+{
+    bka_session_t s;
+    std::unique_ptr<ResNetCifar10> net;
+    bool prepared = false;
+};
+
+static bka_ct_t wrap(Ciphertext &&c)
+{
+    auto *h = new bka_ct_s();
+    h->ct = std::move(c);
+    return h;
+}
+
+extern "C"
+{
+    const char *bka_last_error(void)
+    {
+        return g_err.c_str();
+    }
+    const char *bka_backend(void)
+    {
+#ifdef B200CKKS_FACADE
+        return "engine";
+#else
+        return "reference-seal";
+#endif
+    }
+
+    int bka_session_create(int log_n, const int *bit_sizes, int n_bits, int hamming_weight, int device,
+                           const int *rotation_steps, int n_steps, bka_session_t *out)
+    {
+        BKA_TRY
+        auto s = std::make_unique<bka_session_s>();
+        s->log_n = log_n;
+        s->bits.assign(bit_sizes, bit_sizes + n_bits);
+        const std::size_t N = std::size_t(1) << log_n;
+        s->parms.set_poly_modulus_degree(N);
+        s->parms.set_coeff_modulus(CoeffModulus::Create(N, s->bits));
+        s->parms.set_secret_key_hamming_weight((std::size_t)hamming_weight);
+#ifdef B200CKKS_FACADE
+        s->context = std::make_unique<SEALContext>(s->parms, true, sec_level_type::none, device);
+#else
+        (void)device;
+        s->context = std::make_unique<SEALContext>(s->parms, true, sec_level_type::none);
+#endif
+        s->keygen = std::make_unique<KeyGenerator>(*s->context);
+        s->keygen->create_public_key(s->public_key);
+        s->secret_key = s->keygen->secret_key();
+        s->keygen->create_relin_keys(s->relin_keys);
+        s->encoder = std::make_unique<CKKSEncoder>(*s->context);
+        s->encryptor = std::make_unique<Encryptor>(*s->context, s->public_key);
+        s->evaluator = std::make_unique<Evaluator>(*s->context, *s->encoder);
+        s->decryptor = std::make_unique<Decryptor>(*s->context, s->secret_key);
+        s->add_steps(rotation_steps, n_steps);
+        *out = s.release();
+        BKA_END
+    }
+    int bka_session_destroy(bka_session_t s)
+    {
+        BKA_TRY
+        delete s;
+        BKA_END
+    }
+    int bka_session_add_rotation_steps(bka_session_t s, const int *steps, int n_steps)
+    {
+        BKA_TRY
+        s->add_steps(steps, n_steps);
+        BKA_END
+    }
+    int bka_session_primes(bka_session_t s, uint64_t *primes_out)
+    {
+        BKA_TRY
+        const auto &m = s->context->key_context_data()->parms().coeff_modulus();
+        for (std::size_t i = 0; i < m.size(); i++)
+            primes_out[i] = m[i].value();
+        BKA_END
+    }
+    int bka_session_sync(bka_session_t s)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        s->context->sync();
+#else
+        (void)s;
+#endif
+        BKA_END
+    }
+    int bka_session_stats(bka_session_t s, uint64_t counts_out[9], int reset)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        auto &st = s->evaluator->stats();
+        std::atomic<std::uint64_t> *f[9] = { &st.key_switch_rotate, &st.key_switch_relin, &st.rescale,    &st.multiply, &st.multiply_plain,
+                                             &st.encode_vector,     &st.add,              &st.mod_switch, &st.scalar_op };
+        for (int i = 0; i < 9; i++)
+        {
+            counts_out[i] = f[i]->load();
+            if (reset)
+                f[i]->store(0);
+        }
+#else
+        (void)s;
+        (void)reset;
+        std::memset(counts_out, 0, 9 * sizeof(uint64_t));
+#endif
+        BKA_END
+    }
+    int bka_session_key_residency(bka_session_t s, uint64_t *bytes_out, uint64_t *generated_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        *bytes_out = s->gal_keys.resident_bytes();
+        *generated_out = s->gal_keys.generated();
+#else
+        (void)s;
+        *bytes_out = 0;
+        *generated_out = 0;
+#endif
+        BKA_END
+    }
+
+    // ---- ciphertexts ---------------------------------------------------------------------------------------------
+    int bka_encrypt(bka_session_t s, const double *values, int n_values, int is_complex, double scale, int limbs, bka_ct_t *out)
+    {
+        BKA_TRY
+        Plaintext plain;
+        if (is_complex)
+        {
+            vector<std::complex<double>> v((std::size_t)n_values);
+            for (int i = 0; i < n_values; i++)
+                v[(std::size_t)i] = { values[2 * i], values[2 * i + 1] };
+            s->encoder->encode(v, scale, plain);
+        }
+        else
+            s->encoder->encode(vector<double>(values, values + n_values), scale, plain);
+        Ciphertext ct;
+        s->encryptor->encrypt(plain, ct);
+        if (limbs > 0)
+        {
+            auto cd = s->context->first_context_data();
+            while (cd && (int)cd->parms().coeff_modulus().size() > limbs)
+                cd = cd->next_context_data();
+            if (!cd || (int)cd->parms().coeff_modulus().size() != limbs)
+                throw std::invalid_argument("limbs is out of range");
+            s->evaluator->mod_switch_to_inplace(ct, cd->parms_id());
+        }
+        *out = wrap(std::move(ct));
+        BKA_END
+    }
+    int bka_decrypt(bka_session_t s, bka_ct_t ct, double *out_complex)
+    {
+        BKA_TRY
+        Plaintext plain;
+        s->decryptor->decrypt(ct->ct, plain);
+        vector<std::complex<double>> v;
+        s->encoder->decode(plain, v);
+        std::memcpy(out_complex, v.data(), v.size() * sizeof(std::complex<double>));
+        BKA_END
+    }
+    int bka_ct_clone(bka_ct_t ct, bka_ct_t *out)
+    {
+        BKA_TRY
+        Ciphertext c = ct->ct;
+        *out = wrap(std::move(c));
+        BKA_END
+    }
+    int bka_ct_free(bka_ct_t ct)
+    {
+        BKA_TRY
+        delete ct;
+        BKA_END
+    }
+    int bka_ct_info(bka_ct_t ct, int *size, int *limbs, double *scale)
+    {
+        BKA_TRY
+        if (size)
+            *size = (int)ct->ct.size();
+        if (limbs)
+            *limbs = (int)ct->ct.coeff_modulus_size();
+        if (scale)
+            *scale = ct->ct.scale();
+        BKA_END
+    }
+    int bka_ct_set_scale(bka_ct_t ct, double scale)
+    {
+        BKA_TRY
+        ct->ct.scale() = scale;
+        BKA_END
+    }
+    int bka_ct_mod_switch_to(bka_session_t s, bka_ct_t ct, int limbs)
+    {
+        BKA_TRY
+        auto cd = s->context->first_context_data();
+        while (cd && (int)cd->parms().coeff_modulus().size() > limbs)
+            cd = cd->next_context_data();
+        if (!cd)
+            throw std::invalid_argument("limbs is out of range");
+        s->evaluator->mod_switch_to_inplace(ct->ct, cd->parms_id());
+        BKA_END
+    }
+    int bka_ct_download(bka_ct_t ct, uint64_t *host_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        ct->ct.download(host_out);
+#else
+        std::memcpy(host_out, ct->ct.data(),
+                    ct->ct.size() * ct->ct.coeff_modulus_size() * ct->ct.poly_modulus_degree() * sizeof(uint64_t));
+#endif
+        BKA_END
+    }
+
+    int bka_rotate(bka_session_t s, bka_ct_t ct, int steps)
+    {
+        BKA_TRY
+        s->ensure_keys();
+        s->evaluator->rotate_vector_inplace(ct->ct, steps, s->gal_keys);
+        BKA_END
+    }
+    int bka_multiply_relin_rescale(bka_session_t s, bka_ct_t a, bka_ct_t b)
+    {
+        BKA_TRY
+        s->evaluator->multiply_inplace_reduced_error(a->ct, b->ct, s->relin_keys);
+        s->evaluator->rescale_to_next_inplace(a->ct);
+        BKA_END
+    }
+    int bka_add_reduced_error(bka_session_t s, bka_ct_t a, bka_ct_t b)
+    {
+        BKA_TRY
+        s->evaluator->add_inplace_reduced_error(a->ct, b->ct);
+        BKA_END
+    }
+    int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex)
+    {
+        BKA_TRY
+        if (is_complex)
+        {
+            vector<std::complex<double>> v((std::size_t)n_values);
+            for (int i = 0; i < n_values; i++)
+                v[(std::size_t)i] = { values[2 * i], values[2 * i + 1] };
+            s->evaluator->multiply_vector_inplace_reduced_error(a->ct, v);
+        }
+        else
+        {
+            vector<double> v(values, values + n_values);
+            s->evaluator->multiply_vector_inplace_reduced_error(a->ct, v);
+        }
+        s->evaluator->rescale_to_next_inplace(a->ct);
+        BKA_END
+    }
+
+    // ---- bootstrapping -------------------------------------------------------------------------------------------
+    int bka_bootstrapper_create(bka_session_t s, int loge, int logn, int total_level, double final_scale, int boundary_k,
+                                int sin_cos_deg, int scale_factor, int inverse_deg, bka_bootstrapper_t *out)
+    {
+        BKA_TRY
+        auto h = std::make_unique<bka_bootstrapper_s>();
+        h->s = s;
+        h->b = std::make_unique<Bootstrapper>(loge, logn, s->log_n - 1, total_level, final_scale, boundary_k, sin_cos_deg,
+                                              scale_factor, inverse_deg, *s->context, *s->keygen, *s->encoder, *s->encryptor,
+                                              *s->decryptor, *s->evaluator, s->relin_keys, s->gal_keys);
+        h->b->prepare_mod_polynomial();
+        vector<int> steps;
+        steps.push_back(0);
+        for (int i = 0; i < s->log_n - 1; i++)
+            steps.push_back(1 << i);
+        h->b->addLeftRotKeys_Linear_to_vector_3(steps);
+        s->add_steps(steps.data(), (int)steps.size());
+        *out = h.release();
+        BKA_END
+    }
+    int bka_bootstrapper_destroy(bka_bootstrapper_t b)
+    {
+        BKA_TRY
+        delete b;
+        BKA_END
+    }
+    int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int cap, int *count_out)
+    {
+        BKA_TRY
+        vector<int> steps;
+        b->b->addLeftRotKeys_Linear_to_vector_3(steps);
+        *count_out = (int)steps.size();
+        for (int i = 0; i < (int)steps.size() && i < cap; i++)
+            steps_out[i] = steps[(std::size_t)i];
+        BKA_END
+    }
+    int bka_bootstrapper_lt_coefficients(bka_bootstrapper_t b, int which, int *n_diagonals, int *length, double *data_out)
+    {
+        BKA_TRY
+        if (!b->coeffs)
+        { // coefficient tables do not need keys
+            b->b->slot_vec.push_back(b->b->logn);
+            b->b->generate_LT_coefficient_3();
+            b->coeffs = true;
+        }
+        const std::size_t u = (std::size_t)b->b->slot_index;
+        const Bootstrapper::Diagonals *d = nullptr;
+        switch (which)
+        {
+        case 0: d = &b->b->fftcoeff1[u]; break;
+        case 1: d = &b->b->fftcoeff2[u]; break;
+        case 2: d = &b->b->fftcoeff3[u]; break;
+        case 3: d = &b->b->invfftcoeff1[u]; break;
+        case 4: d = &b->b->invfftcoeff2[u]; break;
+        case 5: d = &b->b->invfftcoeff3[u]; break;
+        default: throw std::invalid_argument("which must be 0..5");
+        }
+        *n_diagonals = (int)d->size();
+        *length = d->empty() ? 0 : (int)(*d)[0].size();
+        if (data_out)
+            for (std::size_t i = 0; i < d->size(); i++)
+                std::memcpy(data_out + 2 * i * (*d)[0].size(), (*d)[i].data(), (*d)[i].size() * sizeof(std::complex<double>));
+        BKA_END
+    }
+    int bka_bootstrap(bka_bootstrapper_t b, bka_ct_t ct, int real_message, bka_ct_t *out)
+    {
+        BKA_TRY
+        b->ready();
+        Ciphertext rtn;
+        if (real_message)
+            b->b->bootstrap_real_3(rtn, ct->ct);
+        else
+            b->b->bootstrap_3(rtn, ct->ct);
+        *out = wrap(std::move(rtn));
+        BKA_END
+    }
+    int bka_modular_reduction(bka_bootstrapper_t b, bka_ct_t ct, bka_ct_t *out)
+    {
+        BKA_TRY
+        Ciphertext rtn;
+        b->b->mod_reducer->modular_reduction(rtn, ct->ct);
+        *out = wrap(std::move(rtn));
+        BKA_END
+    }
+
+    // ---- ReLU ----------------------------------------------------------------------------------------------------
+    int bka_relu(bka_session_t s, bka_ct_t ct, bka_ct_t *out)
+    {
+        BKA_TRY
+        vector<int> deg = { 15, 15, 27 };
+        if (s->relu_tree.empty())
+            for (int d : deg)
+            {
+                minicomp::Tree t;
+                upgrade_oddbaby(d, t);
+                s->relu_tree.push_back(t);
+            }
+        Ciphertext res;
+        minimax_ReLU_seal(3, deg, 13, s->relu_tree, 1.7, 46, *s->encryptor, *s->evaluator, *s->decryptor, *s->encoder,
+                          s->public_key, s->secret_key, s->relin_keys, ct->ct, res);
+        *out = wrap(std::move(res));
+        BKA_END
+    }
+    int bka_oddbaby_tree(int deg, int *tree_out, int cap, int *len_out, int *depth_out, int *m_out, int *l_out)
+    {
+        BKA_TRY
+        minicomp::Tree t;
+        upgrade_oddbaby(deg, t);
+        *len_out = (int)t.tree.size();
+        *depth_out = t.depth;
+        *m_out = t.m;
+        *l_out = t.l;
+        for (int i = 0; i < (int)t.tree.size() && i < cap; i++)
+            tree_out[i] = t.tree[(std::size_t)i];
+        BKA_END
+    }
+
+    // ---- tensors -------------------------------------------------------------------------------------------------
+    static TensorCipher tensor_of(const int p[7], bka_ct_t ct)
+    {
+        return TensorCipher(p[6], p[0], p[1], p[2], p[3], p[4], p[5], ct->ct);
+    }
+    static void parms_of(const TensorCipher &t, int p[7])
+    {
+        p[0] = t.k();
+        p[1] = t.h();
+        p[2] = t.w();
+        p[3] = t.c();
+        p[4] = t.t();
+        p[5] = t.p();
+        p[6] = t.logn();
+    }
+
+    int bka_conv(bka_session_t s, bka_ct_t in, const int in_parms[7], int co, int st, int fh, int fw, const double *weight,
+                 const double *running_var, const double *constant_weight, double epsilon, int end, bka_ct_t *out,
+                 int out_parms[7])
+    {
+        BKA_TRY
+        s->ensure_keys();
+        TensorCipher tin = tensor_of(in_parms, in), tout;
+        vector<Ciphertext> pool;
+        vector<double> data(weight, weight + (std::size_t)fh * fw * tin.c() * co);
+        multiplexed_parallel_convolution_seal(tin, tout, co, st, fh, fw, data, vector<double>(running_var, running_var + co),
+                                              vector<double>(constant_weight, constant_weight + co), epsilon, *s->encoder,
+                                              *s->encryptor, *s->evaluator, s->gal_keys, pool, end != 0);
+        parms_of(tout, out_parms);
+        *out = wrap(tout.cipher());
+        BKA_END
+    }
+    int bka_bn(bka_session_t s, bka_ct_t in, const int parms[7], const double *bias, const double *running_mean,
+               const double *running_var, const double *weight, double epsilon, double B, bka_ct_t *out)
+    {
+        BKA_TRY
+        TensorCipher tin = tensor_of(parms, in), tout;
+        const int c = tin.c();
+        multiplexed_parallel_batch_norm_seal(tin, tout, vector<double>(bias, bias + c), vector<double>(running_mean, running_mean + c),
+                                             vector<double>(running_var, running_var + c), vector<double>(weight, weight + c),
+                                             epsilon, *s->encoder, *s->encryptor, *s->evaluator, B);
+        *out = wrap(tout.cipher());
+        BKA_END
+    }
+    int bka_downsample(bka_session_t s, bka_ct_t in, const int in_parms[7], bka_ct_t *out, int out_parms[7])
+    {
+        BKA_TRY
+        s->ensure_keys();
+        TensorCipher tin = tensor_of(in_parms, in), tout;
+        multiplexed_parallel_downsampling_seal(tin, tout, *s->evaluator, s->gal_keys);
+        parms_of(tout, out_parms);
+        *out = wrap(tout.cipher());
+        BKA_END
+    }
+    int bka_avgpool(bka_session_t s, bka_ct_t in, const int in_parms[7], double B, bka_ct_t *out, int out_parms[7])
+    {
+        BKA_TRY
+        s->ensure_keys();
+        TensorCipher tin = tensor_of(in_parms, in), tout;
+        averagepooling_seal_scale(tin, tout, *s->evaluator, s->gal_keys, B);
+        parms_of(tout, out_parms);
+        *out = wrap(tout.cipher());
+        BKA_END
+    }
+    int bka_fc(bka_session_t s, bka_ct_t in, const int parms[7], const double *matrix, const double *bias, int q, int r,
+               bka_ct_t *out)
+    {
+        BKA_TRY
+        s->ensure_keys();
+        TensorCipher tin = tensor_of(parms, in), tout;
+        matrix_multiplication_seal(tin, tout, vector<double>(matrix, matrix + (std::size_t)q * r), vector<double>(bias, bias + q), q, r,
+                                   *s->evaluator, s->gal_keys);
+        *out = wrap(tout.cipher());
+        BKA_END
+    }
+    int bka_tensor_add(bka_session_t s, bka_ct_t a, bka_ct_t b, bka_ct_t *out)
+    {
+        BKA_TRY
+        Ciphertext c = a->ct;
+        s->evaluator->add_inplace_reduced_error(c, b->ct);
+        *out = wrap(std::move(c));
+        BKA_END
+    }
+
+    // ---- ResNet --------------------------------------------------------------------------------------------------
+    int bka_resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias, const double *bn_mean,
+                          const double *bn_var, const double *bn_weight, const double *linear_weight, const double *linear_bias,
+                          bka_resnet_t *out)
+    {
+        BKA_TRY
+        ResNetParameters p;
+        const std::size_t layers = (std::size_t)layer_num - 1;
+        std::size_t wpos = 0, cpos = 0;
+        for (std::size_t i = 0; i < layers; i++)
+        {
+            int ci, co;
+            resnet_conv_shape((std::size_t)layer_num, i, ci, co);
+            p.conv_weight.emplace_back(conv_weight + wpos, conv_weight + wpos + (std::size_t)9 * ci * co);
+            wpos += (std::size_t)9 * ci * co;
+            p.bn_bias.emplace_back(bn_bias + cpos, bn_bias + cpos + co);
+            p.bn_running_mean.emplace_back(bn_mean + cpos, bn_mean + cpos + co);
+            p.bn_running_var.emplace_back(bn_var + cpos, bn_var + cpos + co);
+            p.bn_weight.emplace_back(bn_weight + cpos, bn_weight + cpos + co);
+            cpos += (std::size_t)co;
+        }
+        p.linear_weight.assign(linear_weight, linear_weight + 640);
+        p.linear_bias.assign(linear_bias, linear_bias + 10);
+        auto h = std::make_unique<bka_resnet_s>();
+        h->s = s;
+        h->net = std::make_unique<ResNetCifar10>((std::size_t)layer_num, std::move(p), *s->context, *s->keygen, *s->encoder,
+                                                 *s->encryptor, *s->decryptor, *s->evaluator, s->public_key, s->secret_key,
+                                                 s->relin_keys, s->gal_keys);
+        vector<int> steps = h->net->galois_steps();
+        s->add_steps(steps.data(), (int)steps.size());
+        *out = h.release();
+        BKA_END
+    }
+    int bka_resnet_destroy(bka_resnet_t net)
+    {
+        BKA_TRY
+        delete net;
+        BKA_END
+    }
+    int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
+                         int *trace_rows)
+    {
+        BKA_TRY
+        net->s->ensure_keys();
+        if (!net->prepared)
+        {
+            net->net->prepare();
+            net->prepared = true;
+        }
+        vector<ResNetTraceRow> trace;
+        vector<double> logits = net->net->infer(vector<double>(image, image + 3072), trace_out ? &trace : nullptr);
+        std::memcpy(logits_out, logits.data(), 10 * sizeof(double));
+        if (trace_rows)
+            *trace_rows = (int)trace.size();
+        if (trace_out)
+            for (int i = 0; i < (int)trace.size() && i < trace_cap; i++)
+            {
+                trace_out[4 * i + 0] = trace[(std::size_t)i].op;
+                trace_out[4 * i + 1] = trace[(std::size_t)i].remaining_level;
+                trace_out[4 * i + 2] = trace[(std::size_t)i].scale;
+                trace_out[4 * i + 3] = trace[(std::size_t)i].milliseconds;
+            }
+        BKA_END
+    }
+}

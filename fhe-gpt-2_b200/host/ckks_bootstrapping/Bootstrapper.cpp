@@ -1,0 +1,707 @@
+// ckks_bootstrapping/Bootstrapper.cpp - see Bootstrapper.h.  Host orchestration only: every ciphertext operation
+// is a seal::Evaluator call, i.e. a launch sequence of the CUDA engine behind the C ABI.
+#include "ckks_bootstrapping/Bootstrapper.h"
+#include "common/func.h"
+#include <algorithm>
+#include <cmath>
+
+using namespace seal;
+using std::complex;
+using std::vector;
+
+namespace
+{
+    // index ranges of a baby-step/giant-step pass over diagonals -totlen..totlen (Bootstrapper.cpp:1953-1956)
+    struct SignedPlan
+    {
+        int gs, basicstart, giantfirst, giantlast;
+        explicit SignedPlan(int totlen)
+        {
+            gs = giantstep(2 * totlen + 1);
+            basicstart = -totlen + gs * (totlen / gs);
+            giantfirst = -(totlen / gs);
+            giantlast = (2 * totlen) / gs + giantfirst;
+        }
+    };
+
+    void push_unique(vector<int> &v, int step)
+    {
+        if (std::find(v.begin(), v.end(), step) == v.end())
+            v.push_back(step);
+    }
+} // namespace
+
+Bootstrapper::Bootstrapper(long _loge, long _logn, long _logNh, long _L, double _final_scale, long _boundary_K,
+                           long _sin_cos_deg, long _scale_factor, long _inverse_deg, SEALContext &_context,
+                           KeyGenerator &_keygen, CKKSEncoder &_encoder, Encryptor &_encryptor, Decryptor &_decryptor,
+                           Evaluator &_evaluator, RelinKeys &_relin_keys, GaloisKeys &_gal_keys)
+    : loge(_loge), logn(_logn), logNh(_logNh), L(_L), final_scale(_final_scale), boundary_K(_boundary_K),
+      sin_cos_deg(_sin_cos_deg), scale_factor(_scale_factor), inverse_deg(_inverse_deg), context(_context),
+      keygen(_keygen), encoder(_encoder), encryptor(_encryptor), decryptor(_decryptor), evaluator(_evaluator),
+      relin_keys(_relin_keys), gal_keys(_gal_keys)
+{
+    n = 1L << logn;
+    Nh = 1L << logNh;
+    mod_reducer = new ModularReducer(boundary_K, (double)loge, sin_cos_deg, scale_factor, inverse_deg, context, encoder,
+                                     encryptor, evaluator, relin_keys, decryptor);
+}
+
+Bootstrapper::~Bootstrapper()
+{
+    delete mod_reducer;
+}
+
+// ---------------------------------------------------------------------------------------------- stage grouping
+Bootstrapper::Split Bootstrapper::split_encode(long logn_) const
+{
+    Split s;
+    s.part[0] = (int)std::floor(logn_ / 3.0);
+    s.part[1] = (int)std::floor((logn_ - s.part[0]) / 2.0);
+    s.part[2] = (int)(logn_ - s.part[0] - s.part[1]);
+    for (int g = 0; g < 3; g++)
+        s.totlen[g] = (1 << s.part[g]) - 1;
+    s.basicstep[0] = 1 << (logn_ - s.part[0]);
+    s.basicstep[1] = 1 << (logn_ - s.part[0] - s.part[1]);
+    s.basicstep[2] = 1;
+    return s;
+}
+
+Bootstrapper::Split Bootstrapper::split_decode(long logn_) const
+{
+    Split s;
+    s.part[2] = (int)std::floor(logn_ / 3.0);
+    s.part[1] = (int)std::floor((logn_ - s.part[2]) / 2.0);
+    s.part[0] = (int)(logn_ - s.part[2] - s.part[1]);
+    for (int g = 0; g < 3; g++)
+        s.totlen[g] = (1 << s.part[g]) - 1;
+    s.basicstep[0] = 1;
+    s.basicstep[1] = 1 << s.part[0];
+    s.basicstep[2] = 1 << (s.part[0] + s.part[1]);
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------------- rotation keys
+void Bootstrapper::addLeftRotKeys_Linear_to_vector_3(vector<int> &steps)
+{
+    const Split s = split_encode(logn);
+    const int N = (int)Nh;
+    const bool sparse = logn != logNh;
+    auto wrap = [N](int step) { return ((step % N) + N) % N; };
+
+    // first group: the reference lists it both in signed form (sized with giantstep(totlen + 1)) and, for sparse
+    // packing, in rotated form (sized with giantstep(2 totlen + 1)); kept verbatim so the key set is the same
+    const int t1 = s.totlen[0], b1 = s.basicstep[0];
+    const int gs1 = giantstep(t1 + 1);
+    const int gs1_e = sparse ? giantstep(2 * t1 + 1) : 0;
+    const int basicstart1 = -t1 + gs1 * (t1 / gs1);
+    const int giantfirst1 = -(t1 / gs1);
+    const int giantlast1 = (2 * t1) / gs1 + giantfirst1;
+    const int giantlast1_e = sparse ? t1 / gs1 : 0;
+    const SignedPlan p2(s.totlen[1]), p3(s.totlen[2]);
+
+    for (int i = basicstart1; i < basicstart1 + gs1; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * b1));
+    for (int i = 1; i < gs1_e; i++)
+        push_unique(steps, i * b1);
+    for (int i = p2.basicstart; i < p2.basicstart + p2.gs; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * s.basicstep[1]));
+    for (int i = p3.basicstart; i < p3.basicstart + p3.gs; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * s.basicstep[2]));
+    for (int i = giantfirst1; i <= giantlast1; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * gs1 * b1));
+    for (int i = 1; i <= giantlast1_e; i++)
+        push_unique(steps, i * gs1_e * b1);
+    for (int i = p2.giantfirst; i <= p2.giantlast; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * p2.gs * s.basicstep[1]));
+    for (int i = p3.giantfirst; i <= p3.giantlast; i++)
+        if (i != 0)
+            push_unique(steps, wrap(i * p3.gs * s.basicstep[2]));
+}
+
+void Bootstrapper::find_slot_index()
+{
+    slot_index = -1;
+    for (std::size_t i = 0; i < slot_vec.size(); i++)
+        if (slot_vec[i] == logn)
+        {
+            slot_index = (long)i;
+            break;
+        }
+    if (slot_index == -1)
+        throw std::invalid_argument("LT coefficients were not generated for this logn");
+}
+
+void Bootstrapper::addBootKeys_3(GaloisKeys &keys)
+{
+    vector<int> other;
+    addBootKeys_3_other_keys(keys, other);
+    slot_vec.push_back(logn);
+    find_slot_index();
+}
+
+void Bootstrapper::addBootKeys_3_other_keys(GaloisKeys &keys, vector<int> &other_keys)
+{
+    vector<int> steps;
+    steps.push_back(0);
+    for (int i = 0; i < logNh; i++)
+        steps.push_back(1 << i);
+    for (int rot : other_keys)
+        push_unique(steps, rot);
+    addLeftRotKeys_Linear_to_vector_3(steps);
+    keygen.create_galois_keys(steps, keys);
+}
+
+void Bootstrapper::change_logn(long new_logn)
+{
+    logn = new_logn;
+    n = 1L << logn;
+    find_slot_index();
+}
+
+// -------------------------------------------------------------------------------------- LT coefficient generation
+namespace
+{
+    // product of stages [first, first + count) of one direction; stage `first` is applied first
+    boot::DiagMatrix merge_stages(long logn, long first, long count, bool decode)
+    {
+        boot::DiagMatrix m = boot::DiagMatrix::identity(1L << logn);
+        for (long i = first; i < first + count; i++)
+            m = (decode ? boot::decode_stage(logn, i) : boot::encode_stage(logn, i)).after(m);
+        return m;
+    }
+    // diagonals pos = -totlen..totlen at offsets pos * basicstep, index pos + totlen
+    Bootstrapper::Diagonals signed_diagonals(const boot::DiagMatrix &m, int totlen, int basicstep)
+    {
+        Bootstrapper::Diagonals d;
+        for (int pos = -totlen; pos <= totlen; pos++)
+            d.push_back(m.get((long)pos * basicstep));
+        return d;
+    }
+    // diagonals pos = 0..totlen of the matrix folded modulo (totlen + 1) * basicstep
+    Bootstrapper::Diagonals rotated_diagonals(const boot::DiagMatrix &m, int totlen, int basicstep)
+    {
+        boot::DiagMatrix f = m.folded((long)(totlen + 1) * basicstep);
+        Bootstrapper::Diagonals d;
+        for (int pos = 0; pos <= totlen; pos++)
+            d.push_back(f.get((long)pos * basicstep));
+        return d;
+    }
+    // append a second period equal to `factor` times the first (slot vectors of period 2n in sparse packing)
+    void extend_period(Bootstrapper::Diagonals &d, complex<double> factor)
+    {
+        for (auto &v : d)
+        {
+            std::size_t len = v.size();
+            v.resize(2 * len);
+            for (std::size_t j = 0; j < len; j++)
+                v[len + j] = factor * v[j];
+        }
+    }
+    void scale_all(Bootstrapper::Diagonals &d, double f)
+    {
+        for (auto &v : d)
+            for (auto &x : v)
+                x *= f;
+    }
+} // namespace
+
+void Bootstrapper::genfftcoeff_3()
+{
+    fftcoeff1.assign(slot_vec.size(), Diagonals());
+    fftcoeff2.assign(slot_vec.size(), Diagonals());
+    fftcoeff3.assign(slot_vec.size(), Diagonals());
+    for (std::size_t u = 0; u < slot_vec.size(); u++)
+    {
+        const long ln = slot_vec[u];
+        const Split s = split_decode(ln);
+        boot::DiagMatrix g1 = merge_stages(ln, 0, s.part[0], true);
+        boot::DiagMatrix g2 = merge_stages(ln, s.part[0], s.part[1], true);
+        boot::DiagMatrix g3 = merge_stages(ln, s.part[0] + s.part[1], s.part[2], true);
+        fftcoeff1[u] = signed_diagonals(g1, s.totlen[0], s.basicstep[0]);
+        fftcoeff2[u] = signed_diagonals(g2, s.totlen[1], s.basicstep[1]);
+        if (ln == logNh)
+            fftcoeff3[u] = rotated_diagonals(g3, s.totlen[2], s.basicstep[2]);
+        else
+        {
+            fftcoeff3[u] = signed_diagonals(g3, s.totlen[2], s.basicstep[2]);
+            extend_period(fftcoeff1[u], 1.0);
+            extend_period(fftcoeff2[u], 1.0);
+            extend_period(fftcoeff3[u], complex<double>(0, 1)); // second half carries the imaginary parts
+        }
+    }
+}
+
+void Bootstrapper::geninvfftcoeff_3()
+{
+    invfftcoeff1.assign(slot_vec.size(), Diagonals());
+    invfftcoeff2.assign(slot_vec.size(), Diagonals());
+    invfftcoeff3.assign(slot_vec.size(), Diagonals());
+    for (std::size_t u = 0; u < slot_vec.size(); u++)
+    {
+        const long ln = slot_vec[u];
+        const Split s = split_encode(ln);
+        boot::DiagMatrix g1 = merge_stages(ln, 0, s.part[0], false);
+        boot::DiagMatrix g2 = merge_stages(ln, s.part[0], s.part[1], false);
+        boot::DiagMatrix g3 = merge_stages(ln, s.part[0] + s.part[1], s.part[2], false);
+        invfftcoeff1[u] = rotated_diagonals(g1, s.totlen[0], s.basicstep[0]);
+        invfftcoeff2[u] = signed_diagonals(g2, s.totlen[1], s.basicstep[1]);
+        invfftcoeff3[u] = signed_diagonals(g3, s.totlen[2], s.basicstep[2]);
+        // 1/K brings the coefficients into the cosine's range; sparse packing also averages the SubSum copies
+        if (ln == logNh)
+            scale_all(invfftcoeff1[u], 1.0 / boundary_K);
+        else
+            scale_all(invfftcoeff1[u], 1.0 / (boundary_K * (double)(1L << (logNh - ln))));
+        scale_all(invfftcoeff3[u], 0.5);
+        if (ln != logNh)
+            extend_period(invfftcoeff3[u], complex<double>(0, -1));
+    }
+}
+
+void Bootstrapper::generate_LT_coefficient_3()
+{
+    genfftcoeff_3();
+    geninvfftcoeff_3();
+    if (slot_index < 0 || (std::size_t)slot_index >= slot_vec.size() || slot_vec[(std::size_t)slot_index] != logn)
+        find_slot_index();
+}
+
+void Bootstrapper::prepare_mod_polynomial()
+{
+    mod_reducer->generate_sin_cos_polynomial();
+    mod_reducer->generate_inverse_sine_polynomial();
+}
+
+// ------------------------------------------------------------------------------------------- linear transforms
+void Bootstrapper::subsum(double scale, Ciphertext &cipher)
+{
+    const int repeatcount = 1 << (logNh - logn);
+    Ciphertext tmp;
+    for (int i = 0; i < logNh - logn; i++)
+    {
+        evaluator.rotate_vector(cipher, 1 << (logn + i), gal_keys, tmp);
+        evaluator.add_inplace_reduced_error(cipher, tmp);
+    }
+    Plaintext tmpplain;
+    encoder.encode(1.0 / repeatcount, scale, tmpplain);
+    evaluator.mod_switch_to_inplace(tmpplain, cipher.parms_id());
+    evaluator.multiply_plain_inplace(cipher, tmpplain);
+    evaluator.rescale_to_next_inplace(cipher);
+}
+
+namespace
+{
+    // sum <- sum + term (first term just moves in)
+    void accumulate(Evaluator &evaluator, Ciphertext &sum, bool &started, Ciphertext &term)
+    {
+        if (!started)
+        {
+            sum = term;
+            started = true;
+        }
+        else
+            evaluator.add_inplace_reduced_error(sum, term);
+    }
+} // namespace
+
+void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
+                                         int coeff_logn, const Diagonals &fftcoeff)
+{
+    const SignedPlan p(totlen);
+    const int N = (int)Nh;
+    auto wrap = [N](int step) { return ((step % N) + N) % N; };
+
+    vector<Ciphertext> babyct((std::size_t)p.gs);
+    for (int i = p.basicstart; i < p.basicstart + p.gs; i++)
+    {
+        if (i == 0)
+            babyct[(std::size_t)(i - p.basicstart)] = cipher;
+        else
+            evaluator.rotate_vector(cipher, wrap(i * basicstep), gal_keys, babyct[(std::size_t)(i - p.basicstart)]);
+    }
+
+    Ciphertext giantct, total, product;
+    bool total_started = false;
+    vector<complex<double>> rotated;
+    for (int i = p.giantfirst; i <= p.giantlast; i++)
+    {
+        // diagonals i*gs + j, pre-rotated by the giant step so that one rotation serves the whole group
+        const int jlast = (i != p.giantlast) ? p.basicstart + p.gs - 1 : totlen - i * p.gs;
+        bool giant_started = false;
+        for (int j = p.basicstart; j <= jlast; j++)
+        {
+            rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[(std::size_t)(i * p.gs + j + totlen)], rotated);
+            evaluator.multiply_vector_reduced_error(babyct[(std::size_t)(j - p.basicstart)], rotated, product);
+            accumulate(evaluator, giantct, giant_started, product);
+        }
+        if (i != 0)
+        {
+            evaluator.rotate_vector(giantct, wrap(i * p.gs * basicstep), gal_keys, product);
+            accumulate(evaluator, total, total_started, product);
+        }
+        else
+            accumulate(evaluator, total, total_started, giantct);
+    }
+    rtncipher = total;
+}
+
+void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
+                                                 int coeff_logn, const Diagonals &fftcoeff)
+{
+    const int gs = giantstep(totlen + 1);
+    const int giantlast = totlen / gs;
+    const int N = (int)Nh;
+    auto wrap = [N](int step) { return ((step % N) + N) % N; };
+
+    vector<Ciphertext> babyct((std::size_t)gs);
+    for (int i = 0; i < gs; i++)
+    {
+        if (i == 0)
+            babyct[0] = cipher;
+        else
+            evaluator.rotate_vector(cipher, wrap(i * basicstep), gal_keys, babyct[(std::size_t)i]);
+    }
+
+    Ciphertext giantct, total, product;
+    bool total_started = false;
+    vector<complex<double>> rotated;
+    for (int i = 0; i <= giantlast; i++)
+    {
+        const int jlast = (i != giantlast) ? gs - 1 : totlen - i * gs;
+        bool giant_started = false;
+        for (int j = 0; j <= jlast; j++)
+        {
+            rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[(std::size_t)(i * gs + j)], rotated);
+            evaluator.multiply_vector_reduced_error(babyct[(std::size_t)j], rotated, product);
+            accumulate(evaluator, giantct, giant_started, product);
+        }
+        if (i != 0)
+        {
+            evaluator.rotate_vector(giantct, wrap(i * gs * basicstep), gal_keys, product);
+            accumulate(evaluator, total, total_started, product);
+        }
+        else
+            accumulate(evaluator, total, total_started, giantct);
+    }
+    rtncipher = total;
+}
+
+// SlotToCoeff: three transforms; the last one also carries the scale correction that makes the output scale
+// exactly final_scale (Bootstrapper.cpp:2399-2412).  last_divisor = 1 (complex) or 2 (real: the conjugate is added
+// afterwards).
+void Bootstrapper::sfl_common(Ciphertext &rtncipher, Ciphertext &cipher, bool full, double last_divisor)
+{
+    const Split s = split_decode(logn);
+    const int coeff_logn = full ? (int)logn : (int)logn + 1;
+    const std::size_t u = (std::size_t)slot_index;
+
+    Ciphertext tmpct, tmpct2;
+    bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], coeff_logn, fftcoeff1[u]);
+    evaluator.rescale_to_next_inplace(tmpct);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], coeff_logn, fftcoeff2[u]);
+    evaluator.rescale_to_next_inplace(tmpct2);
+
+    const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
+    auto curr_level = context.get_context_data(tmpct2.parms_id())->chain_index();
+    const double mod_zero = (double)modulus[0].value();
+    const double curr_mod = (double)modulus[curr_level].value();
+    Diagonals scaled = fftcoeff3[u];
+    for (auto &v : scaled)
+        for (auto &x : v)
+            x = x * curr_mod * mod_zero * final_scale / (last_divisor * tmpct2.scale() * tmpct2.scale() * initial_scale);
+
+    if (full)
+        rotated_bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled);
+    else
+        bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled);
+    evaluator.rescale_to_next_inplace(rtncipher);
+}
+
+void Bootstrapper::sfl_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    sfl_common(rtncipher, cipher, false, 1.0);
+}
+void Bootstrapper::sfl_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    sfl_common(rtncipher, cipher, true, 1.0);
+}
+void Bootstrapper::sfl_half_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    sfl_common(rtncipher, cipher, false, 2.0);
+}
+void Bootstrapper::sfl_full_half_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    sfl_common(rtncipher, cipher, true, 2.0);
+}
+
+void Bootstrapper::sflinv_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    const Split s = split_encode(logn);
+    const std::size_t u = (std::size_t)slot_index;
+    Ciphertext tmpct, tmpct2;
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u]);
+    evaluator.rescale_to_next_inplace(tmpct);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u]);
+    evaluator.rescale_to_next_inplace(tmpct2);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn + 1, invfftcoeff3[u]);
+    evaluator.rescale_to_next_inplace(rtncipher);
+}
+
+void Bootstrapper::sflinv_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    const Split s = split_encode(logn);
+    const std::size_t u = (std::size_t)slot_index;
+    Ciphertext tmpct, tmpct2;
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u]);
+    evaluator.rescale_to_next_inplace(tmpct);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u]);
+    evaluator.rescale_to_next_inplace(tmpct2);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn, invfftcoeff3[u]);
+    evaluator.rescale_to_next_inplace(rtncipher);
+}
+
+// ------------------------------------------------------------------------------------ CoeffToSlot / SlotToCoeff
+void Bootstrapper::coefftoslot_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    Ciphertext t, conj;
+    sflinv_3(t, cipher);
+    evaluator.complex_conjugate(t, gal_keys, conj);
+    evaluator.add_reduced_error(t, conj, rtncipher);
+}
+
+void Bootstrapper::slottocoeff_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    Ciphertext t, rot;
+    sfl_3(t, cipher);
+    evaluator.rotate_vector(t, (int)n, gal_keys, rot);
+    evaluator.add_reduced_error(t, rot, rtncipher);
+}
+
+void Bootstrapper::slottocoeff_half_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    Ciphertext t, rot;
+    sfl_half_3(t, cipher);
+    evaluator.rotate_vector(t, (int)n, gal_keys, rot);
+    evaluator.add_reduced_error(t, rot, rtncipher);
+}
+
+void Bootstrapper::coefftoslot_full_3(Ciphertext &rtncipher1, Ciphertext &rtncipher2, Ciphertext &cipher)
+{
+    Ciphertext z, miz, conj_miz, conj_z;
+    sflinv_full_3(z, cipher);
+    vector<complex<double>> minus_i((std::size_t)Nh, complex<double>(0.0, -1.0));
+    Plaintext plain;
+    encoder.encode(minus_i, 1.0, plain);
+    evaluator.mod_switch_to_inplace(plain, z.parms_id());
+    evaluator.multiply_plain(z, plain, miz);
+    evaluator.complex_conjugate(miz, gal_keys, conj_miz);
+    evaluator.complex_conjugate(z, gal_keys, conj_z);
+    evaluator.add_reduced_error(z, conj_z, rtncipher1);     // 2 Re z
+    evaluator.add_reduced_error(miz, conj_miz, rtncipher2); // 2 Im z
+}
+
+void Bootstrapper::slottocoeff_full_3(Ciphertext &rtncipher, Ciphertext &cipher1, Ciphertext &cipher2)
+{
+    Ciphertext i_im, z;
+    vector<complex<double>> plus_i((std::size_t)Nh, complex<double>(0.0, 1.0));
+    Plaintext plain;
+    encoder.encode(plus_i, 1.0, plain);
+    evaluator.mod_switch_to_inplace(plain, cipher2.parms_id());
+    evaluator.multiply_plain(cipher2, plain, i_im);
+    evaluator.add_reduced_error(cipher1, i_im, z);
+    sfl_full_3(rtncipher, z);
+}
+
+void Bootstrapper::slottocoeff_full_half_3(Ciphertext &rtncipher, Ciphertext &cipher1, Ciphertext &cipher2)
+{
+    Ciphertext i_im, z;
+    vector<complex<double>> plus_i((std::size_t)Nh, complex<double>(0.0, 1.0));
+    Plaintext plain;
+    encoder.encode(plus_i, 1.0, plain);
+    evaluator.mod_switch_to_inplace(plain, cipher2.parms_id());
+    evaluator.multiply_plain(cipher2, plain, i_im);
+    evaluator.add_reduced_error(cipher1, i_im, z);
+    sfl_full_half_3(rtncipher, z);
+}
+
+// -------------------------------------------------------------------------------------------------- ModRaise
+void Bootstrapper::modraise_inplace(Ciphertext &cipher)
+{
+    if (cipher.size() != 2)
+        throw std::invalid_argument("Ciphertexts of size 2 are supported only!");
+    if (cipher.coeff_modulus_size() != 1)
+        throw std::invalid_argument("Ciphertexts in the lowest level are supported only!");
+#ifdef B200CKKS_FACADE
+    // one fused launch: INTT, centred lift of the q0 residues to every limb, NTT (csrc/kernels.cuh LdModRaise)
+    evaluator.modraise_inplace(cipher);
+#else
+    // stock SEAL (used when this file is compiled against the reference library as a test oracle): the same lift
+    // through raw polynomial access
+    if (cipher.is_ntt_form())
+        evaluator.transform_from_ntt_inplace(cipher);
+    Ciphertext low(cipher);
+    cipher.resize(context, context.first_parms_id(), 2);
+    const auto &modulus = context.first_context_data()->parms().coeff_modulus();
+    const std::size_t limbs = cipher.coeff_modulus_size(), N = cipher.poly_modulus_degree();
+    const std::uint64_t q0 = modulus[0].value();
+    for (std::size_t p = 0; p < 2; p++)
+    {
+        const std::uint64_t *src = low.data(p);
+        for (std::size_t j = 0; j < limbs; j++)
+        {
+            const std::uint64_t q = modulus[j].value();
+            const std::uint64_t minus_q0 = j ? q - q0 % q : 0;
+            std::uint64_t *dst = cipher.data(p) + j * N;
+            for (std::size_t i = 0; i < N; i++)
+            {
+                std::uint64_t v = src[i] % q;
+                if (src[i] > (q0 >> 1))
+                {
+                    v += minus_q0;
+                    v -= v >= q ? q : 0;
+                }
+                dst[i] = v;
+            }
+        }
+    }
+    evaluator.transform_to_ntt_inplace(cipher);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ entry points
+// ModRaise + SubSum + CoeffToSlot for sparsely packed ciphertexts (Bootstrapper.cpp:3076-3109)
+void Bootstrapper::sparse_head(Ciphertext &rtn, Ciphertext &cipher)
+{
+    modraise_inplace(cipher);
+    const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
+    cipher.scale() = (double)modulus[0].value();
+
+    Ciphertext rot;
+    for (long i = logn; i < logNh; ++i)
+    {
+        evaluator.rotate_vector(cipher, 1 << i, gal_keys, rot);
+        evaluator.add_inplace(cipher, rot);
+    }
+    if (logn == 0)
+    {
+        vector<complex<double>> cts_vec((std::size_t)Nh);
+        const double f = 1.0 / (2.0 * boundary_K * (double)(1L << logNh));
+        for (long i = 0; i < Nh; i++)
+            cts_vec[(std::size_t)i] = (i % 2 == 0) ? complex<double>(f, 0.0) : complex<double>(0.0, -f);
+        evaluator.multiply_vector_reduced_error(cipher, cts_vec, rtn);
+        evaluator.rescale_to_next_inplace(rtn);
+        Ciphertext conj;
+        evaluator.complex_conjugate(rtn, gal_keys, conj);
+        evaluator.add_inplace_reduced_error(rtn, conj);
+    }
+    else
+        coefftoslot_3(rtn, cipher);
+}
+
+// SlotToCoeff for sparsely packed ciphertexts (Bootstrapper.cpp:3115-3141); half: real-message variant
+void Bootstrapper::sparse_tail(Ciphertext &rtncipher, Ciphertext &modrtn, bool half)
+{
+    if (logn == 0)
+    {
+        const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
+        auto curr_level = context.get_context_data(modrtn.parms_id())->chain_index();
+        const double mod_zero = (double)modulus[0].value();
+        const double curr_mod = (double)modulus[curr_level].value();
+        const double adj = curr_mod * mod_zero * final_scale / (modrtn.scale() * modrtn.scale() * initial_scale);
+        vector<complex<double>> stc_vec((std::size_t)Nh);
+        for (long i = 0; i < Nh; i++)
+            stc_vec[(std::size_t)i] = (i % 2 == 0) ? complex<double>(adj, 0.0) : complex<double>(0.0, adj);
+        evaluator.multiply_vector_reduced_error(modrtn, stc_vec, rtncipher);
+        evaluator.rescale_to_next_inplace(rtncipher);
+        Ciphertext rot;
+        evaluator.rotate_vector(rtncipher, 1, gal_keys, rot);
+        evaluator.add_inplace_reduced_error(rtncipher, rot);
+    }
+    else if (half)
+        slottocoeff_half_3(rtncipher, modrtn);
+    else
+        slottocoeff_3(rtncipher, modrtn);
+    rtncipher.scale() = final_scale;
+}
+
+void Bootstrapper::bootstrap_sparse_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    Ciphertext slots, reduced;
+    sparse_head(slots, cipher);
+    mod_reducer->modular_reduction(reduced, slots);
+    sparse_tail(rtncipher, reduced, false);
+}
+
+void Bootstrapper::bootstrap_sparse_real_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    Ciphertext slots, reduced, conj;
+    sparse_head(slots, cipher);
+    mod_reducer->modular_reduction(reduced, slots);
+    sparse_tail(rtncipher, reduced, true);
+    evaluator.complex_conjugate(rtncipher, gal_keys, conj);
+    evaluator.add_inplace_reduced_error(rtncipher, conj);
+}
+
+void Bootstrapper::bootstrap_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    modraise_inplace(cipher);
+    const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
+    cipher.scale() = (double)modulus[0].value();
+    Ciphertext re, im, mre, mim;
+    coefftoslot_full_3(re, im, cipher);
+    mod_reducer->modular_reduction(mre, re);
+    mod_reducer->modular_reduction(mim, im);
+    slottocoeff_full_3(rtncipher, mre, mim);
+    rtncipher.scale() = final_scale;
+}
+
+void Bootstrapper::bootstrap_full_real_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    modraise_inplace(cipher);
+    const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
+    cipher.scale() = (double)modulus[0].value();
+    Ciphertext re, im, mre, mim, conj;
+    coefftoslot_full_3(re, im, cipher);
+    mod_reducer->modular_reduction(mre, re);
+    mod_reducer->modular_reduction(mim, im);
+    slottocoeff_full_half_3(rtncipher, mre, mim);
+    rtncipher.scale() = final_scale;
+    evaluator.complex_conjugate(rtncipher, gal_keys, conj);
+    evaluator.add_inplace_reduced_error(rtncipher, conj);
+}
+
+void Bootstrapper::bootstrap_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    initial_scale = cipher.scale();
+    if (logn == logNh)
+        bootstrap_full_3(rtncipher, cipher);
+    else
+        bootstrap_sparse_3(rtncipher, cipher);
+}
+
+void Bootstrapper::bootstrap_inplace_3(Ciphertext &cipher)
+{
+    Ciphertext rtncipher;
+    bootstrap_3(rtncipher, cipher);
+    cipher = rtncipher;
+}
+
+void Bootstrapper::bootstrap_real_3(Ciphertext &rtncipher, Ciphertext &cipher)
+{
+    initial_scale = cipher.scale();
+    if (logn == logNh)
+        bootstrap_full_real_3(rtncipher, cipher);
+    else
+        bootstrap_sparse_real_3(rtncipher, cipher);
+}
+
+void Bootstrapper::bootstrap_inplace_real_3(Ciphertext &cipher)
+{
+    Ciphertext rtncipher;
+    bootstrap_real_3(rtncipher, cipher);
+    cipher = rtncipher;
+}

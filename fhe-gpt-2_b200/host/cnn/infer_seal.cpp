@@ -1,0 +1,322 @@
+// cnn/infer_seal.cpp - see infer_seal.h.
+#include "cnn/infer_seal.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <fstream>
+#include <stdexcept>
+
+using namespace seal;
+using std::string;
+using std::vector;
+
+int resnet_end_num(std::size_t layer_num)
+{
+    switch (layer_num)
+    {
+    case 20: return 2;
+    case 32: return 4;
+    case 44: return 6;
+    case 56: return 8;
+    case 110: return 17;
+    default: throw std::invalid_argument("layer_num is not correct");
+    }
+}
+
+void resnet_conv_shape(std::size_t layer_num, std::size_t index, int &ci, int &co)
+{
+    const int blocks = resnet_end_num(layer_num) + 1;
+    if (index == 0)
+    {
+        ci = 3;
+        co = 16;
+        return;
+    }
+    const int pos = (int)index - 1;            // 0 .. 6 * blocks - 1
+    const int stage = pos / (2 * blocks);      // 0, 1, 2 -> 16, 32, 64 channels
+    const bool first_of_stage = pos % (2 * blocks) == 0;
+    co = 16 << stage;
+    ci = (first_of_stage && stage > 0) ? co / 2 : co;
+}
+
+namespace
+{
+    void read_values(const string &path, std::size_t count, vector<double> &out)
+    {
+        std::ifstream in(path);
+        if (!in.is_open())
+            throw std::runtime_error("file is not open: " + path);
+        out.clear();
+        double v;
+        for (std::size_t i = 0; i < count; i++)
+        {
+            if (!(in >> v))
+                throw std::runtime_error("file is too short: " + path);
+            out.push_back(v);
+        }
+    }
+} // namespace
+
+void import_parameters_cifar10(vector<double> &linear_weight, vector<double> &linear_bias, vector<vector<double>> &conv_weight,
+                               vector<vector<double>> &bn_bias, vector<vector<double>> &bn_running_mean,
+                               vector<vector<double>> &bn_running_var, vector<vector<double>> &bn_weight, std::size_t layer_num,
+                               std::size_t end_num, const string &dir)
+{
+    if ((int)end_num != resnet_end_num(layer_num))
+        throw std::invalid_argument("layer number is not valid");
+    const string base = dir + "/resnet" + std::to_string(layer_num) + "_new/";
+    const std::size_t layers = layer_num - 1;
+    conv_weight.assign(layers, {});
+    bn_bias.assign(layers, {});
+    bn_running_mean.assign(layers, {});
+    bn_running_var.assign(layers, {});
+    bn_weight.assign(layers, {});
+    for (std::size_t idx = 0; idx < layers; idx++)
+    {
+        int ci, co;
+        resnet_conv_shape(layer_num, idx, ci, co);
+        string conv, bn;
+        if (idx == 0)
+        {
+            conv = "conv1";
+            bn = "bn1";
+        }
+        else
+        {
+            const std::size_t pos = idx - 1, blocks = end_num + 1;
+            const string block = "layer" + std::to_string(pos / (2 * blocks) + 1) + "_" + std::to_string((pos % (2 * blocks)) / 2);
+            conv = block + "_conv" + std::to_string(pos % 2 + 1);
+            bn = block + "_bn" + std::to_string(pos % 2 + 1);
+        }
+        read_values(base + conv + "_weight.txt", (std::size_t)(9 * ci * co), conv_weight[idx]);
+        read_values(base + bn + "_bias.txt", (std::size_t)co, bn_bias[idx]);
+        read_values(base + bn + "_running_mean.txt", (std::size_t)co, bn_running_mean[idx]);
+        read_values(base + bn + "_running_var.txt", (std::size_t)co, bn_running_var[idx]);
+        read_values(base + bn + "_weight.txt", (std::size_t)co, bn_weight[idx]);
+    }
+    read_values(base + "linear_weight.txt", 10 * 64, linear_weight);
+    read_values(base + "linear_bias.txt", 10, linear_bias);
+}
+
+const vector<int> &resnet_rotation_kinds()
+{
+    // the steps memory_save_rotate is asked for by the convolutions, down-samplings, pooling and the FC layer of the
+    // three stages (infer_seal.cpp:345-362): data of the packing scheme, identical for every depth
+    static const vector<int> kinds = {
+        0,     1,     2,     3,     4,     5,     6,     7,     8,     9,     10,    11,    12,    13,    14,    15,    16,
+        17,    18,    19,    20,    21,    22,    23,    24,    25,    26,    27,    28,    29,    30,    31,    32,    33,
+        56,    62,    63,    64,    66,    84,    124,   128,   132,   256,   512,   959,   960,   990,   991,   1008,  1023,
+        1024,  1036,  1064,  1092,  1952,  1982,  1983,  2016,  2044,  2047,  2048,  2072,  2078,  2100,  3007,  3024,  3040,
+        3052,  3070,  3071,  3072,  3080,  3108,  4031,  4032,  4062,  4063,  4095,  4096,  5023,  5024,  5054,  5055,  5087,
+        5118,  5119,  5120,  6047,  6078,  6079,  6111,  6112,  6142,  6143,  6144,  7071,  7102,  7103,  7135,  7166,  7167,
+        7168,  8095,  8126,  8127,  8159,  8190,  8191,  8192,  9149,  9183,  9184,  9213,  9215,  9216,  10173, 10207, 10208,
+        10237, 10239, 10240, 11197, 11231, 11232, 11261, 11263, 11264, 12221, 12255, 12256, 12285, 12287, 12288, 13214, 13216,
+        13246, 13278, 13279, 13280, 13310, 13311, 13312, 14238, 14240, 14270, 14302, 14303, 14304, 14334, 14335, 15262, 15264,
+        15294, 15326, 15327, 15328, 15358, 15359, 15360, 16286, 16288, 16318, 16350, 16351, 16352, 16382, 16383, 16384, 17311,
+        17375, 18335, 18399, 18432, 19359, 19423, 20383, 20447, 20480, 21405, 21406, 21437, 21469, 21470, 21471, 21501, 21504,
+        22429, 22430, 22461, 22493, 22494, 22495, 22525, 22528, 23453, 23454, 23485, 23517, 23518, 23519, 23549, 24477, 24478,
+        24509, 24541, 24542, 24543, 24573, 24576, 25501, 25565, 25568, 25600, 26525, 26589, 26592, 26624, 27549, 27613, 27616,
+        27648, 28573, 28637, 28640, 28672, 29600, 29632, 29664, 29696, 30624, 30656, 30688, 30720, 31648, 31680, 31712, 31743,
+        31744, 31774, 32636, 32640, 32644, 32672, 32702, 32704, 32706, 32735, 32736, 32737, 32759, 32760, 32761, 32762, 32763,
+        32764, 32765, 32766, 32767
+    };
+    return kinds;
+}
+
+vector<int> ResNetCifar10::coeff_bit_vec()
+{
+    vector<int> bits;
+    bits.push_back(logq);
+    for (int i = 0; i < remaining_level; i++)
+        bits.push_back(logp);
+    for (int i = 0; i < boot_level; i++)
+        bits.push_back(logq);
+    bits.push_back(log_special_prime);
+    return bits;
+}
+
+ResNetCifar10::ResNetCifar10(std::size_t layer_num, ResNetParameters parameters, SEALContext &context, KeyGenerator &keygen,
+                             CKKSEncoder &encoder, Encryptor &encryptor, Decryptor &decryptor, Evaluator &evaluator,
+                             PublicKey &public_key, SecretKey &secret_key, RelinKeys &relin_keys, GaloisKeys &gal_keys)
+    : layer_num_(layer_num), end_num_(resnet_end_num(layer_num)), w_(std::move(parameters)), context_(context), keygen_(keygen),
+      encoder_(encoder), encryptor_(encryptor), decryptor_(decryptor), evaluator_(evaluator), public_key_(public_key),
+      secret_key_(secret_key), relin_keys_(relin_keys), gal_keys_(gal_keys)
+{
+    const std::size_t layers = layer_num - 1;
+    if (w_.conv_weight.size() != layers || w_.bn_bias.size() != layers || w_.bn_running_mean.size() != layers ||
+        w_.bn_running_var.size() != layers || w_.bn_weight.size() != layers || w_.linear_weight.size() != 640 ||
+        w_.linear_bias.size() != 10)
+        throw std::invalid_argument("parameter lists do not match the network depth");
+    for (long i = 0; i < comp_no; i++)
+    {
+        minicomp::Tree tr;
+        upgrade_oddbaby(deg_[(std::size_t)i], tr);
+        tree_.push_back(tr);
+    }
+    const int total_level = remaining_level + boot_level;
+    const double scale = std::pow(2.0, logp);
+    const long sparse_logn[3] = { 14, 13, 12 }; // 16 / 32 / 64-channel stages
+    for (int i = 0; i < 3; i++)
+    {
+        boot_[i] = new Bootstrapper(loge, sparse_logn[i], logN - 1, total_level, scale, boundary_K, boot_deg, scale_factor,
+                                    inverse_deg, context_, keygen_, encoder_, encryptor_, decryptor_, evaluator_, relin_keys_,
+                                    gal_keys_);
+        boot_[i]->prepare_mod_polynomial();
+    }
+}
+
+ResNetCifar10::~ResNetCifar10()
+{
+    for (auto *b : boot_)
+        delete b;
+}
+
+vector<int> ResNetCifar10::galois_steps() const
+{
+    vector<int> steps;
+    steps.push_back(0);
+    for (int i = 0; i < logN - 1; i++)
+        steps.push_back(1 << i);
+    for (int rot : resnet_rotation_kinds())
+        if (std::find(steps.begin(), steps.end(), rot) == steps.end())
+            steps.push_back(rot);
+    for (auto *b : boot_)
+        b->addLeftRotKeys_Linear_to_vector_3(steps);
+    return steps;
+}
+
+void ResNetCifar10::prepare()
+{
+    for (auto *b : boot_)
+    {
+        b->slot_vec.push_back(b->logn);
+        b->generate_LT_coefficient_3();
+    }
+    prepared_ = true;
+}
+
+vector<double> ResNetCifar10::infer(const vector<double> &image_in, vector<ResNetTraceRow> *trace)
+{
+    if (!prepared_)
+        throw std::logic_error("ResNetCifar10::prepare() must be called after the Galois keys were created");
+    if (image_in.size() != 32 * 32 * 3)
+        throw std::invalid_argument("image must hold 32*32*3 values");
+    const long n = 1L << logn, init_p = 8;
+    const int fh = 3, fw = 3;
+    const double epsilon = 0.00001;
+    vector<Ciphertext> cipher_pool; // host-buffer reuse in the reference; not needed on the device
+
+    auto t_prev = std::chrono::high_resolution_clock::now();
+    auto log_op = [&](int op, const TensorCipher &t) {
+        if (!trace)
+            return;
+#ifdef B200CKKS_FACADE
+        context_.sync();
+#endif
+        auto now = std::chrono::high_resolution_clock::now();
+        const Ciphertext &c = t.cipher_ref();
+        trace->push_back({ op, (int)context_.get_context_data(c.parms_id())->chain_index(), c.scale(),
+                           std::chrono::duration<double, std::milli>(now - t_prev).count() });
+        t_prev = now;
+    };
+
+    // pack: 8 copies of the 3 x 32 x 32 image, values divided by B so that activations stay in [-1, 1]
+    vector<double> image((std::size_t)n, 0.0);
+    for (std::size_t i = 0; i < image_in.size(); i++)
+        image[i] = image_in[i];
+    for (long i = n / init_p; i < n; i++)
+        image[(std::size_t)i] = image[(std::size_t)(i % (n / init_p))];
+    for (auto &v : image)
+        v /= B;
+
+    TensorCipher cnn(logn, 1, 32, 32, 3, 3, init_p, image, encryptor_, encoder_, logq), temp;
+    {
+        Ciphertext ctxt = cnn.cipher();
+        for (int i = 0; i < boot_level - 3; i++)
+            evaluator_.mod_switch_to_next_inplace(ctxt);
+        cnn.set_ciphertext(ctxt);
+    }
+    t_prev = std::chrono::high_resolution_clock::now();
+
+    auto conv = [&](int stage, int co, int st) {
+        multiplexed_parallel_convolution_seal(cnn, cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
+                                              w_.bn_running_var[(std::size_t)stage], w_.bn_weight[(std::size_t)stage], epsilon,
+                                              encoder_, encryptor_, evaluator_, gal_keys_, cipher_pool);
+        log_op(0, cnn);
+    };
+    auto bn = [&](int stage) {
+        multiplexed_parallel_batch_norm_seal(cnn, cnn, w_.bn_bias[(std::size_t)stage], w_.bn_running_mean[(std::size_t)stage],
+                                             w_.bn_running_var[(std::size_t)stage], w_.bn_weight[(std::size_t)stage], epsilon,
+                                             encoder_, encryptor_, evaluator_, B);
+        log_op(1, cnn);
+    };
+    auto relu = [&]() {
+        ReLU_seal(cnn, cnn, comp_no, deg_, alpha, tree_, scaled_val, logp, encryptor_, evaluator_, decryptor_, encoder_,
+                  public_key_, secret_key_, relin_keys_, B);
+        log_op(2, cnn);
+    };
+    auto bootstrap = [&](int j) {
+        Ciphertext ctxt = cnn.cipher(), rtn;
+        boot_[j]->bootstrap_real_3(rtn, ctxt);
+        cnn.set_ciphertext(rtn);
+        log_op(3, cnn);
+    };
+
+    // layer 0; its convolution runs at a 2^51 scale, bring the result back to exactly 2^46
+    conv(0, 16, 1);
+    {
+        const auto &modulus = util::iter(context_.first_context_data()->parms().coeff_modulus());
+        Ciphertext ctxt = cnn.cipher();
+        const std::size_t cur_level = ctxt.coeff_modulus_size();
+        Plaintext scaler;
+        const double scale_change = std::pow(2.0, 46) * ((double)modulus[cur_level - 1].value()) / ctxt.scale();
+        encoder_.encode(1.0, scale_change, scaler);
+        evaluator_.mod_switch_to_inplace(scaler, ctxt.parms_id());
+        evaluator_.multiply_plain_inplace(ctxt, scaler);
+        evaluator_.rescale_to_next_inplace(ctxt);
+        ctxt.scale() = std::pow(2.0, 46);
+        cnn.set_ciphertext(ctxt);
+    }
+    bn(0);
+    relu();
+
+    for (int j = 0; j < 3; j++)
+    {
+        const int co = 16 << j;
+        for (int k = 0; k <= end_num_; k++)
+        {
+            int stage = 2 * ((end_num_ + 1) * j + k) + 1;
+            temp = cnn;
+            conv(stage, co, (j >= 1 && k == 0) ? 2 : 1);
+            bn(stage);
+            bootstrap(j);
+            relu();
+
+            stage++;
+            conv(stage, co, 1);
+            bn(stage);
+            if (j >= 1 && k == 0)
+            {
+                multiplexed_parallel_downsampling_seal(temp, temp, evaluator_, gal_keys_);
+                log_op(5, temp);
+            }
+            cnn_add_seal(temp, cnn, cnn, evaluator_);
+            log_op(4, cnn);
+            bootstrap(j);
+            relu();
+        }
+    }
+    averagepooling_seal_scale(cnn, cnn, evaluator_, gal_keys_, B);
+    log_op(6, cnn);
+    matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, 10, 64, evaluator_, gal_keys_);
+    log_op(7, cnn);
+
+    Plaintext plain;
+    decryptor_.decrypt(cnn.cipher(), plain);
+    vector<std::complex<double>> slots;
+    encoder_.decode(plain, slots);
+    vector<double> logits(10);
+    for (int i = 0; i < 10; i++)
+        logits[(std::size_t)i] = slots[(std::size_t)i].real();
+    return logits;
+}

@@ -1,0 +1,91 @@
+// cnn/infer_seal.h - bootstrapped ResNet-20/32/44/56/110 on CIFAR-10 over multiplexed-packed ciphertexts.
+//
+// Restates ResNet_cifar10_seal_sparse and import_parameters_cifar10 of the reference's
+// cnn_ckks/cpu-ckks/single-key/cnn/infer_seal.cpp (:251-584, :3-107): same parameter set (logN 16, primes
+// 51 | 46 x 16 | 51 x 14 | 51, Hamming weight 192, scale 2^46), same rotation-key list, three sparse-slot
+// bootstrappers (logn 14/13/12), the alpha = 13 minimax ReLU and the same layer schedule.  The reference does all of
+// it inside one function that also parses weights and images from text files per image and per OpenMP thread; here
+// the set-up (ResNetCifar10 constructor) is separated from the per-image path (infer) so that one set of keys,
+// bootstrapping matrices and evaluation trees serves every image, and the per-stage log (operation, remaining level,
+// scale, time) is returned instead of being printed.
+#pragma once
+#include "cnn/cnn_seal.h"
+#include <functional>
+#include <string>
+#include <vector>
+
+struct ResNetParameters
+{
+    std::vector<std::vector<double>> conv_weight, bn_bias, bn_running_mean, bn_running_var, bn_weight; // [layer_num - 1]
+    std::vector<double> linear_weight, linear_bias;                                                    // 10 x 64, 10
+};
+
+// number of residual blocks per stage minus one (infer_seal.cpp:397-402)
+int resnet_end_num(std::size_t layer_num);
+// (ci, co) of convolution `index` (0 .. layer_num - 2) in the reference's file order
+void resnet_conv_shape(std::size_t layer_num, std::size_t index, int &ci, int &co);
+
+// reads <dir>/conv1_weight.txt, layer<j>_<k>_conv<1|2>_weight.txt, *_bn*_{bias,running_mean,running_var,weight}.txt,
+// linear_{weight,bias}.txt - the reference's pretrained_parameters/resnet<L>_new layout
+void import_parameters_cifar10(std::vector<double> &linear_weight, std::vector<double> &linear_bias,
+                               std::vector<std::vector<double>> &conv_weight, std::vector<std::vector<double>> &bn_bias,
+                               std::vector<std::vector<double>> &bn_running_mean, std::vector<std::vector<double>> &bn_running_var,
+                               std::vector<std::vector<double>> &bn_weight, std::size_t layer_num, std::size_t end_num,
+                               const std::string &dir = "../../pretrained_parameters");
+
+// CNN rotation steps of infer_seal.cpp:345-362 (the list is the same for every depth)
+const std::vector<int> &resnet_rotation_kinds();
+
+struct ResNetTraceRow
+{
+    int op;               // 0 conv, 1 bn, 2 relu, 3 bootstrap, 4 add, 5 downsample, 6 avgpool, 7 fc
+    int remaining_level;  // chain_index of the result
+    double scale;
+    double milliseconds;
+};
+
+class ResNetCifar10
+{
+public:
+    // constants of infer_seal.cpp:253-304
+    static constexpr double B = 40.0;
+    static constexpr long alpha = 13, comp_no = 3;
+    static constexpr double scaled_val = 1.7;
+    static constexpr long boundary_K = 25, boot_deg = 59, scale_factor = 2, inverse_deg = 1, logN = 16, loge = 10, logn = 15;
+    static constexpr int logp = 46, logq = 51, log_special_prime = 51, remaining_level = 16, boot_level = 14;
+    static std::vector<int> coeff_bit_vec();
+
+    ResNetCifar10(std::size_t layer_num, ResNetParameters parameters, seal::SEALContext &context, seal::KeyGenerator &keygen,
+                  seal::CKKSEncoder &encoder, seal::Encryptor &encryptor, seal::Decryptor &decryptor, seal::Evaluator &evaluator,
+                  seal::PublicKey &public_key, seal::SecretKey &secret_key, seal::RelinKeys &relin_keys, seal::GaloisKeys &gal_keys);
+    ~ResNetCifar10();
+
+    // every rotation step the network and its bootstrappers use (hand to KeyGenerator::create_galois_keys)
+    std::vector<int> galois_steps() const;
+    // after the keys exist: LT coefficients of the three bootstrappers
+    void prepare();
+
+    // image: 32*32*3 values (channel-major).  Returns the 10 logits; appends one row per operation to `trace`.
+    std::vector<double> infer(const std::vector<double> &image, std::vector<ResNetTraceRow> *trace = nullptr);
+
+    std::size_t layer_num() const { return layer_num_; }
+
+private:
+    std::size_t layer_num_;
+    int end_num_;
+    ResNetParameters w_;
+    seal::SEALContext &context_;
+    seal::KeyGenerator &keygen_;
+    seal::CKKSEncoder &encoder_;
+    seal::Encryptor &encryptor_;
+    seal::Decryptor &decryptor_;
+    seal::Evaluator &evaluator_;
+    seal::PublicKey &public_key_;
+    seal::SecretKey &secret_key_;
+    seal::RelinKeys &relin_keys_;
+    seal::GaloisKeys &gal_keys_;
+    std::vector<int> deg_{ 15, 15, 27 };
+    std::vector<minicomp::Tree> tree_;
+    Bootstrapper *boot_[3];
+    bool prepared_ = false;
+};

@@ -1,0 +1,106 @@
+// common/func.h - small integer/slot helpers shared by the restated application layers.
+//
+// Same names and results as the helpers the reference's app code calls (cnn_ckks/common/func.cpp:117-140
+// babycount, :203-213 giantstep, :215-224 rotation; common/MinicompFunc.cpp:11-62 pmod/pow2/ceil_to_int/
+// floor_to_int/log2_long/num_one), written without NTL.  Header-only.
+#pragma once
+#include "seal/seal.h"
+#include <cmath>
+#include <complex>
+#include <stdexcept>
+#include <vector>
+
+namespace minicomp
+{
+    inline long pmod(long a, long b)
+    {
+        long r = a % b;
+        return r < 0 ? r + b : r;
+    }
+    inline long pow2(long n)
+    {
+        return n <= 0 ? 1L : (1L << n);
+    }
+    inline std::size_t ceil_to_int(double x)
+    {
+        return static_cast<std::size_t>(std::ceil(x) + 0.5);
+    }
+    inline int floor_to_int(double x)
+    {
+        return static_cast<int>(std::floor(x) + 0.5);
+    }
+    // exponent of a power of two <= 65536, -1 for anything else
+    inline long log2_long(long n)
+    {
+        if (n > 65536 || n <= 0)
+            throw std::out_of_range("n is too large.");
+        for (int i = 0; i <= 16; i++)
+            if ((1L << i) == n)
+                return i;
+        return -1;
+    }
+    // population count
+    inline long num_one(long n)
+    {
+        long c = 0;
+        for (; n > 0; n >>= 1)
+            c += n & 1;
+        return c;
+    }
+} // namespace minicomp
+
+// baby-step size minimising ceil(M/k) + k - 1 (first minimiser, k <= 3 sqrt(M))
+inline int giantstep(int M)
+{
+    int best = M, arg = 1;
+    for (int k = 1; k <= 3 * std::sqrt((double)M); k++)
+    {
+        int cost = (M + k - 1) / k + k - 1;
+        if (cost < best)
+        {
+            best = cost;
+            arg = k;
+        }
+    }
+    return arg;
+}
+
+// out = the 2^logslot-periodic vector `vec` rotated left by shiftcount, tiled to Nh slots
+inline void rotation(int logslot, int Nh, int shiftcount, const std::vector<std::complex<double>> &vec,
+                     std::vector<std::complex<double>> &rtnvec)
+{
+    const int slotlen = 1 << logslot;
+    const int repeat = Nh / slotlen;
+    rtnvec.resize((std::size_t)repeat * slotlen);
+    int s = shiftcount % slotlen;
+    if (s < 0)
+        s += slotlen;
+    for (int i = 0; i < slotlen; i++)
+    {
+        std::complex<double> v = vec[(std::size_t)((i + s) % slotlen)];
+        for (int j = 0; j < repeat; j++)
+            rtnvec[(std::size_t)j * slotlen + i] = v;
+    }
+}
+
+// Paterson-Stockmeyer split for a degree-`deg` Chebyshev series: k babies, 2^m giants
+inline void babycount(long &mink, long &minm, long deg)
+{
+    auto cost = [deg](long k, long &m) {
+        double dk = static_cast<double>(deg) / k;
+        m = (long)std::ceil(std::log2(dk));
+        return m + k + (long)std::ceil(dk) - 3;
+    };
+    mink = 2;
+    long best = cost(2, minm);
+    for (long k = 3; k < 2 * std::sqrt((double)deg); k++)
+    {
+        long m, c = cost(k, m);
+        if (c < best)
+        {
+            best = c;
+            mink = k;
+            minm = m;
+        }
+    }
+}

@@ -1,0 +1,1631 @@
+// seal/seal.h - the `seal::` C++ API of the reference's modified SEAL 3.6.6, re-hosted on the
+// B200 engine (libb200ckks.so) through the C ABI of include/b200ckks.h.
+//
+// Application code of the reference (cnn_ckks/.../{ckks_bootstrapping,comp,cnn}, gpt2_ckks/.../gpt2)
+// includes "seal/seal.h" and talks to seal::Evaluator / CKKSEncoder / KeyGenerator / Encryptor /
+// Decryptor / Ciphertext / Plaintext / GaloisKeys / RelinKeys / SEALContext.  This header offers the
+// same names, argument meaning, value semantics and exception types, CKKS only:
+//
+//   class                     reference header (native/src/seal/)
+//   EncryptionParameters      encryptionparams.h  (+ fork: set_secret_key_hamming_weight :187-229,
+//                                                    set_sparse_slots :573-575)
+//   Modulus / CoeffModulus    modulus.h, modulus.cpp:143-182
+//   SEALContext / ContextData context.h, context.cpp:455-523
+//   Plaintext / Ciphertext    plaintext.h, ciphertext.h
+//   SecretKey / PublicKey / RelinKeys / GaloisKeys / KeyGenerator
+//                             secretkey.h publickey.h relinkeys.h galoiskeys.h keygenerator.h
+//   CKKSEncoder               ckks.h:148-450
+//   Encryptor / Decryptor     encryptor.h decryptor.h
+//   Evaluator                 evaluator.h (+ fork additions :1192-1285, evaluator.cpp:287-486)
+//
+// Every arithmetic member is ONE call into the CUDA library (no CPU arithmetic here); the fork's
+// composite members (*_reduced_error, *_const, multiply_vector*) are compositions of those calls in
+// exactly the order and with exactly the double-precision scale arithmetic of evaluator.cpp:312-486.
+//
+// Engine-specific behaviour (documented in INTEGRATION.md):
+//   * Galois keys are materialised on the device on first use, at the level of use, and grown on
+//     demand (the reference's 284 full-size keys would need 275 GiB).  Rotation results are unchanged.
+//   * Objects are bound to the CUDA stream of the host thread that uses them (the reference shares
+//     one Evaluator between OpenMP threads; so can callers of this header).
+#pragma once
+#define B200CKKS_FACADE 1
+
+#include "../../../include/b200ckks.h"
+#include <array>
+#include <atomic>
+#include <cmath>
+#include <complex>
+#include <cstdint>
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <shared_mutex>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#define SEAL_NODISCARD [[nodiscard]]
+
+namespace seal
+{
+    // ------------------------------------------------------------------------------ error mapping
+    namespace detail
+    {
+        inline void check(bk_status st)
+        {
+            if (st == BK_OK)
+                return;
+            std::string msg = bk_last_error();
+            switch (st)
+            {
+            case BK_INVALID_ARGUMENT: throw std::invalid_argument(msg);
+            case BK_OUT_OF_RANGE: throw std::out_of_range(msg);
+            case BK_LOGIC_ERROR: throw std::logic_error(msg);
+            default: throw std::runtime_error(msg);
+            }
+        }
+        inline std::uint64_t next_seed()
+        {
+            static std::atomic<std::uint64_t> ctr{ 0 };
+            static const std::uint64_t base = [] {
+                const char *e = std::getenv("B200CKKS_SEED");
+                return e ? std::strtoull(e, nullptr, 0) : 0x5EA1C0DEull;
+            }();
+            return base + 0x9E3779B97F4A7C15ull * (ctr.fetch_add(1) + 1);
+        }
+    } // namespace detail
+
+    enum class scheme_type : std::uint8_t
+    {
+        none = 0x0,
+        bfv = 0x1,
+        ckks = 0x2
+    };
+    enum class sec_level_type : int
+    {
+        none = 0,
+        tc128 = 128,
+        tc192 = 192,
+        tc256 = 256
+    };
+    enum class mm_prof_opt : std::uint64_t
+    {
+        mm_default = 0
+    };
+
+    // memory pools are a host-allocator concept of the reference; kept as an ignorable handle so
+    // that call sites passing a pool still compile
+    class MemoryPoolHandle
+    {
+    public:
+        MemoryPoolHandle() = default;
+        explicit operator bool() const
+        {
+            return true;
+        }
+    };
+    struct MemoryManager
+    {
+        static MemoryPoolHandle GetPool()
+        {
+            return {};
+        }
+        template <class... A>
+        static MemoryPoolHandle GetPool(A...)
+        {
+            return {};
+        }
+    };
+
+    // parms_id: the reference hashes the parameters (encryptionparams.h:487-520); callers only copy
+    // and compare them.  Here: {magic, context serial, coeff_modulus_size, 0}.
+    using parms_id_type = std::array<std::uint64_t, 4>;
+    static constexpr parms_id_type parms_id_zero = { 0, 0, 0, 0 };
+
+    class Modulus
+    {
+    public:
+        Modulus(std::uint64_t value = 0) : value_(value)
+        {}
+        SEAL_NODISCARD std::uint64_t value() const noexcept
+        {
+            return value_;
+        }
+        SEAL_NODISCARD int bit_count() const noexcept
+        {
+            int b = 0;
+            for (std::uint64_t v = value_; v; v >>= 1)
+                b++;
+            return b;
+        }
+        SEAL_NODISCARD bool is_zero() const noexcept
+        {
+            return value_ == 0;
+        }
+        bool operator==(const Modulus &o) const noexcept
+        {
+            return value_ == o.value_;
+        }
+        bool operator!=(const Modulus &o) const noexcept
+        {
+            return value_ != o.value_;
+        }
+
+    private:
+        std::uint64_t value_;
+    };
+
+    class CoeffModulus
+    {
+    public:
+        // modulus.cpp:143-182 (descending NTT-friendly prime search per bit size)
+        static std::vector<Modulus> Create(std::size_t poly_modulus_degree, std::vector<int> bit_sizes)
+        {
+            int log_n = 0;
+            while ((std::size_t(1) << log_n) < poly_modulus_degree)
+                log_n++;
+            if ((std::size_t(1) << log_n) != poly_modulus_degree)
+                throw std::invalid_argument("poly_modulus_degree is invalid");
+            std::vector<std::uint64_t> p(bit_sizes.size());
+            detail::check(bk_coeff_modulus_create(log_n, bit_sizes.data(), (int)bit_sizes.size(), p.data()));
+            return std::vector<Modulus>(p.begin(), p.end());
+        }
+    };
+
+    class EncryptionParameters
+    {
+    public:
+        EncryptionParameters(scheme_type scheme = scheme_type::none) : scheme_(scheme)
+        {
+            if (scheme != scheme_type::ckks && scheme != scheme_type::none)
+                throw std::invalid_argument("unsupported scheme (this engine evaluates CKKS only)");
+        }
+        EncryptionParameters(std::uint8_t scheme) : EncryptionParameters(static_cast<scheme_type>(scheme))
+        {}
+        void set_poly_modulus_degree(std::size_t n)
+        {
+            poly_modulus_degree_ = n;
+        }
+        void set_coeff_modulus(const std::vector<Modulus> &m)
+        {
+            if (m.empty() || m.size() > 62)
+                throw std::invalid_argument("coeff_modulus is invalid");
+            coeff_modulus_ = m;
+        }
+        // fork: encryptionparams.h:187-229
+        void set_secret_key_hamming_weight(std::size_t h)
+        {
+            secret_key_hamming_weight_ = h;
+        }
+        void set_sparse_slots(std::size_t s)
+        {
+            sparse_slots_ = s;
+        }
+        SEAL_NODISCARD scheme_type scheme() const noexcept
+        {
+            return scheme_;
+        }
+        SEAL_NODISCARD std::size_t poly_modulus_degree() const noexcept
+        {
+            return poly_modulus_degree_;
+        }
+        SEAL_NODISCARD const std::vector<Modulus> &coeff_modulus() const noexcept
+        {
+            return coeff_modulus_;
+        }
+        SEAL_NODISCARD std::size_t secret_key_hamming_weight() const noexcept
+        {
+            return secret_key_hamming_weight_;
+        }
+        SEAL_NODISCARD std::size_t sparse_slots() const noexcept
+        {
+            return sparse_slots_;
+        }
+
+    private:
+        friend class SEALContext;
+        scheme_type scheme_;
+        std::size_t poly_modulus_degree_ = 0;
+        std::vector<Modulus> coeff_modulus_;
+        std::size_t secret_key_hamming_weight_ = 0;
+        std::size_t sparse_slots_ = 0;
+    };
+
+    // ------------------------------------------------------------------------------------ context
+    class SEALContext
+    {
+    public:
+        class ContextData
+        {
+        public:
+            SEAL_NODISCARD const EncryptionParameters &parms() const noexcept
+            {
+                return parms_;
+            }
+            SEAL_NODISCARD const parms_id_type &parms_id() const noexcept
+            {
+                return parms_id_;
+            }
+            SEAL_NODISCARD std::size_t chain_index() const noexcept
+            {
+                return chain_index_;
+            }
+            SEAL_NODISCARD int total_coeff_modulus_bit_count() const noexcept
+            {
+                return total_bits_;
+            }
+            SEAL_NODISCARD std::shared_ptr<const ContextData> next_context_data() const noexcept
+            {
+                return next_;
+            }
+            SEAL_NODISCARD std::shared_ptr<const ContextData> prev_context_data() const noexcept
+            {
+                return prev_.lock();
+            }
+
+        private:
+            friend class SEALContext;
+            EncryptionParameters parms_;
+            parms_id_type parms_id_{};
+            std::size_t chain_index_ = 0;
+            int total_bits_ = 0;
+            std::shared_ptr<const ContextData> next_;
+            std::weak_ptr<const ContextData> prev_;
+        };
+
+        // state shared by every object created under this context
+        struct Impl
+        {
+            bk_context_t h = nullptr;
+            int log_n = 0, n_primes = 0, device = 0;
+            std::uint64_t serial = 0;
+            EncryptionParameters parms;
+            // data[l] = context data with l limbs (l = 1 .. n_primes); data[n_primes] is the key level
+            std::vector<std::shared_ptr<ContextData>> data;
+            ~Impl()
+            {
+                if (h)
+                    bk_context_destroy(h);
+            }
+        };
+
+        // device < 0: $B200CKKS_DEVICE, else the process's current CUDA device 0
+        SEALContext(
+            const EncryptionParameters &parms, bool expand_mod_chain = true,
+            sec_level_type sec_level = sec_level_type::tc128, int device = -1)
+            : impl_(std::make_shared<Impl>())
+        {
+            (void)expand_mod_chain;
+            (void)sec_level;
+            if (parms.scheme() != scheme_type::ckks)
+                throw std::invalid_argument("unsupported scheme (this engine evaluates CKKS only)");
+            std::size_t n = parms.poly_modulus_degree();
+            int log_n = 0;
+            while ((std::size_t(1) << log_n) < n)
+                log_n++;
+            if (n == 0 || (std::size_t(1) << log_n) != n)
+                throw std::invalid_argument("poly_modulus_degree is invalid");
+            if (device < 0)
+            {
+                const char *e = std::getenv("B200CKKS_DEVICE");
+                device = e ? std::atoi(e) : 0;
+            }
+            std::vector<std::uint64_t> primes;
+            for (auto &m : parms.coeff_modulus())
+                primes.push_back(m.value());
+            detail::check(bk_context_create(log_n, primes.data(), (int)primes.size(), device, &impl_->h));
+            static std::atomic<std::uint64_t> serial{ 1 };
+            impl_->serial = serial.fetch_add(1);
+            impl_->log_n = log_n;
+            impl_->n_primes = (int)primes.size();
+            impl_->device = device;
+            impl_->parms = parms;
+            if (parms.sparse_slots())
+                detail::check(bk_set_sparse_slots(impl_->h, (int)parms.sparse_slots()));
+            // the modulus-switching chain (context.cpp:455-523)
+            int np = impl_->n_primes;
+            impl_->data.resize(np + 1);
+            for (int l = np; l >= 1; l--)
+            {
+                auto cd = std::make_shared<ContextData>();
+                cd->parms_ = parms;
+                cd->parms_.coeff_modulus_.assign(parms.coeff_modulus().begin(), parms.coeff_modulus().begin() + l);
+                cd->parms_id_ = { 0xB200CCC5ull, impl_->serial, (std::uint64_t)l, 0 };
+                // chain_index counts down to 0 at one limb; the key level sits above the first data level
+                cd->chain_index_ = (std::size_t)(l - 1);
+                cd->total_bits_ = total_bits(parms.coeff_modulus(), l);
+                impl_->data[l] = cd;
+            }
+            for (int l = np; l >= 2; l--)
+            {
+                impl_->data[l]->next_ = impl_->data[l - 1];
+                impl_->data[l - 1]->prev_ = impl_->data[l];
+            }
+        }
+
+        SEAL_NODISCARD std::shared_ptr<const ContextData> get_context_data(const parms_id_type &id) const
+        {
+            if (id[0] != 0xB200CCC5ull || id[1] != impl_->serial || id[2] < 1 || id[2] > (std::uint64_t)impl_->n_primes)
+                return nullptr;
+            return impl_->data[(std::size_t)id[2]];
+        }
+        SEAL_NODISCARD std::shared_ptr<const ContextData> key_context_data() const
+        {
+            return impl_->data[impl_->n_primes];
+        }
+        SEAL_NODISCARD std::shared_ptr<const ContextData> first_context_data() const
+        {
+            return impl_->data[impl_->n_primes > 1 ? impl_->n_primes - 1 : 1];
+        }
+        SEAL_NODISCARD std::shared_ptr<const ContextData> last_context_data() const
+        {
+            return impl_->data[1];
+        }
+        SEAL_NODISCARD const parms_id_type &key_parms_id() const
+        {
+            return key_context_data()->parms_id();
+        }
+        SEAL_NODISCARD const parms_id_type &first_parms_id() const
+        {
+            return first_context_data()->parms_id();
+        }
+        SEAL_NODISCARD const parms_id_type &last_parms_id() const
+        {
+            return last_context_data()->parms_id();
+        }
+        SEAL_NODISCARD bool parameters_set() const
+        {
+            return true;
+        }
+        SEAL_NODISCARD bool using_keyswitching() const
+        {
+            return impl_->n_primes > 1;
+        }
+
+        // ---- engine access (not part of the reference API)
+        SEAL_NODISCARD const std::shared_ptr<Impl> &impl() const
+        {
+            return impl_;
+        }
+        SEAL_NODISCARD bk_context_t handle() const
+        {
+            return impl_->h;
+        }
+        SEAL_NODISCARD parms_id_type parms_id_of_limbs(int limbs) const
+        {
+            return impl_->data[(std::size_t)limbs]->parms_id();
+        }
+        static int limbs_of(const parms_id_type &id)
+        {
+            return (int)id[2];
+        }
+        void sync() const
+        {
+            detail::check(bk_sync(impl_->h));
+        }
+
+    private:
+        static int total_bits(const std::vector<Modulus> &m, int l)
+        {
+            std::vector<std::uint64_t> prod(1, 1);
+            for (int i = 0; i < l; i++)
+            {
+                unsigned __int128 carry = 0;
+                for (auto &w : prod)
+                {
+                    unsigned __int128 t = (unsigned __int128)w * m[i].value() + carry;
+                    w = (std::uint64_t)t;
+                    carry = t >> 64;
+                }
+                if (carry)
+                    prod.push_back((std::uint64_t)carry);
+            }
+            int b = 0;
+            for (std::uint64_t v = prod.back(); v; v >>= 1)
+                b++;
+            return (int)(prod.size() - 1) * 64 + b;
+        }
+        std::shared_ptr<Impl> impl_;
+    };
+
+    using CtxImpl = std::shared_ptr<SEALContext::Impl>;
+
+    // --------------------------------------------------------------------------------- containers
+    class Plaintext
+    {
+    public:
+        Plaintext() = default;
+        Plaintext(const Plaintext &o)
+        {
+            *this = o;
+        }
+        Plaintext(Plaintext &&o) noexcept
+        {
+            swap(o);
+        }
+        Plaintext &operator=(const Plaintext &o)
+        {
+            if (this == &o)
+                return *this;
+            if (!o.h_)
+            {
+                release();
+                scale_ = o.scale_;
+                return *this;
+            }
+            bind(o.ctx_);
+            detail::check(bk_pt_copy(h_, o.h_));
+            scale_ = o.scale_;
+            limbs_ = o.limbs_;
+            return *this;
+        }
+        Plaintext &operator=(Plaintext &&o) noexcept
+        {
+            swap(o);
+            return *this;
+        }
+        ~Plaintext()
+        {
+            release();
+        }
+        SEAL_NODISCARD double &scale() noexcept
+        {
+            return scale_;
+        }
+        SEAL_NODISCARD const double &scale() const noexcept
+        {
+            return scale_;
+        }
+        SEAL_NODISCARD parms_id_type parms_id() const noexcept
+        {
+            return (ctx_ && limbs_) ? ctx_->data[(std::size_t)limbs_]->parms_id() : parms_id_zero;
+        }
+        SEAL_NODISCARD bool is_ntt_form() const noexcept
+        {
+            return limbs_ != 0;
+        }
+        SEAL_NODISCARD std::size_t coeff_count() const noexcept
+        {
+            return ctx_ ? (std::size_t)limbs_ << ctx_->log_n : 0;
+        }
+        // ---- engine access
+        void bind(const CtxImpl &c)
+        {
+            if (h_ && ctx_ == c)
+                return;
+            release();
+            ctx_ = c;
+            detail::check(bk_pt_create(c->h, &h_));
+        }
+        SEAL_NODISCARD bk_pt_t handle() const
+        {
+            return h_;
+        }
+        SEAL_NODISCARD int limbs() const
+        {
+            return limbs_;
+        }
+        void pull()
+        {
+            detail::check(bk_pt_info(h_, &limbs_, &scale_));
+        }
+        void push() const
+        {
+            detail::check(bk_pt_set_scale(h_, scale_));
+        }
+        SEAL_NODISCARD const CtxImpl &ctx() const
+        {
+            return ctx_;
+        }
+
+    private:
+        void release()
+        {
+            if (h_)
+                bk_pt_destroy(h_);
+            h_ = nullptr;
+            limbs_ = 0;
+        }
+        void swap(Plaintext &o) noexcept
+        {
+            std::swap(ctx_, o.ctx_);
+            std::swap(h_, o.h_);
+            std::swap(scale_, o.scale_);
+            std::swap(limbs_, o.limbs_);
+        }
+        CtxImpl ctx_;
+        bk_pt_t h_ = nullptr;
+        double scale_ = 1.0;
+        int limbs_ = 0;
+    };
+
+    class Ciphertext
+    {
+    public:
+        Ciphertext() = default;
+        explicit Ciphertext(MemoryPoolHandle)
+        {}
+        explicit Ciphertext(const SEALContext &context, MemoryPoolHandle = {})
+        {
+            bind(context.impl());
+        }
+        Ciphertext(const Ciphertext &o)
+        {
+            *this = o;
+        }
+        Ciphertext(Ciphertext &&o) noexcept
+        {
+            swap(o);
+        }
+        // deep copy: value semantics as in the reference (ciphertext.h:132-160)
+        Ciphertext &operator=(const Ciphertext &o)
+        {
+            if (this == &o)
+                return *this;
+            if (!o.h_ || !o.size_)
+            {
+                release();
+                scale_ = o.scale_;
+                ntt_ = o.ntt_;
+                return *this;
+            }
+            bind(o.ctx_);
+            detail::check(bk_ct_copy(h_, o.h_));
+            size_ = o.size_;
+            limbs_ = o.limbs_;
+            scale_ = o.scale_;
+            ntt_ = o.ntt_;
+            return *this;
+        }
+        Ciphertext &operator=(Ciphertext &&o) noexcept
+        {
+            swap(o);
+            return *this;
+        }
+        ~Ciphertext()
+        {
+            release();
+        }
+
+        SEAL_NODISCARD double &scale() noexcept
+        {
+            return scale_;
+        }
+        SEAL_NODISCARD const double &scale() const noexcept
+        {
+            return scale_;
+        }
+        SEAL_NODISCARD bool &is_ntt_form() noexcept
+        {
+            return ntt_;
+        }
+        SEAL_NODISCARD bool is_ntt_form() const noexcept
+        {
+            return ntt_;
+        }
+        SEAL_NODISCARD parms_id_type parms_id() const noexcept
+        {
+            return (ctx_ && limbs_) ? ctx_->data[(std::size_t)limbs_]->parms_id() : parms_id_zero;
+        }
+        SEAL_NODISCARD std::size_t size() const noexcept
+        {
+            return (std::size_t)size_;
+        }
+        SEAL_NODISCARD std::size_t coeff_modulus_size() const noexcept
+        {
+            return (std::size_t)limbs_;
+        }
+        SEAL_NODISCARD std::size_t poly_modulus_degree() const noexcept
+        {
+            return ctx_ ? std::size_t(1) << ctx_->log_n : 0;
+        }
+        void reserve(std::size_t)
+        {}
+        void reserve(const SEALContext &context, parms_id_type, std::size_t)
+        {
+            bind(context.impl());
+        }
+        // Ciphertext::resize(context, parms_id, size) (ciphertext.h:229-260)
+        void resize(const SEALContext &context, parms_id_type parms_id, std::size_t size)
+        {
+            auto cd = context.get_context_data(parms_id);
+            if (!cd)
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            bind(context.impl());
+            detail::check(bk_ct_resize(h_, (int)size, SEALContext::limbs_of(parms_id)));
+            size_ = (int)size;
+            limbs_ = SEALContext::limbs_of(parms_id);
+        }
+        void release()
+        {
+            if (h_)
+                bk_ct_destroy(h_);
+            h_ = nullptr;
+            size_ = limbs_ = 0;
+        }
+
+        // ---- engine access (not part of the reference API)
+        void bind(const CtxImpl &c)
+        {
+            if (h_ && ctx_ == c)
+                return;
+            release();
+            ctx_ = c;
+            detail::check(bk_ct_create(c->h, &h_));
+        }
+        SEAL_NODISCARD bk_ct_t handle() const
+        {
+            return h_;
+        }
+        SEAL_NODISCARD const CtxImpl &ctx() const
+        {
+            return ctx_;
+        }
+        void push() const
+        {
+            detail::check(bk_ct_set_scale(h_, scale_));
+            detail::check(bk_ct_set_ntt_form(h_, ntt_ ? 1 : 0));
+        }
+        void pull()
+        {
+            int ntt = 1;
+            detail::check(bk_ct_info(h_, &size_, &limbs_, &scale_, &ntt));
+            ntt_ = ntt != 0;
+        }
+        // raw limbs in the reference's layout [size][limbs][N] (ciphertext.h:335-347)
+        void download(std::uint64_t *host) const
+        {
+            detail::check(bk_ct_download(h_, host));
+        }
+        void upload(const SEALContext &context, const std::uint64_t *host, int size, int limbs, double scale, bool ntt)
+        {
+            bind(context.impl());
+            detail::check(bk_ct_upload(h_, host, size, limbs, scale, ntt ? 1 : 0));
+            pull();
+        }
+
+    private:
+        void swap(Ciphertext &o) noexcept
+        {
+            std::swap(ctx_, o.ctx_);
+            std::swap(h_, o.h_);
+            std::swap(size_, o.size_);
+            std::swap(limbs_, o.limbs_);
+            std::swap(scale_, o.scale_);
+            std::swap(ntt_, o.ntt_);
+        }
+        CtxImpl ctx_;
+        bk_ct_t h_ = nullptr;
+        int size_ = 0, limbs_ = 0;
+        double scale_ = 1.0;
+        bool ntt_ = true;
+    };
+
+    // --------------------------------------------------------------------------------------- keys
+    namespace detail
+    {
+        struct SkHolder
+        {
+            CtxImpl ctx;
+            bk_sk_t h = nullptr;
+            ~SkHolder()
+            {
+                if (h)
+                    bk_sk_destroy(h);
+            }
+        };
+    } // namespace detail
+
+    class SecretKey
+    {
+    public:
+        SEAL_NODISCARD bk_sk_t handle() const
+        {
+            return sk_ ? sk_->h : nullptr;
+        }
+        std::shared_ptr<detail::SkHolder> sk_;
+    };
+
+    class PublicKey
+    {
+    public:
+        SEAL_NODISCARD const Ciphertext &data() const
+        {
+            return ct_;
+        }
+        Ciphertext ct_;
+    };
+
+    class KSwitchKeys
+    {
+    public:
+        virtual ~KSwitchKeys() = default;
+    };
+
+    class RelinKeys : public KSwitchKeys
+    {
+    public:
+        struct Holder
+        {
+            bk_kskey_t h = nullptr;
+            ~Holder()
+            {
+                if (h)
+                    bk_kskey_destroy(h);
+            }
+        };
+        SEAL_NODISCARD bk_kskey_t handle() const
+        {
+            return k_ ? k_->h : nullptr;
+        }
+        std::shared_ptr<Holder> k_;
+    };
+
+    // Galois keys: the set of elements is fixed by create_galois_keys (galoiskeys.h:48-74); each key is
+    // generated on the device the first time a rotation needs it, with exactly the digits/limbs that
+    // level needs, and regenerated larger if a later rotation comes at a higher level.
+    class GaloisKeys : public KSwitchKeys
+    {
+    public:
+        struct State
+        {
+            CtxImpl ctx;
+            std::shared_ptr<detail::SkHolder> sk;
+            bk_gkeys_t h = nullptr;
+            std::set<std::uint32_t> declared;
+            std::map<std::uint32_t, int> resident; // element -> limbs the resident key covers
+            std::uint64_t seed = 0;
+            std::shared_mutex mu;
+            std::uint64_t bytes = 0, generated = 0;
+            ~State()
+            {
+                if (h)
+                    bk_gkeys_destroy(h);
+            }
+        };
+        SEAL_NODISCARD static std::size_t get_index(std::uint32_t galois_elt)
+        {
+            return (galois_elt - 1) >> 1; // galois.h:139
+        }
+        SEAL_NODISCARD bool has_key(std::uint32_t galois_elt) const
+        {
+            return st_ && st_->declared.count(galois_elt) != 0;
+        }
+        // bytes of evaluation key resident in HBM / number of (re)generations so far
+        SEAL_NODISCARD std::uint64_t resident_bytes() const
+        {
+            return st_ ? st_->bytes : 0;
+        }
+        SEAL_NODISCARD std::uint64_t generated() const
+        {
+            return st_ ? st_->generated : 0;
+        }
+        // make sure the key for `elt` covers ciphertexts of `limbs` limbs
+        void ensure(std::uint32_t elt, int limbs) const
+        {
+            State &s = *st_;
+            {
+                std::shared_lock<std::shared_mutex> rl(s.mu);
+                auto it = s.resident.find(elt);
+                if (it != s.resident.end() && it->second >= limbs)
+                    return;
+            }
+            std::unique_lock<std::shared_mutex> wl(s.mu);
+            auto it = s.resident.find(elt);
+            if (it != s.resident.end() && it->second >= limbs)
+                return;
+            int top = s.ctx->n_primes - 1;
+            bk_kskey_t key = nullptr;
+            detail::check(bk_galois_key_generate(
+                s.ctx->h, s.sk->h, elt, s.seed + 7919ull * elt, limbs >= top ? 0 : limbs, &key));
+            std::uint64_t nb = 0;
+            detail::check(bk_kskey_info(key, nullptr, nullptr, &nb));
+            if (it != s.resident.end())
+            {
+                int ol = it->second;
+                s.bytes -= (std::uint64_t)ol * 2 * (ol + 1) * (8ull << s.ctx->log_n);
+            }
+            detail::check(bk_gkeys_set(s.h, elt, key)); // frees the smaller key it replaces
+            s.resident[elt] = limbs;
+            s.bytes += nb;
+            s.generated++;
+        }
+        SEAL_NODISCARD bk_gkeys_t handle() const
+        {
+            return st_ ? st_->h : nullptr;
+        }
+        std::shared_ptr<State> st_;
+    };
+
+    class KeyGenerator
+    {
+    public:
+        // keygenerator.cpp:19-76: samples the secret key (fork: Hamming-weight ternary, :64-76)
+        KeyGenerator(const SEALContext &context) : context_(context)
+        {
+            auto h = std::make_shared<detail::SkHolder>();
+            h->ctx = context.impl();
+            detail::check(bk_sk_generate(
+                context.handle(), (int)context.impl()->parms.secret_key_hamming_weight(), detail::next_seed(), &h->h));
+            sk_.sk_ = h;
+        }
+        KeyGenerator(const SEALContext &context, const SecretKey &sk) : context_(context), sk_(sk)
+        {}
+        SEAL_NODISCARD const SecretKey &secret_key() const
+        {
+            return sk_;
+        }
+        inline void create_public_key(PublicKey &destination) const
+        {
+            destination.ct_.bind(context_.impl());
+            detail::check(bk_pk_generate(context_.handle(), sk_.handle(), detail::next_seed(), destination.ct_.handle()));
+            destination.ct_.pull();
+        }
+        inline void create_relin_keys(RelinKeys &destination)
+        {
+            auto k = std::make_shared<RelinKeys::Holder>();
+            detail::check(bk_relin_key_generate(context_.handle(), sk_.handle(), detail::next_seed(), 0, &k->h));
+            destination.k_ = k;
+        }
+        // keygenerator.h:148 / :213.  The set of keys is fixed here; generation is on first use.
+        inline void create_galois_keys(const std::vector<std::uint32_t> &galois_elts, GaloisKeys &destination)
+        {
+            auto st = std::make_shared<GaloisKeys::State>();
+            st->ctx = context_.impl();
+            st->sk = sk_.sk_;
+            st->seed = detail::next_seed();
+            detail::check(bk_gkeys_create(context_.handle(), &st->h));
+            std::uint32_t two_n = (std::uint32_t)(2u << context_.impl()->log_n);
+            for (auto e : galois_elts)
+            {
+                if (!(e & 1) || e >= two_n)
+                    throw std::invalid_argument("Galois element is not valid");
+                st->declared.insert(e);
+            }
+            destination.st_ = st;
+            if (std::getenv("B200CKKS_EAGER_GALOIS"))
+                for (auto e : st->declared)
+                    destination.ensure(e, context_.impl()->n_primes - 1);
+        }
+        inline void create_galois_keys(const std::vector<int> &steps, GaloisKeys &destination)
+        {
+            std::vector<std::uint32_t> elts;
+            for (int s : steps)
+            {
+                std::uint32_t e = 0;
+                detail::check(bk_galois_elt_from_step(context_.impl()->log_n, s, &e));
+                elts.push_back(e);
+            }
+            create_galois_keys(elts, destination);
+        }
+        // all power-of-two rotations + conjugation (keygenerator.h:271, galois.cpp:97-133)
+        inline void create_galois_keys(GaloisKeys &destination)
+        {
+            std::vector<int> steps{ 0 };
+            int slots_log = context_.impl()->log_n - 1;
+            for (int i = 0; i < slots_log; i++)
+            {
+                steps.push_back(1 << i);
+                steps.push_back(-(1 << i));
+            }
+            create_galois_keys(steps, destination);
+        }
+
+    private:
+        SEALContext context_;
+        SecretKey sk_;
+    };
+
+    // ------------------------------------------------------------------------------------ encoder
+    class CKKSEncoder
+    {
+    public:
+        CKKSEncoder(const SEALContext &context) : context_(context)
+        {}
+        SEAL_NODISCARD std::size_t slot_count() const noexcept
+        {
+            return std::size_t(1) << (context_.impl()->log_n - 1);
+        }
+        // fork: ckks.h:446-450
+        inline void set_sparse_slots(std::size_t sparse_slots)
+        {
+            detail::check(bk_set_sparse_slots(context_.handle(), (int)sparse_slots));
+        }
+
+        template <typename T, typename = std::enable_if_t<
+                                  std::is_same<std::remove_cv_t<T>, double>::value ||
+                                  std::is_same<std::remove_cv_t<T>, std::complex<double>>::value>>
+        inline void encode(
+            const std::vector<T> &values, parms_id_type parms_id, double scale, Plaintext &destination,
+            MemoryPoolHandle = {}) const
+        {
+            if (!context_.get_context_data(parms_id))
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            encode_at(values.data(), values.size(), SEALContext::limbs_of(parms_id), scale, destination, false);
+        }
+        // 2-argument overload = encode at the first (top) level (ckks.h:179-184)
+        template <typename T, typename = std::enable_if_t<
+                                  std::is_same<std::remove_cv_t<T>, double>::value ||
+                                  std::is_same<std::remove_cv_t<T>, std::complex<double>>::value>>
+        inline void encode(const std::vector<T> &values, double scale, Plaintext &destination, MemoryPoolHandle = {}) const
+        {
+            encode(values, context_.first_parms_id(), scale, destination);
+        }
+        inline void encode(double value, parms_id_type parms_id, double scale, Plaintext &destination, MemoryPoolHandle = {}) const
+        {
+            if (!context_.get_context_data(parms_id))
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            destination.bind(context_.impl());
+            detail::check(
+                bk_encode_scalar(context_.handle(), value, SEALContext::limbs_of(parms_id), scale, destination.handle()));
+            destination.pull();
+        }
+        inline void encode(double value, double scale, Plaintext &destination, MemoryPoolHandle = {}) const
+        {
+            encode(value, context_.first_parms_id(), scale, destination);
+        }
+        inline void encode(int value, double scale, Plaintext &destination) const
+        {
+            encode((double)value, scale, destination);
+        }
+
+        inline void decode(const Plaintext &plain, std::vector<std::complex<double>> &destination, MemoryPoolHandle = {}) const
+        {
+            destination.resize(slot_count());
+            plain.push();
+            detail::check(bk_decode(context_.handle(), plain.handle(), reinterpret_cast<double *>(destination.data())));
+        }
+        inline void decode(const Plaintext &plain, std::vector<double> &destination, MemoryPoolHandle = {}) const
+        {
+            std::vector<std::complex<double>> tmp;
+            decode(plain, tmp);
+            destination.resize(tmp.size());
+            for (std::size_t i = 0; i < tmp.size(); i++)
+                destination[i] = tmp[i].real();
+        }
+
+        // ---- engine access: encode(values, scale) at the top level followed by
+        // mod_switch_to_inplace(plain, limbs), computing only the surviving limbs
+        template <typename T>
+        void encode_top_dropped(const std::vector<T> &values, int limbs, double scale, Plaintext &destination) const
+        {
+            encode_at(values.data(), values.size(), limbs, scale, destination, true);
+        }
+
+    private:
+        void encode_at(const double *v, std::size_t n, int limbs, double scale, Plaintext &dst, bool top_dropped) const
+        {
+            dst.bind(context_.impl());
+            auto fn = top_dropped ? bk_encode_top_dropped : bk_encode;
+            detail::check(fn(context_.handle(), v, (int)n, 0, limbs, scale, dst.handle()));
+            dst.pull();
+        }
+        void encode_at(
+            const std::complex<double> *v, std::size_t n, int limbs, double scale, Plaintext &dst, bool top_dropped) const
+        {
+            dst.bind(context_.impl());
+            auto fn = top_dropped ? bk_encode_top_dropped : bk_encode;
+            detail::check(
+                fn(context_.handle(), reinterpret_cast<const double *>(v), (int)n, 1, limbs, scale, dst.handle()));
+            dst.pull();
+        }
+        SEALContext context_;
+    };
+
+    // -------------------------------------------------------------------------- encrypt / decrypt
+    class Encryptor
+    {
+    public:
+        Encryptor(const SEALContext &context, const PublicKey &public_key) : context_(context), pk_(public_key)
+        {}
+        Encryptor(const SEALContext &context, const SecretKey &secret_key) : context_(context), sk_(secret_key)
+        {}
+        Encryptor(const SEALContext &context, const PublicKey &public_key, const SecretKey &secret_key)
+            : context_(context), pk_(public_key), sk_(secret_key)
+        {}
+        // encryptor.cpp:165-239 (public-key encryption at the plaintext's level)
+        inline void encrypt(const Plaintext &plain, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            if (!pk_.ct_.handle())
+                throw std::logic_error("public key is not set");
+            destination.bind(context_.impl());
+            plain.push();
+            detail::check(
+                bk_encrypt(context_.handle(), pk_.ct_.handle(), plain.handle(), detail::next_seed(), destination.handle()));
+            destination.pull();
+        }
+        inline void encrypt_symmetric(const Plaintext &plain, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            if (!sk_.handle())
+                throw std::logic_error("secret key is not set");
+            destination.bind(context_.impl());
+            plain.push();
+            detail::check(
+                bk_encrypt_symmetric(context_.handle(), sk_.handle(), plain.handle(), detail::next_seed(), destination.handle()));
+            destination.pull();
+        }
+
+    private:
+        SEALContext context_;
+        PublicKey pk_;
+        SecretKey sk_;
+    };
+
+    class Decryptor
+    {
+    public:
+        Decryptor(const SEALContext &context, const SecretKey &secret_key) : context_(context), sk_(secret_key)
+        {}
+        // decryptor.cpp:150-183
+        void decrypt(const Ciphertext &encrypted, Plaintext &destination)
+        {
+            if (!encrypted.handle())
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            destination.bind(context_.impl());
+            encrypted.push();
+            detail::check(bk_decrypt(context_.handle(), sk_.handle(), encrypted.handle(), destination.handle()));
+            destination.pull();
+        }
+
+    private:
+        SEALContext context_;
+        SecretKey sk_;
+    };
+
+    // ---------------------------------------------------------------------------------- evaluator
+    // Per-Evaluator operation counters (engine extension; used by the parity tests to pin operation
+    // counts against the reference's call graph).
+    struct EvaluatorStats
+    {
+        std::atomic<std::uint64_t> key_switch_rotate{ 0 }, key_switch_relin{ 0 }, rescale{ 0 }, multiply{ 0 },
+            multiply_plain{ 0 }, encode_vector{ 0 }, add{ 0 }, mod_switch{ 0 }, scalar_op{ 0 };
+    };
+
+    class Evaluator
+    {
+    public:
+        // fork: evaluator.h:84 - the Evaluator carries the encoder it uses for *_const / *_vector
+        Evaluator(const SEALContext &context, CKKSEncoder &encoder) : context_(context), encoder_(encoder)
+        {}
+
+        // ---- negate / add / sub (evaluator.cpp:76-246)
+        void negate_inplace(Ciphertext &encrypted) const
+        {
+            run1(encrypted, [&] { return bk_negate_inplace(h(), encrypted.handle()); });
+        }
+        inline void negate(const Ciphertext &encrypted, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            negate_inplace(destination);
+        }
+        void add_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
+        {
+            stats_.add++;
+            run2(encrypted1, encrypted2, [&] { return bk_add_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
+        }
+        inline void add(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+                add_inplace(destination, encrypted1);
+            else
+            {
+                destination = encrypted1;
+                add_inplace(destination, encrypted2);
+            }
+        }
+        void add_many(const std::vector<Ciphertext> &encrypteds, Ciphertext &destination) const
+        {
+            if (encrypteds.empty())
+                throw std::invalid_argument("encrypteds cannot be empty");
+            for (auto &e : encrypteds)
+                if (&e == &destination)
+                    throw std::invalid_argument("encrypteds must be different from destination");
+            destination = encrypteds[0];
+            for (std::size_t i = 1; i < encrypteds.size(); i++)
+                add_inplace(destination, encrypteds[i]);
+        }
+        void sub_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
+        {
+            stats_.add++;
+            run2(encrypted1, encrypted2, [&] { return bk_sub_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
+        }
+        inline void sub(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+            {
+                sub_inplace(destination, encrypted1);
+                negate_inplace(destination);
+            }
+            else
+            {
+                destination = encrypted1;
+                sub_inplace(destination, encrypted2);
+            }
+        }
+
+        // ---- multiply / square / relinearize (evaluator.cpp:673-814,1000-1116)
+        void multiply_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2, MemoryPoolHandle = {}) const
+        {
+            stats_.multiply++;
+            run2(encrypted1, encrypted2,
+                 [&] { return bk_multiply_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
+        }
+        inline void multiply(
+            const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            if (&encrypted2 == &destination)
+                multiply_inplace(destination, encrypted1);
+            else
+            {
+                destination = encrypted1;
+                multiply_inplace(destination, encrypted2);
+            }
+        }
+        void square_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
+        {
+            stats_.multiply++;
+            run1(encrypted, [&] { return bk_square_inplace(h(), encrypted.handle()); });
+        }
+        inline void square(const Ciphertext &encrypted, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            square_inplace(destination);
+        }
+        void relinearize_inplace(Ciphertext &encrypted, const RelinKeys &relin_keys, MemoryPoolHandle = {}) const
+        {
+            if (encrypted.size() > 2)
+                stats_.key_switch_relin++;
+            run1(encrypted, [&] { return bk_relinearize_inplace(h(), encrypted.handle(), relin_keys.handle()); });
+        }
+        inline void relinearize(
+            const Ciphertext &encrypted, const RelinKeys &relin_keys, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            relinearize_inplace(destination, relin_keys);
+        }
+
+        // ---- modulus switching / rescaling (evaluator.cpp:1118-1414)
+        void mod_switch_to_next_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
+        {
+            stats_.mod_switch++;
+            run1(encrypted, [&] { return bk_mod_switch_to_next_inplace(h(), encrypted.handle()); });
+        }
+        inline void mod_switch_to_next(const Ciphertext &encrypted, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            mod_switch_to_next_inplace(destination);
+        }
+        void mod_switch_to_next_inplace(Plaintext &plain) const
+        {
+            if (plain.limbs() < 2)
+                throw std::invalid_argument("end of modulus switching chain reached");
+            mod_switch_to_inplace(plain, context_.parms_id_of_limbs(plain.limbs() - 1));
+        }
+        void mod_switch_to_inplace(Ciphertext &encrypted, parms_id_type parms_id, MemoryPoolHandle = {}) const
+        {
+            if (!context_.get_context_data(parms_id))
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            if ((int)encrypted.coeff_modulus_size() == SEALContext::limbs_of(parms_id))
+                return;
+            stats_.mod_switch++;
+            run1(encrypted,
+                 [&] { return bk_mod_switch_to_inplace(h(), encrypted.handle(), SEALContext::limbs_of(parms_id)); });
+        }
+        inline void mod_switch_to(
+            const Ciphertext &encrypted, parms_id_type parms_id, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            mod_switch_to_inplace(destination, parms_id);
+        }
+        // evaluator.cpp:1350-1376 -> :1248-1281 (limb truncation; scale check against the target level)
+        void mod_switch_to_inplace(Plaintext &plain, parms_id_type parms_id) const
+        {
+            auto cd = context_.get_context_data(parms_id);
+            if (!cd)
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            if (!plain.handle() || !plain.limbs())
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            int limbs = SEALContext::limbs_of(parms_id);
+            if (limbs > plain.limbs())
+                throw std::invalid_argument("cannot switch to higher level modulus");
+            if (limbs < plain.limbs() &&
+                (plain.scale() <= 0 || (int)std::log2(plain.scale()) >= cd->total_coeff_modulus_bit_count()))
+                throw std::invalid_argument("scale out of bounds");
+            plain.push();
+            detail::check(bk_pt_mod_switch_to(plain.handle(), limbs));
+            plain.pull();
+        }
+        inline void mod_switch_to(const Plaintext &plain, parms_id_type parms_id, Plaintext &destination) const
+        {
+            destination = plain;
+            mod_switch_to_inplace(destination, parms_id);
+        }
+        void rescale_to_next_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
+        {
+            stats_.rescale++;
+            run1(encrypted, [&] { return bk_rescale_to_next_inplace(h(), encrypted.handle()); });
+        }
+        inline void rescale_to_next(const Ciphertext &encrypted, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            rescale_to_next_inplace(destination);
+        }
+        void rescale_to_inplace(Ciphertext &encrypted, parms_id_type parms_id, MemoryPoolHandle = {}) const
+        {
+            if (!context_.get_context_data(parms_id))
+                throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            int target = SEALContext::limbs_of(parms_id);
+            if ((int)encrypted.coeff_modulus_size() < target)
+                throw std::invalid_argument("cannot switch to higher level modulus");
+            while ((int)encrypted.coeff_modulus_size() > target)
+                rescale_to_next_inplace(encrypted);
+        }
+        inline void rescale_to(
+            const Ciphertext &encrypted, parms_id_type parms_id, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            rescale_to_inplace(destination, parms_id);
+        }
+
+        // ---- plaintext operands (evaluator.cpp:1578-1930)
+        void add_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const
+        {
+            runp(encrypted, plain, [&] { return bk_add_plain_inplace(h(), encrypted.handle(), plain.handle()); });
+        }
+        inline void add_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            add_plain_inplace(destination, plain);
+        }
+        void sub_plain_inplace(Ciphertext &encrypted, const Plaintext &plain) const
+        {
+            runp(encrypted, plain, [&] { return bk_sub_plain_inplace(h(), encrypted.handle(), plain.handle()); });
+        }
+        inline void sub_plain(const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            sub_plain_inplace(destination, plain);
+        }
+        void multiply_plain_inplace(Ciphertext &encrypted, const Plaintext &plain, MemoryPoolHandle = {}) const
+        {
+            stats_.multiply_plain++;
+            runp(encrypted, plain, [&] { return bk_multiply_plain_inplace(h(), encrypted.handle(), plain.handle()); });
+        }
+        inline void multiply_plain(
+            const Ciphertext &encrypted, const Plaintext &plain, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            multiply_plain_inplace(destination, plain);
+        }
+
+        // ---- NTT form (evaluator.cpp:2069-2118)
+        void transform_to_ntt_inplace(Ciphertext &encrypted) const
+        {
+            run1(encrypted, [&] { return bk_transform_to_ntt_inplace(h(), encrypted.handle()); });
+        }
+        void transform_from_ntt_inplace(Ciphertext &encrypted_ntt) const
+        {
+            run1(encrypted_ntt, [&] { return bk_transform_from_ntt_inplace(h(), encrypted_ntt.handle()); });
+        }
+
+        // ---- Galois automorphisms (evaluator.cpp:2120-2279, evaluator.h:1120-1190,1321-1341)
+        void apply_galois_inplace(
+            Ciphertext &encrypted, std::uint32_t galois_elt, const GaloisKeys &galois_keys, MemoryPoolHandle = {}) const
+        {
+            if (!galois_keys.handle())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (!galois_keys.has_key(galois_elt))
+                throw std::invalid_argument("Galois key not present");
+            if (!encrypted.handle())
+                throw std::invalid_argument("encrypted is not valid for encryption parameters");
+            galois_keys.ensure(galois_elt, (int)encrypted.coeff_modulus_size());
+            stats_.key_switch_rotate++;
+            std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
+            run1(encrypted,
+                 [&] { return bk_apply_galois_inplace(h(), encrypted.handle(), galois_elt, galois_keys.handle()); });
+        }
+        inline void apply_galois(
+            const Ciphertext &encrypted, std::uint32_t galois_elt, const GaloisKeys &galois_keys, Ciphertext &destination,
+            MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            apply_galois_inplace(destination, galois_elt, galois_keys);
+        }
+        void rotate_vector_inplace(
+            Ciphertext &encrypted, int steps, const GaloisKeys &galois_keys, MemoryPoolHandle = {}) const
+        {
+            if (!galois_keys.handle())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (steps == 0)
+                return;
+            int log_n = context_.impl()->log_n;
+            std::uint32_t elt = 0;
+            detail::check(bk_galois_elt_from_step(log_n, steps, &elt));
+            if (galois_keys.has_key(elt))
+            {
+                apply_galois_inplace(encrypted, elt, galois_keys);
+                return;
+            }
+            // non-adjacent-form fallback over power-of-two keys (evaluator.cpp:2256-2278)
+            std::vector<int> naf;
+            {
+                bool neg = steps < 0;
+                int v = std::abs(steps);
+                for (int i = 0; v; i++)
+                {
+                    int zi = (v & 1) ? 2 - (v & 3) : 0;
+                    v = (v - zi) >> 1;
+                    if (zi)
+                        naf.push_back((neg ? -zi : zi) * (1 << i));
+                }
+            }
+            if (naf.size() == 1)
+                throw std::invalid_argument("Galois key not present");
+            int half = 1 << (log_n - 1);
+            for (int st : naf)
+                if (std::abs(st) != half)
+                    rotate_vector_inplace(encrypted, st, galois_keys);
+        }
+        inline void rotate_vector(
+            const Ciphertext &encrypted, int steps, const GaloisKeys &galois_keys, Ciphertext &destination,
+            MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            rotate_vector_inplace(destination, steps, galois_keys);
+        }
+        inline void complex_conjugate_inplace(
+            Ciphertext &encrypted, const GaloisKeys &galois_keys, MemoryPoolHandle = {}) const
+        {
+            apply_galois_inplace(encrypted, (std::uint32_t)((2u << context_.impl()->log_n) - 1), galois_keys);
+        }
+        inline void complex_conjugate(
+            const Ciphertext &encrypted, const GaloisKeys &galois_keys, Ciphertext &destination, MemoryPoolHandle = {}) const
+        {
+            destination = encrypted;
+            complex_conjugate_inplace(destination, galois_keys);
+        }
+
+        // ---- fork: constants and vectors (evaluator.cpp:287-310, evaluator.h:1192-1213).  The scalar is
+        // encoded inside the element-wise kernel (no plaintext object); results equal encode + mod-switch +
+        // add_plain / multiply_plain.
+        void add_const_inplace(Ciphertext &encrypted, double value) const
+        {
+            stats_.scalar_op++;
+            run1(encrypted, [&] { return bk_add_const_inplace(h(), encrypted.handle(), value); });
+        }
+        inline void add_const(const Ciphertext &encrypted, double value, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            add_const_inplace(destination, value);
+        }
+        void multiply_const_inplace(Ciphertext &encrypted, double value) const
+        {
+            stats_.scalar_op++;
+            run1(encrypted, [&] { return bk_multiply_const_inplace(h(), encrypted.handle(), value); });
+        }
+        inline void multiply_const(const Ciphertext &encrypted, double value, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            multiply_const_inplace(destination, value);
+        }
+        template <typename T>
+        void multiply_vector_inplace(Ciphertext &encrypted, const std::vector<T> &value) const
+        {
+            Plaintext plain;
+            stats_.encode_vector++;
+            encoder_.encode_top_dropped(value, (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
+            multiply_plain_inplace(encrypted, plain);
+        }
+        template <typename T>
+        void multiply_vector(Ciphertext &encrypted, const std::vector<T> &value, Ciphertext &destination) const
+        {
+            destination = encrypted;
+            multiply_vector_inplace(destination, value);
+        }
+        inline void double_inplace(Ciphertext &encrypted) const
+        {
+            add_inplace(encrypted, encrypted);
+        }
+
+        // ---- fork: reduced-error arithmetic (Kim et al. CT-RSA'22; evaluator.cpp:312-486)
+        void add_inplace_reduced_error(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
+        {
+            reduced_error(encrypted1, encrypted2, 0);
+        }
+        inline void add_reduced_error(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+                add_inplace_reduced_error(destination, encrypted1);
+            else
+            {
+                destination = encrypted1;
+                add_inplace_reduced_error(destination, encrypted2);
+            }
+        }
+        void sub_inplace_reduced_error(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
+        {
+            reduced_error(encrypted1, encrypted2, 1);
+        }
+        inline void sub_reduced_error(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
+        {
+            // the reference computes destination - encrypted1 when encrypted2 aliases destination
+            // (evaluator.h:1241-1252); kept as is
+            if (&encrypted2 == &destination)
+                sub_inplace_reduced_error(destination, encrypted1);
+            else
+            {
+                destination = encrypted1;
+                sub_inplace_reduced_error(destination, encrypted2);
+            }
+        }
+        void multiply_inplace_reduced_error(
+            Ciphertext &encrypted1, const Ciphertext &encrypted2, const RelinKeys &relin_keys) const
+        {
+            if (encrypted1.coeff_modulus_size() == encrypted2.coeff_modulus_size())
+            {
+                encrypted1.scale() = encrypted2.scale();
+                multiply_inplace(encrypted1, encrypted2);
+                relinearize_inplace(encrypted1, relin_keys);
+                return;
+            }
+            reduced_error(encrypted1, encrypted2, 2);
+            relinearize_inplace(encrypted1, relin_keys);
+        }
+        inline void multiply_reduced_error(
+            const Ciphertext &encrypted1, const Ciphertext &encrypted2, const RelinKeys &relin_keys,
+            Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+                multiply_inplace_reduced_error(destination, encrypted1, relin_keys);
+            else
+            {
+                destination = encrypted1;
+                multiply_inplace_reduced_error(destination, encrypted2, relin_keys);
+            }
+        }
+        template <typename T, typename = std::enable_if_t<
+                                  std::is_same<std::remove_cv_t<T>, double>::value ||
+                                  std::is_same<std::remove_cv_t<T>, std::complex<double>>::value>>
+        void multiply_vector_inplace_reduced_error(Ciphertext &encrypted, const std::vector<T> &value)
+        {
+            // evaluator.h:1270-1278: encode at the top level with scale = ciphertext scale, drop the
+            // plaintext to the ciphertext's level, multiply_plain
+            Plaintext plain;
+            stats_.encode_vector++;
+            encoder_.encode_top_dropped(value, (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
+            multiply_plain_inplace(encrypted, plain);
+        }
+        template <typename T, typename = std::enable_if_t<
+                                  std::is_same<std::remove_cv_t<T>, double>::value ||
+                                  std::is_same<std::remove_cv_t<T>, std::complex<double>>::value>>
+        inline void multiply_vector_reduced_error(Ciphertext &encrypted, const std::vector<T> &value, Ciphertext &destination)
+        {
+            destination = encrypted;
+            multiply_vector_inplace_reduced_error(destination, value);
+        }
+
+        // ---- engine extensions
+        // Bootstrapper::modraise_inplace (ckks_bootstrapping/Bootstrapper.cpp:2894-2948) as one fused launch
+        void modraise_inplace(Ciphertext &encrypted) const
+        {
+            run1(encrypted, [&] { return bk_modraise_inplace(h(), encrypted.handle()); });
+        }
+        SEAL_NODISCARD EvaluatorStats &stats() const
+        {
+            return stats_;
+        }
+        SEAL_NODISCARD const SEALContext &context() const
+        {
+            return context_;
+        }
+
+    private:
+        Evaluator(const Evaluator &) = delete;
+        Evaluator &operator=(const Evaluator &) = delete;
+
+        bk_context_t h() const
+        {
+            return context_.handle();
+        }
+        static void need(const Ciphertext &c, const char *name)
+        {
+            if (!c.handle() || !c.size())
+                throw std::invalid_argument(std::string(name) + " is not valid for encryption parameters");
+        }
+        template <class F>
+        void run1(Ciphertext &a, F f) const
+        {
+            need(a, "encrypted");
+            a.push();
+            detail::check(f());
+            a.pull();
+        }
+        template <class F>
+        void run2(Ciphertext &a, const Ciphertext &b, F f) const
+        {
+            need(a, "encrypted1");
+            need(b, "encrypted2");
+            if (&a != &b)
+                b.push();
+            a.push();
+            detail::check(f());
+            a.pull();
+        }
+        template <class F>
+        void runp(Ciphertext &a, const Plaintext &p, F f) const
+        {
+            need(a, "encrypted");
+            if (!p.handle())
+                throw std::invalid_argument("plain is not valid for encryption parameters");
+            p.push();
+            a.push();
+            detail::check(f());
+            a.pull();
+        }
+        void apply(Ciphertext &a, const Ciphertext &b, int op) const
+        {
+            if (op == 0)
+                add_inplace(a, b);
+            else if (op == 1)
+                sub_inplace(a, b);
+            else
+                multiply_inplace(a, b);
+        }
+        // the three near-identical bodies of evaluator.cpp:312-486; op: 0 add, 1 sub, 2 multiply
+        void reduced_error(Ciphertext &encrypted1, const Ciphertext &encrypted2, int op) const
+        {
+            std::size_t l1 = encrypted1.coeff_modulus_size(), l2 = encrypted2.coeff_modulus_size();
+            const auto &q = context_.impl()->parms.coeff_modulus();
+            if (l1 == l2)
+            {
+                encrypted1.scale() = encrypted2.scale();
+                apply(encrypted1, encrypted2, op);
+            }
+            else if (l1 < l2)
+            {
+                Ciphertext adjusted;
+                double qlast = static_cast<double>(q[l2 - 1].value());
+                double scale_adjust = encrypted1.scale() * qlast / (encrypted2.scale() * encrypted2.scale());
+                multiply_const(encrypted2, scale_adjust, adjusted);
+                adjusted.scale() = encrypted1.scale() * qlast;
+                rescale_to_next_inplace(adjusted);
+                mod_switch_to_inplace(adjusted, encrypted1.parms_id());
+                encrypted1.scale() = adjusted.scale();
+                apply(encrypted1, adjusted, op);
+            }
+            else
+            {
+                Ciphertext adjusted;
+                double qlast = static_cast<double>(q[l1 - 1].value());
+                double scale_adjust = encrypted2.scale() * qlast / (encrypted1.scale() * encrypted1.scale());
+                multiply_const(encrypted1, scale_adjust, adjusted);
+                adjusted.scale() = encrypted2.scale() * qlast;
+                rescale_to_next_inplace(adjusted);
+                mod_switch_to_inplace(adjusted, encrypted2.parms_id());
+                adjusted.scale() = encrypted2.scale();
+                apply(adjusted, encrypted2, op);
+                encrypted1 = std::move(adjusted);
+            }
+        }
+
+        SEALContext context_;
+        CKKSEncoder &encoder_;
+        mutable EvaluatorStats stats_;
+    };
+
+    namespace util
+    {
+        // `iter(coeff_modulus)[i].value()` is the only iterator idiom the reference's app code needs on
+        // host data (Bootstrapper.cpp:2399-2402, infer_seal.cpp:476)
+        template <class T>
+        inline const std::vector<T> &iter(const std::vector<T> &v)
+        {
+            return v;
+        }
+        struct RNSIter
+        {};
+    } // namespace util
+} // namespace seal

@@ -1,0 +1,292 @@
+"""ctypes binding of the application-layer C ABI (include/b200ckks_app.h): bootstrapping, approximate ReLU,
+multiplexed-packing CNN operators and the ResNet driver, as restated in fhe-gpt-2_b200/host/.
+
+`App()` loads lib/libb200ckks_app.so (the engine; raises if it is missing - there is no CPU fallback).  The same C ABI
+is also exported by oracle/_ref/libapp_ref.so, which is the identical host code compiled against the reference's own
+SEAL; tests load that one through oracle/appref.py as the CPU oracle for the application layers.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+APP_LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libb200ckks_app.so"))
+APP_HEADER_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "..", "include", "b200ckks_app.h"))
+
+OPS = ["conv", "bn", "relu", "bootstrap", "add", "downsample", "avgpool", "fc"]
+STAT_NAMES = ["key_switch_rotate", "key_switch_relin", "rescale", "multiply", "multiply_plain", "encode_vector", "add",
+              "mod_switch", "scalar_op"]
+
+_EXC = {1: ValueError, 2: RuntimeError, 3: IndexError, 4: RuntimeError}
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _iptr(a):
+    return a.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class App:
+    def __init__(self, lib_path=None):
+        path = lib_path or APP_LIB_PATH
+        if not os.path.exists(path):
+            raise ImportError(f"{path} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+        self.L = C.CDLL(path)
+        self.L.bka_last_error.restype = C.c_char_p
+        self.L.bka_backend.restype = C.c_char_p
+
+    def ck(self, rc):
+        if rc:
+            raise _EXC.get(rc, RuntimeError)(self.L.bka_last_error().decode())
+
+    @property
+    def backend(self):
+        return self.L.bka_backend().decode()
+
+    def session(self, log_n, bits, hamming_weight=192, device=0, rotation_steps=()):
+        return Session(self, log_n, bits, hamming_weight, device, rotation_steps)
+
+    def oddbaby_tree(self, deg):
+        buf = np.zeros(4096, dtype=np.int32)
+        n, depth, m, l = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        self.ck(self.L.bka_oddbaby_tree(deg, _iptr(buf), len(buf), C.byref(n), C.byref(depth), C.byref(m), C.byref(l)))
+        return buf[:n.value].tolist(), depth.value, m.value, l.value
+
+
+class Ct:
+    def __init__(self, sess, h):
+        self.s, self.h = sess, h
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.s.h:
+            self.s.app.L.bka_ct_free(self.h)
+            self.h = None
+
+    def info(self):
+        size, limbs, scale = C.c_int(), C.c_int(), C.c_double()
+        self.s.app.ck(self.s.app.L.bka_ct_info(self.h, C.byref(size), C.byref(limbs), C.byref(scale)))
+        return size.value, limbs.value, scale.value
+
+    limbs = property(lambda s: s.info()[1])
+
+    @property
+    def scale(self):
+        return self.info()[2]
+
+    @scale.setter
+    def scale(self, v):
+        self.s.app.ck(self.s.app.L.bka_ct_set_scale(self.h, C.c_double(v)))
+
+    def clone(self):
+        out = C.c_void_p()
+        self.s.app.ck(self.s.app.L.bka_ct_clone(self.h, C.byref(out)))
+        return Ct(self.s, out)
+
+    def download(self):
+        size, limbs, _ = self.info()
+        out = np.zeros((size, limbs, 1 << self.s.log_n), dtype=np.uint64)
+        self.s.app.ck(self.s.app.L.bka_ct_download(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+
+class Session:
+    """EncryptionParameters + SEALContext + keys + encoder/encryptor/evaluator/decryptor (infer_seal.cpp:288-342)."""
+
+    def __init__(self, app, log_n, bits, hamming_weight, device, rotation_steps):
+        self.app, self.log_n, self.bits = app, log_n, list(bits)
+        self.slots = 1 << (log_n - 1)
+        arr = (C.c_int * len(bits))(*bits)
+        st = (C.c_int * max(1, len(rotation_steps)))(*rotation_steps)
+        self.h = C.c_void_p()
+        app.ck(app.L.bka_session_create(log_n, arr, len(bits), hamming_weight, device, st, len(rotation_steps),
+                                        C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.app.L.bka_session_destroy(self.h)
+            self.h = None
+
+    def add_rotation_steps(self, steps):
+        st = (C.c_int * len(steps))(*steps)
+        self.app.ck(self.app.L.bka_session_add_rotation_steps(self.h, st, len(steps)))
+
+    def primes(self):
+        out = np.zeros(len(self.bits), dtype=np.uint64)
+        self.app.ck(self.app.L.bka_session_primes(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def sync(self):
+        self.app.ck(self.app.L.bka_session_sync(self.h))
+
+    def stats(self, reset=False):
+        out = (C.c_uint64 * 9)()
+        self.app.ck(self.app.L.bka_session_stats(self.h, out, int(reset)))
+        return dict(zip(STAT_NAMES, [int(x) for x in out]))
+
+    def key_residency(self):
+        b, g = C.c_uint64(), C.c_uint64()
+        self.app.ck(self.app.L.bka_session_key_residency(self.h, C.byref(b), C.byref(g)))
+        return b.value, g.value
+
+    # -- ciphertexts
+    def encrypt(self, values, scale, limbs=0):
+        v = np.asarray(values)
+        out = C.c_void_p()
+        if np.iscomplexobj(v):
+            v = np.ascontiguousarray(v, dtype=np.complex128)
+            self.app.ck(self.app.L.bka_encrypt(self.h, _dptr(v.view(np.float64)), len(v), 1, C.c_double(scale), limbs,
+                                               C.byref(out)))
+        else:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            self.app.ck(self.app.L.bka_encrypt(self.h, _dptr(v), len(v), 0, C.c_double(scale), limbs, C.byref(out)))
+        return Ct(self, out)
+
+    def decrypt(self, ct):
+        out = np.zeros(self.slots, dtype=np.complex128)
+        self.app.ck(self.app.L.bka_decrypt(self.h, ct.h, _dptr(out.view(np.float64))))
+        return out
+
+    def mod_switch_to(self, ct, limbs):
+        self.app.ck(self.app.L.bka_ct_mod_switch_to(self.h, ct.h, limbs))
+
+    def rotate(self, ct, steps):
+        self.app.ck(self.app.L.bka_rotate(self.h, ct.h, steps))
+
+    def multiply_relin_rescale(self, a, b):
+        self.app.ck(self.app.L.bka_multiply_relin_rescale(self.h, a.h, b.h))
+
+    def add_reduced_error(self, a, b):
+        self.app.ck(self.app.L.bka_add_reduced_error(self.h, a.h, b.h))
+
+    def multiply_vector_rescale(self, a, values):
+        v = np.asarray(values)
+        if np.iscomplexobj(v):
+            v = np.ascontiguousarray(v, dtype=np.complex128)
+            self.app.ck(self.app.L.bka_multiply_vector_rescale(self.h, a.h, _dptr(v.view(np.float64)), len(v), 1))
+        else:
+            v = np.ascontiguousarray(v, dtype=np.float64)
+            self.app.ck(self.app.L.bka_multiply_vector_rescale(self.h, a.h, _dptr(v), len(v), 0))
+
+    # -- application layers
+    def bootstrapper(self, logn, loge=10, total_level=30, final_scale=2.0 ** 46, boundary_k=25, sin_cos_deg=59,
+                     scale_factor=2, inverse_deg=1):
+        return Bootstrapper(self, loge, logn, total_level, final_scale, boundary_k, sin_cos_deg, scale_factor, inverse_deg)
+
+    def relu(self, ct):
+        out = C.c_void_p()
+        self.app.ck(self.app.L.bka_relu(self.h, ct.h, C.byref(out)))
+        return Ct(self, out)
+
+    def conv(self, ct, parms, co, st, weight, running_var, bn_weight, epsilon=1e-5, fh=3, fw=3, end=False):
+        out, op = C.c_void_p(), (C.c_int * 7)()
+        ip = (C.c_int * 7)(*parms)
+        w = np.ascontiguousarray(weight, dtype=np.float64).reshape(-1)
+        rv = np.ascontiguousarray(running_var, dtype=np.float64)
+        bw = np.ascontiguousarray(bn_weight, dtype=np.float64)
+        self.app.ck(self.app.L.bka_conv(self.h, ct.h, ip, co, st, fh, fw, _dptr(w), _dptr(rv), _dptr(bw),
+                                        C.c_double(epsilon), int(end), C.byref(out), op))
+        return Ct(self, out), list(op)
+
+    def bn(self, ct, parms, bias, mean, var, weight, epsilon=1e-5, B=40.0):
+        out = C.c_void_p()
+        ip = (C.c_int * 7)(*parms)
+        a = [np.ascontiguousarray(x, dtype=np.float64) for x in (bias, mean, var, weight)]
+        self.app.ck(self.app.L.bka_bn(self.h, ct.h, ip, _dptr(a[0]), _dptr(a[1]), _dptr(a[2]), _dptr(a[3]),
+                                      C.c_double(epsilon), C.c_double(B), C.byref(out)))
+        return Ct(self, out)
+
+    def downsample(self, ct, parms):
+        out, op = C.c_void_p(), (C.c_int * 7)()
+        self.app.ck(self.app.L.bka_downsample(self.h, ct.h, (C.c_int * 7)(*parms), C.byref(out), op))
+        return Ct(self, out), list(op)
+
+    def avgpool(self, ct, parms, B=40.0):
+        out, op = C.c_void_p(), (C.c_int * 7)()
+        self.app.ck(self.app.L.bka_avgpool(self.h, ct.h, (C.c_int * 7)(*parms), C.c_double(B), C.byref(out), op))
+        return Ct(self, out), list(op)
+
+    def fc(self, ct, parms, matrix, bias, q, r):
+        out = C.c_void_p()
+        m = np.ascontiguousarray(matrix, dtype=np.float64).reshape(-1)
+        b = np.ascontiguousarray(bias, dtype=np.float64)
+        self.app.ck(self.app.L.bka_fc(self.h, ct.h, (C.c_int * 7)(*parms), _dptr(m), _dptr(b), q, r, C.byref(out)))
+        return Ct(self, out)
+
+    def tensor_add(self, a, b):
+        out = C.c_void_p()
+        self.app.ck(self.app.L.bka_tensor_add(self.h, a.h, b.h, C.byref(out)))
+        return Ct(self, out)
+
+    def resnet(self, layer_num, weights):
+        return ResNet(self, layer_num, weights)
+
+
+class Bootstrapper:
+    def __init__(self, sess, loge, logn, total_level, final_scale, boundary_k, sin_cos_deg, scale_factor, inverse_deg):
+        self.s, self.logn = sess, logn
+        self.h = C.c_void_p()
+        sess.app.ck(sess.app.L.bka_bootstrapper_create(sess.h, loge, logn, total_level, C.c_double(final_scale), boundary_k,
+                                                       sin_cos_deg, scale_factor, inverse_deg, C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.s.h:
+            self.s.app.L.bka_bootstrapper_destroy(self.h)
+            self.h = None
+
+    def rotation_steps(self):
+        buf = np.zeros(4096, dtype=np.int32)
+        n = C.c_int()
+        self.s.app.ck(self.s.app.L.bka_bootstrapper_rotation_steps(self.h, _iptr(buf), len(buf), C.byref(n)))
+        return buf[:n.value].tolist()
+
+    def lt_coefficients(self, which):
+        nd, ln = C.c_int(), C.c_int()
+        self.s.app.ck(self.s.app.L.bka_bootstrapper_lt_coefficients(self.h, which, C.byref(nd), C.byref(ln), None))
+        out = np.zeros((nd.value, ln.value), dtype=np.complex128)
+        self.s.app.ck(self.s.app.L.bka_bootstrapper_lt_coefficients(self.h, which, C.byref(nd), C.byref(ln),
+                                                                    _dptr(out.view(np.float64))))
+        return out
+
+    def bootstrap(self, ct, real_message=True):
+        out = C.c_void_p()
+        self.s.app.ck(self.s.app.L.bka_bootstrap(self.h, ct.h, int(real_message), C.byref(out)))
+        return Ct(self.s, out)
+
+    def modular_reduction(self, ct):
+        out = C.c_void_p()
+        self.s.app.ck(self.s.app.L.bka_modular_reduction(self.h, ct.h, C.byref(out)))
+        return Ct(self.s, out)
+
+
+class ResNet:
+    """weights: dict with conv_weight / bn_bias / bn_mean / bn_var / bn_weight (lists of arrays, layer_num - 1 each),
+    linear_weight (10 x 64), linear_bias (10)."""
+
+    def __init__(self, sess, layer_num, weights):
+        self.s = sess
+        cat = lambda k: np.ascontiguousarray(np.concatenate([np.asarray(a, dtype=np.float64).reshape(-1) for a in weights[k]]))
+        self._keep = [cat("conv_weight"), cat("bn_bias"), cat("bn_mean"), cat("bn_var"), cat("bn_weight"),
+                      np.ascontiguousarray(weights["linear_weight"], dtype=np.float64).reshape(-1),
+                      np.ascontiguousarray(weights["linear_bias"], dtype=np.float64)]
+        self.h = C.c_void_p()
+        sess.app.ck(sess.app.L.bka_resnet_create(sess.h, layer_num, *[_dptr(a) for a in self._keep], C.byref(self.h)))
+
+    def __del__(self):
+        if getattr(self, "h", None) and self.s.h:
+            self.s.app.L.bka_resnet_destroy(self.h)
+            self.h = None
+
+    def infer(self, image, trace=True):
+        img = np.ascontiguousarray(image, dtype=np.float64).reshape(-1)
+        assert img.size == 3072
+        logits = np.zeros(10)
+        cap = 4096
+        tr = np.zeros((cap, 4))
+        rows = C.c_int()
+        self.s.app.ck(self.s.app.L.bka_resnet_infer(self.h, _dptr(img), _dptr(logits), _dptr(tr) if trace else None, cap,
+                                                    C.byref(rows)))
+        t = [dict(op=OPS[int(r[0])], level=int(r[1]), scale=float(r[2]), ms=float(r[3])) for r in tr[:rows.value]]
+        return logits, t

@@ -1,0 +1,124 @@
+/* b200ckks_app.h - C ABI of the application layers restated on top of the engine (libb200ckks_app.so):
+ * bootstrapping, approximate ReLU, multiplexed-packing CNN operators and the ResNet driver of
+ * tleong073/FHE-GPT-2's cnn_ckks.  It exists so that the Python harness (tests/, bench.py) and foreign-language
+ * hosts can drive the C++ classes in fhe-gpt-2_b200/host/ - which mirror the reference's own classes - without a
+ * C++ compiler.  A C++ caller uses those classes directly.
+ *
+ * Reference interfaces replaced (paths under cnn_ckks/ in the reference):
+ *   bka_session_*        the set-up block of ResNet_cifar10_seal_sparse, cpu-ckks/single-key/cnn/infer_seal.cpp:288-342
+ *                        (EncryptionParameters, SEALContext, KeyGenerator, pk / relin / Galois keys, encoder, ...)
+ *   bka_bootstrapper_*   class Bootstrapper, cpu-ckks/single-key/ckks_bootstrapping/Bootstrapper.h:14-201
+ *   bka_relu             minimax_ReLU_seal, cpu-ckks/single-key/comp/SEALcomp.cpp:3-60
+ *   bka_conv / bka_bn / bka_downsample / bka_avgpool / bka_fc / bka_tensor_add
+ *                        cpu-ckks/single-key/cnn/cnn_seal.cpp:284-787
+ *   bka_resnet_*         ResNet_cifar10_seal_sparse, cpu-ckks/single-key/cnn/infer_seal.cpp:251-584
+ *
+ * Conventions: as include/b200ckks.h (int status, bka_last_error(), opaque handles).  Slot vectors cross the ABI
+ * as doubles (real) or (re, im) pairs (complex).  All ciphertext arithmetic runs on the GPU.
+ */
+#ifndef B200CKKS_APP_H
+#define B200CKKS_APP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bka_session_s *bka_session_t;
+typedef struct bka_ct_s *bka_ct_t;               /* seal::Ciphertext */
+typedef struct bka_bootstrapper_s *bka_bootstrapper_t;
+typedef struct bka_resnet_s *bka_resnet_t;
+
+const char *bka_last_error(void);
+/* "engine" when linked against libb200ckks.so; "reference-seal" for the CPU oracle build (oracle/_ref). */
+const char *bka_backend(void);
+
+/* ---- session: parameters, keys, encoder, evaluator (infer_seal.cpp:288-342) ------------------------------------
+ * bit_sizes: CoeffModulus::Create sizes, special prime last.  rotation_steps: the steps handed to
+ * KeyGenerator::create_galois_keys (0 = conjugation); more can be added until the first rotation. */
+int bka_session_create(int log_n, const int *bit_sizes, int n_bits, int hamming_weight, int device,
+                       const int *rotation_steps, int n_steps, bka_session_t *out);
+int bka_session_destroy(bka_session_t s);
+int bka_session_add_rotation_steps(bka_session_t s, const int *steps, int n_steps);
+int bka_session_primes(bka_session_t s, uint64_t *primes_out /* n_bits */);
+int bka_session_sync(bka_session_t s);
+/* Evaluator operation counters since the last reset: rotate/conjugate key switches, relinearizations, rescales,
+ * ct x ct multiplications, ct x pt multiplications, vector encodes, additions, mod switches, scalar ops. */
+int bka_session_stats(bka_session_t s, uint64_t counts_out[9], int reset);
+/* bytes of Galois keys resident in HBM and number of key generations so far (engine backend; 0 otherwise) */
+int bka_session_key_residency(bka_session_t s, uint64_t *bytes_out, uint64_t *generated_out);
+
+/* ---- ciphertexts ------------------------------------------------------------------------------------------------ */
+/* encode at the top level with `scale`, encrypt with the public key, mod_switch_to `limbs` (0 = stay on top) */
+int bka_encrypt(bka_session_t s, const double *values, int n_values, int is_complex, double scale, int limbs,
+                bka_ct_t *out);
+int bka_decrypt(bka_session_t s, bka_ct_t ct, double *out_complex /* slot_count (re, im) pairs */);
+int bka_ct_clone(bka_ct_t ct, bka_ct_t *out);
+int bka_ct_free(bka_ct_t ct);
+int bka_ct_info(bka_ct_t ct, int *size, int *limbs, double *scale);
+int bka_ct_set_scale(bka_ct_t ct, double scale);
+int bka_ct_mod_switch_to(bka_session_t s, bka_ct_t ct, int limbs);
+/* raw limbs [size][limbs][N] (for limb-level comparisons) */
+int bka_ct_download(bka_ct_t ct, uint64_t *host_out);
+
+/* a few Evaluator members, enough to compose test programs through this ABI */
+int bka_rotate(bka_session_t s, bka_ct_t ct, int steps);
+int bka_multiply_relin_rescale(bka_session_t s, bka_ct_t a, bka_ct_t b); /* a <- rescale(relin(a * b)) */
+int bka_add_reduced_error(bka_session_t s, bka_ct_t a, bka_ct_t b);      /* a <- a + b */
+int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex);
+
+/* ---- bootstrapping (Bootstrapper.h) ----------------------------------------------------------------------------
+ * create = constructor + prepare_mod_polynomial + slot_vec.push_back(logn) + generate_LT_coefficient_3; the
+ * rotation steps it needs (addLeftRotKeys_Linear_to_vector_3 plus the power-of-two steps and conjugation) are
+ * added to the session's Galois key set. */
+int bka_bootstrapper_create(bka_session_t s, int loge, int logn, int total_level, double final_scale, int boundary_k,
+                            int sin_cos_deg, int scale_factor, int inverse_deg, bka_bootstrapper_t *out);
+int bka_bootstrapper_destroy(bka_bootstrapper_t b);
+/* steps of addLeftRotKeys_Linear_to_vector_3 for this logn, appended to steps_out (capacity cap) */
+int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int cap, int *count_out);
+/* LT coefficients: which = 0..2 SlotToCoeff matrices 1..3, 3..5 CoeffToSlot matrices 1..3.
+ * Returns the number of diagonals and their length; data_out (may be NULL) receives (re, im) pairs. */
+int bka_bootstrapper_lt_coefficients(bka_bootstrapper_t b, int which, int *n_diagonals, int *length, double *data_out);
+/* bootstrap_3 (real_message = 0) / bootstrap_real_3 (real_message = 1); ct is consumed like the reference's input */
+int bka_bootstrap(bka_bootstrapper_t b, bka_ct_t ct, int real_message, bka_ct_t *out);
+/* EvalMod alone: ModularReducer::modular_reduction */
+int bka_modular_reduction(bka_bootstrapper_t b, bka_ct_t ct, bka_ct_t *out);
+
+/* ---- approximate ReLU (alpha = 13: comp_no 3, degrees {15,15,27}, scaled_val 1.7; infer_seal.cpp:255-262) ------ */
+int bka_relu(bka_session_t s, bka_ct_t ct, bka_ct_t *out);
+/* evaluation trees of upgrade_oddbaby(deg): heap array (capacity cap), m, l */
+int bka_oddbaby_tree(int deg, int *tree_out, int cap, int *len_out, int *depth_out, int *m_out, int *l_out);
+
+/* ---- multiplexed-packing tensors (cnn_seal.h:20-46): packing parameters travel as int[7] = k,h,w,c,t,p,logn ---- */
+int bka_conv(bka_session_t s, bka_ct_t in, const int in_parms[7], int co, int st, int fh, int fw, const double *weight,
+             const double *running_var, const double *constant_weight, double epsilon, int end, bka_ct_t *out,
+             int out_parms[7]);
+int bka_bn(bka_session_t s, bka_ct_t in, const int parms[7], const double *bias, const double *running_mean,
+           const double *running_var, const double *weight, double epsilon, double B, bka_ct_t *out);
+int bka_downsample(bka_session_t s, bka_ct_t in, const int in_parms[7], bka_ct_t *out, int out_parms[7]);
+int bka_avgpool(bka_session_t s, bka_ct_t in, const int in_parms[7], double B, bka_ct_t *out, int out_parms[7]);
+int bka_fc(bka_session_t s, bka_ct_t in, const int parms[7], const double *matrix, const double *bias, int q, int r,
+           bka_ct_t *out);
+int bka_tensor_add(bka_session_t s, bka_ct_t a, bka_ct_t b, bka_ct_t *out);
+
+/* ---- ResNet on CIFAR-10 (infer_seal.cpp:251-584) ---------------------------------------------------------------
+ * The session must have been created with the CNN chain.  Weights in the reference's file order:
+ * conv_weight[layer_num-1][9*ci*co], bn_{bias,mean,var,weight}[layer_num-1][co], linear_weight[10*64],
+ * linear_bias[10], each list flattened and concatenated.  create builds the three bootstrappers (logn 14/13/12),
+ * the evaluation trees and registers every rotation step of infer_seal.cpp:345-378. */
+int bka_resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias,
+                      const double *bn_mean, const double *bn_var, const double *bn_weight, const double *linear_weight,
+                      const double *linear_bias, bka_resnet_t *out);
+int bka_resnet_destroy(bka_resnet_t net);
+/* image: 3*32*32 doubles (CHW).  logits_out: 10 doubles.  trace_out (may be NULL): per stage
+ * {op code, remaining level, scale, milliseconds}, up to trace_cap rows; trace_rows receives the row count.
+ * op codes: 0 conv, 1 bn, 2 relu, 3 bootstrap, 4 add, 5 downsample, 6 avgpool, 7 fc. */
+int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
+                     int *trace_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CKKS_APP_H */
