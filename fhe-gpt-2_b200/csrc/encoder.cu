@@ -121,6 +121,7 @@ namespace bk
         BK_CUDA(cudaMemcpy(st->d_index_map, map.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
         BK_CUDA(cudaMemcpy(st->d_roots, roots.data(), n * sizeof(cplx), cudaMemcpyHostToDevice));
         BK_CUDA(cudaMemcpy(st->d_inv_roots, iroots.data(), n * sizeof(cplx), cudaMemcpyHostToDevice));
+        BK_CUDA(cudaDeviceSynchronize());
 
         // Garner / CRT tables (rns.cpp RNSBase::compose semantics, restated as mixed radix)
         const int P = c.n_primes;
@@ -168,6 +169,7 @@ namespace bk
         up(&st->d_prodwords, prodwords);
         up(&st->d_total, total);
         up(&st->d_half, half);
+        BK_CUDA(cudaDeviceSynchronize());
         c.enc = st;
         return *st;
     }

@@ -174,6 +174,9 @@ namespace bk
         BK_CUDA(cudaMemcpy(d_tw, tw.data(), sizeof(ulonglong2) * tw.size(), cudaMemcpyHostToDevice));
         BK_CUDA(cudaMemcpy(d_itw, itw.data(), sizeof(ulonglong2) * itw.size(), cudaMemcpyHostToDevice));
         BK_CUDA(cudaMemcpy(d_inv, inv.data(), sizeof(ulonglong2) * inv.size(), cudaMemcpyHostToDevice));
+        // a pageable host-to-device cudaMemcpy may return before the DMA has landed, and the engine's streams are
+        // non-blocking (no implicit ordering against the legacy stream): drain before any kernel can read the tables
+        BK_CUDA(cudaDeviceSynchronize());
         tables.tw = d_tw;
         tables.itw = d_itw;
         tables.primes = d_primes;
@@ -229,6 +232,7 @@ namespace bk
         uint32_t *d;
         BK_CUDA(cudaMalloc((void **)&d, n * sizeof(uint32_t)));
         BK_CUDA(cudaMemcpy(d, t.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        BK_CUDA(cudaDeviceSynchronize()); // see Context::Context: the copy must have landed before a kernel gathers through it
         galois_tables[elt] = d;
         return d;
     }

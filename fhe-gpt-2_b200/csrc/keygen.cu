@@ -319,6 +319,7 @@ extern "C"
         sk->ctx = ctx;
         BK_CUDA(cudaMalloc((void **)&sk->d, (size_t)c.n_primes * c.n * sizeof(u64)));
         BK_CUDA(cudaMemcpy(sk->d, host, (size_t)c.n_primes * c.n * sizeof(u64), cudaMemcpyHostToDevice));
+        BK_CUDA(cudaDeviceSynchronize());
         *out = sk;
         BK_END
     }

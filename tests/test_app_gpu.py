@@ -1,0 +1,72 @@
+"""Application layers on the B200 engine, through include/b200ckks_app.h: the same cases as tests/test_app_cpu.py
+(small parameters), the bootstrapping entry points at the reference's N = 2^16 parameter set, and the op counts the
+reference's call graph implies."""
+import numpy as np
+import pytest
+
+import app_cases as cases
+import plain_model as pm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def app():
+    from b200ckks.app import App
+
+    a = App()
+    assert a.backend == "engine"
+    return a
+
+
+@pytest.fixture(scope="module")
+def cnn_session(app):
+    s = app.session(cases.SMALL_LOG_N, cases.CNN_SMALL_BITS, hamming_weight=64, rotation_steps=list(range(1, 2048)))
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("k,h,w,c,co,st", [(1, 8, 8, 4, 4, 1), (1, 8, 8, 4, 8, 2), (2, 4, 4, 8, 8, 1), (2, 8, 8, 8, 16, 2),
+                                            (1, 8, 8, 3, 4, 1)])
+def test_conv(cnn_session, k, h, w, c, co, st):
+    cases.case_conv(cnn_session, k, h, w, c, co, st)
+
+
+def test_bn_add_downsample_pool_fc(cnn_session):
+    cases.case_bn_add_downsample_pool_fc(cnn_session)
+
+
+def test_relu_small(app):
+    s = app.session(cases.SMALL_LOG_N, cases.RELU_BITS, hamming_weight=64)
+    cases.case_relu(s)
+    st = s.stats()
+    assert st["key_switch_relin"] == 27          # 8 + 8 + 10 + 1 non-scalar multiplications
+    s.close()
+
+
+@pytest.mark.parametrize("logn,real", [(9, True), (10, False)])
+def test_bootstrap_small(app, logn, real):
+    s = app.session(cases.SMALL_LOG_N, cases.BOOT_BITS, hamming_weight=64)
+    cases.case_bootstrap(s, logn=logn, real=real)
+    s.close()
+
+
+@pytest.fixture(scope="module")
+def big_session(app):
+    s = app.session(16, cases.BOOT_BITS, hamming_weight=192)
+    yield s
+    s.close()
+
+
+@pytest.mark.parametrize("logn,rot,mulplain", [(14, 76, 299), (13, 69, 235), (12, 62, 171)])
+def test_bootstrap_n65536_counts_and_precision(big_session, logn, rot, mulplain):
+    s = big_session
+    s.stats(reset=True)
+    cases.case_bootstrap(s, logn=logn, real=True, tol=1e-4)
+    st = s.stats()
+    # key switches (LT rotations + SubSum + conjugations + rot(n)) and run-time plaintext multiplies
+    assert st["key_switch_rotate"] == rot
+    assert st["encode_vector"] == mulplain
+    assert st["key_switch_relin"] == 18          # 16 in the degree-59 cosine + 2 double-angle steps
+
+
