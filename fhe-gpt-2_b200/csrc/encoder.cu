@@ -556,18 +556,21 @@ namespace bk
             k_enc_scatter<<<(n_values + 255) / 256, 256, 0, s>>>(d_vals, n_values, e.d_index_map, cv, slots);
             c.count();
         }
-        k_ifft_block<<<(unsigned)(n >> FFT_LB), 256, 0, s>>>(cv, e.d_inv_roots, c.log_n);
-        c.count();
         double fix = scale / static_cast<double>(n);
         const int logs = c.log_n - FFT_LB;
-        dispatch_cols(logs, [&](auto L) {
-            k_ifft_cols<decltype(L)::value><<<FFT_B / 256, 256, 0, s>>>(cv, e.d_inv_roots, fix, (double *)re.p, d_max,
-                                                                        c.log_n);
-        });
-        c.count();
+        {
+            ProfScope ps(c, s, TAG_FFT, 2);
+            k_ifft_block<<<(unsigned)(n >> FFT_LB), 256, 0, s>>>(cv, e.d_inv_roots, c.log_n);
+            dispatch_cols(logs, [&](auto L) {
+                k_ifft_cols<decltype(L)::value><<<FFT_B / 256, 256, 0, s>>>(cv, e.d_inv_roots, fix, (double *)re.p, d_max,
+                                                                            c.log_n);
+            });
+        }
+        c.count(2);
         // "encoded values are too large" check (ckks.h:519-527)
         unsigned long long h_max = 0;
         BK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, s));
+        c.d2h_bytes += sizeof(h_max);
         BK_CUDA(cudaStreamSynchronize(s));
         double max_coeff;
         std::memcpy(&max_coeff, &h_max, sizeof(double));
@@ -580,6 +583,8 @@ namespace bk
             Scratch tmp(s, (size_t)limbs * n);
             LdEncode ld{ (const double *)re.p, n, limbs };
             dim3 grid(16, limbs);
+            {
+            ProfScope ps(c, s, TAG_FWD_COLS, limbs);
             switch (c.log_n)
             {
             case 12: k_fwd_cols<4, LdEncode><<<grid, 16, 0, s>>>(ld, tmp.p, c.tables); break;
@@ -588,10 +593,14 @@ namespace bk
             case 15: k_fwd_cols<7, LdEncode><<<grid, 128, 0, s>>>(ld, tmp.p, c.tables); break;
             default: k_fwd_cols<8, LdEncode><<<grid, 256, 0, s>>>(ld, tmp.p, c.tables); break;
             }
+            }
             c.count();
             StPlain st{ out->d, limb_map(limbs), n };
             dim3 grid2((unsigned)(n >> 12), limbs);
-            k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
+            {
+                ProfScope ps(c, s, TAG_FWD_BLOCKS, limbs);
+                k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
+            }
             c.count();
         }
         out->scale = scale;
@@ -615,6 +624,7 @@ extern "C"
             if (is_complex)
             {
                 BK_CUDA(cudaMemcpyAsync(dv.p, values, (size_t)n_values * sizeof(cplx), cudaMemcpyHostToDevice, s));
+                c.h2d_bytes += (size_t)n_values * sizeof(cplx);
                 BK_CUDA(cudaStreamSynchronize(s));
             }
             else
@@ -623,6 +633,7 @@ extern "C"
                 for (int i = 0; i < n_values; i++)
                     tmp[i] = make_double2(values[i], 0.0);
                 BK_CUDA(cudaMemcpyAsync(dv.p, tmp.data(), (size_t)n_values * sizeof(cplx), cudaMemcpyHostToDevice, s));
+                c.h2d_bytes += (size_t)n_values * sizeof(double); // the caller's buffer holds reals
                 BK_CUDA(cudaStreamSynchronize(s));
             }
         }
@@ -727,6 +738,7 @@ extern "C"
         k_dec_gather<<<(sparse + 255) / 256, 256, 0, s>>>(rv, e.d_index_map, (cplx *)outv.p, sparse);
         c.count();
         BK_CUDA(cudaMemcpyAsync(out_complex, outv.p, (size_t)slots * sizeof(cplx), cudaMemcpyDeviceToHost, s));
+        c.d2h_bytes += (size_t)slots * sizeof(cplx);
         BK_CUDA(cudaStreamSynchronize(s));
         BK_END
     }

@@ -277,7 +277,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid(16, jobs);
-        ProfScope ps(c, s, TAG_FWD_COLS);
+        ProfScope ps(c, s, TAG_FWD_COLS, jobs);
         BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
         c.count();
     }
@@ -287,7 +287,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid((unsigned)(c.n >> 12), jobs);
-        ProfScope ps(c, s, TAG_FWD_BLOCKS);
+        ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
         k_fwd_blocks<Store><<<grid, 256, 0, s>>>(in, st, c.tables);
         c.count();
     }
@@ -297,7 +297,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid((unsigned)(c.n >> 12), jobs);
-        ProfScope ps(c, s, TAG_INV_BLOCKS);
+        ProfScope ps(c, s, TAG_INV_BLOCKS, jobs);
         k_inv_blocks<Load><<<grid, 256, 0, s>>>(ld, out, c.tables);
         c.count();
     }
@@ -307,7 +307,7 @@ namespace bk
         if (jobs <= 0)
             return;
         dim3 grid(16, jobs);
-        ProfScope ps(c, s, TAG_INV_COLS);
+        ProfScope ps(c, s, TAG_INV_COLS, jobs);
         BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
         c.count();
     }
@@ -434,7 +434,7 @@ namespace bk
             KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs };
             dim3 grid((unsigned)((n / 2 + 255) / 256), nI);
             {
-                ProfScope ps(c, s, TAG_KS_MAC);
+                ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
                 k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
             }
             c.count();
@@ -765,10 +765,11 @@ extern "C"
     bk_status bk_profile_begin(bk_context_t ctx, int kernel_tag)
     {
         BK_TRY
-        if (kernel_tag < 0 || kernel_tag >= TAG_COUNT)
+        if (kernel_tag != -2 && (kernel_tag < 0 || kernel_tag >= TAG_COUNT))
             throw std::invalid_argument("unknown kernel tag");
         BK_CUDA(cudaStreamSynchronize(ctx->stream()));
         ctx->prof_events.clear();
+        ctx->prof_event_tags.clear();
         ctx->prof_tag = kernel_tag;
         BK_END
     }
@@ -789,6 +790,49 @@ extern "C"
         *launches_out = ctx->prof_events.size();
         *total_ms_out = total;
         ctx->prof_events.clear();
+        ctx->prof_event_tags.clear();
+        BK_END
+    }
+    bk_status bk_profile_end_all(bk_context_t ctx, uint64_t launches_out[8], double total_ms_out[8])
+    {
+        BK_TRY
+        ctx->prof_tag = -1;
+        BK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        for (int t = 0; t < TAG_COUNT; t++)
+        {
+            launches_out[t] = 0;
+            total_ms_out[t] = 0;
+        }
+        for (size_t i = 0; i < ctx->prof_events.size(); i++)
+        {
+            float ms = 0;
+            auto &pr = ctx->prof_events[i];
+            BK_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+            int t = ctx->prof_event_tags[i];
+            launches_out[t]++;
+            total_ms_out[t] += ms;
+            cudaEventDestroy(pr.first);
+            cudaEventDestroy(pr.second);
+        }
+        ctx->prof_events.clear();
+        ctx->prof_event_tags.clear();
+        BK_END
+    }
+    bk_status bk_kernel_counters(bk_context_t ctx, uint64_t launches_out[8], uint64_t units_out[8])
+    {
+        BK_TRY
+        for (int t = 0; t < TAG_COUNT; t++)
+        {
+            launches_out[t] = ctx->tag_launches[t].load();
+            units_out[t] = ctx->tag_units[t].load();
+        }
+        BK_END
+    }
+    bk_status bk_transfer_bytes(bk_context_t ctx, uint64_t *h2d_out, uint64_t *d2h_out)
+    {
+        BK_TRY
+        *h2d_out = ctx->h2d_bytes.load();
+        *d2h_out = ctx->d2h_bytes.load();
         BK_END
     }
     // write `bytes` bytes of junk (> L2) so the next timed region starts with a cold L2
@@ -886,6 +930,7 @@ extern "C"
         ensure_ct(ct, size, limbs, false);
         cudaStream_t s = c.stream();
         BK_CUDA(cudaMemcpyAsync(ct->d, host, (size_t)size * limbs * c.n * sizeof(u64), cudaMemcpyHostToDevice, s));
+        c.h2d_bytes += (size_t)size * limbs * c.n * sizeof(u64);
         BK_CUDA(cudaStreamSynchronize(s));
         ct->scale = scale;
         ct->ntt = is_ntt != 0;
@@ -898,6 +943,7 @@ extern "C"
         cudaStream_t s = c.stream();
         BK_CUDA(cudaMemcpyAsync(host_out, ct->d, (size_t)ct->size * ct->limbs * c.n * sizeof(u64),
                                 cudaMemcpyDeviceToHost, s));
+        c.d2h_bytes += (size_t)ct->size * ct->limbs * c.n * sizeof(u64);
         BK_CUDA(cudaStreamSynchronize(s));
         BK_END
     }
@@ -964,6 +1010,7 @@ extern "C"
         ensure_pt(pt, limbs);
         cudaStream_t s = c.stream();
         BK_CUDA(cudaMemcpyAsync(pt->d, host, (size_t)limbs * c.n * sizeof(u64), cudaMemcpyHostToDevice, s));
+        c.h2d_bytes += (size_t)limbs * c.n * sizeof(u64);
         BK_CUDA(cudaStreamSynchronize(s));
         pt->scale = scale;
         BK_END
@@ -974,6 +1021,7 @@ extern "C"
         Context &c = *pt->ctx;
         cudaStream_t s = c.stream();
         BK_CUDA(cudaMemcpyAsync(host_out, pt->d, (size_t)pt->limbs * c.n * sizeof(u64), cudaMemcpyDeviceToHost, s));
+        c.d2h_bytes += (size_t)pt->limbs * c.n * sizeof(u64);
         BK_CUDA(cudaStreamSynchronize(s));
         BK_END
     }
@@ -1139,10 +1187,13 @@ extern "C"
             ensure_ct(a, mx, l, true);
         size_t per_poly = (size_t)l * c.n;
         int grid = c.ew_grid((size_t)mn * per_poly / 2);
-        if (sub)
-            k_ew<EW_SUB><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
-        else
-            k_ew<EW_ADD><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+        {
+            ProfScope ps_ew(c, s, TAG_ELEMENTWISE, mn * l);
+            if (sub)
+                k_ew<EW_SUB><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+            else
+                k_ew<EW_ADD><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+        }
         c.count();
         if (a_size < b->size)
         {
@@ -1151,6 +1202,7 @@ extern "C"
                                     words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
             if (sub)
             {
+                ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
                 k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, s>>>(a->d + (size_t)a_size * per_poly, nullptr,
                                                                   c.d_primes, c.log_n, l, b->size - a_size, 0);
                 c.count();
@@ -1176,6 +1228,7 @@ extern "C"
         Context &c = *ctx;
         check_ct(ctx, a, "encrypted");
         size_t words = (size_t)a->size * a->limbs * c.n;
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
         k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, nullptr, c.d_primes, c.log_n, a->limbs,
                                                                    a->size, 0);
         c.count();
@@ -1201,10 +1254,13 @@ extern "C"
         const int l = a->limbs;
         size_t words = (size_t)3 * l * c.n;
         u64 *out = alloc_words(c, words);
-        if (a == b)
-            k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
-        else
-            k_tensor<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, b->d, out, c.d_primes, c.log_n, l);
+        {
+            ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, 3 * l);
+            if (a == b)
+                k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
+            else
+                k_tensor<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, b->d, out, c.d_primes, c.log_n, l);
+        }
         c.count();
         adopt(a, out, words, 3, l);
         a->scale = new_scale;
@@ -1226,6 +1282,7 @@ extern "C"
         const int l = a->limbs;
         size_t words = (size_t)3 * l * c.n;
         u64 *out = alloc_words(c, words);
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
         k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
         c.count();
         adopt(a, out, words, 3, l);
@@ -1275,6 +1332,7 @@ extern "C"
             return;
         size_t words = (size_t)a->size * limbs * c.n;
         u64 *out = alloc_words(c, words);
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * limbs);
         k_drop_limbs<<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, out, c.log_n, a->limbs, limbs, a->size);
         c.count();
         adopt(a, out, words, a->size, limbs);
@@ -1350,6 +1408,7 @@ extern "C"
         plain_check(ctx, a, p);
         if (!close_scale(a->scale, p->scale))
             throw std::invalid_argument("scale mismatch");
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
         k_ew<EW_ADD><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
                                                                                     a->limbs, 1, 1);
         c.count();
@@ -1362,6 +1421,7 @@ extern "C"
         plain_check(ctx, a, p);
         if (!close_scale(a->scale, p->scale))
             throw std::invalid_argument("scale mismatch");
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
         k_ew<EW_SUB><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
                                                                                     a->limbs, 1, 1);
         c.count();
@@ -1375,6 +1435,7 @@ extern "C"
         double new_scale = a->scale * p->scale;
         if (!c.scale_in_bounds(new_scale, a->limbs))
             throw std::invalid_argument("scale out of bounds");
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
         k_ew<EW_MUL><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
             a->d, p->d, c.d_primes, c.log_n, a->limbs, a->size, 1);
         c.count();
@@ -1413,6 +1474,7 @@ extern "C"
             throw std::invalid_argument("encrypted is not in NTT form");
         ScalarPack sp;
         scalar_residues(c, value, a->scale, a->limbs, sp.c);
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
         k_scalar_pack<false><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, sp, c.d_primes,
                                                                                             c.log_n, a->limbs, 1);
         c.count();
@@ -1431,6 +1493,7 @@ extern "C"
         double new_scale = a->scale * a->scale;
         if (!c.scale_in_bounds(new_scale, a->limbs))
             throw std::invalid_argument("scale out of bounds");
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
         k_scalar_pack<true><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
             a->d, sp, c.d_primes, c.log_n, a->limbs, a->size);
         c.count();

@@ -71,9 +71,14 @@ namespace bk
         int ks_chunk = 4;
         int sparse_slots = 0;
         std::atomic<uint64_t> launches{ 0 };
+        // bytes moved between host and device by C-ABI calls (uploads, downloads, encode inputs, decode outputs)
+        std::atomic<uint64_t> h2d_bytes{ 0 }, d2h_bytes{ 0 };
+        // per kernel family (KernelTag): launches and limb-polynomials processed, always counted
+        std::atomic<uint64_t> tag_launches[8] = {}, tag_units[8] = {};
         // per-kernel live timing (bk_profile_begin/end): events around every launch of one tag
-        int prof_tag = -1;
+        int prof_tag = -1; // -1 off, -2 every family, else one KernelTag
         std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events;
+        std::vector<int> prof_event_tags;
         std::vector<cudaEvent_t> timer_stack;
 
         std::mutex mu;
@@ -112,7 +117,9 @@ namespace bk
         TAG_INV_COLS = 3,
         TAG_KS_MAC = 4,
         TAG_ELEMENTWISE = 5,
-        TAG_COUNT = 6
+        TAG_FFT = 6,   // encoder / decoder complex FFT passes
+        TAG_OTHER = 7, // samplers, gathers, CRT composition
+        TAG_COUNT = 8
     };
     // RAII: records an event pair around one launch when its tag is being profiled
     struct ProfScope
@@ -120,15 +127,18 @@ namespace bk
         Context &c;
         cudaStream_t s;
         cudaEvent_t stop = nullptr;
-        ProfScope(Context &ctx, cudaStream_t stream, int tag) : c(ctx), s(stream)
+        ProfScope(Context &ctx, cudaStream_t stream, int tag, int units = 1) : c(ctx), s(stream)
         {
-            if (c.prof_tag != tag)
+            c.tag_launches[tag].fetch_add(1, std::memory_order_relaxed);
+            c.tag_units[tag].fetch_add((uint64_t)units, std::memory_order_relaxed);
+            if (c.prof_tag != tag && c.prof_tag != -2)
                 return;
             cudaEvent_t start;
             cudaEventCreate(&start);
             cudaEventCreate(&stop);
             cudaEventRecord(start, s);
             c.prof_events.emplace_back(start, stop);
+            c.prof_event_tags.push_back(tag);
         }
         ~ProfScope()
         {

@@ -150,6 +150,79 @@ extern "C"
         *out = s.release();
         BKA_END
     }
+    int bka_session_create_with_secret(int log_n, const int *bit_sizes, int n_bits, int hamming_weight, int device,
+                                       const int *rotation_steps, int n_steps, const uint64_t *secret_key, bka_session_t *out)
+    {
+        if (!secret_key)
+            return bka_session_create(log_n, bit_sizes, n_bits, hamming_weight, device, rotation_steps, n_steps, out);
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        auto s = std::make_unique<bka_session_s>();
+        s->log_n = log_n;
+        s->bits.assign(bit_sizes, bit_sizes + n_bits);
+        const std::size_t N = std::size_t(1) << log_n;
+        s->parms.set_poly_modulus_degree(N);
+        s->parms.set_coeff_modulus(CoeffModulus::Create(N, s->bits));
+        s->parms.set_secret_key_hamming_weight((std::size_t)hamming_weight);
+        s->context = std::make_unique<SEALContext>(s->parms, true, sec_level_type::none, device);
+        s->secret_key = SecretKey::upload(*s->context, secret_key);
+        s->keygen = std::make_unique<KeyGenerator>(*s->context, s->secret_key);
+        s->keygen->create_public_key(s->public_key);
+        s->keygen->create_relin_keys(s->relin_keys);
+        s->encoder = std::make_unique<CKKSEncoder>(*s->context);
+        s->encryptor = std::make_unique<Encryptor>(*s->context, s->public_key);
+        s->evaluator = std::make_unique<Evaluator>(*s->context, *s->encoder);
+        s->decryptor = std::make_unique<Decryptor>(*s->context, s->secret_key);
+        s->add_steps(rotation_steps, n_steps);
+        *out = s.release();
+#else
+        throw std::logic_error("importing a secret key is an engine-backend feature");
+#endif
+        BKA_END
+    }
+    int bka_session_secret_key(bka_session_t s, uint64_t *host_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        s->secret_key.download(host_out);
+#else
+        (void)s;
+        (void)host_out;
+        throw std::logic_error("exporting the secret key is an engine-backend feature");
+#endif
+        BKA_END
+    }
+    int bka_session_engine_context(bka_session_t s, void **bk_context_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        *bk_context_out = (void *)s->context->handle();
+#else
+        (void)s;
+        *bk_context_out = nullptr;
+#endif
+        BKA_END
+    }
+    int bka_session_level_histogram(bka_session_t s, int which, uint64_t counts_out[64], int reset)
+    {
+        BKA_TRY
+        if (which < 0 || which > 5)
+            throw std::invalid_argument("which must be 0..5");
+#ifdef B200CKKS_FACADE
+        auto &st = s->evaluator->stats();
+        for (int i = 0; i < 64; i++)
+        {
+            counts_out[i] = st.by_limbs[which][i].load();
+            if (reset)
+                st.by_limbs[which][i].store(0);
+        }
+#else
+        (void)s;
+        (void)reset;
+        std::memset(counts_out, 0, 64 * sizeof(uint64_t));
+#endif
+        BKA_END
+    }
     int bka_session_destroy(bka_session_t s)
     {
         BKA_TRY
@@ -584,16 +657,60 @@ extern "C"
         delete net;
         BKA_END
     }
-    int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
-                         int *trace_rows)
+    static void resnet_ready(bka_resnet_t net)
     {
-        BKA_TRY
         net->s->ensure_keys();
         if (!net->prepared)
         {
             net->net->prepare();
             net->prepared = true;
         }
+    }
+    static void copy_trace(const vector<ResNetTraceRow> &trace, double *trace_out, int trace_cap, int *trace_rows)
+    {
+        if (trace_rows)
+            *trace_rows = (int)trace.size();
+        if (trace_out)
+            for (int i = 0; i < (int)trace.size() && i < trace_cap; i++)
+            {
+                trace_out[4 * i + 0] = trace[(std::size_t)i].op;
+                trace_out[4 * i + 1] = trace[(std::size_t)i].remaining_level;
+                trace_out[4 * i + 2] = trace[(std::size_t)i].scale;
+                trace_out[4 * i + 3] = trace[(std::size_t)i].milliseconds;
+            }
+    }
+    int bka_resnet_encrypt_image(bka_resnet_t net, const double *image, bka_ct_t *out)
+    {
+        BKA_TRY
+        TensorCipher t = net->net->encrypt_image(vector<double>(image, image + 3072));
+        *out = wrap(t.cipher());
+        BKA_END
+    }
+    int bka_resnet_infer_encrypted(bka_resnet_t net, bka_ct_t image_ct, bka_ct_t *logits_ct, double *trace_out, int trace_cap,
+                                   int *trace_rows)
+    {
+        BKA_TRY
+        resnet_ready(net);
+        vector<ResNetTraceRow> trace;
+        TensorCipher in(ResNetCifar10::logn, 1, 32, 32, 3, 3, 8, image_ct->ct);
+        TensorCipher outt = net->net->infer_encrypted(in, trace_out ? &trace : nullptr);
+        *logits_ct = wrap(outt.cipher());
+        copy_trace(trace, trace_out, trace_cap, trace_rows);
+        BKA_END
+    }
+    int bka_resnet_decrypt_logits(bka_resnet_t net, bka_ct_t logits_ct, double *logits_out)
+    {
+        BKA_TRY
+        TensorCipher t(ResNetCifar10::logn, 1, 1, 1, 64, 4, 1, logits_ct->ct);
+        vector<double> logits = net->net->decrypt_logits(t);
+        std::memcpy(logits_out, logits.data(), 10 * sizeof(double));
+        BKA_END
+    }
+    int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
+                         int *trace_rows)
+    {
+        BKA_TRY
+        resnet_ready(net);
         vector<ResNetTraceRow> trace;
         vector<double> logits = net->net->infer(vector<double>(image, image + 3072), trace_out ? &trace : nullptr);
         std::memcpy(logits_out, logits.data(), 10 * sizeof(double));

@@ -197,11 +197,41 @@ void ResNetCifar10::prepare()
 
 vector<double> ResNetCifar10::infer(const vector<double> &image_in, vector<ResNetTraceRow> *trace)
 {
-    if (!prepared_)
-        throw std::logic_error("ResNetCifar10::prepare() must be called after the Galois keys were created");
+    return decrypt_logits(infer_encrypted(encrypt_image(image_in), trace));
+}
+
+TensorCipher ResNetCifar10::encrypt_image(const vector<double> &image_in)
+{
     if (image_in.size() != 32 * 32 * 3)
         throw std::invalid_argument("image must hold 32*32*3 values");
     const long n = 1L << logn, init_p = 8;
+    // pack: 8 copies of the 3 x 32 x 32 image, values divided by B so that activations stay in [-1, 1]
+    vector<double> image((std::size_t)n, 0.0);
+    for (std::size_t i = 0; i < image_in.size(); i++)
+        image[i] = image_in[i];
+    for (long i = n / init_p; i < n; i++)
+        image[(std::size_t)i] = image[(std::size_t)(i % (n / init_p))];
+    for (auto &v : image)
+        v /= B;
+    return TensorCipher(logn, 1, 32, 32, 3, 3, init_p, image, encryptor_, encoder_, logq);
+}
+
+vector<double> ResNetCifar10::decrypt_logits(const TensorCipher &output)
+{
+    Plaintext plain;
+    decryptor_.decrypt(output.cipher_ref(), plain);
+    vector<std::complex<double>> slots;
+    encoder_.decode(plain, slots);
+    vector<double> logits(10);
+    for (int i = 0; i < 10; i++)
+        logits[(std::size_t)i] = slots[(std::size_t)i].real();
+    return logits;
+}
+
+TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<ResNetTraceRow> *trace)
+{
+    if (!prepared_)
+        throw std::logic_error("ResNetCifar10::prepare() must be called after the Galois keys were created");
     const int fh = 3, fw = 3;
     const double epsilon = 0.00001;
     vector<Ciphertext> cipher_pool; // host-buffer reuse in the reference; not needed on the device
@@ -220,16 +250,7 @@ vector<double> ResNetCifar10::infer(const vector<double> &image_in, vector<ResNe
         t_prev = now;
     };
 
-    // pack: 8 copies of the 3 x 32 x 32 image, values divided by B so that activations stay in [-1, 1]
-    vector<double> image((std::size_t)n, 0.0);
-    for (std::size_t i = 0; i < image_in.size(); i++)
-        image[i] = image_in[i];
-    for (long i = n / init_p; i < n; i++)
-        image[(std::size_t)i] = image[(std::size_t)(i % (n / init_p))];
-    for (auto &v : image)
-        v /= B;
-
-    TensorCipher cnn(logn, 1, 32, 32, 3, 3, init_p, image, encryptor_, encoder_, logq), temp;
+    TensorCipher cnn = input, temp;
     {
         Ciphertext ctxt = cnn.cipher();
         for (int i = 0; i < boot_level - 3; i++)
@@ -310,13 +331,5 @@ vector<double> ResNetCifar10::infer(const vector<double> &image_in, vector<ResNe
     log_op(6, cnn);
     matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, 10, 64, evaluator_, gal_keys_);
     log_op(7, cnn);
-
-    Plaintext plain;
-    decryptor_.decrypt(cnn.cipher(), plain);
-    vector<std::complex<double>> slots;
-    encoder_.decode(plain, slots);
-    vector<double> logits(10);
-    for (int i = 0; i < 10; i++)
-        logits[(std::size_t)i] = slots[(std::size_t)i].real();
-    return logits;
+    return cnn;
 }

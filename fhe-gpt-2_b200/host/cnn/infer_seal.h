@@ -67,6 +67,11 @@ public:
 
     // image: 32*32*3 values (channel-major).  Returns the 10 logits; appends one row per operation to `trace`.
     std::vector<double> infer(const std::vector<double> &image, std::vector<ResNetTraceRow> *trace = nullptr);
+    // the three phases of infer(): client-side packing and encryption (infer_seal.cpp:434-453), the encrypted network
+    // (:455-537), client-side decryption of the ten logits (:543-551)
+    TensorCipher encrypt_image(const std::vector<double> &image);
+    TensorCipher infer_encrypted(const TensorCipher &input, std::vector<ResNetTraceRow> *trace = nullptr);
+    std::vector<double> decrypt_logits(const TensorCipher &output);
 
     std::size_t layer_num() const { return layer_num_; }
 

@@ -726,6 +726,21 @@ namespace seal
         {
             return sk_ ? sk_->h : nullptr;
         }
+        // ---- engine access: raw [coeff_modulus_size][N] NTT-form words (secretkey.h data() layout), used to hand
+        // one secret to every GPU of a node
+        void download(std::uint64_t *host) const
+        {
+            detail::check(bk_sk_download(handle(), host));
+        }
+        static SecretKey upload(const SEALContext &context, const std::uint64_t *host)
+        {
+            auto h = std::make_shared<detail::SkHolder>();
+            h->ctx = context.impl();
+            detail::check(bk_sk_upload(context.handle(), host, &h->h));
+            SecretKey sk;
+            sk.sk_ = h;
+            return sk;
+        }
         std::shared_ptr<detail::SkHolder> sk_;
     };
 
@@ -1082,6 +1097,13 @@ namespace seal
     {
         std::atomic<std::uint64_t> key_switch_rotate{ 0 }, key_switch_relin{ 0 }, rescale{ 0 }, multiply{ 0 },
             multiply_plain{ 0 }, encode_vector{ 0 }, add{ 0 }, mod_switch{ 0 }, scalar_op{ 0 };
+        // the same events by coeff_modulus_size of the ciphertext operand: [0] key switches (rotate + relinearize),
+        // [1] rescales, [2] vector encode + multiply_plain, [3] ct x ct multiplications, [4] scalar ops, [5] add/sub
+        std::atomic<std::uint64_t> by_limbs[6][64] = {};
+        void hit(int which, std::size_t limbs)
+        {
+            by_limbs[which][limbs < 64 ? limbs : 63]++;
+        }
     };
 
     class Evaluator
@@ -1104,6 +1126,7 @@ namespace seal
         void add_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
         {
             stats_.add++;
+            stats_.hit(5, encrypted1.coeff_modulus_size());
             run2(encrypted1, encrypted2, [&] { return bk_add_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
         }
         inline void add(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
@@ -1130,6 +1153,7 @@ namespace seal
         void sub_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
         {
             stats_.add++;
+            stats_.hit(5, encrypted1.coeff_modulus_size());
             run2(encrypted1, encrypted2, [&] { return bk_sub_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
         }
         inline void sub(const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
@@ -1150,6 +1174,7 @@ namespace seal
         void multiply_inplace(Ciphertext &encrypted1, const Ciphertext &encrypted2, MemoryPoolHandle = {}) const
         {
             stats_.multiply++;
+            stats_.hit(3, encrypted1.coeff_modulus_size());
             run2(encrypted1, encrypted2,
                  [&] { return bk_multiply_inplace(h(), encrypted1.handle(), encrypted2.handle()); });
         }
@@ -1167,6 +1192,7 @@ namespace seal
         void square_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
         {
             stats_.multiply++;
+            stats_.hit(3, encrypted.coeff_modulus_size());
             run1(encrypted, [&] { return bk_square_inplace(h(), encrypted.handle()); });
         }
         inline void square(const Ciphertext &encrypted, Ciphertext &destination, MemoryPoolHandle = {}) const
@@ -1177,7 +1203,10 @@ namespace seal
         void relinearize_inplace(Ciphertext &encrypted, const RelinKeys &relin_keys, MemoryPoolHandle = {}) const
         {
             if (encrypted.size() > 2)
+            {
                 stats_.key_switch_relin++;
+                stats_.hit(0, encrypted.coeff_modulus_size());
+            }
             run1(encrypted, [&] { return bk_relinearize_inplace(h(), encrypted.handle(), relin_keys.handle()); });
         }
         inline void relinearize(
@@ -1246,6 +1275,7 @@ namespace seal
         void rescale_to_next_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
         {
             stats_.rescale++;
+            stats_.hit(1, encrypted.coeff_modulus_size());
             run1(encrypted, [&] { return bk_rescale_to_next_inplace(h(), encrypted.handle()); });
         }
         inline void rescale_to_next(const Ciphertext &encrypted, Ciphertext &destination, MemoryPoolHandle = {}) const
@@ -1323,6 +1353,7 @@ namespace seal
                 throw std::invalid_argument("encrypted is not valid for encryption parameters");
             galois_keys.ensure(galois_elt, (int)encrypted.coeff_modulus_size());
             stats_.key_switch_rotate++;
+            stats_.hit(0, encrypted.coeff_modulus_size());
             std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
             run1(encrypted,
                  [&] { return bk_apply_galois_inplace(h(), encrypted.handle(), galois_elt, galois_keys.handle()); });
@@ -1394,6 +1425,7 @@ namespace seal
         void add_const_inplace(Ciphertext &encrypted, double value) const
         {
             stats_.scalar_op++;
+            stats_.hit(4, encrypted.coeff_modulus_size());
             run1(encrypted, [&] { return bk_add_const_inplace(h(), encrypted.handle(), value); });
         }
         inline void add_const(const Ciphertext &encrypted, double value, Ciphertext &destination) const
@@ -1404,6 +1436,7 @@ namespace seal
         void multiply_const_inplace(Ciphertext &encrypted, double value) const
         {
             stats_.scalar_op++;
+            stats_.hit(4, encrypted.coeff_modulus_size());
             run1(encrypted, [&] { return bk_multiply_const_inplace(h(), encrypted.handle(), value); });
         }
         inline void multiply_const(const Ciphertext &encrypted, double value, Ciphertext &destination) const
@@ -1416,6 +1449,7 @@ namespace seal
         {
             Plaintext plain;
             stats_.encode_vector++;
+            stats_.hit(2, encrypted.coeff_modulus_size());
             encoder_.encode_top_dropped(value, (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
             multiply_plain_inplace(encrypted, plain);
         }
@@ -1495,6 +1529,7 @@ namespace seal
             // plaintext to the ciphertext's level, multiply_plain
             Plaintext plain;
             stats_.encode_vector++;
+            stats_.hit(2, encrypted.coeff_modulus_size());
             encoder_.encode_top_dropped(value, (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
             multiply_plain_inplace(encrypted, plain);
         }

@@ -1,9 +1,9 @@
 """ctypes binding of the application-layer C ABI (include/b200ckks_app.h): bootstrapping, approximate ReLU,
 multiplexed-packing CNN operators and the ResNet driver, as restated in fhe-gpt-2_b200/host/.
 
-`App()` loads lib/libb200ckks_app.so (the engine; raises if it is missing - there is no CPU fallback).  The same C ABI
-is also exported by oracle/_ref/libapp_ref.so, which is the identical host code compiled against the reference's own
-SEAL; tests load that one through oracle/appref.py as the CPU oracle for the application layers.
+`App()` loads lib/libb200ckks_app.so (the engine; raises if it is missing - there is no CPU fallback).  `App(path)`
+binds any other library exporting the same C ABI (the test suite uses that for its CPU checker build of the same host
+sources against the reference's own SEAL).
 """
 import ctypes as C
 import os
@@ -29,6 +29,58 @@ def _iptr(a):
     return a.ctypes.data_as(C.POINTER(C.c_int))
 
 
+KERNEL_FAMILIES = ["fwd_cols", "fwd_blocks", "inv_blocks", "inv_cols", "ks_mac", "elementwise", "fft", "other"]
+
+
+class EngineView:
+    """Measurement helpers of include/b200ckks.h on the bk_context_t behind a session."""
+
+    def __init__(self, handle):
+        from . import lib
+        self.L, self.h = lib(), C.c_void_p(handle)
+
+    def _ck(self, rc):
+        if rc:
+            raise RuntimeError(self.L.bk_last_error().decode())
+
+    def launch_count(self):
+        n = C.c_uint64()
+        self._ck(self.L.bk_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def transfer_bytes(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(self.L.bk_transfer_bytes(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def kernel_counters(self):
+        l, u = (C.c_uint64 * 8)(), (C.c_uint64 * 8)()
+        self._ck(self.L.bk_kernel_counters(self.h, l, u))
+        return {k: (int(l[i]), int(u[i])) for i, k in enumerate(KERNEL_FAMILIES)}
+
+    def profile_begin_all(self):
+        self._ck(self.L.bk_profile_begin(self.h, -2))
+
+    def profile_end_all(self):
+        l, ms = (C.c_uint64 * 8)(), (C.c_double * 8)()
+        self._ck(self.L.bk_profile_end_all(self.h, l, ms))
+        return {k: (int(l[i]), float(ms[i])) for i, k in enumerate(KERNEL_FAMILIES)}
+
+    def timer_begin(self):
+        self._ck(self.L.bk_timer_begin(self.h))
+
+    def timer_end(self):
+        ms = C.c_double()
+        self._ck(self.L.bk_timer_end(self.h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        self._ck(self.L.bk_flush_l2(self.h))
+
+    def set_ks_chunk(self, chunk):
+        self._ck(self.L.bk_context_set_ks_chunk(self.h, chunk))
+
+
 class App:
     def __init__(self, lib_path=None):
         path = lib_path or APP_LIB_PATH
@@ -46,8 +98,8 @@ class App:
     def backend(self):
         return self.L.bka_backend().decode()
 
-    def session(self, log_n, bits, hamming_weight=192, device=0, rotation_steps=()):
-        return Session(self, log_n, bits, hamming_weight, device, rotation_steps)
+    def session(self, log_n, bits, hamming_weight=192, device=0, rotation_steps=(), secret_key=None):
+        return Session(self, log_n, bits, hamming_weight, device, rotation_steps, secret_key)
 
     def oddbaby_tree(self, deg):
         buf = np.zeros(4096, dtype=np.int32)
@@ -95,14 +147,36 @@ class Ct:
 class Session:
     """EncryptionParameters + SEALContext + keys + encoder/encryptor/evaluator/decryptor (infer_seal.cpp:288-342)."""
 
-    def __init__(self, app, log_n, bits, hamming_weight, device, rotation_steps):
+    def __init__(self, app, log_n, bits, hamming_weight, device, rotation_steps, secret_key=None):
         self.app, self.log_n, self.bits = app, log_n, list(bits)
         self.slots = 1 << (log_n - 1)
         arr = (C.c_int * len(bits))(*bits)
         st = (C.c_int * max(1, len(rotation_steps)))(*rotation_steps)
         self.h = C.c_void_p()
-        app.ck(app.L.bka_session_create(log_n, arr, len(bits), hamming_weight, device, st, len(rotation_steps),
-                                        C.byref(self.h)))
+        sk = None
+        if secret_key is not None:
+            sk = np.ascontiguousarray(secret_key, dtype=np.uint64)
+            assert sk.shape == (len(bits), 1 << log_n)
+        app.ck(app.L.bka_session_create_with_secret(log_n, arr, len(bits), hamming_weight, device, st, len(rotation_steps),
+                                                    sk.ctypes.data_as(C.c_void_p) if sk is not None else None,
+                                                    C.byref(self.h)))
+
+    def secret_key(self):
+        out = np.zeros((len(self.bits), 1 << self.log_n), dtype=np.uint64)
+        self.app.ck(self.app.L.bka_session_secret_key(self.h, out.ctypes.data_as(C.c_void_p)))
+        return out
+
+    def engine(self):
+        p = C.c_void_p()
+        self.app.ck(self.app.L.bka_session_engine_context(self.h, C.byref(p)))
+        if not p.value:
+            raise RuntimeError("this backend has no engine context")
+        return EngineView(p.value)
+
+    def level_histogram(self, which, reset=False):
+        out = (C.c_uint64 * 64)()
+        self.app.ck(self.app.L.bka_session_level_histogram(self.h, which, out, int(reset)))
+        return [int(x) for x in out]
 
     def close(self):
         if self.h:
@@ -278,6 +352,27 @@ class ResNet:
         if getattr(self, "h", None) and self.s.h:
             self.s.app.L.bka_resnet_destroy(self.h)
             self.h = None
+
+    def encrypt_image(self, image):
+        img = np.ascontiguousarray(image, dtype=np.float64).reshape(-1)
+        assert img.size == 3072
+        out = C.c_void_p()
+        self.s.app.ck(self.s.app.L.bka_resnet_encrypt_image(self.h, _dptr(img), C.byref(out)))
+        return Ct(self.s, out)
+
+    def infer_encrypted(self, ct, trace=False):
+        out, rows = C.c_void_p(), C.c_int()
+        cap = 4096
+        tr = np.zeros((cap, 4))
+        self.s.app.ck(self.s.app.L.bka_resnet_infer_encrypted(self.h, ct.h, C.byref(out), _dptr(tr) if trace else None, cap,
+                                                              C.byref(rows)))
+        t = [dict(op=OPS[int(r[0])], level=int(r[1]), scale=float(r[2]), ms=float(r[3])) for r in tr[:rows.value]]
+        return Ct(self.s, out), t
+
+    def decrypt_logits(self, ct):
+        logits = np.zeros(10)
+        self.s.app.ck(self.s.app.L.bka_resnet_decrypt_logits(self.h, ct.h, _dptr(logits)))
+        return logits
 
     def infer(self, image, trace=True):
         img = np.ascontiguousarray(image, dtype=np.float64).reshape(-1)

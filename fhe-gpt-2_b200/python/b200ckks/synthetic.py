@@ -1,0 +1,46 @@
+"""Synthetic inputs of the reference's ResNet shapes (there is no network for datasets or checkpoints, and the
+reference's CIFAR image file is missing): random-init weights in the parameter layout of
+cnn_ckks/pretrained_parameters/resnet<L>_new (infer_seal.cpp:3-107) and SURVEY.md 8(d) images."""
+import math
+
+import numpy as np
+
+
+def resnet_shapes(layer_num):
+    """(end_num, [(ci, co) per convolution in the reference's file order])"""
+    end_num = {20: 2, 32: 4, 44: 6, 56: 8, 110: 17}[layer_num]
+    shapes = [(3, 16)]
+    for j in range(3):
+        co = 16 << j
+        for k in range(end_num + 1):
+            shapes.append((co // 2 if (j > 0 and k == 0) else co, co))
+            shapes.append((co, co))
+    return end_num, shapes
+
+
+def random_weights(layer_num, seed=0):
+    """He-style convolutions and near-identity batch-norm statistics: activations stay well inside the [-B, B] = [-40, 40]
+    range the network's approximate ReLU covers."""
+    rng = np.random.default_rng(seed)
+    _, shapes = resnet_shapes(layer_num)
+    w = dict(conv_weight=[], bn_bias=[], bn_mean=[], bn_var=[], bn_weight=[])
+    for ci, co in shapes:
+        w["conv_weight"].append(rng.normal(0, math.sqrt(2.0 / (9 * ci)), 9 * ci * co) * 0.5)
+        w["bn_bias"].append(rng.normal(0, 0.1, co))
+        w["bn_mean"].append(rng.normal(0, 0.1, co))
+        w["bn_var"].append(rng.uniform(0.5, 1.5, co))
+        w["bn_weight"].append(rng.uniform(0.5, 1.0, co))
+    w["linear_weight"] = rng.normal(0, 0.3, 640)
+    w["linear_bias"] = rng.normal(0, 0.1, 10)
+    return w
+
+
+def synthetic_image(image_id):
+    """3072 i.i.d. N(0,1) values clipped to [-2.5, 2.5] (normalised-CIFAR-like), seed = image id, CHW order."""
+    return np.clip(np.random.default_rng(image_id).normal(0, 1, 3072), -2.5, 2.5)
+
+
+def shard(n_items, rank, world):
+    """items of rank `rank` when n_items independent units are dealt round-robin to `world` ranks
+    (image i -> GPU i mod G, the engine's counterpart of the reference's OpenMP loop over images, infer_seal.cpp:404)"""
+    return list(range(rank, n_items, world))

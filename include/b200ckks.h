@@ -87,6 +87,13 @@ bk_status bk_timer_end(bk_context_t ctx, double *ms_out);
  * pass, 4 key-switch inner product (k_ks_mac), 5 element-wise. */
 bk_status bk_profile_begin(bk_context_t ctx, int kernel_tag);
 bk_status bk_profile_end(bk_context_t ctx, uint64_t *launches_out, double *total_ms_out);
+/* kernel_tag = -2 in bk_profile_begin times every family at once; this returns launches and milliseconds per
+ * family: 0-5 as above, 6 encoder/decoder FFT, 7 other. */
+bk_status bk_profile_end_all(bk_context_t ctx, uint64_t launches_out[8], double total_ms_out[8]);
+/* always-on counters per kernel family: launches and limb-polynomials processed since context creation */
+bk_status bk_kernel_counters(bk_context_t ctx, uint64_t launches_out[8], uint64_t units_out[8]);
+/* bytes the C-ABI calls have copied host->device / device->host so far (uploads, encode inputs, downloads, ...) */
+bk_status bk_transfer_bytes(bk_context_t ctx, uint64_t *h2d_out, uint64_t *d2h_out);
 /* overwrite a 192 MiB scratch buffer (> the 126 MB L2) on the caller's stream. */
 bk_status bk_flush_l2(bk_context_t ctx);
 

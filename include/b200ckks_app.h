@@ -40,7 +40,19 @@ const char *bka_backend(void);
  * KeyGenerator::create_galois_keys (0 = conjugation); more can be added until the first rotation. */
 int bka_session_create(int log_n, const int *bit_sizes, int n_bits, int hamming_weight, int device,
                        const int *rotation_steps, int n_steps, bka_session_t *out);
+/* same, with a given secret key ([n_bits][N] NTT-form words from bka_session_secret_key of another session with the
+ * same parameters; NULL = sample a fresh one): one secret for every GPU of a node (engine backend only) */
+int bka_session_create_with_secret(int log_n, const int *bit_sizes, int n_bits, int hamming_weight, int device,
+                                   const int *rotation_steps, int n_steps, const uint64_t *secret_key, bka_session_t *out);
+int bka_session_secret_key(bka_session_t s, uint64_t *host_out /* [n_bits][N] */);
 int bka_session_destroy(bka_session_t s);
+/* the engine's bk_context_t behind this session (include/b200ckks.h), for its measurement helpers; NULL on the
+ * reference-SEAL backend */
+int bka_session_engine_context(bka_session_t s, void **bk_context_out);
+/* operation counts by coeff_modulus_size of the ciphertext operand since the last reset.  which: 0 key switches
+ * (rotate + relinearize), 1 rescales, 2 vector encode + multiply_plain, 3 ct x ct multiplications, 4 scalar ops,
+ * 5 additions */
+int bka_session_level_histogram(bka_session_t s, int which, uint64_t counts_out[64], int reset);
 int bka_session_add_rotation_steps(bka_session_t s, const int *steps, int n_steps);
 int bka_session_primes(bka_session_t s, uint64_t *primes_out /* n_bits */);
 int bka_session_sync(bka_session_t s);
@@ -117,6 +129,12 @@ int bka_resnet_destroy(bka_resnet_t net);
  * op codes: 0 conv, 1 bn, 2 relu, 3 bootstrap, 4 add, 5 downsample, 6 avgpool, 7 fc. */
 int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
                      int *trace_rows);
+/* the three phases of bka_resnet_infer separately: client-side packing + encryption (infer_seal.cpp:434-453), the
+ * encrypted network on a ciphertext resident in HBM (:455-537), client-side decryption of the logits (:543-551) */
+int bka_resnet_encrypt_image(bka_resnet_t net, const double *image, bka_ct_t *out);
+int bka_resnet_infer_encrypted(bka_resnet_t net, bka_ct_t image_ct, bka_ct_t *logits_ct, double *trace_out, int trace_cap,
+                               int *trace_rows);
+int bka_resnet_decrypt_logits(bka_resnet_t net, bka_ct_t logits_ct, double *logits_out);
 
 #ifdef __cplusplus
 }

@@ -208,37 +208,10 @@ def minimax_relu(x, degs=(15, 15, 27), scaled_val=1.7):
 
 
 # ------------------------------------------------------------------------------------------- the network
-def resnet_shapes(layer_num):
-    end_num = {20: 2, 32: 4, 44: 6, 56: 8, 110: 17}[layer_num]
-    shapes = [(3, 16)]
-    for j in range(3):
-        co = 16 << j
-        for k in range(end_num + 1):
-            shapes.append((co // 2 if (j > 0 and k == 0) else co, co))
-            shapes.append((co, co))
-    return end_num, shapes
+import sys as _sys
 
-
-def random_weights(layer_num, seed=0):
-    """random-init weights of the ResNet architecture (He-style convolutions, BN statistics near identity) in the
-    reference's parameter layout; activations stay well inside the [-B, B] range the approximate ReLU covers."""
-    rng = np.random.default_rng(seed)
-    _, shapes = resnet_shapes(layer_num)
-    w = dict(conv_weight=[], bn_bias=[], bn_mean=[], bn_var=[], bn_weight=[])
-    for ci, co in shapes:
-        w["conv_weight"].append(rng.normal(0, math.sqrt(2.0 / (9 * ci)), 9 * ci * co) * 0.5)
-        w["bn_bias"].append(rng.normal(0, 0.1, co))
-        w["bn_mean"].append(rng.normal(0, 0.1, co))
-        w["bn_var"].append(rng.uniform(0.5, 1.5, co))
-        w["bn_weight"].append(rng.uniform(0.5, 1.0, co))
-    w["linear_weight"] = rng.normal(0, 0.3, 640)
-    w["linear_bias"] = rng.normal(0, 0.1, 10)
-    return w
-
-
-def synthetic_image(image_id):
-    """3072 i.i.d. N(0,1) values clipped to [-2.5, 2.5], seed = image id, CHW order."""
-    return np.clip(np.random.default_rng(image_id).normal(0, 1, 3072), -2.5, 2.5)
+_sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "fhe-gpt-2_b200", "python")))
+from b200ckks.synthetic import random_weights, resnet_shapes, synthetic_image  # noqa: E402,F401  (shared synthetic inputs)
 
 
 def resnet_forward(layer_num, w, image, relu=minimax_relu, collect=None):

@@ -413,7 +413,8 @@ extern "C"
         OP_MULTIPLY_REDUCED_ERROR = 18,
         OP_NTT_FWD = 19,
         OP_NTT_INV = 20,
-        OP_MOD_SWITCH_TO = 21, // iarg = target limbs
+        OP_MOD_SWITCH_TO = 21,
+        OP_MULTIPLY_VECTOR = 22  // darg = the constant every slot holds
     };
 
     static void do_op(Ref *r, int op, Ciphertext &a, int b, int iarg, double darg)
@@ -484,6 +485,13 @@ extern "C"
         case OP_MOD_SWITCH_TO:
             ev.mod_switch_to_inplace(a, pid_for_limbs(r, iarg));
             break;
+        case OP_MULTIPLY_VECTOR:
+        {
+            // evaluator.h:1270-1278 with a constant slot vector: encode at the top level, drop, multiply_plain
+            vector<double> v(r->encoder->slot_count(), darg);
+            r->evaluator->multiply_vector_inplace_reduced_error(a, v);
+            break;
+        }
         default:
             throw invalid_argument("unknown op");
         }

@@ -16,7 +16,7 @@ OPS = dict(
     add=1, sub=2, multiply=3, square=4, relinearize=5, rescale=6, mod_switch_next=7, rotate=8,
     conjugate=9, negate=10, add_plain=11, sub_plain=12, multiply_plain=13, add_const=14,
     multiply_const=15, add_reduced_error=16, sub_reduced_error=17, multiply_reduced_error=18,
-    ntt_fwd=19, ntt_inv=20, mod_switch_to=21,
+    ntt_fwd=19, ntt_inv=20, mod_switch_to=21, multiply_vector=22,
 )
 
 CNN_BITS = [51] + [46] * 16 + [51] * 14 + [51]  # infer_seal.cpp:288-322

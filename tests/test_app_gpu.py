@@ -70,3 +70,36 @@ def test_bootstrap_n65536_counts_and_precision(big_session, logn, rot, mulplain)
     assert st["key_switch_relin"] == 18          # 16 in the degree-59 cosine + 2 double-angle steps
 
 
+
+
+def test_resnet20_end_to_end_matches_model_and_reference_trajectory(app):
+    """config 1 of BASELINE.json (./cnn 20 10 0 0) on a synthetic image with random-init weights: decrypted logits
+    against the float64 model of the same network, and the stage-by-stage (operation, remaining level, scale) trace
+    against the reference's committed run log."""
+    import json
+    import os
+
+    from b200ckks import synthetic
+
+    s = app.session(16, cases.BOOT_BITS, hamming_weight=192)
+    w = synthetic.random_weights(20, seed=0)
+    net = s.resnet(20, w)
+    img = synthetic.synthetic_image(0)
+    logits, trace = net.infer(img)
+    want = pm.resnet_forward(20, w, img)
+    # tolerance: 18 bootstraps (~1e-5 each on values <= 1) and 19 polynomial ReLUs, amplified by B = 40 in the pooling
+    assert np.abs(logits - want).max() < 5e-3
+    assert int(np.argmax(logits)) == int(np.argmax(want))
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet20_trajectory.json")))
+    assert [r["op"] for r in trace] == [r["op"] for r in gold["rows"]]
+    for got, ref in zip(trace, gold["rows"]):
+        if ref["level"] is not None:
+            assert got["level"] == ref["level"], (got, ref)
+            assert abs(got["scale"] / ref["scale"] - 1) < 2e-5, (got, ref)       # the log prints 6 significant digits
+    # a second image through the split path (encrypted image resident in HBM) agrees with the one-call path
+    ct = net.encrypt_image(img)
+    out, _ = net.infer_encrypted(ct)
+    assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3
+    kb, _ = s.key_residency()
+    assert kb < 100 * 2 ** 30            # level-pruned keys fit one B200 (the reference's layout needs 275 GiB)
+    s.close()

@@ -29,6 +29,17 @@ def test_every_declared_symbol_is_exported():
     assert not missing, missing
 
 
+def test_every_declared_app_symbol_is_exported():
+    from b200ckks import app
+
+    text = open(app.APP_HEADER_PATH).read()
+    names = set(re.findall(r"\b(bka_[a-z0-9_]+)\s*\(", text))
+    assert len(names) > 40
+    lib = ctypes.CDLL(app.APP_LIB_PATH)
+    missing = [n for n in sorted(names) if not hasattr(lib, n)]
+    assert not missing, missing
+
+
 def test_coeff_modulus_create_matches_golden_chain():
     got = bk.coeff_modulus_create(16, refseal.CNN_BITS)
     assert [int(v) for v in got] == GOLDEN_CNN_PRIMES
@@ -83,4 +94,5 @@ def test_product_path_never_touches_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", ".hpp")):
                 src = open(os.path.join(dp, f), errors="ignore").read()
-                assert "refseal" not in src and "ckks_port" not in src and "libseal_ref" not in src, f
+                for word in ("refseal", "ckks_port", "libseal_ref", "appref", "libapp_ref", "plain_model"):
+                    assert word not in src, (f, word)
