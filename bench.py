@@ -285,6 +285,7 @@ def run_engine(args):
             "ops_per_image": {k: v // args.steps for k, v in stats.items()},
             "galois_keys": {"resident_gib": round(key_bytes / 2 ** 30, 2), "generated": key_gens,
                             "setup_and_warmup_seconds": round(setup_s, 1)},
+            "plaintext_cache": {k: (round(v / 2 ** 30, 2) if k == "bytes" else v) for k, v in sess.plain_cache().items()},
             "check": {"logits_image0": [round(float(x), 4) for x in first_logits],
                       "max_logit_difference_between_timed_paths": drift},
         }

@@ -567,16 +567,22 @@ namespace bk
             });
         }
         c.count(2);
-        // "encoded values are too large" check (ckks.h:519-527)
-        unsigned long long h_max = 0;
-        BK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, s));
-        c.d2h_bytes += sizeof(h_max);
-        BK_CUDA(cudaStreamSynchronize(s));
-        double max_coeff;
-        std::memcpy(&max_coeff, &h_max, sizeof(double));
-        int max_coeff_bit_count = static_cast<int>(std::ceil(std::log2(std::max<>(max_coeff, 1.0)))) + 1;
-        if (max_coeff_bit_count >= c.total_bits[check_limbs])
-            throw std::invalid_argument("encoded values are too large");
+        // "encoded values are too large" check (ckks.h:519-527): ceil(log2(max |coeff|)) + 1 >= total bit count.
+        // A finite double is below 2^1024, so for moduli of more than 1025 bits the condition cannot hold and the
+        // device-to-host read of the maximum (a full drain of the stream) is skipped - that is every run-time encode
+        // of the reference's apps, which encode at the top level (ckks.h:179-184).
+        if (c.total_bits[check_limbs] <= 1025)
+        {
+            unsigned long long h_max = 0;
+            BK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(h_max), cudaMemcpyDeviceToHost, s));
+            c.d2h_bytes += sizeof(h_max);
+            BK_CUDA(cudaStreamSynchronize(s));
+            double max_coeff;
+            std::memcpy(&max_coeff, &h_max, sizeof(double));
+            int max_coeff_bit_count = static_cast<int>(std::ceil(std::log2(std::max<>(max_coeff, 1.0)))) + 1;
+            if (max_coeff_bit_count >= c.total_bits[check_limbs])
+                throw std::invalid_argument("encoded values are too large");
+        }
         ensure_pt(out, limbs);
         // RNS decomposition fused into the first NTT pass (ckks.h:536-634)
         {
@@ -621,21 +627,17 @@ extern "C"
         Scratch dv(s, (size_t)2 * std::max(n_values, 1));
         if (n_values > 0)
         {
+            // through the pinned ring: the call returns without waiting for the copy, the caller's buffer is free
+            cudaEvent_t done;
+            cplx *stage = (cplx *)c.staging((size_t)n_values * sizeof(cplx), &done);
             if (is_complex)
-            {
-                BK_CUDA(cudaMemcpyAsync(dv.p, values, (size_t)n_values * sizeof(cplx), cudaMemcpyHostToDevice, s));
-                c.h2d_bytes += (size_t)n_values * sizeof(cplx);
-                BK_CUDA(cudaStreamSynchronize(s));
-            }
+                std::memcpy(stage, values, (size_t)n_values * sizeof(cplx));
             else
-            {
-                std::vector<cplx> tmp(n_values);
                 for (int i = 0; i < n_values; i++)
-                    tmp[i] = make_double2(values[i], 0.0);
-                BK_CUDA(cudaMemcpyAsync(dv.p, tmp.data(), (size_t)n_values * sizeof(cplx), cudaMemcpyHostToDevice, s));
-                c.h2d_bytes += (size_t)n_values * sizeof(double); // the caller's buffer holds reals
-                BK_CUDA(cudaStreamSynchronize(s));
-            }
+                    stage[i] = make_double2(values[i], 0.0);
+            BK_CUDA(cudaMemcpyAsync(dv.p, stage, (size_t)n_values * sizeof(cplx), cudaMemcpyHostToDevice, s));
+            BK_CUDA(cudaEventRecord(done, s));
+            c.h2d_bytes += (size_t)n_values * sizeof(cplx);
         }
         encode_device(c, s, (const cplx *)dv.p, n_values, limbs, check_limbs, scale, out);
     }

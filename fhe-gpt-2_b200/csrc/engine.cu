@@ -188,6 +188,14 @@ namespace bk
         cudaSetDevice(device);
         cudaDeviceSynchronize();
         destroy_encoder(*this);
+        for (auto &kv : staging_rings)
+        {
+            for (auto &e : kv.second->done)
+                if (e)
+                    cudaEventDestroy(e);
+            cudaFreeHost(kv.second->host);
+            delete kv.second;
+        }
         for (auto &kv : streams)
             cudaStreamDestroy(kv.second);
         for (auto &kv : galois_tables)
@@ -218,6 +226,38 @@ namespace bk
         BK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         streams[id] = s;
         return s;
+    }
+
+    char *Context::staging(size_t bytes, cudaEvent_t *done_out)
+    {
+        activate();
+        StagingRing *r;
+        {
+            std::lock_guard<std::mutex> g(mu);
+            auto &slot = staging_rings[std::this_thread::get_id()];
+            if (!slot)
+                slot = new StagingRing();
+            r = slot;
+        }
+        const size_t need = std::max(bytes, n * sizeof(u64)); // a full slot vector of complex doubles is N * 8 bytes
+        if (r->slot_bytes < need)
+        {
+            if (r->host)
+            {
+                BK_CUDA(cudaStreamSynchronize(stream()));
+                cudaFreeHost(r->host);
+            }
+            BK_CUDA(cudaMallocHost((void **)&r->host, need * StagingRing::SLOTS));
+            r->slot_bytes = need;
+            for (auto &e : r->done)
+                if (!e)
+                    BK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        }
+        const int i = r->next;
+        r->next = (i + 1) % StagingRing::SLOTS;
+        BK_CUDA(cudaEventSynchronize(r->done[i])); // returns at once unless the ring has wrapped onto an in-flight copy
+        *done_out = r->done[i];
+        return r->host + (size_t)i * r->slot_bytes;
     }
 
     const uint32_t *Context::galois_table(uint32_t elt)

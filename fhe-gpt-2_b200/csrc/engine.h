@@ -54,6 +54,18 @@ namespace bk
 
     struct EncoderState; // encoder.cu
 
+    // Pinned host staging for slot vectors on their way to the encoder: the caller's (pageable) buffer is copied
+    // into the next slot of a small ring and leaves with cudaMemcpyAsync, so an encode never has to drain the
+    // stream before it returns.  A slot is reused once the event recorded after its copy has completed.
+    struct StagingRing
+    {
+        static constexpr int SLOTS = 8;
+        char *host = nullptr;
+        size_t slot_bytes = 0;
+        cudaEvent_t done[SLOTS] = {};
+        int next = 0;
+    };
+
     struct Context
     {
         int log_n = 0;
@@ -83,6 +95,7 @@ namespace bk
 
         std::mutex mu;
         std::unordered_map<std::thread::id, cudaStream_t> streams;
+        std::unordered_map<std::thread::id, StagingRing *> staging_rings;
         std::unordered_map<uint32_t, uint32_t *> galois_tables; // device tables
 
         EncoderState *enc = nullptr; // built lazily on first encode/decode (encoder.cu)
@@ -91,6 +104,9 @@ namespace bk
         Context(int log_n, const uint64_t *primes, int n_primes, int device);
         ~Context();
         cudaStream_t stream();
+        // next free pinned slot of the calling thread's ring (>= bytes); *done_out must be recorded on the stream
+        // after the copy that reads the slot
+        char *staging(size_t bytes, cudaEvent_t *done_out);
         const uint32_t *galois_table(uint32_t elt);
         void count(int k = 1)
         {

@@ -287,6 +287,20 @@ extern "C"
         BKA_END
     }
 
+    int bka_session_plain_cache(bka_session_t s, uint64_t *bytes_out, uint64_t *hits_out, uint64_t *misses_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        *bytes_out = s->evaluator->cached_plaintext_bytes();
+        *hits_out = s->evaluator->stats().cache_hits.load();
+        *misses_out = s->evaluator->stats().cache_misses.load();
+#else
+        (void)s;
+        *bytes_out = *hits_out = *misses_out = 0;
+#endif
+        BKA_END
+    }
+
     // ---- ciphertexts ---------------------------------------------------------------------------------------------
     int bka_encrypt(bka_session_t s, const double *values, int n_values, int is_complex, double scale, int limbs, bka_ct_t *out)
     {

@@ -1,7 +1,9 @@
 // ckks_bootstrapping/Bootstrapper.cpp - see Bootstrapper.h.  Host orchestration only: every ciphertext operation
 // is a seal::Evaluator call, i.e. a launch sequence of the CUDA engine behind the C ABI.
 #include "ckks_bootstrapping/Bootstrapper.h"
+#include "common/cached.h"
 #include "common/func.h"
+#include <cstring>
 #include <algorithm>
 #include <cmath>
 
@@ -48,6 +50,9 @@ Bootstrapper::Bootstrapper(long _loge, long _logn, long _logNh, long _L, double 
 
 Bootstrapper::~Bootstrapper()
 {
+    for (auto *list : { &fftcoeff1, &fftcoeff2, &fftcoeff3, &invfftcoeff1, &invfftcoeff2, &invfftcoeff3 })
+        for (auto &d : *list)
+            forget_named(evaluator, &d);
     delete mod_reducer;
 }
 
@@ -309,7 +314,8 @@ namespace
 } // namespace
 
 void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
-                                         int coeff_logn, const Diagonals &fftcoeff)
+                                         int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
+                                         std::uint64_t cache_variant)
 {
     const SignedPlan p(totlen);
     const int N = (int)Nh;
@@ -334,8 +340,12 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
         bool giant_started = false;
         for (int j = p.basicstart; j <= jlast; j++)
         {
-            rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[(std::size_t)(i * p.gs + j + totlen)], rotated);
-            evaluator.multiply_vector_reduced_error(babyct[(std::size_t)(j - p.basicstart)], rotated, product);
+            const std::size_t diag = (std::size_t)(i * p.gs + j + totlen);
+            product = babyct[(std::size_t)(j - p.basicstart)];
+            multiply_vector_named(evaluator, product, cache_owner, diag, cache_variant, [&]() -> const vector<complex<double>> & {
+                rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[diag], rotated);
+                return rotated;
+            });
             accumulate(evaluator, giantct, giant_started, product);
         }
         if (i != 0)
@@ -350,7 +360,8 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
 }
 
 void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
-                                                 int coeff_logn, const Diagonals &fftcoeff)
+                                                 int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
+                                                 std::uint64_t cache_variant)
 {
     const int gs = giantstep(totlen + 1);
     const int giantlast = totlen / gs;
@@ -375,8 +386,12 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
         bool giant_started = false;
         for (int j = 0; j <= jlast; j++)
         {
-            rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[(std::size_t)(i * gs + j)], rotated);
-            evaluator.multiply_vector_reduced_error(babyct[(std::size_t)j], rotated, product);
+            const std::size_t diag = (std::size_t)(i * gs + j);
+            product = babyct[(std::size_t)j];
+            multiply_vector_named(evaluator, product, cache_owner, diag, cache_variant, [&]() -> const vector<complex<double>> & {
+                rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[diag], rotated);
+                return rotated;
+            });
             accumulate(evaluator, giantct, giant_started, product);
         }
         if (i != 0)
@@ -400,24 +415,34 @@ void Bootstrapper::sfl_common(Ciphertext &rtncipher, Ciphertext &cipher, bool fu
     const std::size_t u = (std::size_t)slot_index;
 
     Ciphertext tmpct, tmpct2;
-    bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], coeff_logn, fftcoeff1[u]);
+    bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], coeff_logn, fftcoeff1[u], &fftcoeff1[u]);
     evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], coeff_logn, fftcoeff2[u]);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], coeff_logn, fftcoeff2[u], &fftcoeff2[u]);
     evaluator.rescale_to_next_inplace(tmpct2);
 
     const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
     auto curr_level = context.get_context_data(tmpct2.parms_id())->chain_index();
     const double mod_zero = (double)modulus[0].value();
     const double curr_mod = (double)modulus[curr_level].value();
+    // the scale correction multiplies every entry by the same real factor; its bit pattern names the variant
+    const double s2 = tmpct2.scale() * tmpct2.scale();
     Diagonals scaled = fftcoeff3[u];
     for (auto &v : scaled)
         for (auto &x : v)
-            x = x * curr_mod * mod_zero * final_scale / (last_divisor * tmpct2.scale() * tmpct2.scale() * initial_scale);
+            x = x * curr_mod * mod_zero * final_scale / (last_divisor * s2 * initial_scale);
+    const double probe[4] = { curr_mod, last_divisor, s2, initial_scale };
+    std::uint64_t variant = 0x5CA1ED;
+    for (double d : probe)
+    {
+        std::uint64_t b;
+        std::memcpy(&b, &d, sizeof(b));
+        variant = (variant ^ b) * 0x9E3779B97F4A7C15ull + (variant >> 31);
+    }
 
     if (full)
-        rotated_bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled);
+        rotated_bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant);
     else
-        bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled);
+        bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant);
     evaluator.rescale_to_next_inplace(rtncipher);
 }
 
@@ -443,11 +468,11 @@ void Bootstrapper::sflinv_3(Ciphertext &rtncipher, Ciphertext &cipher)
     const Split s = split_encode(logn);
     const std::size_t u = (std::size_t)slot_index;
     Ciphertext tmpct, tmpct2;
-    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u]);
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u]);
     evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u]);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u]);
     evaluator.rescale_to_next_inplace(tmpct2);
-    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn + 1, invfftcoeff3[u]);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn + 1, invfftcoeff3[u], &invfftcoeff3[u]);
     evaluator.rescale_to_next_inplace(rtncipher);
 }
 
@@ -456,11 +481,11 @@ void Bootstrapper::sflinv_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
     const Split s = split_encode(logn);
     const std::size_t u = (std::size_t)slot_index;
     Ciphertext tmpct, tmpct2;
-    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u]);
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u]);
     evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u]);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u]);
     evaluator.rescale_to_next_inplace(tmpct2);
-    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn, invfftcoeff3[u]);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn, invfftcoeff3[u], &invfftcoeff3[u]);
     evaluator.rescale_to_next_inplace(rtncipher);
 }
 

@@ -70,10 +70,14 @@ public:
     void prepare_mod_polynomial();
 
     void subsum(double scale, seal::Ciphertext &cipher);
+    // cache_owner / cache_variant name the matrix for the engine's plaintext cache (common/cached.h): pass the
+    // address of a Diagonals object that outlives the call, and a variant if its values were rescaled
     void bsgs_linear_transform(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher, int totlen, int basicstep,
-                               int coeff_logn, const Diagonals &fftcoeff);
+                               int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner = nullptr,
+                               std::uint64_t cache_variant = 0);
     void rotated_bsgs_linear_transform(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher, int totlen, int basicstep,
-                                       int coeff_logn, const Diagonals &fftcoeff);
+                                       int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner = nullptr,
+                                       std::uint64_t cache_variant = 0);
 
     void sfl_3(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher);
     void sfl_full_3(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher);

@@ -1,6 +1,7 @@
 // cnn/cnn_seal.cpp - see cnn_seal.h.  The host side only builds plaintext slot vectors (weights, masks) and decides
 // the order of Evaluator calls; rotations, plaintext multiplications, rescales and additions all run on the GPU.
 #include "cnn/cnn_seal.h"
+#include "common/cached.h"
 #include "common/func.h"
 #include <cmath>
 #include <stdexcept>
@@ -82,12 +83,10 @@ void memory_save_rotate(const Ciphertext &cipher_in, Ciphertext &cipher_out, int
     cipher_out = std::move(temp);
 }
 
-void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, int co, int st, int fh, int fw,
-                                           const vector<double> &data, vector<double> running_var,
-                                           vector<double> constant_weight, double epsilon, CKKSEncoder &encoder,
-                                           Encryptor &encryptor, Evaluator &evaluator, GaloisKeys &gal_keys,
-                                           vector<Ciphertext> & /*cipher_pool: host-memory reuse, not needed here*/, bool end)
+ConvPlan build_conv_plan(const TensorCipher &cnn_in, int co, int st, int fh, int fw, const vector<double> &data,
+                         const vector<double> &running_var, const vector<double> &constant_weight, double epsilon)
 {
+    ConvPlan P;
     const int ki = cnn_in.k(), hi = cnn_in.h(), wi = cnn_in.w(), ci = cnn_in.c(), ti = cnn_in.t(), pi = cnn_in.p(),
               logn = cnn_in.logn();
     if (st != 1 && st != 2)
@@ -106,25 +105,29 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
     if (st == 2 && (hi % 2 == 1 || wi % 2 == 1))
         throw std::invalid_argument("hi or wi is not even");
 
-    const int ho = hi / st, wo = wi / st, ko = ki * st;
+    P.ki = ki, P.hi = hi, P.wi = wi, P.ci = ci, P.ti = ti, P.pi = pi, P.logn = logn;
+    P.co = co, P.st = st, P.fh = fh, P.fw = fw;
+    P.ho = hi / st, P.wo = wi / st, P.ko = ki * st;
+    const int ho = P.ho, wo = P.wo, ko = P.ko;
     const long n = 1L << logn;
-    const int to = (co + ko * ko - 1) / (ko * ko);
-    const int po = copies_that_fit(n, (long)ko * ko * ho * wo * to);
-    const long q = (co + pi - 1) / pi;
+    P.to = (co + ko * ko - 1) / (ko * ko);
+    P.po = copies_that_fit(n, (long)ko * ko * ho * wo * P.to);
+    P.q = (co + pi - 1) / pi;
+    const int to = P.to;
+    const long q = P.q;
     if (n % pi != 0)
         throw std::out_of_range("n is not divisible by pi");
-    if (n % po != 0)
+    if (n % P.po != 0)
         throw std::out_of_range("n is not divisible by po");
     if ((long)ki * ki * hi * wi * ti * pi > n)
         throw std::out_of_range("ki^2 hi wi ti pi is larger than n");
-    if ((long)ko * ko * ho * wo * to * po > n)
+    if ((long)ko * ko * ho * wo * to * P.po > n)
         throw std::out_of_range("ko^2 ho wo to po is larger than n");
 
-    // ---- plaintext operands -------------------------------------------------------------------------------------
     // tap (i1, i2), output-channel group g: slot -> weight of (input channel at that slot, output channel = copy + pi g)
     // shifted by the tap, zero where the tap would read outside the image
     const long per_copy = n / pi, plane = (long)ki * ki * hi * wi, row = (long)ki * wi;
-    vector<vector<vector<double>>> tap_weights((std::size_t)(fh * fw), vector<vector<double>>((std::size_t)q, vector<double>((std::size_t)n, 0.0)));
+    P.tap_weights.assign((std::size_t)(fh * fw) * (std::size_t)q, vector<double>((std::size_t)n, 0.0));
     for (long slot = 0; slot < n; slot++)
     {
         const long r = slot % per_copy, copy = slot / per_copy;
@@ -150,25 +153,38 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
                     const long oc = copy + (long)pi * g;
                     if (oc >= co)
                         continue;
-                    tap_weights[(std::size_t)(i1 * fw + i2)][(std::size_t)g][(std::size_t)slot] =
+                    P.tap_weights[(std::size_t)((i1 * fw + i2) * q + g)][(std::size_t)slot] =
                         data[(std::size_t)((long)fh * fw * ci * oc + (long)fh * fw * ch + fw * i1 + i2)];
                 }
             }
         }
     }
     // output channel j: 1/sqrt(var + eps) * bn weight at the slots of channel j in the output layout, else 0
-    vector<vector<double>> select_one_vec((std::size_t)co, vector<double>((std::size_t)n, 0.0));
+    P.select_one_vec.assign((std::size_t)co, vector<double>((std::size_t)n, 0.0));
     for (int u = 0; u < to; u++)
         for (int v1 = 0; v1 < ko * ho; v1++)
             for (int v2 = 0; v2 < ko * wo; v2++)
             {
                 const int j = ko * ko * u + ko * (v1 % ko) + v2 % ko;
                 if (j < co)
-                    select_one_vec[(std::size_t)j][(std::size_t)((long)ko * ko * ho * wo * u + (long)ko * wo * v1 + v2)] =
+                    P.select_one_vec[(std::size_t)j][(std::size_t)((long)ko * ko * ho * wo * u + (long)ko * wo * v1 + v2)] =
                         constant_weight[(std::size_t)j] / std::sqrt(running_var[(std::size_t)j] + epsilon);
             }
+    return P;
+}
 
-    // ---- ciphertext side ----------------------------------------------------------------------------------------
+void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, TensorCipher &cnn_out, const ConvPlan &P,
+                                              CKKSEncoder &encoder, Encryptor &encryptor, Evaluator &evaluator,
+                                              GaloisKeys &gal_keys, bool end, bool named)
+{
+    if (cnn_in.k() != P.ki || cnn_in.h() != P.hi || cnn_in.w() != P.wi || cnn_in.c() != P.ci || cnn_in.t() != P.ti ||
+        cnn_in.p() != P.pi || cnn_in.logn() != P.logn)
+        throw std::invalid_argument("the convolution plan was built for a different input tensor");
+    const int ki = P.ki, hi = P.hi, wi = P.wi, ti = P.ti, pi = P.pi, logn = P.logn, co = P.co, fh = P.fh, fw = P.fw;
+    const int ko = P.ko, ho = P.ho, wo = P.wo, to = P.to, po = P.po;
+    const long n = 1L << logn, q = P.q;
+    const void *owner = named ? (const void *)&P : nullptr;
+
     Ciphertext ctxt_in = cnn_in.cipher(), ct_zero, temp, sum, total_sum, var;
 
     // the fh x fw shifted copies of the input
@@ -192,13 +208,13 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
     {
         // weighted sum over the filter taps
         Accumulator taps{ evaluator, sum };
-        for (int i1 = 0; i1 < fh; i1++)
-            for (int i2 = 0; i2 < fw; i2++)
-            {
-                evaluator.multiply_vector_reduced_error(ctxt_rot[(std::size_t)(i1 * fw + i2)],
-                                                        tap_weights[(std::size_t)(i1 * fw + i2)][(std::size_t)g], temp);
-                taps.add(temp);
-            }
+        for (int t = 0; t < fh * fw; t++)
+        {
+            temp = ctxt_rot[(std::size_t)t];
+            const std::size_t idx = (std::size_t)(t * q + g);
+            multiply_vector_named(evaluator, temp, owner, idx, 0, [&]() -> const vector<double> & { return P.tap_weights[idx]; });
+            taps.add(temp);
+        }
         evaluator.rescale_to_next_inplace(sum);
         var = sum;
 
@@ -238,7 +254,8 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
                          (int)((n / pi) * (j4 % pi) - j4 % ko - (long)(j4 / (ko * ko)) * ko * ko * ho * wo -
                                (long)((j4 % (ko * ko)) / ko) * ko * wo),
                          evaluator, gal_keys);
-            evaluator.multiply_vector_inplace_reduced_error(temp, select_one_vec[(std::size_t)j4]);
+            multiply_vector_named(evaluator, temp, owner, (std::size_t)j4, 1,
+                                  [&]() -> const vector<double> & { return P.select_one_vec[(std::size_t)j4]; });
             total.add(temp);
         }
     }
@@ -256,6 +273,17 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
         var = sum;
     }
     cnn_out = TensorCipher(logn, ko, ho, wo, co, to, po, var);
+}
+
+void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, int co, int st, int fh, int fw,
+                                           const vector<double> &data, vector<double> running_var,
+                                           vector<double> constant_weight, double epsilon, CKKSEncoder &encoder,
+                                           Encryptor &encryptor, Evaluator &evaluator, GaloisKeys &gal_keys,
+                                           vector<Ciphertext> & /*cipher_pool: host-memory reuse, not needed here*/, bool end)
+{
+    // the reference rebuilds the weight and mask vectors on every call; so does this entry point (nothing is cached)
+    ConvPlan plan = build_conv_plan(cnn_in, co, st, fh, fw, data, running_var, constant_weight, epsilon);
+    multiplexed_parallel_convolution_planned(cnn_in, cnn_out, plan, encoder, encryptor, evaluator, gal_keys, end, false);
 }
 
 void multiplexed_parallel_batch_norm_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, vector<double> bias,

@@ -47,6 +47,27 @@ public:
     void set_ciphertext(seal::Ciphertext cipher) { cipher_ = std::move(cipher); }
 };
 
+// Everything of a convolution that depends on the weights and the input tensor's packing only: the fh*fw*q shifted
+// weight vectors and the co select-and-scale masks (cnn_seal.cpp:329-399 of the reference builds them inside every
+// call).  Built once per layer, a plan also names those vectors for the engine's plaintext cache (common/cached.h).
+struct ConvPlan
+{
+    int ki, hi, wi, ci, ti, pi, logn; // input packing
+    int co, st, fh, fw;
+    int ko, ho, wo, to, po;
+    long q;
+    std::vector<std::vector<double>> tap_weights;    // [(i1 * fw + i2) * q + g][slot]
+    std::vector<std::vector<double>> select_one_vec; // [output channel][slot]
+};
+ConvPlan build_conv_plan(const TensorCipher &cnn_in, int co, int st, int fh, int fw, const std::vector<double> &data,
+                         const std::vector<double> &running_var, const std::vector<double> &constant_weight, double epsilon);
+// named: let the engine keep the plan's encoded vectors resident (the plan must then outlive the evaluator's use of
+// it, or evaluator.forget_cached(&plan) must be called first)
+void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, TensorCipher &cnn_out, const ConvPlan &plan,
+                                              seal::CKKSEncoder &encoder, seal::Encryptor &encryptor,
+                                              seal::Evaluator &evaluator, seal::GaloisKeys &gal_keys, bool end = false,
+                                              bool named = true);
+
 void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, int co, int st, int fh, int fw,
                                            const std::vector<double> &data, std::vector<double> running_var,
                                            std::vector<double> constant_weight, double epsilon, seal::CKKSEncoder &encoder,

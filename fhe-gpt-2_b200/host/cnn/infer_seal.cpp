@@ -1,5 +1,6 @@
 // cnn/infer_seal.cpp - see infer_seal.h.
 #include "cnn/infer_seal.h"
+#include "common/cached.h"
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -147,6 +148,7 @@ ResNetCifar10::ResNetCifar10(std::size_t layer_num, ResNetParameters parameters,
         w_.bn_running_var.size() != layers || w_.bn_weight.size() != layers || w_.linear_weight.size() != 640 ||
         w_.linear_bias.size() != 10)
         throw std::invalid_argument("parameter lists do not match the network depth");
+    conv_plans_.resize(layers);
     for (long i = 0; i < comp_no; i++)
     {
         minicomp::Tree tr;
@@ -167,6 +169,9 @@ ResNetCifar10::ResNetCifar10(std::size_t layer_num, ResNetParameters parameters,
 
 ResNetCifar10::~ResNetCifar10()
 {
+    for (auto &p : conv_plans_)
+        if (p)
+            forget_named(evaluator_, p.get());
     for (auto *b : boot_)
         delete b;
 }
@@ -234,7 +239,6 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
         throw std::logic_error("ResNetCifar10::prepare() must be called after the Galois keys were created");
     const int fh = 3, fw = 3;
     const double epsilon = 0.00001;
-    vector<Ciphertext> cipher_pool; // host-buffer reuse in the reference; not needed on the device
 
     auto t_prev = std::chrono::high_resolution_clock::now();
     auto log_op = [&](int op, const TensorCipher &t) {
@@ -260,9 +264,13 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     t_prev = std::chrono::high_resolution_clock::now();
 
     auto conv = [&](int stage, int co, int st) {
-        multiplexed_parallel_convolution_seal(cnn, cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
-                                              w_.bn_running_var[(std::size_t)stage], w_.bn_weight[(std::size_t)stage], epsilon,
-                                              encoder_, encryptor_, evaluator_, gal_keys_, cipher_pool);
+        // weights and masks of a layer are the same for every image: built once, their encodings stay in HBM
+        std::unique_ptr<ConvPlan> &plan = conv_plans_[(std::size_t)stage];
+        if (!plan)
+            plan = std::make_unique<ConvPlan>(build_conv_plan(cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
+                                                              w_.bn_running_var[(std::size_t)stage],
+                                                              w_.bn_weight[(std::size_t)stage], epsilon));
+        multiplexed_parallel_convolution_planned(cnn, cnn, *plan, encoder_, encryptor_, evaluator_, gal_keys_);
         log_op(0, cnn);
     };
     auto bn = [&](int stage) {

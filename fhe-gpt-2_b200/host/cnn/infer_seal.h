@@ -11,6 +11,7 @@
 #pragma once
 #include "cnn/cnn_seal.h"
 #include <functional>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -92,5 +93,6 @@ private:
     std::vector<int> deg_{ 15, 15, 27 };
     std::vector<minicomp::Tree> tree_;
     Bootstrapper *boot_[3];
+    std::vector<std::unique_ptr<ConvPlan>> conv_plans_; // one per convolution, built at its first use
     bool prepared_ = false;
 };

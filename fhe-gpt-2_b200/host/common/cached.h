@@ -1,0 +1,34 @@
+// common/cached.h - "multiply by a slot vector that has a name".
+//
+// The reference encodes every plaintext operand at run time, every time (evaluator.h:1270-1278): 299 diagonals per
+// bootstrap, 9q + co masks per convolution.  Those vectors are parameters of the network.  Call sites that can name
+// their vector (owner object, index, variant) go through this helper; on the engine the encoded plaintext then stays
+// resident in HBM and is reused when the same vector meets the same level and scale again (seal::Evaluator::
+// multiply_vector_inplace_cached), on stock SEAL it is the reference's multiply_vector_inplace_reduced_error.
+#pragma once
+#include "seal/seal.h"
+#include <cstdint>
+
+template <class Make>
+inline void multiply_vector_named(seal::Evaluator &evaluator, seal::Ciphertext &encrypted, const void *owner,
+                                  std::uint64_t index, std::uint64_t variant, Make &&make)
+{
+#ifdef B200CKKS_FACADE
+    evaluator.multiply_vector_inplace_cached(encrypted, owner, index, variant, make);
+#else
+    (void)owner;
+    (void)index;
+    (void)variant;
+    evaluator.multiply_vector_inplace_reduced_error(encrypted, make());
+#endif
+}
+
+inline void forget_named(seal::Evaluator &evaluator, const void *owner)
+{
+#ifdef B200CKKS_FACADE
+    evaluator.forget_cached(owner);
+#else
+    (void)evaluator;
+    (void)owner;
+#endif
+}

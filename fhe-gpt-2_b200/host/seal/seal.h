@@ -37,6 +37,7 @@
 #include <complex>
 #include <cstdint>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -45,6 +46,7 @@
 #include <stdexcept>
 #include <string>
 #include <type_traits>
+#include <unordered_map>
 #include <vector>
 
 #define SEAL_NODISCARD [[nodiscard]]
@@ -1097,6 +1099,7 @@ namespace seal
     {
         std::atomic<std::uint64_t> key_switch_rotate{ 0 }, key_switch_relin{ 0 }, rescale{ 0 }, multiply{ 0 },
             multiply_plain{ 0 }, encode_vector{ 0 }, add{ 0 }, mod_switch{ 0 }, scalar_op{ 0 };
+        std::atomic<std::uint64_t> cache_hits{ 0 }, cache_misses{ 0 }; // multiply_vector_inplace_cached
         // the same events by coeff_modulus_size of the ciphertext operand: [0] key switches (rotate + relinearize),
         // [1] rescales, [2] vector encode + multiply_plain, [3] ct x ct multiplications, [4] scalar ops, [5] add/sub
         std::atomic<std::uint64_t> by_limbs[6][64] = {};
@@ -1543,6 +1546,79 @@ namespace seal
         }
 
         // ---- engine extensions
+        // multiply_vector_inplace_reduced_error for a slot vector the caller can NAME: (owner, index, variant)
+        // identifies the vector, make() produces it.  The encoded plaintext (top-level encode dropped to the
+        // ciphertext's level at the ciphertext's scale, exactly as evaluator.h:1270-1278) is kept in HBM and
+        // reused whenever the same vector meets the same level and scale again - the bootstrapping diagonals and
+        // the convolution weight masks are parameters of the network, encoded once instead of once per use.
+        // Results are identical to the uncached member.  owner == nullptr disables the cache.
+        template <class Make>
+        void multiply_vector_inplace_cached(
+            Ciphertext &encrypted, const void *owner, std::uint64_t index, std::uint64_t variant, Make &&make)
+        {
+            stats_.encode_vector++;
+            stats_.hit(2, encrypted.coeff_modulus_size());
+            if (!owner || !cache_budget_bytes())
+            {
+                Plaintext plain;
+                encoder_.encode_top_dropped(make(), (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
+                multiply_plain_inplace(encrypted, plain);
+                return;
+            }
+            std::uint64_t scale_bits;
+            static_assert(sizeof(double) == sizeof(std::uint64_t), "");
+            double sc = encrypted.scale();
+            std::memcpy(&scale_bits, &sc, sizeof(sc));
+            PlainKey key{ owner, index, variant, scale_bits, (int)encrypted.coeff_modulus_size() };
+            const Plaintext *hit = nullptr;
+            {
+                std::shared_lock<std::shared_mutex> rl(cache_mu_);
+                auto it = plain_cache_.find(key);
+                if (it != plain_cache_.end())
+                    hit = it->second.get();
+            }
+            if (!hit)
+            {
+                auto plain = std::make_unique<Plaintext>();
+                encoder_.encode_top_dropped(make(), key.limbs, sc, *plain);
+                std::uint64_t bytes = (std::uint64_t)key.limbs * (8ull << context_.impl()->log_n);
+                std::unique_lock<std::shared_mutex> wl(cache_mu_);
+                if (cache_bytes_ + bytes > cache_budget_bytes())
+                { // over budget: use it once, do not keep it
+                    wl.unlock();
+                    multiply_plain_inplace(encrypted, *plain);
+                    return;
+                }
+                context_.sync(); // other host threads (streams) may pick the plaintext up from now on
+                auto ins = plain_cache_.emplace(key, std::move(plain));
+                hit = ins.first->second.get();
+                if (ins.second)
+                {
+                    cache_bytes_ += bytes;
+                    stats_.cache_misses++;
+                }
+            }
+            else
+                stats_.cache_hits++;
+            multiply_plain_inplace(encrypted, *hit);
+        }
+        // drop every cached plaintext of `owner` (call before the owner's storage is released or rewritten)
+        void forget_cached(const void *owner) const
+        {
+            std::unique_lock<std::shared_mutex> wl(cache_mu_);
+            for (auto it = plain_cache_.begin(); it != plain_cache_.end();)
+                if (it->first.owner == owner)
+                {
+                    cache_bytes_ -= (std::uint64_t)it->first.limbs * (8ull << context_.impl()->log_n);
+                    it = plain_cache_.erase(it);
+                }
+                else
+                    ++it;
+        }
+        SEAL_NODISCARD std::uint64_t cached_plaintext_bytes() const
+        {
+            return cache_bytes_;
+        }
         // Bootstrapper::modraise_inplace (ckks_bootstrapping/Bootstrapper.cpp:2894-2948) as one fused launch
         void modraise_inplace(Ciphertext &encrypted) const
         {
@@ -1646,9 +1722,42 @@ namespace seal
             }
         }
 
+        struct PlainKey
+        {
+            const void *owner;
+            std::uint64_t index, variant, scale_bits;
+            int limbs;
+            bool operator==(const PlainKey &o) const
+            {
+                return owner == o.owner && index == o.index && variant == o.variant && scale_bits == o.scale_bits &&
+                       limbs == o.limbs;
+            }
+        };
+        struct PlainKeyHash
+        {
+            std::size_t operator()(const PlainKey &k) const
+            {
+                std::uint64_t h = (std::uint64_t)(std::uintptr_t)k.owner;
+                for (std::uint64_t v : { k.index, k.variant, k.scale_bits, (std::uint64_t)k.limbs })
+                    h = (h ^ v) * 0x9E3779B97F4A7C15ull + (h >> 29);
+                return (std::size_t)h;
+            }
+        };
+        static std::uint64_t cache_budget_bytes()
+        {
+            static const std::uint64_t b = [] {
+                const char *e = std::getenv("B200CKKS_PLAIN_CACHE_GIB");
+                return (std::uint64_t)((e ? std::atof(e) : 32.0) * 1073741824.0);
+            }();
+            return b;
+        }
+
         SEALContext context_;
         CKKSEncoder &encoder_;
         mutable EvaluatorStats stats_;
+        mutable std::unordered_map<PlainKey, std::unique_ptr<Plaintext>, PlainKeyHash> plain_cache_;
+        mutable std::shared_mutex cache_mu_;
+        mutable std::uint64_t cache_bytes_ = 0;
     };
 
     namespace util

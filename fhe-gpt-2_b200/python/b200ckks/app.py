@@ -205,6 +205,11 @@ class Session:
         self.app.ck(self.app.L.bka_session_key_residency(self.h, C.byref(b), C.byref(g)))
         return b.value, g.value
 
+    def plain_cache(self):
+        b, h, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self.app.ck(self.app.L.bka_session_plain_cache(self.h, C.byref(b), C.byref(h), C.byref(m)))
+        return dict(bytes=b.value, hits=h.value, misses=m.value)
+
     # -- ciphertexts
     def encrypt(self, values, scale, limbs=0):
         v = np.asarray(values)

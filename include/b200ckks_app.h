@@ -61,6 +61,9 @@ int bka_session_sync(bka_session_t s);
 int bka_session_stats(bka_session_t s, uint64_t counts_out[9], int reset);
 /* bytes of Galois keys resident in HBM and number of key generations so far (engine backend; 0 otherwise) */
 int bka_session_key_residency(bka_session_t s, uint64_t *bytes_out, uint64_t *generated_out);
+/* encoded plaintext operands kept resident in HBM (bootstrapping diagonals, convolution weight masks; see
+ * host/common/cached.h): bytes, and hits / misses of the cache since the session was created */
+int bka_session_plain_cache(bka_session_t s, uint64_t *bytes_out, uint64_t *hits_out, uint64_t *misses_out);
 
 /* ---- ciphertexts ------------------------------------------------------------------------------------------------ */
 /* encode at the top level with `scale`, encrypt with the public key, mod_switch_to `limbs` (0 = stay on top) */

@@ -72,7 +72,7 @@ def test_bootstrap_n65536_counts_and_precision(big_session, logn, rot, mulplain)
 
 
 
-def test_resnet20_end_to_end_matches_model_and_reference_trajectory(app):
+def test_resnet20_end_to_end_matches_model_and_reference_trajectory(big_session):
     """config 1 of BASELINE.json (./cnn 20 10 0 0) on a synthetic image with random-init weights: decrypted logits
     against the float64 model of the same network, and the stage-by-stage (operation, remaining level, scale) trace
     against the reference's committed run log."""
@@ -81,7 +81,7 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(app):
 
     from b200ckks import synthetic
 
-    s = app.session(16, cases.BOOT_BITS, hamming_weight=192)
+    s = big_session       # same parameter set; its bootstrapping keys are reused
     w = synthetic.random_weights(20, seed=0)
     net = s.resnet(20, w)
     img = synthetic.synthetic_image(0)
@@ -102,4 +102,3 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(app):
     assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3
     kb, _ = s.key_residency()
     assert kb < 100 * 2 ** 30            # level-pruned keys fit one B200 (the reference's layout needs 275 GiB)
-    s.close()
