@@ -8,6 +8,7 @@
 #include "engine.h"
 #include <cmath>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 
@@ -181,6 +182,12 @@ namespace bk
         tables.itw = d_itw;
         tables.primes = d_primes;
         tables.log_n = log_n;
+        tables.wide = 1;
+        for (uint64_t q : primes)
+            if (q >> 57)
+                tables.wide = 0; // the unreduced forward butterflies need 66 q < 2^64
+        if (std::getenv("B200CKKS_CLASSIC_NTT"))
+            tables.wide = 0;
     }
 
     Context::~Context()

@@ -119,6 +119,7 @@ struct LdModRaise
 // ---------------------------------------------------------------- forward block-pass stores
 struct StPlain
 {
+    static constexpr bool RAW = false;
     __device__ __forceinline__ bool skip(int) const { return false; }
     u64 *dst;
     JobMap map;
@@ -136,6 +137,7 @@ struct StPlain
 // LdKsDigit; the I == J job is skipped (its operand is the NTT-form input itself).
 struct StKsDigit
 {
+    static constexpr bool RAW = true; // k_ks_mac multiplies whatever 64-bit representative it is given
     u64 *dst;
     size_t n;
     int l, I0, special_prime;
@@ -155,6 +157,7 @@ struct StKsDigit
 // Rescale tail (rns.cpp:786-806): dst[p][i] = (x[p][i] - NTT_i(t)) * q_last^-1 mod q_i.
 struct StRescale
 {
+    static constexpr bool RAW = false;
     __device__ __forceinline__ bool skip(int) const { return false; }
     const u64 *x;  // [polys][limbs_in][N]
     u64 *dst;      // [polys][limbs_out][N]
@@ -180,6 +183,7 @@ struct StRescale
 // or nothing.
 struct StModDown
 {
+    static constexpr bool RAW = false;
     __device__ __forceinline__ bool skip(int) const { return false; }
     const u64 *acc;  // [2][l+1][N]
     u64 *dst;        // [2][l][N]

@@ -27,6 +27,7 @@ struct NttTables
     const ulonglong2 *itw; // [n_primes][N] inverse, same indexing
     const PrimeDev *primes;
     int log_n;
+    int wide; // every modulus is below 2^57: forward transforms may use the unreduced butterflies below
 };
 
 // ---- butterflies ---------------------------------------------------------------------------
@@ -44,6 +45,43 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64
     u64 d = X + two_q - Y;
     X = s - (s >= two_q ? two_q : 0ull);
     Y = mul_shoup_lazy(d, w.x, w.y, q);
+}
+
+// Unreduced forward butterfly for moduli below 2^57.  Nothing is reduced between stages: with t in [0,4q)
+//   X' = X + t,   Y' = X + 4q - t,
+// both outputs grow by at most 4q per stage, so 16 stages starting below 2q stay below 66q < 2^64.  The Shoup
+// quotient is taken from three of the four 32x32 partial products (x1 w1 + hi(x1 w0) + hi(x0 w1)); it undershoots
+// floor(x ws / 2^64) by at most 2, hence t = x w - quot q lies in [0,4q) instead of [0,2q).  Residues mod q are
+// unaffected, and every value is brought back to [0,q) before it leaves the transform.
+__device__ __forceinline__ void ct_bfly_wide(u64 &X, u64 &Y, ulonglong2 w, u64 neg_q, u64 four_q)
+{
+    const unsigned y0 = (unsigned)Y, y1 = (unsigned)(Y >> 32);
+    const unsigned s0 = (unsigned)w.y, s1 = (unsigned)(w.y >> 32);
+    const u64 quot = (u64)y1 * s1 + __umulhi(y1, s0) + __umulhi(y0, s1);
+    const u64 t = Y * w.x + quot * neg_q;
+    const u64 x = X;
+    X = x + t;
+    Y = x + four_q - t;
+}
+
+template <int LOGS>
+__device__ __forceinline__ void fwd_radix_wide(u64 *x, const ulonglong2 *__restrict__ tw, unsigned idx0, u64 neg_q, u64 four_q)
+{
+    constexpr int S = 1 << LOGS;
+#pragma unroll
+    for (int j = 0; j < LOGS; j++)
+    {
+        const int half = S >> (j + 1);
+#pragma unroll
+        for (int k = 0; k < S; k++)
+        {
+            if (!(k & half))
+            {
+                ulonglong2 w = __ldg(tw + ((idx0 << j) + (unsigned)(k >> (LOGS - j))));
+                ct_bfly_wide(x[k], x[k + half], w, neg_q, four_q);
+            }
+        }
+    }
 }
 
 // LOGS forward stages on S = 2^LOGS registers.  Stage j pairs (k, k + S/2^(j+1)); its twiddle
@@ -143,7 +181,12 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = ld.load(job, (t + TR * k) * 256 + col, pd);
-    fwd_radix<4>(x, tw, 1u, pd.q, pd.two_q);
+    const bool wide = T.wide != 0;
+    const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
+    if (wide)
+        fwd_radix_wide<4>(x, tw, 1u, neg_q, four_q);
+    else
+        fwd_radix<4>(x, tw, 1u, pd.q, pd.two_q);
     if (LOG2 > 0)
     {
 #pragma unroll
@@ -161,7 +204,12 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
         }
 #pragma unroll
         for (int g = 0; g < G; g++)
-            fwd_radix<LOG2>(x + g * S2, tw, 16u + (unsigned)(t * G + g), pd.q, pd.two_q);
+        {
+            if (wide)
+                fwd_radix_wide<LOG2>(x + g * S2, tw, 16u + (unsigned)(t * G + g), neg_q, four_q);
+            else
+                fwd_radix<LOG2>(x + g * S2, tw, 16u + (unsigned)(t * G + g), pd.q, pd.two_q);
+        }
         u64 *o = out + (size_t)job * n;
 #pragma unroll
         for (int g = 0; g < G; g++)
@@ -211,7 +259,12 @@ __global__ void __launch_bounds__(256) k_fwd_blocks(const u64 *__restrict__ in, 
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = src[t + 16 * k];
-    fwd_radix<4>(x, tw, B, pd.q, pd.two_q);
+    const bool wide = T.wide != 0;
+    const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
+    if (wide)
+        fwd_radix_wide<4>(x, tw, B, neg_q, four_q);
+    else
+        fwd_radix<4>(x, tw, B, pd.q, pd.two_q);
 #pragma unroll
     for (int k = 0; k < 16; k++)
         s[swz(t + 16 * k)] = x[k];
@@ -219,7 +272,19 @@ __global__ void __launch_bounds__(256) k_fwd_blocks(const u64 *__restrict__ in, 
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = s[swz(16 * t + k)];
-    fwd_radix<4>(x, tw, 16u * B + (unsigned)t, pd.q, pd.two_q);
+    if (wide)
+    {
+        fwd_radix_wide<4>(x, tw, 16u * B + (unsigned)t, neg_q, four_q);
+        // back to [0,q) unless the consumer takes unreduced words (Store::RAW: the key-switch inner product)
+        if (!Store::RAW)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                x[k] = barrett64(x[k], pd);
+        }
+    }
+    else
+        fwd_radix<4>(x, tw, 16u * B + (unsigned)t, pd.q, pd.two_q);
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = st.pre(job, blk, t, k, x[k], pd);
