@@ -102,3 +102,38 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(big_session)
     assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3
     kb, _ = s.key_residency()
     assert kb < 100 * 2 ** 30            # level-pruned keys fit one B200 (the reference's layout needs 275 GiB)
+
+
+GPT2_BITS = [49] + [46] * 21 + [49] * 14 + [60]     # gpt2 util.h:22-27 (INIT macro): 37 primes, 60-bit special prime
+
+
+def test_gpt2_chain_full_slot_bootstrap_and_rotations(app):
+    """config 5's fixture (gpt2_ckks/run/run_approx_test.cpp:704-737 SingleBootstrap): INIT parameters, full-slot
+    Bootstrapper (logn = 15), bootstrap_3 on a ciphertext switched down to one limb, plus the packed-matmul primitives
+    the GPT-2 operators are made of (rotate / multiply_vector / multiply+relin+rescale at that chain)."""
+    s = app.session(16, GPT2_BITS, hamming_weight=192)
+    rng = np.random.default_rng(5)
+    # (a) rotate-and-sum with a mask, the inner loop of row_matrix_multiplication_seal / quickSum (MatrixMul.cpp:118, Fold.cpp:20)
+    x, m = rng.uniform(-1, 1, s.slots), rng.uniform(-1, 1, s.slots)
+    s.add_rotation_steps([1, 2, 4, 8, 2048])
+    ct = s.encrypt(x, 2.0 ** 46, limbs=8)
+    acc = ct.clone()
+    want = x.copy()
+    for st in (1, 2, 4, 8):
+        r = acc.clone()
+        s.rotate(r, st)
+        s.add_reduced_error(acc, r)
+        want = want + np.roll(want, -st)
+    s.multiply_vector_rescale(acc, m)
+    assert np.abs(s.decrypt(acc).real - want * m).max() < 1e-5
+    sq = acc.clone()
+    s.multiply_relin_rescale(sq, acc)
+    assert np.abs(s.decrypt(sq).real - (want * m) ** 2).max() < 1e-4
+    # (b) full-slot bootstrapping of a complex message (bootstrap_3 -> bootstrap_full_3)
+    z = rng.uniform(-1, 1, s.slots) + 1j * rng.uniform(-1, 1, s.slots)
+    boot = s.bootstrapper(15, total_level=35)
+    out = boot.bootstrap(s.encrypt(z, 2.0 ** 46, limbs=1), real_message=False)
+    size, limbs, scale = out.info()
+    assert limbs == 22 and scale == 2.0 ** 46          # 35 levels - 14 consumed: remaining_level 21
+    assert np.abs(s.decrypt(out) - z).max() < 2e-4
+    s.close()

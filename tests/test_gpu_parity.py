@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 import refseal
-from util import (CNN_BITS, SMALL_BITS, assert_ct_equal, rand_slots, ref_fresh_ct, to_engine)
+from util import (CNN_BITS, GPT2_BITS, SMALL_BITS, assert_ct_equal, rand_slots, ref_fresh_ct, to_engine)
 
 pytestmark = pytest.mark.gpu
 
@@ -401,3 +401,36 @@ def test_cnn_parameters_ks_chunk_invariance(cnn):
         eng.rotate_vector_inplace(e2, 1, gk)
         assert_ct_equal(e2, ref, a, f"rotate chunk={chunk}")
     eng.set_ks_chunk(4)
+
+
+# ---- N = 2^16, the GPT-2 parameter set (gpt2 util.h:22-27: 49 | 46x21 | 49x14 | 60, 37 primes) ----------------
+# the 60-bit special prime is above 2^57, so this chain runs the classic (reduced) forward butterflies
+@pytest.mark.parametrize("limbs", [36, 22, 2])
+def test_gpt2_parameters_keyswitch_rescale(limbs):
+    import b200ckks as bk
+
+    ref = refseal.RefSeal(16, GPT2_BITS, hamming_weight=192, seed=9)
+    eng = bk.Context(16, ref.primes)
+    rk = eng.upload_kskey(ref.relin_key(), max_limbs=limbs)
+    ref.make_galois_keys([3])
+    gk = eng.galois_keys()
+    elt = ref.galois_elt(3)
+    gk.set(elt, eng.upload_kskey(ref.galois_key(elt), max_limbs=limbs))
+    rng = np.random.default_rng(limbs)
+    scale = 2.0 ** 46
+    a = ref_fresh_ct(ref, rand_slots(rng, 32768, complex_=True), limbs, scale)
+    b = ref_fresh_ct(ref, rand_slots(rng, 32768), limbs, scale)
+    ea, eb = to_engine(eng, ref, a), to_engine(eng, ref, b)
+    ref.op("rotate", a, iarg=3)
+    eng.rotate_vector_inplace(ea, 3, gk)
+    assert_ct_equal(ea, ref, a, "rotate")
+    ref.op("multiply", a, b)
+    eng.multiply_inplace(ea, eb)
+    ref.op("relinearize", a)
+    eng.relinearize_inplace(ea, rk)
+    assert_ct_equal(ea, ref, a, "multiply + relinearize")
+    ref.op("rescale", a)
+    eng.rescale_to_next_inplace(ea)
+    assert_ct_equal(ea, ref, a, "rescale")
+    eng.close()
+    ref.close()
