@@ -325,7 +325,14 @@ namespace bk
             return;
         dim3 grid(16, jobs);
         ProfScope ps(c, s, TAG_FWD_COLS, jobs);
-        BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+        if (c.tables.wide)
+        {
+            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+        }
+        else
+        {
+            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+        }
         c.count();
     }
     template <class Store>
@@ -335,7 +342,10 @@ namespace bk
             return;
         dim3 grid((unsigned)(c.n >> 12), jobs);
         ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
-        k_fwd_blocks<Store><<<grid, 256, 0, s>>>(in, st, c.tables);
+        if (c.tables.wide)
+            k_fwd_blocks<Store, true><<<grid, 256, 0, s>>>(in, st, c.tables);
+        else
+            k_fwd_blocks<Store, false><<<grid, 256, 0, s>>>(in, st, c.tables);
         c.count();
     }
     template <class Load>
@@ -443,6 +453,19 @@ namespace bk
         return std::fabs(a - b) < std::numeric_limits<double>::epsilon() * f;
     }
 
+    // threads per CTA of k_ks_mac: 128-thread CTAs (two coefficients per thread) make a 4-modulus chunk 1024 CTAs, all
+    // resident at once on 148 SMs (7 per SM at 66 registers) - 256-thread CTAs left a nearly empty second wave
+    static int ks_mac_threads()
+    {
+        static const int t = [] {
+            const char *e = std::getenv("B200CKKS_KS_MAC_THREADS");
+            int v = e ? std::atoi(e) : 128;
+            return (v == 64 || v == 128 || v == 256) ? v : 128;
+        }();
+        return t;
+    }
+#define KS_MAC_THREADS ks_mac_threads()
+
     // ------------------------------------------------------------------------------- key switch
     // Evaluator::switch_key_inplace (evaluator.cpp:2281-2525) with the Galois permutation of
     // apply_galois_inplace (:2191-2207) fused in.  target: [l][N] NTT form.  If perm != null the
@@ -478,11 +501,11 @@ namespace bk
             launch_fwd_cols(c, s, ld, inter.p, nI * l);
             StKsDigit st{ inter.p, n, l, I0, sp };
             launch_fwd_blocks(c, s, inter.p, st, nI * l);
-            KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs };
-            dim3 grid((unsigned)((n / 2 + 255) / 256), nI);
+            KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs, 0 };
+            dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
             {
                 ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
-                k_ks_mac<<<grid, 256, 0, s>>>(a, c.tables);
+                k_ks_mac<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
             }
             c.count();
         }
@@ -495,6 +518,66 @@ namespace bk
             LdDivRound ld2{ tlast.p, n, l, c.primes[sp] };
             launch_fwd_cols(c, s, ld2, inter.p, 2 * l);
             StModDown st2{ acc.p, out, base0, base1, perm, c.inv_last(sp), n, l };
+            launch_fwd_blocks(c, s, inter.p, st2, 2 * l);
+        }
+    }
+
+    // Hoisted rotations (Halevi-Shoup): one decomposition + digit NTT of c1 serves every automorphism of the set; per
+    // element only the inner product (digits read through the Galois table), ModDown and the gathered c0 remain.
+    // The digits are those of c1, not of sigma(c1): a valid decomposition of sigma(c1) with the same bounds, but NOT
+    // the residues Evaluator::rotate_vector produces (evaluator.cpp:2191-2214 permutes first) - results decrypt to the
+    // same values up to key-switching noise, limbs differ.  Opt-in through bk_rotate_hoisted only.
+    static void key_switch_hoisted(Context &c, cudaStream_t s, const bk_ct_s *in, int count, const uint32_t *const *perms,
+                                   const bk_kskey_t *keys, u64 *const *outs)
+    {
+        const int l = in->limbs;
+        for (int k = 0; k < count; k++)
+            if (keys[k]->digits < l || keys[k]->klimbs < l)
+                throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (key pruned below "
+                                            "this level)");
+        const size_t n = c.n;
+        const int sp = c.n_primes - 1;
+        const int chunk = std::max(1, std::min(c.ks_chunk, l + 1));
+        const u64 *c0 = in->d, *c1 = in->d + (size_t)l * n;
+        Scratch ttarget(s, (size_t)l * n);
+        Scratch inter(s, (size_t)std::max(chunk * l, 2 * l) * n);
+        Scratch acc(s, (size_t)count * 2 * (l + 1) * n);
+        Scratch tlast(s, 2 * n);
+        {
+            LdInvPlain ld{ c1, limb_map(l), n, nullptr };
+            launch_inv_blocks(c, s, ld, inter.p, l);
+            StInvPlain st{ ttarget.p, limb_map(l), n };
+            launch_inv_cols(c, s, inter.p, st, l);
+        }
+        for (int I0 = 0; I0 <= l; I0 += chunk)
+        {
+            int nI = std::min(chunk, l + 1 - I0);
+            LdKsDigit ld{ ttarget.p, c.d_primes, n, l, I0, sp };
+            launch_fwd_cols(c, s, ld, inter.p, nI * l);
+            StKsDigit st{ inter.p, n, l, I0, sp };
+            launch_fwd_blocks(c, s, inter.p, st, nI * l);
+            for (int k = 0; k < count; k++)
+            {
+                KsMacArgs a{ inter.p, c1, perms[k], keys[k]->d, acc.p + (size_t)k * 2 * (l + 1) * n, n, l, I0, sp,
+                             keys[k]->klimbs, 1 };
+                dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
+                {
+                    ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
+                    k_ks_mac<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                }
+                c.count();
+            }
+        }
+        for (int k = 0; k < count; k++)
+        {
+            u64 *ak = acc.p + (size_t)k * 2 * (l + 1) * n;
+            LdInvLimbOf ld{ ak, n, l + 1, l, sp };
+            launch_inv_blocks(c, s, ld, inter.p, 2);
+            StInvAddHalf st{ tlast.p, n, sp };
+            launch_inv_cols(c, s, inter.p, st, 2);
+            LdDivRound ld2{ tlast.p, n, l, c.primes[sp] };
+            launch_fwd_cols(c, s, ld2, inter.p, 2 * l);
+            StModDown st2{ ak, outs[k], c0, nullptr, perms[k], c.inv_last(sp), n, l };
             launch_fwd_blocks(c, s, inter.p, st2, 2 * l);
         }
     }
@@ -1431,6 +1514,47 @@ extern "C"
         rotate_internal(*ctx, a, steps, gk);
         BK_END
     }
+    bk_status bk_apply_galois_hoisted(bk_context_t ctx, bk_ct_t in, const uint32_t *galois_elts, int count, bk_gkeys_t gk,
+                                      bk_ct_t *outs)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        check_ct(ctx, in, "encrypted");
+        if (!gk || gk->ctx != ctx)
+            throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        if (in->size > 2)
+            throw std::invalid_argument("encrypted size must be 2");
+        if (!in->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (count < 1 || count > 256)
+            throw std::invalid_argument("count is out of range");
+        std::vector<const uint32_t *> perms(count);
+        std::vector<bk_kskey_t> keys(count);
+        std::vector<u64 *> bufs(count);
+        const int l = in->limbs;
+        const size_t words = (size_t)2 * l * c.n;
+        for (int k = 0; k < count; k++)
+        {
+            if (!(galois_elts[k] & 1) || galois_elts[k] >= 2 * c.n)
+                throw std::invalid_argument("Galois element is not valid");
+            keys[k] = find_gkey(gk, galois_elts[k]);
+            if (!keys[k])
+                throw std::invalid_argument("Galois key not present");
+            if (!outs[k] || outs[k]->ctx != ctx || outs[k] == in)
+                throw std::invalid_argument("destination is not valid");
+            perms[k] = c.galois_table(galois_elts[k]);
+        }
+        for (int k = 0; k < count; k++)
+            bufs[k] = alloc_words(c, words);
+        key_switch_hoisted(c, c.stream(), in, count, perms.data(), keys.data(), bufs.data());
+        for (int k = 0; k < count; k++)
+        {
+            adopt(outs[k], bufs[k], words, 2, l);
+            outs[k]->scale = in->scale;
+            outs[k]->ntt = true;
+        }
+        BK_END
+    }
     bk_status bk_complex_conjugate_inplace(bk_context_t ctx, bk_ct_t a, bk_gkeys_t gk)
     {
         BK_TRY
@@ -1487,6 +1611,42 @@ extern "C"
             a->d, p->d, c.d_primes, c.log_n, a->limbs, a->size, 1);
         c.count();
         a->scale = new_scale;
+        BK_END
+    }
+
+    // acc <- acc + a (*) p in one pass (multiply_plain followed by add_inplace: evaluator.cpp:1891-1930, :103-163).
+    // An empty acc (size 0) is initialised with the product.  Residues equal those of the two separate calls.
+    bk_status bk_multiply_plain_accumulate(bk_context_t ctx, bk_ct_t acc, bk_ct_t a, bk_pt_t p)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        plain_check(ctx, a, p);
+        if (!acc || acc->ctx != ctx || acc == a)
+            throw std::invalid_argument("destination is not valid for encryption parameters");
+        double new_scale = a->scale * p->scale;
+        if (!c.scale_in_bounds(new_scale, a->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        const bool first = acc->size == 0 || !acc->d;
+        if (!first)
+        {
+            if (acc->size != a->size || acc->limbs != a->limbs)
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+            if (!acc->ntt)
+                throw std::invalid_argument("NTT form mismatch");
+        }
+        else
+            ensure_ct(acc, a->size, a->limbs, false);
+        const size_t total2 = (size_t)a->size * a->limbs * c.n / 2;
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
+        if (first)
+            k_mul_plain_acc<true><<<c.ew_grid(total2), 256, 0, c.stream()>>>(acc->d, a->d, p->d, c.d_primes, c.log_n,
+                                                                                  a->limbs, a->size);
+        else
+            k_mul_plain_acc<false><<<c.ew_grid(total2), 256, 0, c.stream()>>>(acc->d, a->d, p->d, c.d_primes, c.log_n,
+                                                                                   a->limbs, a->size);
+        c.count();
+        acc->scale = new_scale;
+        acc->ntt = true;
         BK_END
     }
 

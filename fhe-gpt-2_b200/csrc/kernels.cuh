@@ -293,6 +293,7 @@ struct KsMacArgs
     u64 *acc;              // [2][l+1][N]
     size_t n;
     int l, I0, special_prime, klimbs;
+    int gather_digits;     // hoisted rotations: the digits were computed before the automorphism, read them through perm
 };
 
 __device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p)
@@ -332,6 +333,12 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
             }
             else
                 x = *reinterpret_cast<const ulonglong2 *>(src + e);
+        }
+        else if (a.gather_digits)
+        {
+            const u64 *src = a.digits + ((size_t)iloc * a.l + J) * n;
+            x.x = src[a.perm[e]];
+            x.y = src[a.perm[e + 1]];
         }
         else
             x = *reinterpret_cast<const ulonglong2 *>(dig + (size_t)J * n);
@@ -406,6 +413,36 @@ __global__ void __launch_bounds__(256) k_ew(u64 *__restrict__ a, const u64 *__re
             va.y = mulmod(va.y, vb.y, pd);
         }
         *reinterpret_cast<ulonglong2 *>(a + e) = va;
+    }
+}
+
+// acc[p][l][i] (= or +=) a[p][l][i] * pt[l][i]: the "multiply by a plaintext diagonal and accumulate" step of the
+// BSGS linear transforms and of the convolution taps in one pass over the data (dyadic_product_coeffmod +
+// add_poly_coeffmod, polyarithsmallmod.cpp:111-169,18-43).
+template <bool FIRST>
+__global__ void __launch_bounds__(256) k_mul_plain_acc(u64 *__restrict__ acc, const u64 *__restrict__ a,
+                                                       const u64 *__restrict__ pt, const PrimeDev *primes, int log_n,
+                                                       int limbs, int polys)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = (size_t)polys * per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        size_t e = i * 2, ep = e % per_poly;
+        const PrimeDev pd = primes[(int)(ep >> log_n)];
+        ulonglong2 va = *reinterpret_cast<const ulonglong2 *>(a + e);
+        ulonglong2 vp = *reinterpret_cast<const ulonglong2 *>(pt + ep);
+        ulonglong2 r;
+        r.x = mulmod(va.x, vp.x, pd);
+        r.y = mulmod(va.y, vp.y, pd);
+        if (!FIRST)
+        {
+            ulonglong2 vc = *reinterpret_cast<const ulonglong2 *>(acc + e);
+            r.x = addmod(vc.x, r.x, pd.q);
+            r.y = addmod(vc.y, r.y, pd.q);
+        }
+        *reinterpret_cast<ulonglong2 *>(acc + e) = r;
     }
 }
 

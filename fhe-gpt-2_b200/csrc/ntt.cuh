@@ -155,7 +155,7 @@ __device__ __forceinline__ int swz(int e)
 //          (must return a value < 4q of prime(job)).
 // Output: lazy values in [0,4q) at out[job*N + idx].
 // ============================================================================================
-template <int LOGR, class Load>
+template <int LOGR, class Load, bool WIDE = false>
 __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out, NttTables T)
 {
     constexpr int R = 1 << LOGR;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = ld.load(job, (t + TR * k) * 256 + col, pd);
-    const bool wide = T.wide != 0;
+    constexpr bool wide = WIDE; // host dispatch: T.wide (every modulus below 2^57)
     const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
     if (wide)
         fwd_radix_wide<4>(x, tw, 1u, neg_q, four_q);
@@ -237,8 +237,8 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 //               e = 16t + k, v in [0,4q); returns the value to be staged;
 //          void post(int job, int idx, u64 v, const PrimeDev&)                  - coalesced order.
 // ============================================================================================
-template <class Store>
-__global__ void __launch_bounds__(256) k_fwd_blocks(const u64 *__restrict__ in, Store st, NttTables T)
+template <class Store, bool WIDE = false>
+__global__ void __launch_bounds__(256, WIDE ? 3 : 2) k_fwd_blocks(const u64 *__restrict__ in, Store st, NttTables T)
 {
     __shared__ u64 sm[4096];
     const int job = blockIdx.y;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) k_fwd_blocks(const u64 *__restrict__ in, 
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = src[t + 16 * k];
-    const bool wide = T.wide != 0;
+    constexpr bool wide = WIDE;
     const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
     if (wide)
         fwd_radix_wide<4>(x, tw, B, neg_q, four_q);

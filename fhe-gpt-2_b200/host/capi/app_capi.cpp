@@ -457,6 +457,18 @@ extern "C"
         delete b;
         BKA_END
     }
+    int bka_bootstrapper_set_hoisting(bka_bootstrapper_t b, int on, int *previous)
+    {
+        BKA_TRY
+        if (previous)
+            *previous = b->b->hoisting ? 1 : 0;
+#ifdef B200CKKS_FACADE
+        b->b->hoisting = on != 0;
+#else
+        (void)on; // stock SEAL has no hoisted rotation
+#endif
+        BKA_END
+    }
     int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int cap, int *count_out)
     {
         BKA_TRY

@@ -3,8 +3,9 @@
 #include "ckks_bootstrapping/Bootstrapper.h"
 #include "common/cached.h"
 #include "common/func.h"
-#include <cstring>
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <cmath>
 
 using namespace seal;
@@ -44,6 +45,11 @@ Bootstrapper::Bootstrapper(long _loge, long _logn, long _logNh, long _L, double 
 {
     n = 1L << logn;
     Nh = 1L << logNh;
+#ifdef B200CKKS_FACADE
+    hoisting = std::getenv("B200CKKS_NO_HOIST") == nullptr;
+#else
+    hoisting = false;
+#endif
     mod_reducer = new ModularReducer(boundary_K, (double)loge, sin_cos_deg, scale_factor, inverse_deg, context, encoder,
                                      encryptor, evaluator, relin_keys, decryptor);
 }
@@ -322,7 +328,18 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
     auto wrap = [N](int step) { return ((step % N) + N) % N; };
 
     vector<Ciphertext> babyct((std::size_t)p.gs);
-    for (int i = p.basicstart; i < p.basicstart + p.gs; i++)
+    bool babies_done = false;
+#ifdef B200CKKS_FACADE
+    if (hoisting)
+    {
+        vector<int> steps;
+        for (int i = p.basicstart; i < p.basicstart + p.gs; i++)
+            steps.push_back(i == 0 ? 0 : wrap(i * basicstep));
+        evaluator.rotate_vector_hoisted(cipher, steps, gal_keys, babyct);
+        babies_done = true;
+    }
+#endif
+    for (int i = p.basicstart; !babies_done && i < p.basicstart + p.gs; i++)
     {
         if (i == 0)
             babyct[(std::size_t)(i - p.basicstart)] = cipher;
@@ -341,12 +358,11 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
         for (int j = p.basicstart; j <= jlast; j++)
         {
             const std::size_t diag = (std::size_t)(i * p.gs + j + totlen);
-            product = babyct[(std::size_t)(j - p.basicstart)];
-            multiply_vector_named(evaluator, product, cache_owner, diag, cache_variant, [&]() -> const vector<complex<double>> & {
-                rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[diag], rotated);
-                return rotated;
-            });
-            accumulate(evaluator, giantct, giant_started, product);
+            multiply_vector_named_accumulate(evaluator, giantct, giant_started, babyct[(std::size_t)(j - p.basicstart)], cache_owner,
+                                             diag, cache_variant, [&]() -> const vector<complex<double>> & {
+                                                 rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[diag], rotated);
+                                                 return rotated;
+                                             });
         }
         if (i != 0)
         {
@@ -369,7 +385,18 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
     auto wrap = [N](int step) { return ((step % N) + N) % N; };
 
     vector<Ciphertext> babyct((std::size_t)gs);
-    for (int i = 0; i < gs; i++)
+    bool babies_done = false;
+#ifdef B200CKKS_FACADE
+    if (hoisting)
+    {
+        vector<int> steps;
+        for (int i = 0; i < gs; i++)
+            steps.push_back(i == 0 ? 0 : wrap(i * basicstep));
+        evaluator.rotate_vector_hoisted(cipher, steps, gal_keys, babyct);
+        babies_done = true;
+    }
+#endif
+    for (int i = 0; !babies_done && i < gs; i++)
     {
         if (i == 0)
             babyct[0] = cipher;
@@ -387,12 +414,11 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
         for (int j = 0; j <= jlast; j++)
         {
             const std::size_t diag = (std::size_t)(i * gs + j);
-            product = babyct[(std::size_t)j];
-            multiply_vector_named(evaluator, product, cache_owner, diag, cache_variant, [&]() -> const vector<complex<double>> & {
-                rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[diag], rotated);
-                return rotated;
-            });
-            accumulate(evaluator, giantct, giant_started, product);
+            multiply_vector_named_accumulate(evaluator, giantct, giant_started, babyct[(std::size_t)j], cache_owner, diag,
+                                             cache_variant, [&]() -> const vector<complex<double>> & {
+                                                 rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[diag], rotated);
+                                                 return rotated;
+                                             });
         }
         if (i != 0)
         {

@@ -50,6 +50,12 @@ public:
 
     ModularReducer *mod_reducer;
 
+    // Baby-step rotations of a BSGS transform rotate one ciphertext by many steps.  On the engine they can share one
+    // decomposition (Evaluator::rotate_vector_hoisted): same decrypted values up to key-switching noise, different
+    // limbs than the reference's one-by-one rotations.  Off = the reference's exact operation sequence.  Default: on,
+    // unless $B200CKKS_NO_HOIST is set; always off on stock SEAL.
+    bool hoisting;
+
     Bootstrapper(long _loge, long _logn, long _logNh, long _L, double _final_scale, long _boundary_K, long _sin_cos_deg,
                  long _scale_factor, long _inverse_deg, seal::SEALContext &_context, seal::KeyGenerator &_keygen,
                  seal::CKKSEncoder &_encoder, seal::Encryptor &_encryptor, seal::Decryptor &_decryptor,

@@ -203,17 +203,16 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
     }
 
     const int d = (int)log2_long(ki), c = (int)log2_long(ti);
-    Accumulator total{ evaluator, total_sum };
+    bool total_started = false;
     for (long g = 0; g < q; g++)
     {
         // weighted sum over the filter taps
-        Accumulator taps{ evaluator, sum };
+        bool taps_started = false;
         for (int t = 0; t < fh * fw; t++)
         {
-            temp = ctxt_rot[(std::size_t)t];
             const std::size_t idx = (std::size_t)(t * q + g);
-            multiply_vector_named(evaluator, temp, owner, idx, 0, [&]() -> const vector<double> & { return P.tap_weights[idx]; });
-            taps.add(temp);
+            multiply_vector_named_accumulate(evaluator, sum, taps_started, ctxt_rot[(std::size_t)t], owner, idx, 0,
+                                             [&]() -> const vector<double> & { return P.tap_weights[idx]; });
         }
         evaluator.rescale_to_next_inplace(sum);
         var = sum;
@@ -254,9 +253,8 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
                          (int)((n / pi) * (j4 % pi) - j4 % ko - (long)(j4 / (ko * ko)) * ko * ko * ho * wo -
                                (long)((j4 % (ko * ko)) / ko) * ko * wo),
                          evaluator, gal_keys);
-            multiply_vector_named(evaluator, temp, owner, (std::size_t)j4, 1,
-                                  [&]() -> const vector<double> & { return P.select_one_vec[(std::size_t)j4]; });
-            total.add(temp);
+            multiply_vector_named_accumulate(evaluator, total_sum, total_started, temp, owner, (std::size_t)j4, 1,
+                                             [&]() -> const vector<double> & { return P.select_one_vec[(std::size_t)j4]; });
         }
     }
     evaluator.rescale_to_next_inplace(total_sum);

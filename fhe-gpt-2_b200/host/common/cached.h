@@ -23,6 +23,31 @@ inline void multiply_vector_named(seal::Evaluator &evaluator, seal::Ciphertext &
 #endif
 }
 
+// sum <- sum + encrypted * (named vector); `started` tells whether sum holds a value yet.  The reference's loops read
+//   multiply_vector_reduced_error(x, v, tmp); if (first) sum = tmp; else add_inplace_reduced_error(sum, tmp);
+template <class Make>
+inline void multiply_vector_named_accumulate(seal::Evaluator &evaluator, seal::Ciphertext &sum, bool &started,
+                                             const seal::Ciphertext &encrypted, const void *owner, std::uint64_t index,
+                                             std::uint64_t variant, Make &&make)
+{
+#ifdef B200CKKS_FACADE
+    if (!started)
+        sum.release();
+    evaluator.multiply_vector_accumulate_cached(sum, encrypted, owner, index, variant, make);
+#else
+    (void)owner;
+    (void)index;
+    (void)variant;
+    seal::Ciphertext product;
+    evaluator.multiply_vector_reduced_error(const_cast<seal::Ciphertext &>(encrypted), make(), product);
+    if (!started)
+        sum = product;
+    else
+        evaluator.add_inplace_reduced_error(sum, product);
+#endif
+    started = true;
+}
+
 inline void forget_named(seal::Evaluator &evaluator, const void *owner)
 {
 #ifdef B200CKKS_FACADE

@@ -1100,6 +1100,7 @@ namespace seal
         std::atomic<std::uint64_t> key_switch_rotate{ 0 }, key_switch_relin{ 0 }, rescale{ 0 }, multiply{ 0 },
             multiply_plain{ 0 }, encode_vector{ 0 }, add{ 0 }, mod_switch{ 0 }, scalar_op{ 0 };
         std::atomic<std::uint64_t> cache_hits{ 0 }, cache_misses{ 0 }; // multiply_vector_inplace_cached
+        std::atomic<std::uint64_t> hoisted_rotations{ 0 };             // rotate_vector_hoisted (also counted as rotations)
         // the same events by coeff_modulus_size of the ciphertext operand: [0] key switches (rotate + relinearize),
         // [1] rescales, [2] vector encode + multiply_plain, [3] ct x ct multiplications, [4] scalar ops, [5] add/sub
         std::atomic<std::uint64_t> by_limbs[6][64] = {};
@@ -1546,6 +1547,54 @@ namespace seal
         }
 
         // ---- engine extensions
+        // destination[k] = rotate_vector(encrypted, steps[k]) for every k, sharing one decomposition and digit NTT
+        // of `encrypted` among all rotations (hoisting; bk_apply_galois_hoisted).  The results decrypt to the same
+        // values as rotate_vector up to key-switching noise but are NOT limb-identical to it: use it where the
+        // reference's semantics are "rotate one ciphertext by many steps" and a tolerance is acceptable (the baby
+        // steps of a BSGS linear transform).  Steps without a declared key, and step 0, take the ordinary path.
+        void rotate_vector_hoisted(
+            const Ciphertext &encrypted, const std::vector<int> &steps, const GaloisKeys &galois_keys,
+            std::vector<Ciphertext> &destination) const
+        {
+            if (!galois_keys.handle())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            need(encrypted, "encrypted");
+            destination.resize(steps.size());
+            std::vector<std::uint32_t> elts;
+            std::vector<bk_ct_t> outs;
+            std::vector<std::size_t> which;
+            for (std::size_t k = 0; k < steps.size(); k++)
+            {
+                std::uint32_t elt = 0;
+                if (steps[k] != 0)
+                    detail::check(bk_galois_elt_from_step(context_.impl()->log_n, steps[k], &elt));
+                if (steps[k] == 0 || !galois_keys.has_key(elt))
+                {
+                    rotate_vector(encrypted, steps[k], galois_keys, destination[k]);
+                    continue;
+                }
+                galois_keys.ensure(elt, (int)encrypted.coeff_modulus_size());
+                destination[k].bind(context_.impl());
+                elts.push_back(elt);
+                outs.push_back(destination[k].handle());
+                which.push_back(k);
+            }
+            if (elts.empty())
+                return;
+            encrypted.push();
+            {
+                std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
+                detail::check(bk_apply_galois_hoisted(h(), encrypted.handle(), elts.data(), (int)elts.size(),
+                                                      galois_keys.handle(), outs.data()));
+            }
+            for (std::size_t k : which)
+            {
+                destination[k].pull();
+                stats_.key_switch_rotate++;
+                stats_.hoisted_rotations++;
+                stats_.hit(0, encrypted.coeff_modulus_size());
+            }
+        }
         // multiply_vector_inplace_reduced_error for a slot vector the caller can NAME: (owner, index, variant)
         // identifies the vector, make() produces it.  The encoded plaintext (top-level encode dropped to the
         // ciphertext's level at the ciphertext's scale, exactly as evaluator.h:1270-1278) is kept in HBM and
@@ -1558,49 +1607,47 @@ namespace seal
         {
             stats_.encode_vector++;
             stats_.hit(2, encrypted.coeff_modulus_size());
-            if (!owner || !cache_budget_bytes())
-            {
-                Plaintext plain;
-                encoder_.encode_top_dropped(make(), (int)encrypted.coeff_modulus_size(), encrypted.scale(), plain);
-                multiply_plain_inplace(encrypted, plain);
+            std::unique_ptr<Plaintext> once;
+            const Plaintext &plain = named_plaintext((int)encrypted.coeff_modulus_size(), encrypted.scale(), owner, index,
+                                                     variant, make, once);
+            multiply_plain_inplace(encrypted, plain);
+        }
+        // accumulator <- accumulator + encrypted * (named vector), the two calls
+        //   multiply_vector_reduced_error(encrypted, v, tmp); add_inplace_reduced_error(accumulator, tmp)
+        // of a BSGS / convolution-tap loop as one pass over the data (bk_multiply_plain_accumulate); an accumulator
+        // without data is initialised with the product.  Same residues and scale bookkeeping as the two calls.
+        template <class Make>
+        void multiply_vector_accumulate_cached(
+            Ciphertext &accumulator, const Ciphertext &encrypted, const void *owner, std::uint64_t index,
+            std::uint64_t variant, Make &&make)
+        {
+            need(encrypted, "encrypted");
+            if (accumulator.handle() && accumulator.size() && accumulator.coeff_modulus_size() != encrypted.coeff_modulus_size())
+            { // different levels: the reduced-error add has to walk one operand down first
+                Ciphertext product = encrypted;
+                multiply_vector_inplace_cached(product, owner, index, variant, make);
+                add_inplace_reduced_error(accumulator, product);
                 return;
             }
-            std::uint64_t scale_bits;
-            static_assert(sizeof(double) == sizeof(std::uint64_t), "");
-            double sc = encrypted.scale();
-            std::memcpy(&scale_bits, &sc, sizeof(sc));
-            PlainKey key{ owner, index, variant, scale_bits, (int)encrypted.coeff_modulus_size() };
-            const Plaintext *hit = nullptr;
+            stats_.encode_vector++;
+            stats_.multiply_plain++;
+            stats_.hit(2, encrypted.coeff_modulus_size());
+            std::unique_ptr<Plaintext> once;
+            const Plaintext &plain = named_plaintext((int)encrypted.coeff_modulus_size(), encrypted.scale(), owner, index,
+                                                     variant, make, once);
+            const bool first = !accumulator.handle() || !accumulator.size();
+            if (!first)
             {
-                std::shared_lock<std::shared_mutex> rl(cache_mu_);
-                auto it = plain_cache_.find(key);
-                if (it != plain_cache_.end())
-                    hit = it->second.get();
+                stats_.add++;
+                stats_.hit(5, accumulator.coeff_modulus_size());
             }
-            if (!hit)
-            {
-                auto plain = std::make_unique<Plaintext>();
-                encoder_.encode_top_dropped(make(), key.limbs, sc, *plain);
-                std::uint64_t bytes = (std::uint64_t)key.limbs * (8ull << context_.impl()->log_n);
-                std::unique_lock<std::shared_mutex> wl(cache_mu_);
-                if (cache_bytes_ + bytes > cache_budget_bytes())
-                { // over budget: use it once, do not keep it
-                    wl.unlock();
-                    multiply_plain_inplace(encrypted, *plain);
-                    return;
-                }
-                context_.sync(); // other host threads (streams) may pick the plaintext up from now on
-                auto ins = plain_cache_.emplace(key, std::move(plain));
-                hit = ins.first->second.get();
-                if (ins.second)
-                {
-                    cache_bytes_ += bytes;
-                    stats_.cache_misses++;
-                }
-            }
-            else
-                stats_.cache_hits++;
-            multiply_plain_inplace(encrypted, *hit);
+            accumulator.bind(context_.impl());
+            if (!first)
+                accumulator.push();
+            encrypted.push();
+            plain.push();
+            detail::check(bk_multiply_plain_accumulate(h(), accumulator.handle(), encrypted.handle(), plain.handle()));
+            accumulator.pull();
         }
         // drop every cached plaintext of `owner` (call before the owner's storage is released or rewritten)
         void forget_cached(const void *owner) const
@@ -1750,6 +1797,50 @@ namespace seal
                 return (std::uint64_t)((e ? std::atof(e) : 32.0) * 1073741824.0);
             }();
             return b;
+        }
+
+        // the encoded plaintext of a named vector at (limbs, scale): from the cache, or encoded now (and kept if the
+        // budget allows; otherwise handed back through `once`, which then owns it)
+        template <class Make>
+        const Plaintext &named_plaintext(int limbs, double scale, const void *owner, std::uint64_t index, std::uint64_t variant,
+                                         Make &&make, std::unique_ptr<Plaintext> &once) const
+        {
+            if (!owner || !cache_budget_bytes())
+            {
+                once = std::make_unique<Plaintext>();
+                encoder_.encode_top_dropped(make(), limbs, scale, *once);
+                return *once;
+            }
+            std::uint64_t scale_bits;
+            static_assert(sizeof(double) == sizeof(std::uint64_t), "");
+            std::memcpy(&scale_bits, &scale, sizeof(scale));
+            PlainKey key{ owner, index, variant, scale_bits, limbs };
+            {
+                std::shared_lock<std::shared_mutex> rl(cache_mu_);
+                auto it = plain_cache_.find(key);
+                if (it != plain_cache_.end())
+                {
+                    stats_.cache_hits++;
+                    return *it->second;
+                }
+            }
+            auto plain = std::make_unique<Plaintext>();
+            encoder_.encode_top_dropped(make(), limbs, scale, *plain);
+            std::uint64_t bytes = (std::uint64_t)limbs * (8ull << context_.impl()->log_n);
+            std::unique_lock<std::shared_mutex> wl(cache_mu_);
+            if (cache_bytes_ + bytes > cache_budget_bytes())
+            { // over budget: use it once, do not keep it
+                once = std::move(plain);
+                return *once;
+            }
+            context_.sync(); // other host threads (streams) may pick the plaintext up from now on
+            auto ins = plain_cache_.emplace(key, std::move(plain));
+            if (ins.second)
+            {
+                cache_bytes_ += bytes;
+                stats_.cache_misses++;
+            }
+            return *ins.first->second;
         }
 
         SEALContext context_;

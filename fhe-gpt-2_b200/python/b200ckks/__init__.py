@@ -468,6 +468,14 @@ class Context:
     def rotate_vector_inplace(self, a, steps, gk):
         _ck(_L.bk_rotate_vector_inplace(self.h, a.h, steps, gk.h))
 
+    def apply_galois_hoisted(self, a, elts, gk):
+        """outs[k] = apply_galois(a, elts[k]) with one shared decomposition (tolerance mode, see include/b200ckks.h)"""
+        outs = [Ciphertext(self) for _ in elts]
+        arr = (C.c_uint32 * len(elts))(*elts)
+        hs = (C.c_void_p * len(elts))(*[o.h for o in outs])
+        _ck(_L.bk_apply_galois_hoisted(self.h, a.h, arr, len(elts), gk.h, hs))
+        return outs
+
     def complex_conjugate_inplace(self, a, gk):
         _ck(_L.bk_complex_conjugate_inplace(self.h, a.h, gk.h))
 

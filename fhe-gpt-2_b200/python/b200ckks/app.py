@@ -315,6 +315,11 @@ class Bootstrapper:
             self.s.app.L.bka_bootstrapper_destroy(self.h)
             self.h = None
 
+    def set_hoisting(self, on):
+        prev = C.c_int()
+        self.s.app.ck(self.s.app.L.bka_bootstrapper_set_hoisting(self.h, int(on), C.byref(prev)))
+        return bool(prev.value)
+
     def rotation_steps(self):
         buf = np.zeros(4096, dtype=np.int32)
         n = C.c_int()

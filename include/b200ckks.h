@@ -164,9 +164,20 @@ bk_status bk_mod_switch_to_inplace(bk_context_t ctx, bk_ct_t a, int limbs);    /
 bk_status bk_apply_galois_inplace(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk); /* :2120-2222 */
 bk_status bk_rotate_vector_inplace(bk_context_t ctx, bk_ct_t a, int steps, bk_gkeys_t gk);         /* :2224-2279 */
 bk_status bk_complex_conjugate_inplace(bk_context_t ctx, bk_ct_t a, bk_gkeys_t gk);                /* evaluator.h:1321-1341 */
+/* Hoisted automorphisms (engine extension; the reference carries the idea as dead code, Bootstrapper.cpp:2088-2230,
+ * keygenerator.cpp:236-304): outs[k] = apply_galois(in, galois_elts[k]) for all k with ONE decomposition and digit NTT
+ * of `in`.  Decrypts to the same values as bk_apply_galois_inplace up to key-switching noise, but the limbs are not
+ * those of evaluator.cpp:2120-2222 (which permutes before decomposing) - a tolerance-mode fast path for the baby steps
+ * of BSGS linear transforms.  outs[k] must be distinct ciphertext objects different from `in`. */
+bk_status bk_apply_galois_hoisted(bk_context_t ctx, bk_ct_t in, const uint32_t *galois_elts, int count, bk_gkeys_t gk,
+                                  bk_ct_t *outs);
 bk_status bk_add_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);        /* :1578-1650 */
 bk_status bk_sub_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);        /* :1652-1724 */
 bk_status bk_multiply_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);   /* :1726-1761,1891-1930 */
+/* acc <- acc + a (*) p: multiply_plain (:1891-1930) and add_inplace (:103-163) in one pass over the data; an empty
+ * acc (size 0) is initialised with the product.  acc takes the product's scale (the reduced-error add overwrites
+ * scales the same way, :316-321).  Residues equal those of the two separate calls. */
+bk_status bk_multiply_plain_accumulate(bk_context_t ctx, bk_ct_t acc, bk_ct_t a, bk_pt_t p);
 bk_status bk_transform_to_ntt_inplace(bk_context_t ctx, bk_ct_t a);            /* :2069-2118 */
 bk_status bk_transform_from_ntt_inplace(bk_context_t ctx, bk_ct_t a);
 /* fork: add_const / multiply_const (evaluator.cpp:287-302): scalar encode (ckks.cpp:77-153)

@@ -91,6 +91,9 @@ int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *value
 int bka_bootstrapper_create(bka_session_t s, int loge, int logn, int total_level, double final_scale, int boundary_k,
                             int sin_cos_deg, int scale_factor, int inverse_deg, bka_bootstrapper_t *out);
 int bka_bootstrapper_destroy(bka_bootstrapper_t b);
+/* baby-step rotations through one shared decomposition (engine; default on unless $B200CKKS_NO_HOIST) or one by one
+ * exactly as the reference issues them (0).  Returns the previous setting in *previous (may be NULL). */
+int bka_bootstrapper_set_hoisting(bka_bootstrapper_t b, int on, int *previous);
 /* steps of addLeftRotKeys_Linear_to_vector_3 for this logn, appended to steps_out (capacity cap) */
 int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int cap, int *count_out);
 /* LT coefficients: which = 0..2 SlotToCoeff matrices 1..3, 3..5 CoeffToSlot matrices 1..3.

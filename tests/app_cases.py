@@ -95,7 +95,7 @@ def case_relu(sess, seed=3):
     assert np.abs(y - np.maximum(x, 0)).max() < 2.0 ** -13  # the alpha = 13 guarantee (run_compare.cpp: ShowFailure_ReLU)
 
 
-def case_bootstrap(sess, logn, real=True, seed=4, tol=5e-5):
+def case_bootstrap(sess, logn, real=True, seed=4, tol=5e-5, hoisting=None):
     rng = np.random.default_rng(seed)
     n = 1 << logn
     if real:
@@ -104,6 +104,8 @@ def case_bootstrap(sess, logn, real=True, seed=4, tol=5e-5):
         x = rng.uniform(-1, 1, n) + 1j * rng.uniform(-1, 1, n)
     xs = np.tile(x, sess.slots // n)
     boot = sess.bootstrapper(logn)
+    if hoisting is not None:
+        boot.set_hoisting(hoisting)
     ct = sess.encrypt(xs, 2.0 ** 46, limbs=1)
     out = boot.bootstrap(ct, real_message=real)
     size, limbs, scale = out.info()

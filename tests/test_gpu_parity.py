@@ -434,3 +434,32 @@ def test_gpt2_parameters_keyswitch_rescale(limbs):
     assert_ct_equal(ea, ref, a, "rescale")
     eng.close()
     ref.close()
+
+
+def test_hoisted_rotations_decrypt_like_plain_rotations(small):
+    """bk_apply_galois_hoisted (engine extension): one decomposition for a set of automorphisms.  Same slots as
+    rotate_vector up to key-switching noise; NOT the reference's limbs (the decomposition precedes the automorphism),
+    which is why only the opt-in BSGS fast path uses it."""
+    import b200ckks as bk
+
+    ref, eng, rk, gk = small
+    rng = np.random.default_rng(77)
+    x = rand_slots(rng, 4096, complex_=True)
+    sk = eng.upload_secret_key(ref.secret_key())
+    for limbs in (5, 2):
+        a = ref_fresh_ct(ref, x, limbs, 2.0 ** 40)
+        ea = to_engine(eng, ref, a)
+        steps = [1, -3, 64]
+        elts = [ref.galois_elt(s) for s in steps] + [ref.galois_elt(0)]
+        outs = eng.apply_galois_hoisted(ea, elts, gk)
+        for st, o in zip(steps, outs):
+            got = eng.decode(eng.decrypt(sk, o))
+            assert np.abs(got - np.roll(x, -st)).max() < 1e-6
+            plain = ea.copy()
+            eng.rotate_vector_inplace(plain, st, gk)
+            assert o.info() == plain.info()
+            # same message, different (equally valid) key-switching noise: the limbs are not the reference's
+            assert not np.array_equal(o.download(), plain.download())
+        assert np.abs(eng.decode(eng.decrypt(sk, outs[-1])) - np.conj(x)).max() < 1e-6
+    with pytest.raises(bk.InvalidArgument):
+        eng.apply_galois_hoisted(ea, [ref.galois_elt(7)], gk)        # no such key
