@@ -172,10 +172,12 @@ def run_engine(args):
         sess.level_histogram(i, reset=True)
     launches0 = eng.launch_count()
     outs = []
+    torch.cuda.profiler.start()      # cudaProfilerStart: `ncu --profile-from-start off` captures the timed region only
     eng.timer_begin()
     for k in range(args.steps):
         outs.append(net.infer_encrypted(enc[k])[0])
     ms = eng.timer_end()
+    torch.cuda.profiler.stop()
     launches = eng.launch_count() - launches0
     barrier()
     clocks = sampler.stop() if rank == 0 else None
