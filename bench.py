@@ -300,6 +300,15 @@ def run_engine(args):
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
+def host_threads():
+    """cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which the explicit num_threads clause of the
+    timing loop overrides; the affinity mask is what really bounds the OpenMP team)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def measure_reference_ops(threads, reps):
     """Per-operation seconds of the reference's own SEAL at the CNN parameters, `threads` independent ciphertexts at a
     time (how infer_seal.cpp:404 parallelises), at a few levels; returns {op: {limbs: seconds}}."""
@@ -354,7 +363,7 @@ def cpu_baseline(hist, reps=1, threads=None):
 
     if not refseal.available():
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref not built"}
-    T = threads or min(refseal.lib().ref_max_threads(), os.cpu_count() or 1)
+    T = threads or host_threads()
     per_op = measure_reference_ops(T, reps)
     sec, parts = compose_seconds_per_image(per_op, hist)
     return {"value": T / sec, "unit": UNIT, "cores": T, "kind": "reference", "seconds_per_image_per_thread": sec,
@@ -380,7 +389,7 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "no committed operation histogram for this depth"}))
         return
     hist = json.load(open(HIST_PATH))
-    T = min(refseal.lib().ref_max_threads(), os.cpu_count() or 1)
+    T = host_threads()
     for _ in range(args.warmup):
         measure_reference_ops(T, 1)
     t0 = time.perf_counter()
