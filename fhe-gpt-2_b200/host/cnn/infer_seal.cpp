@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <fstream>
+#include <iostream>
 #include <stdexcept>
 
 using namespace seal;
@@ -340,4 +341,188 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, 10, 64, evaluator_, gal_keys_);
     log_op(7, cnn);
     return cnn;
+}
+
+// ------------------------------------------------------------------------------------------ the reference's driver
+namespace
+{
+    bool readable(const string &path)
+    {
+        std::ifstream f(path);
+        return f.is_open();
+    }
+
+    // random-init weights of the architecture (He-style convolutions, near-identity batch-norm statistics)
+    ResNetParameters random_parameters(std::size_t layer_num, unsigned long long seed)
+    {
+        ResNetParameters p;
+        unsigned long long state = seed * 0x9E3779B97F4A7C15ull + 0x5EA1ull;
+        auto uni = [&state]() { // xorshift64*, uniform in (0,1)
+            state ^= state >> 12;
+            state ^= state << 25;
+            state ^= state >> 27;
+            return ((state * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0) + 1e-17;
+        };
+        auto normal = [&uni]() { return std::sqrt(-2.0 * std::log(uni())) * std::cos(2.0 * M_PI * uni()); };
+        const std::size_t layers = layer_num - 1;
+        for (std::size_t i = 0; i < layers; i++)
+        {
+            int ci, co;
+            resnet_conv_shape(layer_num, i, ci, co);
+            vector<double> w((std::size_t)(9 * ci * co)), b((std::size_t)co), m((std::size_t)co), v((std::size_t)co), g((std::size_t)co);
+            const double sd = 0.5 * std::sqrt(2.0 / (9.0 * ci));
+            for (auto &x : w)
+                x = sd * normal();
+            for (int c = 0; c < co; c++)
+            {
+                b[(std::size_t)c] = 0.1 * normal();
+                m[(std::size_t)c] = 0.1 * normal();
+                v[(std::size_t)c] = 0.5 + uni();
+                g[(std::size_t)c] = 0.5 + 0.5 * uni();
+            }
+            p.conv_weight.push_back(w);
+            p.bn_bias.push_back(b);
+            p.bn_running_mean.push_back(m);
+            p.bn_running_var.push_back(v);
+            p.bn_weight.push_back(g);
+        }
+        p.linear_weight.resize(640);
+        for (auto &x : p.linear_weight)
+            x = 0.3 * normal();
+        p.linear_bias.assign(10, 0.0);
+        return p;
+    }
+
+    const char *op_title(int op)
+    {
+        static const char *t[] = { "multiplexed parallel convolution...", "multiplexed parallel batch normalization...",
+                                   "approximate ReLU...", "bootstrapping...", "cipher add...",
+                                   "multiplexed parallel downsampling...", "average pooling...", "fully connected layer..." };
+        return t[op];
+    }
+} // namespace
+
+void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id,
+                                const string &result_dir, const string &weights_dir, const string &images_dir)
+{
+    const int end_num = resnet_end_num(layer_num);
+
+    std::cout << "Setting Parameters" << std::endl;
+    EncryptionParameters parms(scheme_type::ckks);
+    const std::size_t poly_modulus_degree = std::size_t(1) << ResNetCifar10::logN;
+    parms.set_poly_modulus_degree(poly_modulus_degree);
+    parms.set_coeff_modulus(CoeffModulus::Create(poly_modulus_degree, ResNetCifar10::coeff_bit_vec()));
+    parms.set_secret_key_hamming_weight(192);
+
+    SEALContext context(parms);
+    KeyGenerator keygen(context);
+    PublicKey public_key;
+    keygen.create_public_key(public_key);
+    SecretKey secret_key = keygen.secret_key();
+    RelinKeys relin_keys;
+    keygen.create_relin_keys(relin_keys);
+    GaloisKeys gal_keys;
+    CKKSEncoder encoder(context);
+    Encryptor encryptor(context, public_key);
+    Evaluator evaluator(context, encoder);
+    Decryptor decryptor(context, secret_key);
+
+    ResNetParameters parameters;
+    const string probe = weights_dir + "/resnet" + std::to_string(layer_num) + "_new/conv1_weight.txt";
+    const bool pretrained = readable(probe);
+    if (pretrained)
+        import_parameters_cifar10(parameters.linear_weight, parameters.linear_bias, parameters.conv_weight, parameters.bn_bias,
+                                  parameters.bn_running_mean, parameters.bn_running_var, parameters.bn_weight, layer_num,
+                                  (std::size_t)end_num, weights_dir);
+    else
+    {
+        std::cout << "no pretrained parameters at " << probe << ": random-init weights" << std::endl;
+        parameters = random_parameters(layer_num, 0);
+    }
+
+    std::cout << "Generating Optimal Minimax Polynomials..." << std::endl;
+    ResNetCifar10 net(layer_num, parameters, context, keygen, encoder, encryptor, decryptor, evaluator, public_key, secret_key,
+                      relin_keys, gal_keys);
+    std::cout << "Adding Bootstrapping Keys..." << std::endl;
+    keygen.create_galois_keys(net.galois_steps(), gal_keys);
+    std::cout << "Generating Linear Transformation Coefficients..." << std::endl;
+    net.prepare();
+
+    const string stem = result_dir + "/resnet" + std::to_string(layer_num) + "_cifar10_";
+    std::ofstream out_share(stem + "label_" + std::to_string(start_image_id) + "_" + std::to_string(end_image_id));
+    const bool have_images = readable(images_dir + "/test_values.txt");
+    if (!have_images)
+        std::cout << "no " << images_dir << "/test_values.txt: synthetic images, labels not checked" << std::endl;
+
+    auto all_start = std::chrono::high_resolution_clock::now();
+    for (std::size_t image_id = start_image_id; image_id <= end_image_id; image_id++)
+    {
+        vector<double> image(32 * 32 * 3);
+        int image_label = -1;
+        if (have_images)
+        {
+            std::ifstream in(images_dir + "/test_values.txt");
+            double val;
+            for (std::size_t i = 0; i < 32 * 32 * 3 * image_id; i++)
+                in >> val;
+            for (auto &v : image)
+                in >> v;
+            std::ifstream in_label(images_dir + "/test_label.txt");
+            for (std::size_t i = 0; i <= image_id; i++)
+                in_label >> image_label;
+        }
+        else
+        {
+            unsigned long long state = (image_id + 1) * 0xD1B54A32D192ED03ull;
+            auto uni = [&state]() {
+                state ^= state >> 12;
+                state ^= state << 25;
+                state ^= state >> 27;
+                return ((state * 0x2545F4914F6CDD1Dull) >> 11) * (1.0 / 9007199254740992.0) + 1e-17;
+            };
+            for (auto &v : image)
+                v = std::max(-2.5, std::min(2.5, std::sqrt(-2.0 * std::log(uni())) * std::cos(2.0 * M_PI * uni())));
+        }
+
+        vector<ResNetTraceRow> trace;
+        auto t0 = std::chrono::high_resolution_clock::now();
+        vector<double> logits = net.infer(image, &trace);
+        const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+
+        std::ofstream output(stem + "image" + std::to_string(image_id) + ".txt");
+        // the reference opens a "layer k" section at every convolution (infer_seal.cpp:465-536)
+        int layer = 0;
+        for (const auto &r : trace)
+        {
+            if (r.op == 0 || r.op == 6)
+                output << "layer " << (r.op == 6 ? (int)layer_num - 1 : layer++) << std::endl;
+            output << op_title(r.op) << std::endl;
+            output << "time : " << (long)r.milliseconds << " ms" << std::endl;
+            output << "remaining level : " << r.remaining_level << std::endl;
+            output << "scale: " << r.scale << std::endl << std::endl;
+        }
+        std::size_t label = 0;
+        double max_score = -100.0;
+        output << "( ";
+        for (std::size_t i = 0; i < 10; i++)
+        {
+            output << "(" << logits[i] << ",0)" << (i < 9 ? ", " : ")");
+            if (max_score < logits[i])
+            {
+                label = i;
+                max_score = logits[i];
+            }
+        }
+        output << std::endl;
+        output << "total time : " << (long)total_ms << " ms" << std::endl;
+        output << "image label: " << image_label << std::endl;
+        output << "inferred label: " << label << std::endl;
+        output << "max score: " << max_score << std::endl;
+        out_share << "image_id: " << image_id << ", image label: " << image_label << ", inferred label: " << label << std::endl;
+        std::cout << "image " << image_id << ": total time : " << (long)total_ms << " ms, inferred label: " << label
+                  << ", max score: " << max_score << std::endl;
+    }
+    const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - all_start).count();
+    std::cout << "all threads time : " << (long)all_ms << " ms" << std::endl;
+    out_share << std::endl << "all threads time : " << (long)all_ms << " ms" << std::endl;
 }

@@ -37,6 +37,16 @@ void import_parameters_cifar10(std::vector<double> &linear_weight, std::vector<d
 // CNN rotation steps of infer_seal.cpp:345-362 (the list is the same for every depth)
 const std::vector<int> &resnet_rotation_kinds();
 
+// The reference's entry point (infer_seal.cpp:251-584; run/run_cnn.cpp calls it): parameters, keys, bootstrappers, then
+// images start..end one after the other.  Weights from <weights_dir>/resnet<L>_new and images / labels from
+// <images_dir>/test_values.txt, test_label.txt when those exist (defaults: the reference's relative paths), otherwise
+// random-init weights and synthetic images.  Writes <result_dir>/resnet<L>_cifar10_image<id>.txt in the reference's
+// log format and <result_dir>/resnet<L>_cifar10_label_<start>_<end>.
+void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id,
+                                const std::string &result_dir = "../../result",
+                                const std::string &weights_dir = "../../pretrained_parameters",
+                                const std::string &images_dir = "../../../testFile");
+
 struct ResNetTraceRow
 {
     int op;               // 0 conv, 1 bn, 2 relu, 3 bootstrap, 4 add, 5 downsample, 6 avgpool, 7 fc
