@@ -5,6 +5,8 @@
 // CPU oracle for the application layers that runs the identical host code on the reference library.
 #include "../../../include/b200ckks_app.h"
 #include "cnn/infer_seal.h"
+#include "gpt2/approx.h"
+#include "gpt2/test_util.h"
 #include <algorithm>
 #include <cstring>
 #include <memory>
@@ -750,6 +752,278 @@ extern "C"
                 trace_out[4 * i + 2] = trace[(std::size_t)i].scale;
                 trace_out[4 * i + 3] = trace[(std::size_t)i].milliseconds;
             }
+        BKA_END
+    }
+
+    // ---- GPT-2 operators (gpt2/approx.h) -----------------------------------------------------------------------------
+    int bka_gpt2_call(bka_session_t s, bka_bootstrapper_t boot, const char *op_name, bka_ct_t *in, int n_in, const double *dparams,
+                      int n_d, const int *iparams, int n_i, bka_ct_t *out, int out_cap, int *n_out)
+    {
+        BKA_TRY
+        const std::string op(op_name);
+        s->ensure_keys();
+        CKKSEncoder &enc = *s->encoder;
+        Encryptor &cr = *s->encryptor;
+        Decryptor &de = *s->decryptor;
+        Evaluator &ev = *s->evaluator;
+        GaloisKeys &gk = s->gal_keys;
+        RelinKeys &rk = s->relin_keys;
+        KeyGenerator &kg = *s->keygen;
+
+        auto need = [&](int cts, int ints, int doubles) {
+            if (n_in < cts || n_i < ints || n_d < doubles)
+                throw std::invalid_argument("bka_gpt2_call(" + op + "): too few arguments");
+        };
+        // the operators that take a Bootstrapper& only to pass it on (sign_function never touches it) get a bare one
+        std::unique_ptr<Bootstrapper> bare;
+        auto bootstrapper = [&]() -> Bootstrapper & {
+            if (boot)
+            {
+                boot->ready();
+                return *boot->b;
+            }
+            if (!bare)
+                bare = std::make_unique<Bootstrapper>(10, s->log_n - 1, s->log_n - 1, (int)s->bits.size() - 2, gpt2::encode_scale(), 25,
+                                                      59, 2, 1, *s->context, kg, enc, cr, de, ev, rk, gk);
+            return *bare;
+        };
+        vector<Ciphertext> results;
+        auto range = [&](int from, int count) {
+            gpt2::vc v;
+            for (int i = 0; i < count; i++)
+                v.push_back(in[from + i]->ct);
+            return v;
+        };
+        Ciphertext r;
+        if (op == "quickSum")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::quickSum(x, r, iparams[0], enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "sign_f" || op == "sign_g" || op == "gelu_p" || op == "gelu_q")
+        {
+            need(1, 0, 0);
+            Ciphertext x = in[0]->ct;
+            (op == "sign_f"   ? gpt2::compute_sign_f
+             : op == "sign_g" ? gpt2::compute_sign_g
+             : op == "gelu_p" ? gpt2::compute_gelu_p
+                              : gpt2::compute_gelu_q)(x, r, enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "cheby_basis")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::build_cheby_basis(x, results, iparams[0], enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "sign")
+        {
+            need(1, 2, 0);
+            gpt2::TensorCipher t(in[0]->ct), o;
+            gpt2::sign_function(t, o, iparams[0], iparams[1], bootstrapper(), enc, cr, de, ev, gk, rk);
+            results.push_back(o.cipher());
+        }
+        else if (op == "gelu")
+        {
+            need(1, 0, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::compute_gelu(x, r, bootstrapper(), enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "exp")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::compute_exp(x, r, iparams[0], enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "inverse")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::compute_inverse(x, r, iparams[0], enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "taylor" || op == "inv_sqrt")
+        {
+            need(1, 1, 1);
+            Ciphertext x = in[0]->ct;
+            if (op == "taylor")
+                gpt2::taylor_expand(x, r, iparams[0], dparams[0], enc, cr, de, ev, gk, rk);
+            else
+                gpt2::compute_inv_sqrt(x, r, iparams[0], dparams[0], enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "layernorm")
+        {
+            need(1, 1, 2 * iparams[0]);
+            Ciphertext x = in[0]->ct;
+            const int rs = iparams[0];
+            gpt2::compute_layernorm(x, r, vector<double>(dparams, dparams + rs), vector<double>(dparams + rs, dparams + 2 * rs), rs, enc,
+                                    cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "max")
+        {
+            need(2, 0, 0);
+            Ciphertext a = in[0]->ct, b = in[1]->ct;
+            gpt2::computeMax(a, b, r, bootstrapper(), enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "quickMax")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::quickMax(x, r, iparams[0], bootstrapper(), enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "smax" || op == "softmax")
+        {
+            need(1, 2, 0);
+            Ciphertext x = in[0]->ct;
+            if (op == "smax")
+                gpt2::compute_smax(x, iparams[0], iparams[1], enc, cr, de, ev, gk, rk);
+            else
+                gpt2::compute_softmax(x, iparams[0], bootstrapper(), enc, cr, de, ev, gk, rk);
+            results.push_back(x);
+        }
+        else if (op == "mask_out")
+        {
+            need(1, 2, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::mask_out(x, r, iparams[0], iparams[1], enc, ev, rk);
+            results.push_back(r);
+        }
+        else if (op == "rotate_inplace" || op == "surefire_rotate")
+        {
+            need(1, 1, 0);
+            Ciphertext x = in[0]->ct;
+            if (op == "rotate_inplace")
+                gpt2::rotate_inplace(x, iparams[0], ev, gk);
+            else
+                gpt2::surefire_rotate(x, iparams[0], kg, ev);
+            results.push_back(x);
+        }
+        else if (op == "fake_bootstrap")
+        {
+            need(1, 0, 0);
+            Ciphertext x = in[0]->ct;
+            gpt2::fakeBootstrap(x, r, enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "bootstrap")
+        {
+            need(1, 0, 0);
+            if (!boot)
+                throw std::invalid_argument("bka_gpt2_call(bootstrap): a bootstrapper is required");
+            Ciphertext x = in[0]->ct;
+            gpt2::bootstrap(x, r, bootstrapper(), ev);
+            results.push_back(r);
+        }
+        else if (op == "init_output")
+        {
+            need(0, 1, 0);
+            gpt2::init_output(iparams[0], results, enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "pack_from_row")
+        {
+            need(0, 2, iparams[0] * iparams[1]);
+            gpt2::vvec m((std::size_t)iparams[0]);
+            for (int i = 0; i < iparams[0]; i++)
+                m[(std::size_t)i].assign(dparams + (std::size_t)i * iparams[1], dparams + (std::size_t)(i + 1) * iparams[1]);
+            gpt2::pack_from_row(m, results, enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "expand_bias")
+        {
+            need(0, 0, 1);
+            vector<double> b(dparams, dparams + n_d);
+            gpt2::expand_bias(b, r, enc, cr, de, ev, gk, rk);
+            results.push_back(r);
+        }
+        else if (op == "pack_tight" || op == "unpack_tight")
+        {
+            const int ni = op == "pack_tight" ? 8 : 3, no = op == "pack_tight" ? 3 : 8;
+            need(ni + no, 0, 0);
+            gpt2::vc a = range(0, ni);
+            results = range(ni, no);
+            (op == "pack_tight" ? gpt2::pack_tight : gpt2::unpack_tight)(a, results, enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "row_matmul" || op == "attn_proj_row" || op == "attn_proj_col")
+        {
+            // iparams: n_left, n_weights, n_outputs, A_rows, A_cols, W_rows, W_cols; in: left.., weights.., bias, outputs..
+            need(0, 7, 0);
+            const int nl = iparams[0], nw = iparams[1], no = iparams[2];
+            need(nl + nw + 1 + no, 7, 0);
+            gpt2::vc left = range(0, nl), weights = range(nl, nw);
+            Ciphertext bias = in[nl + nw]->ct;
+            results = range(nl + nw + 1, no);
+            if (op == "row_matmul")
+                gpt2::row_matrix_multiplication_seal(left, weights, bias, results, iparams[3], iparams[4], iparams[5], iparams[6], enc, cr,
+                                                     de, ev, gk, rk);
+            else
+                (op == "attn_proj_row" ? gpt2::attn_proj_row_seal : gpt2::attn_proj_col_seal)(
+                    left, weights, bias, results, iparams[3], iparams[4], iparams[5], iparams[6], kg, enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "col_matmul")
+        {
+            need(0, 2, 0);
+            const int rows = iparams[0], cols = iparams[1];
+            need(2 * rows, 2, 0);
+            vector<gpt2::TensorCipher> left, right, outs;
+            for (int i = 0; i < rows; i++)
+            {
+                left.emplace_back(in[i]->ct);
+                right.emplace_back(in[rows + i]->ct);
+            }
+            gpt2::Config config;
+            gpt2::col_matrix_multiplication_seal(left, right, outs, {}, rows, cols, config, enc, cr, de, ev, gk, rk);
+            for (auto &t : outs)
+                results.push_back(t.cipher());
+        }
+        else if (op == "qk_matmul" || op == "sv_matmul")
+        {
+            // iparams: heads, n_outputs; in: first.., second.., outputs..
+            need(0, 2, 0);
+            const int h = iparams[0], no = iparams[1];
+            need(2 * h + no, 2, 0);
+            gpt2::vc a = range(0, h), b = range(h, h);
+            results = range(2 * h, no);
+            (op == "qk_matmul" ? gpt2::qk_matmul : gpt2::sv_matmul)(a, b, results, 128, 768, 768, 128, kg, enc, cr, de, ev, gk, rk);
+        }
+        else if (op == "augment_row" || op == "augment_col")
+        {
+            // iparams: n, padded_row_size, idx; in: A.., cached..; out: A..
+            need(0, 3, 0);
+            const int n = iparams[0];
+            need(2 * n, 3, 0);
+            results = range(0, n);
+            gpt2::vc cached = range(n, n);
+            (op == "augment_row" ? gpt2::augment_value_row : gpt2::augment_value_col)(results, cached, iparams[1], iparams[2], enc, cr, de,
+                                                                                     ev, gk, rk);
+        }
+        else
+            throw std::invalid_argument("bka_gpt2_call: unknown operator " + op);
+
+        if ((int)results.size() > out_cap)
+            throw std::out_of_range("bka_gpt2_call(" + op + "): out_cap too small");
+        for (std::size_t i = 0; i < results.size(); i++)
+            out[i] = wrap(std::move(results[i]));
+        if (n_out)
+            *n_out = (int)results.size();
+        BKA_END
+    }
+    int bka_gpt2_init_chain(int *bits_out, int bits_cap, int *n_bits, int *steps_out, int steps_cap, int *n_steps)
+    {
+        BKA_TRY
+        const vector<int> bits = gpt2::init_coeff_bit_vec(), steps = gpt2::init_rotation_steps();
+        if ((int)bits.size() > bits_cap || (int)steps.size() > steps_cap)
+            throw std::out_of_range("bka_gpt2_init_chain: capacity too small");
+        std::copy(bits.begin(), bits.end(), bits_out);
+        std::copy(steps.begin(), steps.end(), steps_out);
+        *n_bits = (int)bits.size();
+        *n_steps = (int)steps.size();
         BKA_END
     }
 }

@@ -101,6 +101,13 @@ class App:
     def session(self, log_n, bits, hamming_weight=192, device=0, rotation_steps=(), secret_key=None):
         return Session(self, log_n, bits, hamming_weight, device, rotation_steps, secret_key)
 
+    def gpt2_init_chain(self):
+        """(bit sizes, rotation steps) of the reference's GPT-2 INIT macro (gpt2/util.h:37-75)."""
+        bits, steps = np.zeros(64, dtype=np.int32), np.zeros(256, dtype=np.int32)
+        nb, ns = C.c_int(), C.c_int()
+        self.ck(self.L.bka_gpt2_init_chain(_iptr(bits), len(bits), C.byref(nb), _iptr(steps), len(steps), C.byref(ns)))
+        return bits[:nb.value].tolist(), steps[:ns.value].tolist()
+
     def oddbaby_tree(self, deg):
         buf = np.zeros(4096, dtype=np.int32)
         n, depth, m, l = C.c_int(), C.c_int(), C.c_int(), C.c_int()
@@ -150,6 +157,7 @@ class Session:
     def __init__(self, app, log_n, bits, hamming_weight, device, rotation_steps, secret_key=None):
         self.app, self.log_n, self.bits = app, log_n, list(bits)
         self.slots = 1 << (log_n - 1)
+        self.top_limbs = len(self.bits) - 1      # data limbs of a fresh ciphertext
         arr = (C.c_int * len(bits))(*bits)
         st = (C.c_int * max(1, len(rotation_steps)))(*rotation_steps)
         self.h = C.c_void_p()
@@ -301,6 +309,18 @@ class Session:
 
     def resnet(self, layer_num, weights):
         return ResNet(self, layer_num, weights)
+
+    def gpt2(self, op, cts=(), i=(), d=(), boot=None, out_cap=256):
+        """One GPT-2 operator of gpt2/approx.h by name (see include/b200ckks_app.h); returns a list of Ct."""
+        ins = (C.c_void_p * max(1, len(cts)))(*[c.h for c in cts])
+        ip = np.ascontiguousarray(np.asarray(i, dtype=np.int32).ravel())
+        dp = np.ascontiguousarray(np.asarray(d, dtype=np.float64).ravel())
+        outs = (C.c_void_p * out_cap)()
+        n = C.c_int()
+        self.app.ck(self.app.L.bka_gpt2_call(self.h, boot.h if boot is not None else None, op.encode(), ins, len(cts),
+                                             _dptr(dp) if dp.size else None, int(dp.size), _iptr(ip) if ip.size else None,
+                                             int(ip.size), outs, out_cap, C.byref(n)))
+        return [Ct(self, C.c_void_p(outs[k])) for k in range(n.value)]
 
 
 class Bootstrapper:

@@ -104,6 +104,27 @@ int bka_bootstrap(bka_bootstrapper_t b, bka_ct_t ct, int real_message, bka_ct_t 
 /* EvalMod alone: ModularReducer::modular_reduction */
 int bka_modular_reduction(bka_bootstrapper_t b, bka_ct_t ct, bka_ct_t *out);
 
+/* ---- GPT-2 operators (gpt2_ckks/gpt2-ckks/single-key/gpt2/approx.h: MatrixMul.cpp, PolyApprox.cpp, IterApprox.cpp,
+ * Fold.cpp, pack.cpp, optimize.cpp, util.cpp) ---------------------------------------------------------------------
+ * One entry point selected by operator name; ciphertext arguments in `in`, the operator's integer / double
+ * arguments in iparams / dparams, results as new handles in `out` (count in *n_out).  Inputs are never modified
+ * (operators the reference runs in place work on a copy that is returned).  `boot` may be NULL except for
+ * "bootstrap", "quickMax" below 18 limbs and "softmax".
+ *   quickSum(i: n)  sign_f  sign_g  gelu_p  gelu_q  cheby_basis(i: n)  sign(i: df, dg)  gelu  exp(i: r)
+ *   inverse(i: iters)  taylor(i: iters; d: guess)  inv_sqrt(i: iters; d: guess)
+ *   layernorm(i: row_size; d: gamma[row_size], beta[row_size])  max(2 cts)  quickMax(i: n)
+ *   smax(i: r, gamma)  softmax(i: r, unused)  mask_out(i: start, length)  rotate_inplace(i: steps)
+ *   surefire_rotate(i: shift)  fake_bootstrap  bootstrap  init_output(i: count)
+ *   pack_from_row(i: rows, cols; d: matrix)  expand_bias(d: bias)  pack_tight(8 + 3 cts)  unpack_tight(3 + 8 cts)
+ *   row_matmul / attn_proj_row / attn_proj_col(i: n_left, n_weights, n_outputs, A_rows, A_cols, W_rows, W_cols;
+ *       cts: left.., weights.., bias, outputs..)   col_matmul(i: rows, cols; cts: left.., right..)
+ *   qk_matmul / sv_matmul(i: heads, n_outputs; cts: first.., second.., outputs..)
+ *   augment_row / augment_col(i: n, padded_row_size, idx; cts: A.., cached..) */
+int bka_gpt2_call(bka_session_t s, bka_bootstrapper_t boot, const char *op, bka_ct_t *in, int n_in, const double *dparams, int n_d,
+                  const int *iparams, int n_i, bka_ct_t *out, int out_cap, int *n_out);
+/* the 37-prime chain {49, 46 x 21, 49 x 14, 60} and the rotation-step list of the reference's INIT macro (util.h:37-75) */
+int bka_gpt2_init_chain(int *bits_out, int bits_cap, int *n_bits, int *steps_out, int steps_cap, int *n_steps);
+
 /* ---- approximate ReLU (alpha = 13: comp_no 3, degrees {15,15,27}, scaled_val 1.7; infer_seal.cpp:255-262) ------ */
 int bka_relu(bka_session_t s, bka_ct_t ct, bka_ct_t *out);
 /* evaluation trees of upgrade_oddbaby(deg): heap array (capacity cap), m, l */

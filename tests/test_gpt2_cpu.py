@@ -1,0 +1,115 @@
+"""GPT-2 operators on the CPU.  (1) The float64 slot model oracle/gpt2_model.py is pinned to the expected vectors of the
+reference's own doctest cases (gpt2_ckks/run/run_approx_test.cpp).  (2) The restated operators of
+fhe-gpt-2_b200/host/gpt2, compiled against the REFERENCE's own SEAL (oracle/_ref/libapp_ref.so), reproduce the model
+and the level trajectories; tests/test_gpt2_gpu.py runs the identical cases on the engine."""
+import numpy as np
+import pytest
+
+import appref
+import gpt2_cases as cases
+import gpt2_model as gm
+
+
+def test_model_reproduces_the_reference_doctest_vectors():
+    fn = {"sign_f": gm.sign_f, "sign_g": gm.sign_g, "sign": lambda x: gm.sign_function(x, 2, 2), "gelu_p": gm.gelu_p,
+          "gelu_q": gm.gelu_q, "exp": lambda x: gm.exp(x, 6)}
+    for op, (v, want) in cases.KAT.items():
+        got = fn[op](np.array(v, dtype=float))
+        # the vectors are printed with 8-10 significant digits
+        assert np.abs(got - want).max() <= 5e-9 * (1 + np.abs(want).max()), op
+    v = np.zeros(64)
+    v[:16] = [1, 2, 3, 4, 5, 6, 7, 8] * 2
+    assert np.array_equal(gm.quick_sum(v, 8)[:8], np.full(8, 36.0))                      # run_approx_test.cpp:616-640
+    a, b = np.array([0.1, 0.5, 0.003, 0.4, -0.2]), np.array([0.3, 0.1, 0.1, -0.6, 0.0001])
+    assert np.abs(gm.compute_max(a, b) - np.maximum(a, b)).max() < 1e-3                    # :642-672
+    v = np.zeros(64)
+    v[:16] = [.1, .2, .3, .4, .5, .6, .7, .8] * 2
+    assert np.abs(gm.quick_max(v, 8)[:8] - 0.8).max() < 1e-3                               # :674-709
+
+
+def test_model_packing_and_matmul_are_linear_algebra():
+    rng = np.random.default_rng(0)
+    # PackFromRow of run_approx_test.cpp:104-170: A[i][j] = 768 i + j, fold format -> tight format = 0, 1, 2, ...
+    A = np.arange(128 * 768, dtype=float).reshape(128, 768)
+    fold = gm.pack_plain_row(A)
+    assert fold.shape == (8, 32768) and fold[1, 2048 + 5] == A[17, 5]
+    tight = gm.pack_tight(list(fold), [np.zeros(32768) for _ in range(3)])
+    assert np.array_equal(np.concatenate(tight), np.arange(3 * 32768, dtype=float))
+    # RowMatMul shapes of run_approx_test.cpp:233-303 (8 x 2048, ones) on the model
+    ones = gm.pack_plain_row(np.ones((8, 2048)))
+    out = gm.row_matmul([ones[0]], [ones[0]], np.zeros(32768), [np.zeros(32768)], 2048, 8)[0]
+    assert all(out[i * 16 + j] == 2048.0 for i in range(8) for j in range(8))
+    # ColMatMul
+    x, y = np.zeros(16), np.zeros(16)
+    x[:3], y[:6] = [1, 2, 3], [4, 5, 6, 4, 5, 6]
+    outs = gm.col_matmul([x], [y], 3)
+    assert [list(o[:3]) for o in outs] == [[4, 10, 18], [5, 12, 12], [6, 8, 15]]
+    # smax rows sum to one over the 128 scores of each 256-slot chunk (gamma is truncated to int as in the reference)
+    s = np.zeros(32768)
+    for i in range(128):
+        s[i * 256:i * 256 + 128] = rng.uniform(-1, 1, 128)
+    p = gm.smax(s, 0.1)
+    sums = np.array([p[i * 256:i * 256 + 128].sum() for i in range(128)])
+    # four Goldschmidt steps leave a factor 1 - (1 - d)^16 with d = 0.001 * sum(exp) ~ 0.15: rows sum to ~0.93
+    assert np.abs(sums - 1).max() < 0.15
+
+
+needs_ref = pytest.mark.skipif(not appref.available(), reason="oracle/_ref/libapp_ref.so not built")
+
+
+@pytest.fixture(scope="module")
+def app():
+    return appref.app()
+
+
+@pytest.fixture(scope="module")
+def poly_session(app):
+    s = app.session(cases.SMALL_LOG_N, cases.POLY_BITS, hamming_weight=64, rotation_steps=cases.pow2_steps(2048))
+    yield s
+    s.close()
+
+
+@needs_ref
+def test_init_chain_is_the_reference_macro(app):
+    bits, steps = app.gpt2_init_chain()
+    assert bits == [49] + [46] * 21 + [49] * 14 + [60]          # util.h:45-48 with run_approx_test.cpp:22-27
+    assert steps[:15] == [1 << i for i in range(15)] and 32640 in steps and 30720 in steps and len(set(steps)) == len(steps)
+
+
+@needs_ref
+def test_fold_and_mask(poly_session):
+    cases.case_fold_and_mask(poly_session)
+
+
+@needs_ref
+def test_polynomials(poly_session):
+    cases.case_polynomials(poly_session)
+
+
+@needs_ref
+def test_iterations(poly_session):
+    cases.case_iterations(poly_session)
+
+
+@needs_ref
+def test_max(poly_session):
+    cases.case_max(poly_session)
+
+
+@needs_ref
+def test_gelu_level_trajectory(poly_session):
+    limbs, scale = cases.case_gelu_levels(poly_session)
+    assert limbs == 23 - 19 and 0.5 < scale / cases.SCALE < 2.0
+
+
+@needs_ref
+def test_col_matmul(poly_session):
+    cases.case_col_matmul(poly_session)
+
+
+@needs_ref
+def test_row_matmul(app):
+    steps = cases.row_matmul_steps(2048, 64, 16, 1, 1)
+    s = app.session(cases.SMALL_LOG_N, cases.SHORT_BITS, hamming_weight=64, rotation_steps=steps)
+    cases.case_row_matmul(s, W_rows=64, rows=16)
+    s.close()
