@@ -850,6 +850,36 @@ extern "C"
         BK_CUDA(cudaStreamSynchronize(ctx->stream()));
         BK_END
     }
+    bk_status bk_sync_device(bk_context_t ctx)
+    {
+        BK_TRY
+        ctx->activate();
+        BK_CUDA(cudaDeviceSynchronize());
+        BK_END
+    }
+    bk_status bk_event_record(bk_context_t ctx, bk_event_t *event_out)
+    {
+        BK_TRY
+        cudaStream_t s = ctx->stream();
+        cudaEvent_t e;
+        BK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        BK_CUDA(cudaEventRecord(e, s));
+        *event_out = reinterpret_cast<bk_event_t>(e);
+        BK_END
+    }
+    bk_status bk_stream_wait_event(bk_context_t ctx, bk_event_t event)
+    {
+        BK_TRY
+        BK_CUDA(cudaStreamWaitEvent(ctx->stream(), reinterpret_cast<cudaEvent_t>(event), 0));
+        BK_END
+    }
+    bk_status bk_event_destroy(bk_event_t event)
+    {
+        BK_TRY
+        if (event)
+            BK_CUDA(cudaEventDestroy(reinterpret_cast<cudaEvent_t>(event)));
+        BK_END
+    }
     bk_status bk_stream(bk_context_t ctx, void **stream_out)
     {
         BK_TRY

@@ -8,9 +8,13 @@
 #include "gpt2/approx.h"
 #include "gpt2/test_util.h"
 #include <algorithm>
+#include <condition_variable>
 #include <cstring>
+#include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
+#include <thread>
 
 using namespace seal;
 using std::vector;
@@ -94,11 +98,94 @@ struct bka_bootstrapper_s
     }
 };
 
+// Host threads that each run whole images on their own CUDA stream - the reference's `#pragma omp parallel for` over
+// images (infer_seal.cpp:404) with a fixed set of threads, so that the engine's per-thread streams and staging rings
+// are created once.
+class ImageWorkers
+{
+public:
+    ~ImageWorkers()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_)
+            t.join();
+    }
+    // runs job(i) for i in [0, n) on up to `width` workers; rethrows the first exception
+    void run(int n, int width, const std::function<void(int)> &job)
+    {
+        width = std::max(1, std::min(width, n));
+        while ((int)threads_.size() < width)
+            threads_.emplace_back([this] { loop(); });
+        std::unique_lock<std::mutex> g(mu_);
+        job_ = &job;
+        next_ = 0;
+        total_ = n;
+        width_ = width;
+        pending_ = n;
+        error_ = nullptr;
+        ++generation_;
+        cv_.notify_all();
+        done_.wait(g, [this] { return pending_ == 0; });
+        job_ = nullptr;
+        if (error_)
+            std::rethrow_exception(error_);
+    }
+
+private:
+    void loop()
+    {
+        std::uint64_t seen = 0;
+        std::unique_lock<std::mutex> g(mu_);
+        for (;;)
+        {
+            cv_.wait(g, [&] { return stop_ || (generation_ != seen && next_ < total_ && active_ < width_); });
+            if (stop_)
+                return;
+            ++active_;
+            while (next_ < total_)
+            {
+                const int i = next_++;
+                const auto *job = job_;
+                g.unlock();
+                std::exception_ptr err;
+                try
+                {
+                    (*job)(i);
+                }
+                catch (...)
+                {
+                    err = std::current_exception();
+                }
+                g.lock();
+                if (err && !error_)
+                    error_ = err;
+                if (--pending_ == 0)
+                    done_.notify_all();
+            }
+            --active_;
+            seen = generation_;
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)> *job_ = nullptr;
+    int next_ = 0, total_ = 0, width_ = 0, active_ = 0, pending_ = 0;
+    std::uint64_t generation_ = 0;
+    std::exception_ptr error_;
+    bool stop_ = false;
+};
+
 struct bka_resnet_s
 {
     bka_session_t s;
     std::unique_ptr<ResNetCifar10> net;
     bool prepared = false;
+    ImageWorkers workers;
 };
 
 static bka_ct_t wrap(Ciphertext &&c)
@@ -724,6 +811,49 @@ extern "C"
         TensorCipher outt = net->net->infer_encrypted(in, trace_out ? &trace : nullptr);
         *logits_ct = wrap(outt.cipher());
         copy_trace(trace, trace_out, trace_cap, trace_rows);
+        BKA_END
+    }
+    // n images, up to `in_flight` of them at a time, one host thread and CUDA stream each.  The workers' streams
+    // start behind everything the caller has enqueued and the caller's stream continues behind all of them, so CUDA
+    // events recorded by the caller around this call bracket the whole batch on the device.
+    static void run_images(bka_resnet_t net, int n, int in_flight, const std::function<void(int)> &job)
+    {
+#ifdef B200CKKS_FACADE
+        SEALContext &context = *net->s->context;
+        SEALContext::Mark begin = context.mark();
+        std::vector<SEALContext::Mark> ends((std::size_t)n);
+        net->workers.run(n, in_flight, [&](int i) {
+            context.after(begin);
+            job(i);
+            ends[(std::size_t)i] = context.mark();
+        });
+        for (auto &m : ends)
+            context.after(m);
+#else
+        net->workers.run(n, in_flight, [&](int i) { job(i); });
+#endif
+    }
+    int bka_resnet_infer_encrypted_batch(bka_resnet_t net, bka_ct_t *image_cts, int n_images, int in_flight, bka_ct_t *logits_cts)
+    {
+        BKA_TRY
+        resnet_ready(net);
+        std::vector<Ciphertext> results((std::size_t)n_images);
+        run_images(net, n_images, in_flight, [&](int i) {
+            TensorCipher in(ResNetCifar10::logn, 1, 32, 32, 3, 3, 8, image_cts[i]->ct);
+            results[(std::size_t)i] = net->net->infer_encrypted(in, nullptr).cipher();
+        });
+        for (int i = 0; i < n_images; i++)
+            logits_cts[i] = wrap(std::move(results[(std::size_t)i]));
+        BKA_END
+    }
+    int bka_resnet_infer_batch(bka_resnet_t net, const double *images, int n_images, int in_flight, double *logits_out)
+    {
+        BKA_TRY
+        resnet_ready(net);
+        run_images(net, n_images, in_flight, [&](int i) {
+            vector<double> logits = net->net->infer(vector<double>(images + (std::size_t)i * 3072, images + (std::size_t)(i + 1) * 3072));
+            std::memcpy(logits_out + (std::size_t)i * 10, logits.data(), 10 * sizeof(double));
+        });
         BKA_END
     }
     int bka_resnet_decrypt_logits(bka_resnet_t net, bka_ct_t logits_ct, double *logits_out)

@@ -267,10 +267,13 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     auto conv = [&](int stage, int co, int st) {
         // weights and masks of a layer are the same for every image: built once, their encodings stay in HBM
         std::unique_ptr<ConvPlan> &plan = conv_plans_[(std::size_t)stage];
-        if (!plan)
-            plan = std::make_unique<ConvPlan>(build_conv_plan(cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
-                                                              w_.bn_running_var[(std::size_t)stage],
-                                                              w_.bn_weight[(std::size_t)stage], epsilon));
+        {
+            std::lock_guard<std::mutex> guard(plan_mu_); // images may run on several host threads (infer_seal.cpp:404)
+            if (!plan)
+                plan = std::make_unique<ConvPlan>(build_conv_plan(cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
+                                                                  w_.bn_running_var[(std::size_t)stage],
+                                                                  w_.bn_weight[(std::size_t)stage], epsilon));
+        }
         multiplexed_parallel_convolution_planned(cnn, cnn, *plan, encoder_, encryptor_, evaluator_, gal_keys_);
         log_op(0, cnn);
     };

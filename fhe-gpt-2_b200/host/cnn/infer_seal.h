@@ -12,6 +12,7 @@
 #include "cnn/cnn_seal.h"
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -104,5 +105,6 @@ private:
     std::vector<minicomp::Tree> tree_;
     Bootstrapper *boot_[3];
     std::vector<std::unique_ptr<ConvPlan>> conv_plans_; // one per convolution, built at its first use
+    std::mutex plan_mu_;
     bool prepared_ = false;
 };

@@ -408,6 +408,39 @@ namespace seal
         {
             detail::check(bk_sync(impl_->h));
         }
+        // fork / join between host threads that each drive their own stream: `mark()` records the work the calling
+        // thread has enqueued so far, `after(mark)` orders the calling thread's later work behind it (no host block)
+        struct Mark
+        {
+            bk_event_t e = nullptr;
+            Mark() = default;
+            Mark(const Mark &) = delete;
+            Mark &operator=(const Mark &) = delete;
+            Mark(Mark &&o) noexcept : e(o.e)
+            {
+                o.e = nullptr;
+            }
+            Mark &operator=(Mark &&o) noexcept
+            {
+                std::swap(e, o.e);
+                return *this;
+            }
+            ~Mark()
+            {
+                if (e)
+                    bk_event_destroy(e);
+            }
+        };
+        SEAL_NODISCARD Mark mark() const
+        {
+            Mark m;
+            detail::check(bk_event_record(impl_->h, &m.e));
+            return m;
+        }
+        void after(const Mark &m) const
+        {
+            detail::check(bk_stream_wait_event(impl_->h, m.e));
+        }
 
     private:
         static int total_bits(const std::vector<Modulus> &m, int l)
@@ -844,7 +877,10 @@ namespace seal
             {
                 int ol = it->second;
                 s.bytes -= (std::uint64_t)ol * 2 * (ol + 1) * (8ull << s.ctx->log_n);
+                detail::check(bk_sync_device(s.ctx->h)); // rotations of other host threads may still read the old key
             }
+            else
+                detail::check(bk_sync(s.ctx->h)); // the new key is complete before other streams can pick it up
             detail::check(bk_gkeys_set(s.h, elt, key)); // frees the smaller key it replaces
             s.resident[elt] = limbs;
             s.bytes += nb;

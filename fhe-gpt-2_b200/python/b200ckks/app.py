@@ -415,3 +415,18 @@ class ResNet:
                                                     C.byref(rows)))
         t = [dict(op=OPS[int(r[0])], level=int(r[1]), scale=float(r[2]), ms=float(r[3])) for r in tr[:rows.value]]
         return logits, t
+
+    def infer_batch(self, images, in_flight):
+        """bka_resnet_infer_batch: images (n, 3072) on the host -> logits (n, 10); `in_flight` images at a time, one host
+        thread and CUDA stream each (the reference's OpenMP image loop, infer_seal.cpp:404)."""
+        imgs = np.ascontiguousarray(images, dtype=np.float64).reshape(-1, 3072)
+        logits = np.zeros((imgs.shape[0], 10))
+        self.s.app.ck(self.s.app.L.bka_resnet_infer_batch(self.h, _dptr(imgs), imgs.shape[0], int(in_flight), _dptr(logits)))
+        return logits
+
+    def infer_encrypted_batch(self, cts, in_flight):
+        """bka_resnet_infer_encrypted_batch: inputs and outputs stay in HBM."""
+        ins = (C.c_void_p * len(cts))(*[c.h for c in cts])
+        outs = (C.c_void_p * len(cts))()
+        self.s.app.ck(self.s.app.L.bka_resnet_infer_encrypted_batch(self.h, ins, len(cts), int(in_flight), outs))
+        return [Ct(self.s, C.c_void_p(outs[k])) for k in range(len(cts))]

@@ -75,6 +75,15 @@ bk_status bk_context_set_ks_chunk(bk_context_t ctx, int chunk);
 bk_status bk_sync(bk_context_t ctx);
 /* CUDA stream of the calling host thread (cudaStream_t as void*), for event timing / interop. */
 bk_status bk_stream(bk_context_t ctx, void **stream_out);
+/* block until every stream of the device has drained (before an object other host threads may be reading is freed). */
+bk_status bk_sync_device(bk_context_t ctx);
+/* Hand-over points between host threads (the reference runs one image per OpenMP thread over shared keys,
+ * infer_seal.cpp:404): bk_event_record marks the work enqueued so far on the calling thread's stream,
+ * bk_stream_wait_event makes the calling thread's stream wait for such a mark without blocking the host. */
+typedef struct bk_event_s *bk_event_t;
+bk_status bk_event_record(bk_context_t ctx, bk_event_t *event_out);
+bk_status bk_stream_wait_event(bk_context_t ctx, bk_event_t event);
+bk_status bk_event_destroy(bk_event_t event);
 /* number of kernels this context has launched so far (all threads). */
 bk_status bk_launch_count(bk_context_t ctx, uint64_t *count_out);
 

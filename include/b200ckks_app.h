@@ -162,6 +162,12 @@ int bka_resnet_encrypt_image(bka_resnet_t net, const double *image, bka_ct_t *ou
 int bka_resnet_infer_encrypted(bka_resnet_t net, bka_ct_t image_ct, bka_ct_t *logits_ct, double *trace_out, int trace_cap,
                                int *trace_rows);
 int bka_resnet_decrypt_logits(bka_resnet_t net, bka_ct_t logits_ct, double *logits_out);
+/* The reference's image loop (`#pragma omp parallel for` over images sharing the keys, infer_seal.cpp:404-577):
+ * n_images images, up to in_flight of them concurrently, one host thread and one CUDA stream per image in flight.
+ * images: n_images x 3072 doubles, logits_out: n_images x 10.  The encrypted variant keeps inputs and outputs in
+ * HBM.  Work of the batch is ordered after what the calling thread enqueued before and before what it enqueues next. */
+int bka_resnet_infer_batch(bka_resnet_t net, const double *images, int n_images, int in_flight, double *logits_out);
+int bka_resnet_infer_encrypted_batch(bka_resnet_t net, bka_ct_t *image_cts, int n_images, int in_flight, bka_ct_t *logits_cts);
 
 #ifdef __cplusplus
 }

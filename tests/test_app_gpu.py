@@ -106,6 +106,15 @@ def test_resnet20_end_to_end_matches_model_and_reference_trajectory(big_session)
     assert np.abs(net.decrypt_logits(out) - logits).max() < 5e-3      # same keys: only fresh-encryption noise differs
     kb, _ = s.key_residency()
     assert kb < 100 * 2 ** 30            # level-pruned keys fit one B200 (the reference's layout needs 275 GiB)
+    # the reference's image loop (one image per OpenMP thread over shared keys, infer_seal.cpp:404): three images, two
+    # in flight on their own host threads / CUDA streams, agree with the images run one after the other
+    imgs = np.stack([synthetic.synthetic_image(i) for i in range(3)])
+    alone = [logits, net.infer(imgs[1], trace=False)[0], net.infer(imgs[2], trace=False)[0]]
+    together = net.infer_batch(imgs, 2)
+    assert np.abs(together - np.stack(alone)).max() < 5e-3
+    cts = [net.encrypt_image(imgs[i]) for i in range(3)]
+    outs = net.infer_encrypted_batch(cts, 3)
+    assert np.abs(np.stack([net.decrypt_logits(o) for o in outs]) - np.stack(alone)).max() < 5e-3
 
 
 GPT2_BITS = [49] + [46] * 21 + [49] * 14 + [60]     # gpt2 util.h:22-27 (INIT macro): 37 primes, 60-bit special prime
