@@ -272,9 +272,14 @@ def run_engine(args):
             kernels[fam] = {"launches": n_launch, "ms": round(fam_ms, 2), "share_of_kernel_time": round(fam_ms / total_kernel_ms, 4),
                             "limb_polys": units, "algorithmic_GBps": round(gbs, 1), "frac_of_hbm_peak": round(gbs / peak, 4)}
         dom = max(kernels, key=lambda k: kernels[k]["ms"])
-        traffic = None
+        # DRAM bytes of this kernel from an `ncu --set full` capture.  ncu over the ~94k launches of an image is
+        # impractical, so the capture is the same kernel inside an l = 31 key switch (its dominant caller here); the
+        # algorithmic bytes of THAT launch are given beside it (traffic / traffic_algorithmic_bytes = re-read factor).
+        traffic, traffic_algo = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(f"{dom}_resnet20")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(f"{dom}_resnet20", tj.get(f"{dom}_l31"))
+            traffic_algo = tj.get(f"{dom}_l31_algorithmic")
         except Exception:
             pass
         d = kernels[dom]
@@ -282,6 +287,8 @@ def run_engine(args):
                                             "inv_blocks": "k_inv_blocks", "inv_cols": "k_inv_cols", "ks_mac": "k_ks_mac",
                                             "elementwise": "k_ew / k_scalar_pack", "fft": "k_fft_*", "other": "other"}[dom],
                 "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": traffic,
+                "traffic_algorithmic_bytes": traffic_algo,
+                "traffic_source": "profiles/r1_ncu_full_keyswitch_l31.md (one launch of this kernel in an l=31 key-switch chunk)",
                 "peak_source": which, "launches_per_step": d["launches"], "ms_per_launch": round(d["ms"] / d["launches"], 5),
                 "kernel_share_of_step": round(d["ms"] / prof_ms, 4),
                 "algorithmic_bytes_per_launch": int(d["limb_polys"] * ALGO_BYTES_PER_UNIT[dom] / d["launches"]),
