@@ -2,7 +2,11 @@
 #include "cnn/infer_seal.h"
 #include "common/cached.h"
 #include <algorithm>
+#include <atomic>
 #include <chrono>
+#include <cstdlib>
+#include <mutex>
+#include <thread>
 #include <cmath>
 #include <fstream>
 #include <iostream>
@@ -457,8 +461,28 @@ void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_i
     if (!have_images)
         std::cout << "no " << images_dir << "/test_values.txt: synthetic images, labels not checked" << std::endl;
 
+    // the reference's `#pragma omp parallel for num_threads(50)` over images (infer_seal.cpp:404): here
+    // $B200CKKS_IMAGES_IN_FLIGHT host threads (default 1), each with its own CUDA stream, over the shared keys
+    int in_flight = 1;
+    if (const char *e = std::getenv("B200CKKS_IMAGES_IN_FLIGHT"))
+        in_flight = std::max(1, std::atoi(e));
+    in_flight = (int)std::min<std::size_t>((std::size_t)in_flight, end_image_id - start_image_id + 1);
+    if (in_flight > 1)
+    { // the first image alone: it builds the convolution plans, generates the level-pruned keys and fills the cache
+        vector<double> warm(32 * 32 * 3, 0.0);
+        net.infer(warm, nullptr);
+    }
+#ifdef B200CKKS_FACADE
+    context.sync(); // set-up ran on this thread's stream; the image threads start from a drained device
+#endif
+    std::mutex report_mu;
+    std::atomic<std::size_t> next_image{ start_image_id };
+    std::exception_ptr failure;
     auto all_start = std::chrono::high_resolution_clock::now();
-    for (std::size_t image_id = start_image_id; image_id <= end_image_id; image_id++)
+    auto image_loop = [&]() {
+    try
+    {
+    for (std::size_t image_id = next_image++; image_id <= end_image_id; image_id = next_image++)
     {
         vector<double> image(32 * 32 * 3);
         int image_label = -1;
@@ -521,10 +545,31 @@ void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_i
         output << "image label: " << image_label << std::endl;
         output << "inferred label: " << label << std::endl;
         output << "max score: " << max_score << std::endl;
+        std::lock_guard<std::mutex> guard(report_mu);
         out_share << "image_id: " << image_id << ", image label: " << image_label << ", inferred label: " << label << std::endl;
         std::cout << "image " << image_id << ": total time : " << (long)total_ms << " ms, inferred label: " << label
                   << ", max score: " << max_score << std::endl;
     }
+    }
+    catch (...)
+    {
+        std::lock_guard<std::mutex> guard(report_mu);
+        if (!failure)
+            failure = std::current_exception();
+    }
+    };
+    if (in_flight <= 1)
+        image_loop();
+    else
+    {
+        vector<std::thread> threads;
+        for (int t = 0; t < in_flight; t++)
+            threads.emplace_back(image_loop);
+        for (auto &t : threads)
+            t.join();
+    }
+    if (failure)
+        std::rethrow_exception(failure);
     const double all_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - all_start).count();
     std::cout << "all threads time : " << (long)all_ms << " ms" << std::endl;
     out_share << std::endl << "all threads time : " << (long)all_ms << " ms" << std::endl;

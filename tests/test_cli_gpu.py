@@ -56,3 +56,22 @@ def test_cnn_cli_resnet20_log_format(tmp_path):
     assert re.search(r"total time : \d+ ms", log)
     share = open(os.path.join(out, "resnet20_cifar10_label_0_0")).read()
     assert "image_id: 0" in share and "all threads time" in share
+
+
+@pytest.mark.gpu
+def test_cnn_cli_images_in_flight(tmp_path):
+    """./cnn 20 10 0 2 with two images in flight (the reference's OpenMP image loop): one log per image, same logits
+    for the same synthetic image as a run with one image at a time would give (seeded keys)."""
+    out = str(tmp_path / "result")
+    env = dict(os.environ, B200CKKS_IMAGES_IN_FLIGHT="2", B200CKKS_SEED="0x5EA1C0DE")
+    r = subprocess.run([os.path.join(LIB, "cnn"), "20", "10", "0", "2", out], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=1500, env=env)
+    assert r.returncode == 0, r.stdout[-2000:]
+    logits = []
+    for i in range(3):
+        log = open(os.path.join(out, f"resnet20_cifar10_image{i}.txt")).read()
+        logits.append([float(x) for x in re.findall(r"\(([-0-9.eE+]+),0\)", log)])
+        assert len(logits[-1]) == 10 and log.count("bootstrapping...") == 18
+    assert logits[0] != logits[1]                      # different synthetic images
+    share = open(os.path.join(out, "resnet20_cifar10_label_0_2")).read()
+    assert sorted(int(x) for x in re.findall(r"image_id: (\d+)", share)) == [0, 1, 2]
