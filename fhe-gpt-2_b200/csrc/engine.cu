@@ -83,6 +83,8 @@ namespace bk
             throw std::invalid_argument("poly_modulus_degree must be 2^12 .. 2^16");
         if (n_primes < 2 || n_primes > 62)
             throw std::invalid_argument("coeff_modulus size is invalid");
+        if (const char *e = std::getenv("B200CKKS_HYBRID_KS"))
+            hybrid = std::atoi(e) != 0;
         int dev_count = 0;
         if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
             throw NoDevice("no CUDA device: this engine has no CPU path");
@@ -207,6 +209,19 @@ namespace bk
             cudaStreamDestroy(kv.second);
         for (auto &kv : galois_tables)
             cudaFree(kv.second);
+        for (auto &kv : hplans)
+        {
+            HybridPlan *P = kv.second;
+            cudaFree(P->d_prescale);
+            cudaFree(P->d_limb_primes);
+            cudaFree(P->d_w);
+            cudaFree(P->d_sprescale);
+            cudaFree(P->d_sprimes);
+            cudaFree(P->d_ws);
+            cudaFree(P->d_psinv);
+            cudaFree(P->d_keyfactor);
+            delete P;
+        }
         cudaFree(d_primes);
         cudaFree(d_tw);
         cudaFree(d_itw);
@@ -466,6 +481,214 @@ namespace bk
     }
 #define KS_MAC_THREADS ks_mac_threads()
 
+    // ------------------------------------------------------------------- hybrid key switch (tolerance mode)
+    // Shape of the key switch at level l of a chain with `top` data primes: alpha special moduli (the special prime plus
+    // alpha - 1 idle primes above the level; at most top - l + 1 exist) and digits of dsize = alpha - 1 primes, so that
+    // P_S exceeds every digit by a whole prime and the key-switching noise stays at the level of SEAL's 46-bit digits
+    // over a 51-bit special prime.  The pair minimises the NTT-equivalent work: l inverse NTTs, dnum (l + alpha) - l digit
+    // NTTs, the basis conversions (dsize multiply-adds per converted coefficient, ~1/8 of an NTT each) and the ModDown
+    // over alpha moduli.  alpha = 1 is SEAL's own scheme (one digit per prime); it is kept at the top level, where no
+    // prime is idle, and at l <= 5, where a key switch is a handful of latency-bound launches either way.
+    void hybrid_shape(int l, int top, int &alpha, int &dsize)
+    {
+        alpha = 1;
+        dsize = 1;
+        if (l <= 5)
+            return;
+        double best_cost = (double)l + (double)l * (l + 1) - l + l * (double)l / 8.0 + 2.0 + 2.0 * l / 8.0 + 2.0 * l;
+        for (int a = 2; a <= std::min(top - l + 1, 17); a++)
+        {
+            const int ds = a - 1, d = (l + ds - 1) / ds;
+            double cost = l + (double)d * (l + a) - l + d * ds * (double)l / 8.0 + 2.0 * a + 2.0 * a * l / 8.0 + 2.0 * l;
+            if (cost < best_cost - 1e-9)
+            {
+                best_cost = cost;
+                alpha = a;
+                dsize = ds;
+            }
+        }
+    }
+
+    template <class T> static T *upload_sync(const std::vector<T> &v)
+    {
+        T *d = nullptr;
+        BK_CUDA(cudaMalloc((void **)&d, std::max<size_t>(1, v.size()) * sizeof(T)));
+        if (!v.empty())
+            BK_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+
+    const HybridPlan &hybrid_plan(Context &c, int l)
+    {
+        {
+            std::lock_guard<std::mutex> g(c.mu);
+            auto it = c.hplans.find(l);
+            if (it != c.hplans.end())
+                return *it->second;
+        }
+        c.activate();
+        const int top = c.top_limbs(), sp = c.n_primes - 1;
+        auto P = std::make_unique<HybridPlan>();
+        P->l = l;
+        hybrid_shape(l, top, P->alpha, P->dsize);
+        P->dnum = (l + P->dsize - 1) / P->dsize;
+        P->ne = l + P->alpha;
+        const int alpha = P->alpha, dsize = P->dsize, dnum = P->dnum, ne = P->ne;
+        auto eprime = [&](int e) { return e < l + alpha - 1 ? e : sp; };
+        auto q = [&](int prime_index) { return c.primes[(size_t)prime_index]; };
+        // product of the digit's primes except `skip`, modulo m
+        auto digit_hat = [&](int d, int skip, uint64_t m) {
+            uint64_t r = 1 % m;
+            for (int j = d * dsize; j < std::min((d + 1) * dsize, l); j++)
+                if (j != skip)
+                    r = bk::mulmod(r, q(j) % m, m);
+            return r;
+        };
+        auto special_hat = [&](int skip, uint64_t m) {
+            uint64_t r = 1 % m;
+            for (int b = 0; b < alpha; b++)
+                if (b != skip)
+                    r = bk::mulmod(r, q(eprime(l + b)) % m, m);
+            return r;
+        };
+        std::vector<ulonglong2> prescale((size_t)l), sprescale((size_t)2 * alpha), psinv((size_t)l);
+        std::vector<int> limb_primes((size_t)l), sprimes((size_t)2 * alpha);
+        std::vector<u64> w((size_t)ne * dnum * dsize, 0), ws((size_t)l * alpha), keyfactor((size_t)dnum * ne, 0);
+        for (int i = 0; i < l; i++)
+        {
+            uint64_t v = bk::invmod(digit_hat(i / dsize, i, q(i)), q(i));
+            prescale[(size_t)i] = make_ulonglong2(v, bk::shoup(v, q(i)));
+            limb_primes[(size_t)i] = i;
+            uint64_t ps = special_hat(-1, q(i));
+            uint64_t pi = bk::invmod(ps, q(i));
+            psinv[(size_t)i] = make_ulonglong2(pi, bk::shoup(pi, q(i)));
+            for (int a = 0; a < alpha; a++)
+                ws[(size_t)i * alpha + a] = special_hat(a, q(i));
+            keyfactor[(size_t)(i / dsize) * ne + i] = ps;
+        }
+        for (int e = 0; e < ne; e++)
+            for (int d = 0; d < dnum; d++)
+                for (int a = 0; a < dsize && d * dsize + a < l; a++)
+                    w[((size_t)e * dnum + d) * dsize + a] = digit_hat(d, d * dsize + a, q(eprime(e)));
+        for (int p = 0; p < 2; p++)
+            for (int a = 0; a < alpha; a++)
+            {
+                uint64_t m = q(eprime(l + a));
+                uint64_t v = bk::invmod(special_hat(a, m), m);
+                sprescale[(size_t)p * alpha + a] = make_ulonglong2(v, bk::shoup(v, m));
+                sprimes[(size_t)p * alpha + a] = eprime(l + a);
+            }
+        P->d_prescale = upload_sync(prescale);
+        P->d_limb_primes = upload_sync(limb_primes);
+        P->d_w = upload_sync(w);
+        P->d_sprescale = upload_sync(sprescale);
+        P->d_sprimes = upload_sync(sprimes);
+        P->d_ws = upload_sync(ws);
+        P->d_psinv = upload_sync(psinv);
+        P->d_keyfactor = upload_sync(keyfactor);
+        BK_CUDA(cudaDeviceSynchronize()); // pageable uploads must have landed before any stream reads them
+        std::lock_guard<std::mutex> g(c.mu);
+        auto ins = c.hplans.emplace(l, P.get());
+        if (ins.second)
+            P.release();
+        return *ins.first->second;
+    }
+
+    static int hyb_chunk(const HybridPlan &P)
+    {
+        // digit NTT outputs of one chunk stay in L2: at most ~96 limb-polynomials (48 MiB at N = 2^16)
+        return std::max(1, std::min(P.ne, 96 / P.dnum));
+    }
+
+    // steps B and C for one accumulator: digits of `y` extended and multiplied into `hk`, then ModDown into out
+    static void hyb_extend_and_mac(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *y, u64 *inter,
+                                   const u64 *target_ntt, int count, const uint32_t *const *perms, bk_hybkey_s *const *keys,
+                                   u64 *acc /*[count][2][ne][N]*/, int gather)
+    {
+        const size_t n = c.n;
+        const int chunk = hyb_chunk(P);
+        for (int e0 = 0; e0 < P.ne; e0 += chunk)
+        {
+            const int nE = std::min(chunk, P.ne - e0);
+            LdHybDigit ld{ y, P.d_w, n, h, e0 };
+            launch_fwd_cols(c, s, ld, inter, nE * P.dnum);
+            StHybDigit st{ inter, n, h, e0 };
+            launch_fwd_blocks(c, s, inter, st, nE * P.dnum);
+            for (int k = 0; k < count; k++)
+            {
+                HybMacArgs a{ inter, target_ntt, perms[k], keys[k]->d, acc + (size_t)k * 2 * P.ne * n, n, h, e0, gather };
+                dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE);
+                {
+                    ProfScope ps(c, s, TAG_KS_MAC, nE * 2 * P.dnum);
+                    k_ks_mac_hyb<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                }
+                c.count();
+            }
+        }
+    }
+
+    static void hyb_mod_down(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *acc, u64 *inter, u64 *tl,
+                             u64 *out, const u64 *base0, const u64 *base1, const uint32_t *perm)
+    {
+        const size_t n = c.n;
+        LdInvSpecials ld{ acc, n, h };
+        launch_inv_blocks(c, s, ld, inter, 2 * P.alpha);
+        StInvScaled st{ tl, n, P.d_sprescale, P.d_sprimes };
+        launch_inv_cols(c, s, inter, st, 2 * P.alpha);
+        LdHybDown ld2{ tl, P.d_ws, n, h };
+        launch_fwd_cols(c, s, ld2, inter, 2 * P.l);
+        StModDown st2{ acc, out, base0, base1, perm, P.d_psinv, n, P.l, P.ne };
+        launch_fwd_blocks(c, s, inter, st2, 2 * P.l);
+    }
+
+    // Same contract as key_switch below; the key is the level-l hybrid key of `key`'s recipe.
+    static void key_switch_hybrid(Context &c, cudaStream_t s, const u64 *target, const uint32_t *perm, const u64 *base0,
+                                  const u64 *base1, u64 *out, int l, bk_kskey_t key)
+    {
+        const HybridPlan &P = hybrid_plan(c, l);
+        bk_hybkey_s *hk = hybrid_key(c, key, l);
+        const size_t n = c.n;
+        const HybDims h{ l, P.alpha, P.dsize, P.dnum, c.n_primes - 1 };
+        Scratch y(s, (size_t)l * n);
+        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch acc(s, (size_t)2 * P.ne * n);
+        Scratch tl(s, (size_t)2 * P.alpha * n);
+        {
+            LdInvPlain ld{ target, limb_map(l), n, perm };
+            launch_inv_blocks(c, s, ld, inter.p, l);
+            StInvScaled st{ y.p, n, P.d_prescale, P.d_limb_primes };
+            launch_inv_cols(c, s, inter.p, st, l);
+        }
+        hyb_extend_and_mac(c, s, P, h, y.p, inter.p, target, 1, &perm, &hk, acc.p, 0);
+        hyb_mod_down(c, s, P, h, acc.p, inter.p, tl.p, out, base0, base1, perm);
+    }
+
+    static void key_switch_hoisted_hybrid(Context &c, cudaStream_t s, const bk_ct_s *in, int count, const uint32_t *const *perms,
+                                          const bk_kskey_t *keys, u64 *const *outs)
+    {
+        const int l = in->limbs;
+        const HybridPlan &P = hybrid_plan(c, l);
+        std::vector<bk_hybkey_s *> hks((size_t)count);
+        for (int k = 0; k < count; k++)
+            hks[(size_t)k] = hybrid_key(c, keys[k], l);
+        const size_t n = c.n;
+        const HybDims h{ l, P.alpha, P.dsize, P.dnum, c.n_primes - 1 };
+        const u64 *c0 = in->d, *c1 = in->d + (size_t)l * n;
+        Scratch y(s, (size_t)l * n);
+        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch acc(s, (size_t)count * 2 * P.ne * n);
+        Scratch tl(s, (size_t)2 * P.alpha * n);
+        {
+            LdInvPlain ld{ c1, limb_map(l), n, nullptr };
+            launch_inv_blocks(c, s, ld, inter.p, l);
+            StInvScaled st{ y.p, n, P.d_prescale, P.d_limb_primes };
+            launch_inv_cols(c, s, inter.p, st, l);
+        }
+        hyb_extend_and_mac(c, s, P, h, y.p, inter.p, c1, count, perms, hks.data(), acc.p, 1);
+        for (int k = 0; k < count; k++)
+            hyb_mod_down(c, s, P, h, acc.p + (size_t)k * 2 * P.ne * n, inter.p, tl.p, outs[k], c0, nullptr, perms[k]);
+    }
+
     // ------------------------------------------------------------------------------- key switch
     // Evaluator::switch_key_inplace (evaluator.cpp:2281-2525) with the Galois permutation of
     // apply_galois_inplace (:2191-2207) fused in.  target: [l][N] NTT form.  If perm != null the
@@ -474,6 +697,20 @@ namespace bk
     static void key_switch(Context &c, cudaStream_t s, const u64 *target, const uint32_t *perm, const u64 *base0,
                            const u64 *base1, u64 *out, int l, bk_kskey_t key)
     {
+        bk_kskey_s level_view; // hybrid mode at a level whose shape is SEAL's own: its level key is a pruned SEAL key
+        if (c.hybrid && key->sk)
+        {
+            if (hybrid_plan(c, l).alpha > 1)
+            {
+                key_switch_hybrid(c, s, target, perm, base0, base1, out, l, key);
+                return;
+            }
+            bk_hybkey_s *hk = hybrid_key(c, key, l);
+            level_view.ctx = key->ctx;
+            level_view.d = hk->d;
+            level_view.digits = level_view.klimbs = l;
+            key = &level_view;
+        }
         if (key->digits < l || key->klimbs < l)
             throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (key pruned below "
                                         "this level)");
@@ -531,6 +768,26 @@ namespace bk
                                    const bk_kskey_t *keys, u64 *const *outs)
     {
         const int l = in->limbs;
+        std::vector<bk_kskey_s> level_views;
+        std::vector<bk_kskey_t> level_keys;
+        if (c.hybrid && count > 0 && keys[0]->sk)
+        {
+            if (hybrid_plan(c, l).alpha > 1)
+            {
+                key_switch_hoisted_hybrid(c, s, in, count, perms, keys, outs);
+                return;
+            }
+            level_views = std::vector<bk_kskey_s>((size_t)count);
+            for (int k = 0; k < count; k++)
+            {
+                bk_hybkey_s *hk = hybrid_key(c, keys[k], l);
+                level_views[(size_t)k].ctx = keys[k]->ctx;
+                level_views[(size_t)k].d = hk->d;
+                level_views[(size_t)k].digits = level_views[(size_t)k].klimbs = l;
+                level_keys.push_back(&level_views[(size_t)k]);
+            }
+            keys = level_keys.data();
+        }
         for (int k = 0; k < count; k++)
             if (keys[k]->digits < l || keys[k]->klimbs < l)
                 throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (key pruned below "
@@ -848,6 +1105,23 @@ extern "C"
     {
         BK_TRY
         BK_CUDA(cudaStreamSynchronize(ctx->stream()));
+        BK_END
+    }
+    bk_status bk_context_set_hybrid(bk_context_t ctx, int on)
+    {
+        BK_TRY
+        ctx->hybrid = on != 0;
+        BK_END
+    }
+    bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys)
+    {
+        BK_TRY
+        if (on)
+            *on = ctx->hybrid ? 1 : 0;
+        if (key_bytes)
+            *key_bytes = ctx->hybrid_key_bytes.load();
+        if (keys)
+            *keys = ctx->hybrid_keys.load();
         BK_END
     }
     bk_status bk_sync_device(bk_context_t ctx)
@@ -1236,6 +1510,12 @@ extern "C"
             key->ctx->activate();
             cudaStreamSynchronize(key->ctx->stream());
             cudaFree(key->d);
+            for (auto &kv : key->hyb)
+            {
+                key->ctx->hybrid_key_bytes.fetch_sub(kv.second->words * sizeof(u64));
+                cudaFree(kv.second->d);
+                delete kv.second;
+            }
             delete key;
         }
         BK_END

@@ -66,6 +66,21 @@ namespace bk
         int next = 0;
     };
 
+    // Level-aware hybrid key switching (tolerance mode): constants of one level, see kernels.cuh (HybDims) and
+    // engine.cu (hybrid_plan / key_switch_hybrid).  All pointers are device memory owned by the context.
+    struct HybridPlan
+    {
+        int l = 0, alpha = 1, dsize = 1, dnum = 0, ne = 0; // alpha special moduli, digits of dsize primes
+        ulonglong2 *d_prescale = nullptr;  // [l] {(Q_d / q_i)^-1 mod q_i, shoup}
+        int *d_limb_primes = nullptr;      // [l] identity map for the scaled INTT store
+        u64 *d_w = nullptr;                // [ne][dnum][dsize] (Q_d / q_i) mod p_e
+        ulonglong2 *d_sprescale = nullptr; // [2 alpha] {(P_S / p_a)^-1 mod p_a, shoup}, repeated for both polynomials
+        int *d_sprimes = nullptr;          // [2 alpha] prime index of each special limb
+        u64 *d_ws = nullptr;               // [l][alpha] (P_S / p_a) mod q_i
+        ulonglong2 *d_psinv = nullptr;     // [l] {P_S^-1 mod q_i, shoup}
+        u64 *d_keyfactor = nullptr;        // [dnum][ne] P_S mod q_e on the digit's own limbs, 0 elsewhere
+    };
+
     struct Context
     {
         int log_n = 0;
@@ -82,6 +97,11 @@ namespace bk
         NttTables tables{};
         int ks_chunk = 4;
         int sparse_slots = 0;
+        // hybrid key switching: generated keys are level-specific and not in SEAL's layout ($B200CKKS_HYBRID_KS=1 or
+        // bk_context_set_hybrid before any key is generated)
+        bool hybrid = false;
+        std::map<int, HybridPlan *> hplans;
+        std::atomic<uint64_t> hybrid_key_bytes{ 0 }, hybrid_keys{ 0 };
         std::atomic<uint64_t> launches{ 0 };
         // bytes moved between host and device by C-ABI calls (uploads, downloads, encode inputs, decode outputs)
         std::atomic<uint64_t> h2d_bytes{ 0 }, d2h_bytes{ 0 };
@@ -173,7 +193,16 @@ namespace bk
     void ensure_pt(bk_pt_t pt, int limbs);
     void destroy_encoder(Context &c);
     void rescale_core(Context &c, bk_ct_t a);
+    // hybrid key switching: constants of level l (engine.cu) and the level-l key of a key recipe (keygen.cu)
+    void hybrid_shape(int l, int top, int &alpha, int &dsize);
+    const HybridPlan &hybrid_plan(Context &c, int l);
 } // namespace bk
+struct bk_kskey_s;
+struct bk_hybkey_s;
+namespace bk
+{
+    bk_hybkey_s *hybrid_key(Context &c, bk_kskey_s *key, int l);
+}
 
 struct bk_context_s : bk::Context
 {
@@ -199,12 +228,27 @@ struct bk_pt_s
     double scale = 1.0;
 };
 
+struct bk_sk_s;
+struct bk_hybkey_s
+{
+    u64 *d = nullptr; // [dnum][2][l + alpha][N]: limbs 0 .. l + alpha - 2, then the special prime
+    int l = 0, alpha = 0, dsize = 0, dnum = 0;
+    size_t words = 0;
+};
 struct bk_kskey_s
 {
     bk::Context *ctx;
     u64 *d = nullptr; // [digits][2][klimbs+1][N], the special prime's limb at index klimbs
     int digits = 0, klimbs = 0;
     size_t words = 0;
+    // hybrid mode: the key is a recipe (secret key, what it switches from, seed) and one level-specific key per level
+    // it has been used at, generated on first use
+    bk_sk_s *sk = nullptr;
+    int kind = 0;       // 0 uploaded / SEAL layout only, 1 relinearization (s^2), 2 Galois (elt)
+    uint32_t elt = 0;
+    uint64_t seed = 0;
+    std::mutex hmu;
+    std::map<int, bk_hybkey_s *> hyb;
 };
 
 struct bk_gkeys_s

@@ -193,11 +193,13 @@ struct StModDown
     const ulonglong2 *inv; // [n_primes] {P^-1 mod q_i, shoup}
     size_t n;
     int l;
+    int acc_limbs = 0;     // limbs per polynomial of acc; 0 = l + 1 (one special prime)
     __device__ __forceinline__ int prime(int job) const { return job % l; }
     __device__ __forceinline__ u64 pre(int job, int blk, int t, int k, u64 v, const PrimeDev &pd) const
     {
         int p = job / l, i = job % l;
-        u64 r = acc[((size_t)p * (l + 1) + i) * n + (size_t)blk * 256 + 16 * t + k];
+        int al = acc_limbs ? acc_limbs : l + 1;
+        u64 r = acc[((size_t)p * al + i) * n + (size_t)blk * 256 + 16 * t + k];
         u64 d = r + 2 * pd.two_q - v;
         ulonglong2 f = inv[i];
         return csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
@@ -356,6 +358,181 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
     r1.y = barrett128(l1y, h1y, pd);
     *reinterpret_cast<ulonglong2 *>(a.acc + (size_t)I * n + e) = r0;
     *reinterpret_cast<ulonglong2 *>(a.acc + ((size_t)(a.l + 1) + I) * n + e) = r1;
+}
+
+// ============================================================================================
+// Level-aware hybrid key switching (tolerance mode; engine.cu: key_switch_hybrid).  At level l the primes above
+// the level are idle, so alpha - 1 of them join the special prime as temporary special moduli P_S; the l limbs are
+// grouped into dnum = ceil(l / dsize) digits of dsize primes (dsize = alpha - 1, or 1 when alpha = 1).  Extended limb e in [0, l + alpha): prime e for
+// e < l + alpha - 1, the special prime for the last one.  All operands below are coefficient-form residues that were
+// pre-multiplied by (Q_d / q_i)^-1 mod q_i on their way out of the inverse NTT, so a basis conversion is the plain
+// inner product  x mod p = sum_i y_i * ((Q_d / q_i) mod p)  with a 128-bit accumulator and one Barrett reduction.
+// ============================================================================================
+struct HybDims
+{
+    int l, alpha, dsize, dnum, special_prime; // alpha special moduli, digits of dsize primes (dsize < alpha keeps the
+                                              // key-switching noise a full prime below the digit size)
+    __device__ __forceinline__ int ne() const { return l + alpha; }
+    __device__ __forceinline__ int eprime(int e) const { return e < l + alpha - 1 ? e : special_prime; }
+    __device__ __forceinline__ bool own(int e, int d) const { return e < l && e / dsize == d; }
+};
+
+// canonical INTT output times a per-limb constant (Shoup), canonical
+struct StInvScaled
+{
+    u64 *dst;
+    size_t n;
+    const ulonglong2 *scale; // [jobs] {c, shoup(c)}
+    const int *primes;       // [jobs] prime index of each job
+    __device__ __forceinline__ int prime(int job) const { return primes[job]; }
+    __device__ __forceinline__ void store(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        v = csub(v, pd.q);
+        ulonglong2 f = scale[job];
+        dst[(size_t)job * n + idx] = csub(mul_shoup_lazy(v, f.x, f.y, pd.q), pd.q);
+    }
+};
+
+// digit extension: job = eloc * dnum + d -> digit d converted to extended limb e = e0 + eloc; the digit's own limbs are
+// skipped (their NTT form is the input itself)
+struct LdHybDigit
+{
+    const u64 *y;  // [l][N] pre-scaled coefficient form
+    const u64 *w;  // [ne][dnum][dsize]  (Q_d / q_{d dsize + a}) mod p_e
+    size_t n;
+    HybDims h;
+    int e0;
+    __device__ __forceinline__ bool skip(int job) const { return h.own(e0 + job / h.dnum, job % h.dnum); }
+    __device__ __forceinline__ int prime(int job) const { return h.eprime(e0 + job / h.dnum); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        const int d = job % h.dnum, e = e0 + job / h.dnum;
+        const int first = d * h.dsize, cnt = min(h.dsize, h.l - first);
+        const u64 *wv = w + ((size_t)e * h.dnum + d) * h.dsize;
+        u64 lo = 0, hi = 0;
+        for (int a = 0; a < cnt; a++)
+            mac128(lo, hi, y[(size_t)(first + a) * n + idx], wv[a]);
+        return barrett128(lo, hi, pd);
+    }
+};
+
+struct StHybDigit
+{
+    static constexpr bool RAW = true;
+    u64 *dst;
+    size_t n;
+    HybDims h;
+    int e0;
+    __device__ __forceinline__ bool skip(int job) const { return h.own(e0 + job / h.dnum, job % h.dnum); }
+    __device__ __forceinline__ int prime(int job) const { return h.eprime(e0 + job / h.dnum); }
+    __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
+    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &) const
+    {
+        dst[(size_t)job * n + idx] = v;
+    }
+};
+
+// the alpha special limbs of both accumulator polynomials: job = p * alpha + a -> acc[p][l + a]
+struct LdInvSpecials
+{
+    static constexpr bool TLAYOUT = false;
+    const u64 *acc; // [2][ne][N]
+    size_t n;
+    HybDims h;
+    __device__ __forceinline__ int prime(int job) const { return h.eprime(h.l + job % h.alpha); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const
+    {
+        return acc[((size_t)(job / h.alpha) * h.ne() + h.l + job % h.alpha) * n + idx];
+    }
+    __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
+};
+
+// ModDown source: job = p * l + i -> sum_a t[p][a] * ((P_S / p_a) mod q_i)
+struct LdHybDown
+{
+    const u64 *t;  // [2][alpha][N] pre-scaled coefficient form
+    const u64 *ws; // [l][alpha]
+    size_t n;
+    HybDims h;
+    __device__ __forceinline__ bool skip(int) const { return false; }
+    __device__ __forceinline__ int prime(int job) const { return job % h.l; }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        const int p = job / h.l, i = job % h.l;
+        const u64 *wv = ws + (size_t)i * h.alpha;
+        u64 lo = 0, hi = 0;
+        for (int a = 0; a < h.alpha; a++)
+            mac128(lo, hi, t[((size_t)p * h.alpha + a) * n + idx], wv[a]);
+        return barrett128(lo, hi, pd);
+    }
+};
+
+struct HybMacArgs
+{
+    const u64 *digits;     // [nE][dnum][N] NTT form, lazy; own-limb slots unused
+    const u64 *target_ntt; // [l][N] NTT form
+    const uint32_t *perm;  // Galois table or null
+    const u64 *key;        // [dnum][2][ne][N]
+    u64 *acc;              // [2][ne][N]
+    size_t n;
+    HybDims h;
+    int e0;
+    int gather_digits;
+};
+
+// acc_p[e] = sum_d ext_d[e] * key[d][p][e]; grid = (ceil(N / 2 / threads), nE)
+static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTables T)
+{
+    const int eloc = blockIdx.y;
+    const int e = a.e0 + eloc;
+    const size_t n = a.n;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= n)
+        return;
+    const PrimeDev pd = T.primes[a.h.eprime(e)];
+    const int ne = a.h.ne();
+    const size_t kstride = (size_t)ne * n;
+    const u64 *k0 = a.key + (size_t)e * n + i;
+    u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+    for (int d = 0; d < a.h.dnum; d++)
+    {
+        ulonglong2 x;
+        if (a.h.own(e, d))
+        {
+            const u64 *src = a.target_ntt + (size_t)e * n;
+            if (a.perm)
+            {
+                x.x = src[a.perm[i]];
+                x.y = src[a.perm[i + 1]];
+            }
+            else
+                x = *reinterpret_cast<const ulonglong2 *>(src + i);
+        }
+        else
+        {
+            const u64 *src = a.digits + ((size_t)eloc * a.h.dnum + d) * n;
+            if (a.gather_digits)
+            {
+                x.x = src[a.perm[i]];
+                x.y = src[a.perm[i + 1]];
+            }
+            else
+                x = *reinterpret_cast<const ulonglong2 *>(src + i);
+        }
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)d * 2 * kstride);
+        ulonglong2 w1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride);
+        mac128(l0x, h0x, x.x, w0.x);
+        mac128(l0y, h0y, x.y, w0.y);
+        mac128(l1x, h1x, x.x, w1.x);
+        mac128(l1y, h1y, x.y, w1.y);
+    }
+    ulonglong2 r0, r1;
+    r0.x = barrett128(l0x, h0x, pd);
+    r0.y = barrett128(l0y, h0y, pd);
+    r1.x = barrett128(l1x, h1x, pd);
+    r1.y = barrett128(l1y, h1y, pd);
+    *reinterpret_cast<ulonglong2 *>(a.acc + (size_t)e * n + i) = r0;
+    *reinterpret_cast<ulonglong2 *>(a.acc + ((size_t)ne + e) * n + i) = r1;
 }
 
 // ============================================================================================

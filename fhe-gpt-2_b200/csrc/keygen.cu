@@ -145,7 +145,8 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
                                                   const u64 *__restrict__ e_ntt /*[limbs][N]*/,
                                                   const u64 *__restrict__ newkey /*[n_primes][N] or null*/,
                                                   int add_limb, u64 factor, JobMap map, const PrimeDev *primes,
-                                                  int log_n, int limbs, u64 seed, unsigned stream)
+                                                  int log_n, int limbs, u64 seed, unsigned stream,
+                                                  const u64 *__restrict__ factors = nullptr /*[limbs], 0 = none*/)
 {
     const size_t n = size_t(1) << log_n;
     const size_t total = (size_t)limbs * n;
@@ -159,7 +160,13 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
         u64 s = sk[(size_t)pi * n + idx];
         u64 v = addmod(mulmod(a, s, pd), e_ntt[i], pd.q);
         v = v ? pd.q - v : 0ull;
-        if (newkey && l == add_limb)
+        if (newkey && factors)
+        {
+            u64 f = factors[l];
+            if (f)
+                v = addmod(v, mulmod(f, newkey[(size_t)pi * n + idx], pd), pd.q);
+        }
+        else if (newkey && l == add_limb)
             v = addmod(v, mulmod(factor, newkey[(size_t)pi * n + idx], pd), pd.q);
         size_t o = i;
         if (TRANSPOSED)
@@ -230,7 +237,7 @@ namespace bk
     static std::atomic<unsigned> g_stream_counter{ 1 };
 
     // one kswitch key for `newkey` ([n_primes][N] NTT form), pruned to max_limbs
-    static bk_kskey_t make_kskey(Context &c, bk_sk_t sk, const u64 *newkey, u64 seed, int max_limbs)
+    static bk_kskey_t make_kskey(Context &c, bk_sk_t sk, const u64 *newkey, u64 seed, int max_limbs, int kind, uint32_t elt)
     {
         const int top = c.top_limbs();
         const int sp = c.n_primes - 1;
@@ -239,6 +246,17 @@ namespace bk
         const size_t n = c.n;
         auto key = new bk_kskey_s();
         key->ctx = static_cast<bk_context_t>(&c);
+        key->sk = sk;
+        key->kind = kind;
+        key->elt = elt;
+        key->seed = seed;
+        if (c.hybrid)
+        {
+            // a recipe only: the level-specific keys are generated by hybrid_key() at the levels that use them
+            key->digits = top;
+            key->klimbs = top;
+            return key;
+        }
         key->digits = kl;
         key->klimbs = kl;
         key->words = (size_t)kl * 2 * (kl + 1) * n;
@@ -264,6 +282,74 @@ namespace bk
         }
         BK_CUDA(cudaStreamSynchronize(s));
         return key;
+    }
+
+    // what the key switches from, [n_primes][N] NTT form: s^2 (keygenerator.cpp:133-162) or sigma_elt(s) (:199-227)
+    static void compute_newkey(Context &c, cudaStream_t s, bk_sk_t sk, int kind, uint32_t elt, u64 *out)
+    {
+        const size_t words = (size_t)c.n_primes * c.n;
+        if (kind == 1)
+        {
+            BK_CUDA(cudaMemcpyAsync(out, sk->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            k_ew<EW_MUL><<<c.ew_grid(words / 2), 256, 0, s>>>(out, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
+        }
+        else
+        {
+            const uint32_t *perm = c.galois_table(elt);
+            k_permute_limbs<<<c.ew_grid(words), 256, 0, s>>>(sk->d, out, perm, c.log_n, c.n_primes);
+        }
+        c.count();
+    }
+
+    // The level-l key of a recipe: dnum digits, digit d = (b_d, a_d) over the l + alpha extended moduli with
+    // b_d = -(a_d s + e_d) + [P_S mod q_i] s' on the limbs of digit d (HybridPlan::d_keyfactor), where s' is the key
+    // being switched from and P_S the product of the alpha special moduli of this level.
+    bk_hybkey_s *hybrid_key(Context &c, bk_kskey_s *key, int l)
+    {
+        std::lock_guard<std::mutex> guard(key->hmu);
+        auto it = key->hyb.find(l);
+        if (it != key->hyb.end())
+            return it->second;
+        if (!key->sk || !key->kind)
+            throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (no recipe for a level key)");
+        const HybridPlan &P = hybrid_plan(c, l);
+        cudaStream_t s = c.stream();
+        const size_t n = c.n;
+        const int ne = P.ne;
+        auto hk = std::make_unique<bk_hybkey_s>();
+        hk->l = l;
+        hk->alpha = P.alpha;
+        hk->dsize = P.dsize;
+        hk->dnum = P.dnum;
+        hk->words = (size_t)P.dnum * 2 * ne * n;
+        BK_CUDA(cudaMalloc((void **)&hk->d, hk->words * sizeof(u64)));
+        JobMap map = limb_map(ne);
+        map.special_pos = ne - 1;
+        map.special_prime = c.n_primes - 1;
+        Scratch newkey(s, (size_t)c.n_primes * n);
+        compute_newkey(c, s, key->sk, key->kind, key->elt, newkey.p);
+        Scratch small(s, (n + 1) / 2);
+        Scratch e_ntt(s, (size_t)ne * n);
+        const u64 seed = key->seed + 0x9E3779B97F4A7C15ull * (u64)(l + 1);
+        for (int d = 0; d < P.dnum; d++)
+        {
+            unsigned st_e = g_stream_counter.fetch_add(2);
+            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st_e, 1);
+            c.count();
+            ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, ne, map);
+            u64 *c0 = hk->d + ((size_t)d * 2) * ne * n;
+            u64 *c1 = c0 + (size_t)ne * n;
+            k_sym_zero<false><<<c.ew_grid((size_t)ne * n), 256, 0, s>>>(c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map, c.d_primes,
+                                                                      c.log_n, ne, seed, st_e + 1,
+                                                                      P.d_keyfactor + (size_t)d * ne);
+            c.count();
+        }
+        BK_CUDA(cudaStreamSynchronize(s)); // complete before other host threads (streams) can pick it up
+        c.hybrid_key_bytes.fetch_add(hk->words * sizeof(u64));
+        c.hybrid_keys.fetch_add(1);
+        bk_hybkey_s *raw = hk.release();
+        key->hyb[l] = raw;
+        return raw;
     }
 }
 
@@ -383,7 +469,7 @@ extern "C"
         BK_CUDA(cudaMemcpyAsync(sq.p, sk->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
         k_ew<EW_MUL><<<c.ew_grid(words / 2), 256, 0, s>>>(sq.p, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
         c.count();
-        *out = make_kskey(c, sk, sq.p, seed, max_limbs);
+        *out = make_kskey(c, sk, sq.p, seed, max_limbs, 1, 0);
         BK_END
     }
 
@@ -403,7 +489,7 @@ extern "C"
         const uint32_t *perm = c.galois_table(galois_elt);
         k_permute_limbs<<<c.ew_grid(words), 256, 0, s>>>(sk->d, rot.p, perm, c.log_n, c.n_primes);
         c.count();
-        *out = make_kskey(c, sk, rot.p, seed, max_limbs);
+        *out = make_kskey(c, sk, rot.p, seed, max_limbs, 2, galois_elt);
         BK_END
     }
 

@@ -801,6 +801,7 @@ namespace seal
         struct Holder
         {
             bk_kskey_t h = nullptr;
+            std::shared_ptr<detail::SkHolder> sk; // hybrid mode generates level keys from the secret key on first use
             ~Holder()
             {
                 if (h)
@@ -847,16 +848,28 @@ namespace seal
         // bytes of evaluation key resident in HBM / number of (re)generations so far
         SEAL_NODISCARD std::uint64_t resident_bytes() const
         {
-            return st_ ? st_->bytes : 0;
+            if (!st_)
+                return 0;
+            std::uint64_t level_keys = 0;
+            bk_context_hybrid(st_->ctx->h, nullptr, &level_keys, nullptr); // hybrid mode: the level-specific keys
+            return st_->bytes + level_keys;
         }
         SEAL_NODISCARD std::uint64_t generated() const
         {
-            return st_ ? st_->generated : 0;
+            if (!st_)
+                return 0;
+            std::uint64_t level_keys = 0;
+            bk_context_hybrid(st_->ctx->h, nullptr, nullptr, &level_keys);
+            return st_->generated + level_keys;
         }
         // make sure the key for `elt` covers ciphertexts of `limbs` limbs
         void ensure(std::uint32_t elt, int limbs) const
         {
             State &s = *st_;
+            int hybrid = 0;
+            bk_context_hybrid(s.ctx->h, &hybrid, nullptr, nullptr);
+            if (hybrid)
+                limbs = s.ctx->n_primes - 1; // the engine object is a recipe; it makes its own key per level on first use
             {
                 std::shared_lock<std::shared_mutex> rl(s.mu);
                 auto it = s.resident.find(elt);
@@ -921,6 +934,7 @@ namespace seal
         {
             auto k = std::make_shared<RelinKeys::Holder>();
             detail::check(bk_relin_key_generate(context_.handle(), sk_.handle(), detail::next_seed(), 0, &k->h));
+            k->sk = sk_.sk_;
             destination.k_ = k;
         }
         // keygenerator.h:148 / :213.  The set of keys is fixed here; generation is on first use.

@@ -328,6 +328,15 @@ class Context:
         _ck(_L.bk_kskey_import_device(self.h, C.c_void_p(dev_ptr), digits, limbs, C.byref(h)))
         return KSwitchKey(self, h)
 
+    def set_hybrid(self, on=True):
+        """Level-aware hybrid key switching for keys generated from now on (tolerance mode, include/b200ckks.h)."""
+        _ck(_L.bk_context_set_hybrid(self.h, int(bool(on))))
+
+    def hybrid_info(self):
+        on, nbytes, keys = C.c_int(), C.c_uint64(), C.c_uint64()
+        _ck(_L.bk_context_hybrid(self.h, C.byref(on), C.byref(nbytes), C.byref(keys)))
+        return bool(on.value), nbytes.value, keys.value
+
     def set_ks_chunk(self, chunk):
         _ck(_L.bk_context_set_ks_chunk(self.h, chunk))
 

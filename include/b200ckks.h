@@ -75,6 +75,14 @@ bk_status bk_context_set_ks_chunk(bk_context_t ctx, int chunk);
 bk_status bk_sync(bk_context_t ctx);
 /* CUDA stream of the calling host thread (cudaStream_t as void*), for event timing / interop. */
 bk_status bk_stream(bk_context_t ctx, void **stream_out);
+/* Level-aware hybrid key switching (tolerance mode, off by default; $B200CKKS_HYBRID_KS=1 turns it on at context
+ * creation).  Keys generated while it is on are recipes: at each level l a rotation / relinearization is first used at,
+ * a level-specific key with ceil(l / alpha) digits over l + alpha moduli is generated on the device, the alpha - 1 idle
+ * primes above the level joining the special prime as temporary special moduli.  Decrypted results equal those of
+ * Evaluator::switch_key_inplace (evaluator.cpp:2281-2525) up to key-switching noise; ciphertext limbs do not, and the
+ * keys are not in SEAL's layout.  Uploaded keys (bk_kskey_upload) always take SEAL's path. */
+bk_status bk_context_set_hybrid(bk_context_t ctx, int on);
+bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys);
 /* block until every stream of the device has drained (before an object other host threads may be reading is freed). */
 bk_status bk_sync_device(bk_context_t ctx);
 /* Hand-over points between host threads (the reference runs one image per OpenMP thread over shared keys,
