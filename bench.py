@@ -123,6 +123,8 @@ def run_engine(args):
 
     # ---- keys: one secret for the node (rank 0 samples it, NCCL broadcast), evaluation keys derived per GPU ----
     os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")
+    hybrid = not args.no_hybrid
+    os.environ["B200CKKS_HYBRID_KS"] = "1" if hybrid else "0"
     app = App()
     t_setup = time.perf_counter()
     sk_words = len(CNN_BITS) * (1 << LOG_N)
@@ -311,7 +313,11 @@ def run_engine(args):
             "config": {"workload": f"ResNet-{args.layers} CIFAR-10 with bootstrapping (reference: ./cnn {args.layers} 10 i j), {K} image(s) in "
                                    "flight per GPU per step; logN=16 RNS-CKKS, primes 51|46x16|51x14|51, Hamming weight 192, scale 2^46; synthetic "
                                    "images (N(0,1) clipped, seed = image id), random-init weights of the architecture",
-                       "images_per_step_per_gpu": K, "images_in_flight_per_gpu": K, "log_n": LOG_N, "layers": args.layers,
+                       "images_per_step_per_gpu": K, "images_in_flight_per_gpu": K,
+                       "key_switching": ("level-aware hybrid (idle primes above the level as temporary special moduli; decrypted "
+                                         "values equal the reference's, limbs do not)" if hybrid
+                                         else "one digit per prime as in the reference (bit-exact limbs)"),
+                       "log_n": LOG_N, "layers": args.layers,
                        "l2": "working set larger than L2: every bootstrap streams ~60 GiB of level-pruned Galois keys and "
                              "31-limb ciphertexts (31 MiB each) against a 126 MB L2",
                        "parallelism": f"dp{world}: image i -> rank i mod {world}; secret key broadcast once over NCCL, evaluation "
@@ -462,6 +468,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--layers", type=int, default=20)
+    ap.add_argument("--no-hybrid", action="store_true",
+                    help="key switching exactly as the reference decomposes it (one digit per prime); default: level-aware "
+                         "hybrid key switching (tolerance mode)")
     ap.add_argument("--in-flight", type=int, default=4, help="images in flight per GPU (a step = that many images per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--dump-histogram", default=None, help="write the per-level operation counts of one inference (JSON)")

@@ -594,6 +594,23 @@ namespace bk
         return *ins.first->second;
     }
 
+    static void launch_hyb_conv(Context &c, cudaStream_t s, const HybConvArgs &a, int groups, int ds)
+    {
+        dim3 grid((unsigned)((c.n / 2 + 127) / 128), (unsigned)groups);
+        ProfScope ps(c, s, TAG_ELEMENTWISE, groups * a.nT);
+        switch (ds)
+        {
+#define BK_HYB_CONV_CASE(DS) case DS: k_hyb_conv<DS><<<grid, 128, 0, s>>>(a, c.tables); break;
+            BK_HYB_CONV_CASE(1) BK_HYB_CONV_CASE(2) BK_HYB_CONV_CASE(3) BK_HYB_CONV_CASE(4) BK_HYB_CONV_CASE(5)
+            BK_HYB_CONV_CASE(6) BK_HYB_CONV_CASE(7) BK_HYB_CONV_CASE(8) BK_HYB_CONV_CASE(9) BK_HYB_CONV_CASE(10)
+            BK_HYB_CONV_CASE(11) BK_HYB_CONV_CASE(12) BK_HYB_CONV_CASE(13) BK_HYB_CONV_CASE(14) BK_HYB_CONV_CASE(15)
+            BK_HYB_CONV_CASE(16) BK_HYB_CONV_CASE(17)
+#undef BK_HYB_CONV_CASE
+        default: throw std::logic_error("hybrid key switch: digit size out of range");
+        }
+        c.count();
+    }
+
     static int hyb_chunk(const HybridPlan &P)
     {
         // digit NTT outputs of one chunk stay in L2: at most ~96 limb-polynomials (48 MiB at N = 2^16)
@@ -601,7 +618,7 @@ namespace bk
     }
 
     // steps B and C for one accumulator: digits of `y` extended and multiplied into `hk`, then ModDown into out
-    static void hyb_extend_and_mac(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *y, u64 *inter,
+    static void hyb_extend_and_mac(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *y, u64 *conv, u64 *inter,
                                    const u64 *target_ntt, int count, const uint32_t *const *perms, bk_hybkey_s *const *keys,
                                    u64 *acc /*[count][2][ne][N]*/, int gather)
     {
@@ -610,7 +627,9 @@ namespace bk
         for (int e0 = 0; e0 < P.ne; e0 += chunk)
         {
             const int nE = std::min(chunk, P.ne - e0);
-            LdHybDigit ld{ y, P.d_w, n, h, e0 };
+            HybConvArgs cv{ y, P.d_w, conv, n, h, e0, nE, 0 };
+            launch_hyb_conv(c, s, cv, P.dnum, P.dsize);
+            LdHybPlain ld{ conv, n, h, e0 };
             launch_fwd_cols(c, s, ld, inter, nE * P.dnum);
             StHybDigit st{ inter, n, h, e0 };
             launch_fwd_blocks(c, s, inter, st, nE * P.dnum);
@@ -627,7 +646,7 @@ namespace bk
         }
     }
 
-    static void hyb_mod_down(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *acc, u64 *inter, u64 *tl,
+    static void hyb_mod_down(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *acc, u64 *conv, u64 *inter, u64 *tl,
                              u64 *out, const u64 *base0, const u64 *base1, const uint32_t *perm)
     {
         const size_t n = c.n;
@@ -635,8 +654,9 @@ namespace bk
         launch_inv_blocks(c, s, ld, inter, 2 * P.alpha);
         StInvScaled st{ tl, n, P.d_sprescale, P.d_sprimes };
         launch_inv_cols(c, s, inter, st, 2 * P.alpha);
-        LdHybDown ld2{ tl, P.d_ws, n, h };
-        launch_fwd_cols(c, s, ld2, inter, 2 * P.l);
+        HybConvArgs cv{ tl, P.d_ws, conv, n, h, 0, P.l, 1 };
+        launch_hyb_conv(c, s, cv, 2, P.alpha);
+        launch_fwd_cols(c, s, LdPlain{ conv, limb_map(P.l), n }, inter, 2 * P.l);
         StModDown st2{ acc, out, base0, base1, perm, P.d_psinv, n, P.l, P.ne };
         launch_fwd_blocks(c, s, inter, st2, 2 * P.l);
     }
@@ -651,6 +671,7 @@ namespace bk
         const HybDims h{ l, P.alpha, P.dsize, P.dnum, c.n_primes - 1 };
         Scratch y(s, (size_t)l * n);
         Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
         Scratch acc(s, (size_t)2 * P.ne * n);
         Scratch tl(s, (size_t)2 * P.alpha * n);
         {
@@ -659,8 +680,8 @@ namespace bk
             StInvScaled st{ y.p, n, P.d_prescale, P.d_limb_primes };
             launch_inv_cols(c, s, inter.p, st, l);
         }
-        hyb_extend_and_mac(c, s, P, h, y.p, inter.p, target, 1, &perm, &hk, acc.p, 0);
-        hyb_mod_down(c, s, P, h, acc.p, inter.p, tl.p, out, base0, base1, perm);
+        hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, target, 1, &perm, &hk, acc.p, 0);
+        hyb_mod_down(c, s, P, h, acc.p, conv.p, inter.p, tl.p, out, base0, base1, perm);
     }
 
     static void key_switch_hoisted_hybrid(Context &c, cudaStream_t s, const bk_ct_s *in, int count, const uint32_t *const *perms,
@@ -676,6 +697,7 @@ namespace bk
         const u64 *c0 = in->d, *c1 = in->d + (size_t)l * n;
         Scratch y(s, (size_t)l * n);
         Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
         Scratch acc(s, (size_t)count * 2 * P.ne * n);
         Scratch tl(s, (size_t)2 * P.alpha * n);
         {
@@ -684,9 +706,9 @@ namespace bk
             StInvScaled st{ y.p, n, P.d_prescale, P.d_limb_primes };
             launch_inv_cols(c, s, inter.p, st, l);
         }
-        hyb_extend_and_mac(c, s, P, h, y.p, inter.p, c1, count, perms, hks.data(), acc.p, 1);
+        hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, c1, count, perms, hks.data(), acc.p, 1);
         for (int k = 0; k < count; k++)
-            hyb_mod_down(c, s, P, h, acc.p + (size_t)k * 2 * P.ne * n, inter.p, tl.p, outs[k], c0, nullptr, perms[k]);
+            hyb_mod_down(c, s, P, h, acc.p + (size_t)k * 2 * P.ne * n, conv.p, inter.p, tl.p, outs[k], c0, nullptr, perms[k]);
     }
 
     // ------------------------------------------------------------------------------- key switch

@@ -467,6 +467,69 @@ struct LdHybDown
     }
 };
 
+// Basis conversion as its own kernel (the NTT column pass then loads plain words and keeps its register budget):
+// every thread keeps the DS source residues of two coefficients in registers and produces all targets of the chunk.
+//   digits  (down == 0): source group dd = digit d, targets t = extended limbs e0 .. e0 + nT - 1, out job = t * dnum + d
+//   ModDown (down == 1): source group dd = polynomial p (alpha special limbs), targets t = limbs 0 .. l - 1, job = p * l + t
+struct HybConvArgs
+{
+    const u64 *src; // digits: y [l][N]; ModDown: t [2][alpha][N]
+    const u64 *w;   // digits: [ne][dnum][dsize]; ModDown: [l][alpha]
+    u64 *out;
+    size_t n;
+    HybDims h;
+    int e0, nT, down;
+};
+
+template <int DS>
+static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTables T)
+{
+    const size_t n = a.n;
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+    if (i >= n)
+        return;
+    const int dd = blockIdx.y;
+    const int first = a.down ? dd * a.h.alpha : dd * a.h.dsize;
+    const int cnt = a.down ? a.h.alpha : min(a.h.dsize, a.h.l - first);
+    ulonglong2 y[DS];
+#pragma unroll
+    for (int k = 0; k < DS; k++)
+        y[k] = k < cnt ? *reinterpret_cast<const ulonglong2 *>(a.src + (size_t)(first + k) * n + i) : make_ulonglong2(0, 0);
+    for (int t = 0; t < a.nT; t++)
+    {
+        const int e = a.e0 + t;
+        if (!a.down && a.h.own(e, dd))
+            continue;
+        const PrimeDev pd = T.primes[a.down ? e : a.h.eprime(e)];
+        const u64 *wv = a.down ? a.w + (size_t)e * a.h.alpha : a.w + ((size_t)e * a.h.dnum + dd) * a.h.dsize;
+        u64 lx = 0, hx = 0, ly = 0, hy = 0;
+#pragma unroll
+        for (int k = 0; k < DS; k++)
+        {
+            const u64 wk = k < cnt ? wv[k] : 0;
+            mac128(lx, hx, y[k].x, wk);
+            mac128(ly, hy, y[k].y, wk);
+        }
+        ulonglong2 r;
+        r.x = barrett128(lx, hx, pd);
+        r.y = barrett128(ly, hy, pd);
+        const size_t job = a.down ? (size_t)dd * a.h.l + t : (size_t)t * a.h.dnum + dd;
+        *reinterpret_cast<ulonglong2 *>(a.out + job * n + i) = r;
+    }
+}
+
+// column-pass loader over an already converted buffer; own-limb jobs are skipped as in LdHybDigit
+struct LdHybPlain
+{
+    const u64 *src; // [nE][dnum][N]
+    size_t n;
+    HybDims h;
+    int e0;
+    __device__ __forceinline__ bool skip(int job) const { return h.own(e0 + job / h.dnum, job % h.dnum); }
+    __device__ __forceinline__ int prime(int job) const { return h.eprime(e0 + job / h.dnum); }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const { return src[(size_t)job * n + idx]; }
+};
+
 struct HybMacArgs
 {
     const u64 *digits;     // [nE][dnum][N] NTT form, lazy; own-limb slots unused

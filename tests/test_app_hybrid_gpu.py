@@ -1,0 +1,56 @@
+"""The application layers with level-aware hybrid key switching switched on ($B200CKKS_HYBRID_KS=1, tolerance mode):
+bootstrapped ResNet-20 end to end against the float64 model and the reference's level / scale trajectory, images in
+flight, and the residency of the level-specific keys."""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "fhe-gpt-2_b200", "python"))
+import app_cases as cases
+import plain_model as pm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def hybrid_session():
+    from b200ckks.app import App
+
+    old = os.environ.get("B200CKKS_HYBRID_KS")
+    os.environ["B200CKKS_HYBRID_KS"] = "1"          # read when the engine context is created
+    try:
+        s = App().session(16, cases.BOOT_BITS, hamming_weight=192)
+    finally:
+        if old is None:
+            del os.environ["B200CKKS_HYBRID_KS"]
+        else:
+            os.environ["B200CKKS_HYBRID_KS"] = old
+    yield s
+    s.close()
+
+
+def test_resnet20_hybrid_key_switching(hybrid_session):
+    from b200ckks import synthetic
+
+    s = hybrid_session
+    w = synthetic.random_weights(20, seed=0)
+    net = s.resnet(20, w)
+    img = synthetic.synthetic_image(0)
+    logits, trace = net.infer(img)
+    want = pm.resnet_forward(20, w, img)
+    assert np.abs(logits - want).max() < 3e-2          # same budget as the reference path (tests/test_app_gpu.py)
+    assert int(np.argmax(logits)) == int(np.argmax(want))
+    gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet20_trajectory.json")))
+    assert [r["op"] for r in trace] == [r["op"] for r in gold["rows"]]
+    for got, ref in zip(trace, gold["rows"]):
+        if ref["level"] is not None:
+            assert got["level"] == ref["level"] and abs(got["scale"] / ref["scale"] - 1) < 2e-5, (got, ref)
+    imgs = np.stack([synthetic.synthetic_image(i) for i in range(2)])
+    together = net.infer_batch(imgs, 2)
+    assert np.abs(together[0] - logits).max() < 5e-3
+    kb, generated = s.key_residency()
+    # level-specific keys: ceil(l / (alpha - 1)) digits over l + alpha moduli instead of l digits over l + 1
+    assert 2 ** 30 < kb < 45 * 2 ** 30, kb
