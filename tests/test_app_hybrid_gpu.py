@@ -52,5 +52,6 @@ def test_resnet20_hybrid_key_switching(hybrid_session):
     together = net.infer_batch(imgs, 2)
     assert np.abs(together[0] - logits).max() < 5e-3
     kb, generated = s.key_residency()
-    # level-specific keys: ceil(l / (alpha - 1)) digits over l + alpha moduli instead of l digits over l + 1
-    assert 2 ** 30 < kb < 45 * 2 ** 30, kb
+    # level-specific keys: ceil(l / (alpha - 1)) digits over l + alpha moduli instead of l digits over l + 1 (4x smaller
+    # at l = 20); the CoeffToSlot keys at l = 29..31, where no or few primes are idle, keep SEAL's shape and dominate
+    assert 2 ** 30 < kb < 70 * 2 ** 30, kb
