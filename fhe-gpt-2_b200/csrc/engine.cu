@@ -596,7 +596,7 @@ namespace bk
 
     static void launch_hyb_conv(Context &c, cudaStream_t s, const HybConvArgs &a, int groups, int ds)
     {
-        dim3 grid((unsigned)((c.n / 2 + 127) / 128), (unsigned)groups);
+        dim3 grid((unsigned)((c.n / 2 + 127) / 128), (unsigned)groups, (unsigned)((a.nT + HYB_CONV_TARGETS - 1) / HYB_CONV_TARGETS));
         ProfScope ps(c, s, TAG_ELEMENTWISE, groups * a.nT);
         switch (ds)
         {

@@ -481,6 +481,7 @@ struct HybConvArgs
     int e0, nT, down;
 };
 
+constexpr int HYB_CONV_TARGETS = 8;
 template <int DS>
 static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTables T)
 {
@@ -495,7 +496,9 @@ static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTable
 #pragma unroll
     for (int k = 0; k < DS; k++)
         y[k] = k < cnt ? *reinterpret_cast<const ulonglong2 *>(a.src + (size_t)(first + k) * n + i) : make_ulonglong2(0, 0);
-    for (int t = 0; t < a.nT; t++)
+    // blockIdx.z selects a slice of HYB_CONV_TARGETS targets, so that small digit counts still fill the machine
+    const int t_begin = blockIdx.z * HYB_CONV_TARGETS, t_end = min(a.nT, t_begin + HYB_CONV_TARGETS);
+    for (int t = t_begin; t < t_end; t++)
     {
         const int e = a.e0 + t;
         if (!a.down && a.h.own(e, dd))

@@ -10,6 +10,8 @@ sys.path.insert(0, os.path.join(ROOT, "fhe-gpt-2_b200", "python"))
 import b200ckks as bk
 
 log_n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+# --ncu-level L: bracket ONE hybrid rotation at level L with cudaProfilerStart/Stop (ncu --profile-from-start off)
+ncu_level = int(sys.argv[sys.argv.index("--ncu-level") + 1]) if "--ncu-level" in sys.argv else 0
 bits = [51] + [46] * 16 + [51] * 14 + [51]
 levels = [31, 30, 29, 28, 24, 20, 17, 12, 8, 5, 3, 2, 1]
 primes = bk.coeff_modulus_create(log_n, bits)
@@ -46,4 +48,15 @@ for hybrid in (False, True):
             e_mul = np.abs(dec(m) - x * x).max()
         print(f"  l={l:2d} rotate err {e_rot:.2e}  mul+relin err {e_mul:.2e}  rotate {us:8.1f} us")
     print("  ", eng.hybrid_info())
+    if hybrid and ncu_level:
+        import ctypes
+        cudart = ctypes.CDLL("libcudart.so")
+        c = ct.copy()
+        eng.mod_switch_to_inplace(c, ncu_level)
+        eng.rotate_vector_inplace(c, 5, gk)
+        eng.sync()
+        cudart.cudaProfilerStart()
+        eng.rotate_vector_inplace(c, 5, gk)
+        eng.sync()
+        cudart.cudaProfilerStop()
     eng.close()
