@@ -119,6 +119,7 @@ def run_engine(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     # ---- keys: one secret for the node (rank 0 samples it, NCCL broadcast), evaluation keys derived per GPU ----
