@@ -734,11 +734,43 @@ extern "C"
     }
 
     // ---- ResNet --------------------------------------------------------------------------------------------------
+    static void resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias, const double *bn_mean,
+                              const double *bn_var, const double *bn_weight, const double *linear_weight, const double *linear_bias,
+                              const ResNetVariant &variant, const double *sc_weight, const double *sc_bias, const double *sc_mean,
+                              const double *sc_var, const double *sc_gamma, bka_resnet_t *out);
     int bka_resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias, const double *bn_mean,
                           const double *bn_var, const double *bn_weight, const double *linear_weight, const double *linear_bias,
                           bka_resnet_t *out)
     {
         BKA_TRY
+        resnet_create(s, layer_num, conv_weight, bn_bias, bn_mean, bn_var, bn_weight, linear_weight, linear_bias,
+                      ResNetVariant::cifar10(), nullptr, nullptr, nullptr, nullptr, nullptr, out);
+        BKA_END
+    }
+    int bka_resnet_create_cifar100(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias,
+                                   const double *bn_mean, const double *bn_var, const double *bn_weight, const double *linear_weight,
+                                   const double *linear_bias, const double *shortcut_weight, const double *shortcut_bn_bias,
+                                   const double *shortcut_bn_mean, const double *shortcut_bn_var, const double *shortcut_bn_weight,
+                                   bka_resnet_t *out)
+    {
+        BKA_TRY
+        resnet_create(s, layer_num, conv_weight, bn_bias, bn_mean, bn_var, bn_weight, linear_weight, linear_bias,
+                      ResNetVariant::cifar100(), shortcut_weight, shortcut_bn_bias, shortcut_bn_mean, shortcut_bn_var,
+                      shortcut_bn_weight, out);
+        BKA_END
+    }
+    int bka_resnet_classes(bka_resnet_t net, int *classes_out)
+    {
+        BKA_TRY
+        *classes_out = net->net->classes();
+        BKA_END
+    }
+    static void resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias, const double *bn_mean,
+                              const double *bn_var, const double *bn_weight, const double *linear_weight, const double *linear_bias,
+                              const ResNetVariant &variant, const double *sc_weight, const double *sc_bias, const double *sc_mean,
+                              const double *sc_var, const double *sc_gamma, bka_resnet_t *out)
+    {
+        {
         ResNetParameters p;
         const std::size_t layers = (std::size_t)layer_num - 1;
         std::size_t wpos = 0, cpos = 0;
@@ -754,17 +786,32 @@ extern "C"
             p.bn_weight.emplace_back(bn_weight + cpos, bn_weight + cpos + co);
             cpos += (std::size_t)co;
         }
-        p.linear_weight.assign(linear_weight, linear_weight + 640);
-        p.linear_bias.assign(linear_bias, linear_bias + 10);
+        p.linear_weight.assign(linear_weight, linear_weight + (std::size_t)variant.classes * 64);
+        p.linear_bias.assign(linear_bias, linear_bias + variant.classes);
+        if (variant.shortcut_conv)
+        {
+            std::size_t wp = 0, cp = 0;
+            for (int j = 0; j < 2; j++)
+            {
+                const std::size_t ci = 16u << j, co = 32u << j;
+                p.shortcut_weight.emplace_back(sc_weight + wp, sc_weight + wp + ci * co);
+                wp += ci * co;
+                p.shortcut_bn_bias.emplace_back(sc_bias + cp, sc_bias + cp + co);
+                p.shortcut_bn_mean.emplace_back(sc_mean + cp, sc_mean + cp + co);
+                p.shortcut_bn_var.emplace_back(sc_var + cp, sc_var + cp + co);
+                p.shortcut_bn_weight.emplace_back(sc_gamma + cp, sc_gamma + cp + co);
+                cp += co;
+            }
+        }
         auto h = std::make_unique<bka_resnet_s>();
         h->s = s;
         h->net = std::make_unique<ResNetCifar10>((std::size_t)layer_num, std::move(p), *s->context, *s->keygen, *s->encoder,
                                                  *s->encryptor, *s->decryptor, *s->evaluator, s->public_key, s->secret_key,
-                                                 s->relin_keys, s->gal_keys);
+                                                 s->relin_keys, s->gal_keys, variant);
         vector<int> steps = h->net->galois_steps();
         s->add_steps(steps.data(), (int)steps.size());
         *out = h.release();
-        BKA_END
+        }
     }
     int bka_resnet_destroy(bka_resnet_t net)
     {
@@ -852,7 +899,7 @@ extern "C"
         resnet_ready(net);
         run_images(net, n_images, in_flight, [&](int i) {
             vector<double> logits = net->net->infer(vector<double>(images + (std::size_t)i * 3072, images + (std::size_t)(i + 1) * 3072));
-            std::memcpy(logits_out + (std::size_t)i * 10, logits.data(), 10 * sizeof(double));
+            std::memcpy(logits_out + (std::size_t)i * logits.size(), logits.data(), logits.size() * sizeof(double));
         });
         BKA_END
     }
@@ -861,7 +908,7 @@ extern "C"
         BKA_TRY
         TensorCipher t(ResNetCifar10::logn, 1, 1, 1, 64, 4, 1, logits_ct->ct);
         vector<double> logits = net->net->decrypt_logits(t);
-        std::memcpy(logits_out, logits.data(), 10 * sizeof(double));
+        std::memcpy(logits_out, logits.data(), logits.size() * sizeof(double));
         BKA_END
     }
     int bka_resnet_infer(bka_resnet_t net, const double *image, double *logits_out, double *trace_out, int trace_cap,
@@ -871,7 +918,7 @@ extern "C"
         resnet_ready(net);
         vector<ResNetTraceRow> trace;
         vector<double> logits = net->net->infer(vector<double>(image, image + 3072), trace_out ? &trace : nullptr);
-        std::memcpy(logits_out, logits.data(), 10 * sizeof(double));
+        std::memcpy(logits_out, logits.data(), logits.size() * sizeof(double));
         if (trace_rows)
             *trace_rows = (int)trace.size();
         if (trace_out)

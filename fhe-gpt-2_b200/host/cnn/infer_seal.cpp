@@ -104,6 +104,53 @@ void import_parameters_cifar10(vector<double> &linear_weight, vector<double> &li
     read_values(base + "linear_bias.txt", 10, linear_bias);
 }
 
+void import_parameters_cifar100(ResNetParameters &p, std::size_t layer_num, const string &dir)
+{
+    // infer_seal.cpp:108-250: same file names as CIFAR-10 under <dir>/resnet32_cifar100, plus the two shortcuts
+    const std::size_t end_num = (std::size_t)resnet_end_num(layer_num), layers = layer_num - 1;
+    const string base = dir + "/resnet" + std::to_string(layer_num) + "_cifar100/";
+    p.conv_weight.assign(layers, {});
+    p.bn_bias.assign(layers, {});
+    p.bn_running_mean.assign(layers, {});
+    p.bn_running_var.assign(layers, {});
+    p.bn_weight.assign(layers, {});
+    for (std::size_t idx = 0; idx < layers; idx++)
+    {
+        int ci, co;
+        resnet_conv_shape(layer_num, idx, ci, co);
+        string conv = "conv1", bn = "bn1";
+        if (idx > 0)
+        {
+            const std::size_t pos = idx - 1, blocks = end_num + 1;
+            const string block = "layer" + std::to_string(pos / (2 * blocks) + 1) + "_" + std::to_string((pos % (2 * blocks)) / 2);
+            conv = block + "_conv" + std::to_string(pos % 2 + 1);
+            bn = block + "_bn" + std::to_string(pos % 2 + 1);
+        }
+        read_values(base + conv + "_weight.txt", (std::size_t)(9 * ci * co), p.conv_weight[idx]);
+        read_values(base + bn + "_bias.txt", (std::size_t)co, p.bn_bias[idx]);
+        read_values(base + bn + "_running_mean.txt", (std::size_t)co, p.bn_running_mean[idx]);
+        read_values(base + bn + "_running_var.txt", (std::size_t)co, p.bn_running_var[idx]);
+        read_values(base + bn + "_weight.txt", (std::size_t)co, p.bn_weight[idx]);
+    }
+    p.shortcut_weight.assign(2, {});
+    p.shortcut_bn_bias.assign(2, {});
+    p.shortcut_bn_mean.assign(2, {});
+    p.shortcut_bn_var.assign(2, {});
+    p.shortcut_bn_weight.assign(2, {});
+    for (std::size_t j = 0; j < 2; j++)
+    {
+        const std::size_t ci = 16u << j, co = 32u << j;
+        const string sc = base + "layer" + std::to_string(j + 2) + "_0_shortcut_";
+        read_values(sc + "0_weight.txt", ci * co, p.shortcut_weight[j]);
+        read_values(sc + "1_bias.txt", co, p.shortcut_bn_bias[j]);
+        read_values(sc + "1_running_mean.txt", co, p.shortcut_bn_mean[j]);
+        read_values(sc + "1_running_var.txt", co, p.shortcut_bn_var[j]);
+        read_values(sc + "1_weight.txt", co, p.shortcut_bn_weight[j]);
+    }
+    read_values(base + "linear_weight.txt", 100 * 64, p.linear_weight);
+    read_values(base + "linear_bias.txt", 100, p.linear_bias);
+}
+
 const vector<int> &resnet_rotation_kinds()
 {
     // the steps memory_save_rotate is asked for by the convolutions, down-samplings, pooling and the FC layer of the
@@ -143,17 +190,23 @@ vector<int> ResNetCifar10::coeff_bit_vec()
 
 ResNetCifar10::ResNetCifar10(std::size_t layer_num, ResNetParameters parameters, SEALContext &context, KeyGenerator &keygen,
                              CKKSEncoder &encoder, Encryptor &encryptor, Decryptor &decryptor, Evaluator &evaluator,
-                             PublicKey &public_key, SecretKey &secret_key, RelinKeys &relin_keys, GaloisKeys &gal_keys)
-    : layer_num_(layer_num), end_num_(resnet_end_num(layer_num)), w_(std::move(parameters)), context_(context), keygen_(keygen),
+                             PublicKey &public_key, SecretKey &secret_key, RelinKeys &relin_keys, GaloisKeys &gal_keys,
+                             ResNetVariant variant)
+    : B(variant.B), layer_num_(layer_num), end_num_(resnet_end_num(layer_num)), variant_(variant), w_(std::move(parameters)),
+      context_(context), keygen_(keygen),
       encoder_(encoder), encryptor_(encryptor), decryptor_(decryptor), evaluator_(evaluator), public_key_(public_key),
       secret_key_(secret_key), relin_keys_(relin_keys), gal_keys_(gal_keys)
 {
     const std::size_t layers = layer_num - 1;
     if (w_.conv_weight.size() != layers || w_.bn_bias.size() != layers || w_.bn_running_mean.size() != layers ||
-        w_.bn_running_var.size() != layers || w_.bn_weight.size() != layers || w_.linear_weight.size() != 640 ||
-        w_.linear_bias.size() != 10)
+        w_.bn_running_var.size() != layers || w_.bn_weight.size() != layers ||
+        w_.linear_weight.size() != (std::size_t)variant_.classes * 64 || w_.linear_bias.size() != (std::size_t)variant_.classes)
         throw std::invalid_argument("parameter lists do not match the network depth");
-    conv_plans_.resize(layers);
+    if (variant_.shortcut_conv &&
+        (w_.shortcut_weight.size() != 2 || w_.shortcut_bn_bias.size() != 2 || w_.shortcut_bn_mean.size() != 2 ||
+         w_.shortcut_bn_var.size() != 2 || w_.shortcut_bn_weight.size() != 2))
+        throw std::invalid_argument("two shortcut convolutions are required");
+    conv_plans_.resize(layers + 2); // the last two slots: shortcut convolutions of stages 2 and 3
     for (long i = 0; i < comp_no; i++)
     {
         minicomp::Tree tr;
@@ -190,6 +243,9 @@ vector<int> ResNetCifar10::galois_steps() const
     for (int rot : resnet_rotation_kinds())
         if (std::find(steps.begin(), steps.end(), rot) == steps.end())
             steps.push_back(rot);
+    // the fully connected layer rotates by 63 .. -(classes - 1); the reference's list stops at -9 (ten classes)
+    for (int k = 10; k < variant_.classes; k++)
+        steps.push_back((1 << logn) - k);
     for (auto *b : boot_)
         b->addLeftRotKeys_Linear_to_vector_3(steps);
     return steps;
@@ -232,9 +288,9 @@ vector<double> ResNetCifar10::decrypt_logits(const TensorCipher &output)
     decryptor_.decrypt(output.cipher_ref(), plain);
     vector<std::complex<double>> slots;
     encoder_.decode(plain, slots);
-    vector<double> logits(10);
-    for (int i = 0; i < 10; i++)
-        logits[(std::size_t)i] = slots[(std::size_t)i].real();
+    vector<double> logits((std::size_t)variant_.classes);
+    for (std::size_t i = 0; i < logits.size(); i++)
+        logits[i] = slots[i].real();
     return logits;
 }
 
@@ -242,7 +298,6 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
 {
     if (!prepared_)
         throw std::logic_error("ResNetCifar10::prepare() must be called after the Galois keys were created");
-    const int fh = 3, fw = 3;
     const double epsilon = 0.00001;
 
     auto t_prev = std::chrono::high_resolution_clock::now();
@@ -268,18 +323,21 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     }
     t_prev = std::chrono::high_resolution_clock::now();
 
-    auto conv = [&](int stage, int co, int st) {
-        // weights and masks of a layer are the same for every image: built once, their encodings stay in HBM
-        std::unique_ptr<ConvPlan> &plan = conv_plans_[(std::size_t)stage];
+    // weights and masks of a layer are the same for every image: built once, their encodings stay in HBM
+    auto planned_conv = [&](TensorCipher &t, std::size_t slot, int co, int st, int f, const vector<double> &weight,
+                            const vector<double> &var, const vector<double> &gamma) {
+        std::unique_ptr<ConvPlan> &plan = conv_plans_[slot];
         {
             std::lock_guard<std::mutex> guard(plan_mu_); // images may run on several host threads (infer_seal.cpp:404)
             if (!plan)
-                plan = std::make_unique<ConvPlan>(build_conv_plan(cnn, co, st, fh, fw, w_.conv_weight[(std::size_t)stage],
-                                                                  w_.bn_running_var[(std::size_t)stage],
-                                                                  w_.bn_weight[(std::size_t)stage], epsilon));
+                plan = std::make_unique<ConvPlan>(build_conv_plan(t, co, st, f, f, weight, var, gamma, epsilon));
         }
-        multiplexed_parallel_convolution_planned(cnn, cnn, *plan, encoder_, encryptor_, evaluator_, gal_keys_);
-        log_op(0, cnn);
+        multiplexed_parallel_convolution_planned(t, t, *plan, encoder_, encryptor_, evaluator_, gal_keys_);
+        log_op(0, t);
+    };
+    auto conv = [&](int stage, int co, int st) {
+        planned_conv(cnn, (std::size_t)stage, co, st, 3, w_.conv_weight[(std::size_t)stage], w_.bn_running_var[(std::size_t)stage],
+                     w_.bn_weight[(std::size_t)stage]);
     };
     auto bn = [&](int stage) {
         multiplexed_parallel_batch_norm_seal(cnn, cnn, w_.bn_bias[(std::size_t)stage], w_.bn_running_mean[(std::size_t)stage],
@@ -332,7 +390,18 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
             stage++;
             conv(stage, co, 1);
             bn(stage);
-            if (j >= 1 && k == 0)
+            if (j >= 1 && k == 0 && variant_.shortcut_conv)
+            {
+                // CIFAR-100: 1x1 stride-2 convolution + batch norm on the shortcut (infer_seal.cpp:826-831)
+                const std::size_t sc = (std::size_t)j - 1;
+                planned_conv(temp, layer_num_ - 1 + sc, co, 2, 1, w_.shortcut_weight[sc], w_.shortcut_bn_var[sc],
+                             w_.shortcut_bn_weight[sc]);
+                multiplexed_parallel_batch_norm_seal(temp, temp, w_.shortcut_bn_bias[sc], w_.shortcut_bn_mean[sc],
+                                                     w_.shortcut_bn_var[sc], w_.shortcut_bn_weight[sc], epsilon, encoder_,
+                                                     encryptor_, evaluator_, B);
+                log_op(1, temp);
+            }
+            else if (j >= 1 && k == 0)
             {
                 multiplexed_parallel_downsampling_seal(temp, temp, evaluator_, gal_keys_);
                 log_op(5, temp);
@@ -345,7 +414,7 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     }
     averagepooling_seal_scale(cnn, cnn, evaluator_, gal_keys_, B);
     log_op(6, cnn);
-    matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, 10, 64, evaluator_, gal_keys_);
+    matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, variant_.classes, 64, evaluator_, gal_keys_);
     log_op(7, cnn);
     return cnn;
 }
@@ -360,7 +429,7 @@ namespace
     }
 
     // random-init weights of the architecture (He-style convolutions, near-identity batch-norm statistics)
-    ResNetParameters random_parameters(std::size_t layer_num, unsigned long long seed)
+    ResNetParameters random_parameters(std::size_t layer_num, unsigned long long seed, const ResNetVariant &variant = {})
     {
         ResNetParameters p;
         unsigned long long state = seed * 0x9E3779B97F4A7C15ull + 0x5EA1ull;
@@ -393,10 +462,30 @@ namespace
             p.bn_running_var.push_back(v);
             p.bn_weight.push_back(g);
         }
-        p.linear_weight.resize(640);
+        p.linear_weight.resize((std::size_t)variant.classes * 64);
         for (auto &x : p.linear_weight)
             x = 0.3 * normal();
-        p.linear_bias.assign(10, 0.0);
+        p.linear_bias.assign((std::size_t)variant.classes, 0.0);
+        if (variant.shortcut_conv)
+            for (int j = 0; j < 2; j++)
+            {
+                const int ci = 16 << j, co = 32 << j;
+                vector<double> w((std::size_t)(ci * co)), b((std::size_t)co), m((std::size_t)co), v((std::size_t)co), g((std::size_t)co);
+                for (auto &x : w)
+                    x = 0.5 * std::sqrt(2.0 / ci) * normal();
+                for (int c = 0; c < co; c++)
+                {
+                    b[(std::size_t)c] = 0.1 * normal();
+                    m[(std::size_t)c] = 0.1 * normal();
+                    v[(std::size_t)c] = 0.5 + uni();
+                    g[(std::size_t)c] = 0.5 + 0.5 * uni();
+                }
+                p.shortcut_weight.push_back(w);
+                p.shortcut_bn_bias.push_back(b);
+                p.shortcut_bn_mean.push_back(m);
+                p.shortcut_bn_var.push_back(v);
+                p.shortcut_bn_weight.push_back(g);
+            }
         return p;
     }
 
@@ -409,10 +498,28 @@ namespace
     }
 } // namespace
 
+static void resnet_driver(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id, const string &result_dir,
+                          const string &weights_dir, const string &images_dir, const ResNetVariant &variant);
+
 void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id,
                                 const string &result_dir, const string &weights_dir, const string &images_dir)
 {
+    resnet_driver(layer_num, start_image_id, end_image_id, result_dir, weights_dir, images_dir, ResNetVariant::cifar10());
+}
+
+void ResNet_cifar100_seal_sparse(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id,
+                                 const string &result_dir, const string &weights_dir, const string &images_dir)
+{
+    if (layer_num != 32)
+        throw std::invalid_argument("layer number is not correct"); // infer_seal.cpp:615
+    resnet_driver(layer_num, start_image_id, end_image_id, result_dir, weights_dir, images_dir, ResNetVariant::cifar100());
+}
+
+static void resnet_driver(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id, const string &result_dir,
+                          const string &weights_dir, const string &images_dir, const ResNetVariant &variant)
+{
     const int end_num = resnet_end_num(layer_num);
+    const string dataset = "cifar" + std::to_string(variant.classes);
 
     std::cout << "Setting Parameters" << std::endl;
     EncryptionParameters parms(scheme_type::ckks);
@@ -435,27 +542,30 @@ void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_i
     Decryptor decryptor(context, secret_key);
 
     ResNetParameters parameters;
-    const string probe = weights_dir + "/resnet" + std::to_string(layer_num) + "_new/conv1_weight.txt";
+    const string probe = weights_dir + "/resnet" + std::to_string(layer_num) + (variant.shortcut_conv ? "_cifar100" : "_new") +
+                         "/conv1_weight.txt";
     const bool pretrained = readable(probe);
-    if (pretrained)
+    if (pretrained && variant.shortcut_conv)
+        import_parameters_cifar100(parameters, layer_num, weights_dir);
+    else if (pretrained)
         import_parameters_cifar10(parameters.linear_weight, parameters.linear_bias, parameters.conv_weight, parameters.bn_bias,
                                   parameters.bn_running_mean, parameters.bn_running_var, parameters.bn_weight, layer_num,
                                   (std::size_t)end_num, weights_dir);
     else
     {
         std::cout << "no pretrained parameters at " << probe << ": random-init weights" << std::endl;
-        parameters = random_parameters(layer_num, 0);
+        parameters = random_parameters(layer_num, 0, variant);
     }
 
     std::cout << "Generating Optimal Minimax Polynomials..." << std::endl;
     ResNetCifar10 net(layer_num, parameters, context, keygen, encoder, encryptor, decryptor, evaluator, public_key, secret_key,
-                      relin_keys, gal_keys);
+                      relin_keys, gal_keys, variant);
     std::cout << "Adding Bootstrapping Keys..." << std::endl;
     keygen.create_galois_keys(net.galois_steps(), gal_keys);
     std::cout << "Generating Linear Transformation Coefficients..." << std::endl;
     net.prepare();
 
-    const string stem = result_dir + "/resnet" + std::to_string(layer_num) + "_cifar10_";
+    const string stem = result_dir + "/resnet" + std::to_string(layer_num) + "_" + dataset + "_";
     std::ofstream out_share(stem + "label_" + std::to_string(start_image_id) + "_" + std::to_string(end_image_id));
     const bool have_images = readable(images_dir + "/test_values.txt");
     if (!have_images)
@@ -531,9 +641,9 @@ void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_i
         std::size_t label = 0;
         double max_score = -100.0;
         output << "( ";
-        for (std::size_t i = 0; i < 10; i++)
+        for (std::size_t i = 0; i < logits.size(); i++)
         {
-            output << "(" << logits[i] << ",0)" << (i < 9 ? ", " : ")");
+            output << "(" << logits[i] << ",0)" << (i + 1 < logits.size() ? ", " : ")");
             if (max_score < logits[i])
             {
                 label = i;

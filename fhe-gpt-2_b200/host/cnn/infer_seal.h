@@ -19,7 +19,20 @@
 struct ResNetParameters
 {
     std::vector<std::vector<double>> conv_weight, bn_bias, bn_running_mean, bn_running_var, bn_weight; // [layer_num - 1]
-    std::vector<double> linear_weight, linear_bias;                                                    // 10 x 64, 10
+    std::vector<double> linear_weight, linear_bias;                                                    // classes x 64, classes
+    // CIFAR-100 variant (the commented-out ResNet_cifar100_seal_sparse, infer_seal.cpp:585-891): the two down-sampling
+    // shortcuts are 1x1 stride-2 convolutions with their own batch norm instead of the zero-padding shortcut
+    std::vector<std::vector<double>> shortcut_weight, shortcut_bn_bias, shortcut_bn_mean, shortcut_bn_var, shortcut_bn_weight; // [2]
+};
+
+// approximation boundary, class count and shortcut type of the two datasets (infer_seal.cpp:253 / :588)
+struct ResNetVariant
+{
+    double B = 40.0;
+    int classes = 10;
+    bool shortcut_conv = false;
+    static ResNetVariant cifar10() { return {}; }
+    static ResNetVariant cifar100() { return { 65.0, 100, true }; }
 };
 
 // number of residual blocks per stage minus one (infer_seal.cpp:397-402)
@@ -47,6 +60,16 @@ void ResNet_cifar10_seal_sparse(std::size_t layer_num, std::size_t start_image_i
                                 const std::string &result_dir = "../../result",
                                 const std::string &weights_dir = "../../pretrained_parameters",
                                 const std::string &images_dir = "../../../testFile");
+// The CIFAR-100 driver the fork has commented out (infer_seal.cpp:585-891; run_cnn.cpp:24): ResNet-32, B = 65, 1x1
+// stride-2 shortcut convolutions, 100 classes.  Weights from <weights_dir>/resnet32_cifar100, images from
+// <images_dir>/test_values.txt when present, otherwise random-init weights and synthetic images.
+void ResNet_cifar100_seal_sparse(std::size_t layer_num, std::size_t start_image_id, std::size_t end_image_id,
+                                 const std::string &result_dir = "../../result",
+                                 const std::string &weights_dir = "../../pretrained_parameters",
+                                 const std::string &images_dir = "../../../testFile_cifar100");
+// reads <dir>/... as import_parameters_cifar10 plus layer{2,3}_0_shortcut_0_weight.txt and
+// layer{2,3}_0_shortcut_1_{bias,running_mean,running_var,weight}.txt (infer_seal.cpp:108-250)
+void import_parameters_cifar100(ResNetParameters &parameters, std::size_t layer_num, const std::string &dir);
 
 struct ResNetTraceRow
 {
@@ -60,7 +83,6 @@ class ResNetCifar10
 {
 public:
     // constants of infer_seal.cpp:253-304
-    static constexpr double B = 40.0;
     static constexpr long alpha = 13, comp_no = 3;
     static constexpr double scaled_val = 1.7;
     static constexpr long boundary_K = 25, boot_deg = 59, scale_factor = 2, inverse_deg = 1, logN = 16, loge = 10, logn = 15;
@@ -69,7 +91,8 @@ public:
 
     ResNetCifar10(std::size_t layer_num, ResNetParameters parameters, seal::SEALContext &context, seal::KeyGenerator &keygen,
                   seal::CKKSEncoder &encoder, seal::Encryptor &encryptor, seal::Decryptor &decryptor, seal::Evaluator &evaluator,
-                  seal::PublicKey &public_key, seal::SecretKey &secret_key, seal::RelinKeys &relin_keys, seal::GaloisKeys &gal_keys);
+                  seal::PublicKey &public_key, seal::SecretKey &secret_key, seal::RelinKeys &relin_keys, seal::GaloisKeys &gal_keys,
+                  ResNetVariant variant = ResNetVariant::cifar10());
     ~ResNetCifar10();
 
     // every rotation step the network and its bootstrappers use (hand to KeyGenerator::create_galois_keys)
@@ -86,10 +109,13 @@ public:
     std::vector<double> decrypt_logits(const TensorCipher &output);
 
     std::size_t layer_num() const { return layer_num_; }
+    int classes() const { return variant_.classes; }
+    const double B; // approximation boundary: activations are carried divided by B
 
 private:
     std::size_t layer_num_;
     int end_num_;
+    ResNetVariant variant_;
     ResNetParameters w_;
     seal::SEALContext &context_;
     seal::KeyGenerator &keygen_;

@@ -30,10 +30,14 @@ int main(int argc, char **argv)
     std::cout << "dataset: CIFAR-" << dataset << std::endl;
     std::cout << "start image: " << start << std::endl;
     std::cout << "end image: " << end << std::endl;
-    if (dataset != 10)
-        throw std::invalid_argument("only CIFAR-10 is live in the reference (run_cnn.cpp:23-25)");
+    if (dataset != 10 && dataset != 100)
+        throw std::invalid_argument("dataset number is not correct");
     const std::string result_dir = argc > 5 ? argv[5] : "result";
     std::filesystem::create_directories(result_dir);
-    ResNet_cifar10_seal_sparse((std::size_t)layer, (std::size_t)start, (std::size_t)end, result_dir);
+    // run_cnn.cpp:23-25: the CIFAR-100 call is commented out in the fork; it is live here
+    if (dataset == 10)
+        ResNet_cifar10_seal_sparse((std::size_t)layer, (std::size_t)start, (std::size_t)end, result_dir);
+    else
+        ResNet_cifar100_seal_sparse((std::size_t)layer, (std::size_t)start, (std::size_t)end, result_dir);
     return 0;
 }

@@ -376,7 +376,15 @@ class ResNet:
                       np.ascontiguousarray(weights["linear_weight"], dtype=np.float64).reshape(-1),
                       np.ascontiguousarray(weights["linear_bias"], dtype=np.float64)]
         self.h = C.c_void_p()
-        sess.app.ck(sess.app.L.bka_resnet_create(sess.h, layer_num, *[_dptr(a) for a in self._keep], C.byref(self.h)))
+        if "shortcut_weight" in weights:      # CIFAR-100 variant: 1x1 stride-2 shortcut convolutions, 100 classes, B = 65
+            self._keep += [cat("shortcut_weight"), cat("shortcut_bn_bias"), cat("shortcut_bn_mean"), cat("shortcut_bn_var"),
+                           cat("shortcut_bn_weight")]
+            sess.app.ck(sess.app.L.bka_resnet_create_cifar100(sess.h, layer_num, *[_dptr(a) for a in self._keep], C.byref(self.h)))
+        else:
+            sess.app.ck(sess.app.L.bka_resnet_create(sess.h, layer_num, *[_dptr(a) for a in self._keep], C.byref(self.h)))
+        n = C.c_int()
+        sess.app.ck(sess.app.L.bka_resnet_classes(self.h, C.byref(n)))
+        self.classes = n.value
 
     def __del__(self):
         if getattr(self, "h", None) and self.s.h:
@@ -400,14 +408,14 @@ class ResNet:
         return Ct(self.s, out), t
 
     def decrypt_logits(self, ct):
-        logits = np.zeros(10)
+        logits = np.zeros(self.classes)
         self.s.app.ck(self.s.app.L.bka_resnet_decrypt_logits(self.h, ct.h, _dptr(logits)))
         return logits
 
     def infer(self, image, trace=True):
         img = np.ascontiguousarray(image, dtype=np.float64).reshape(-1)
         assert img.size == 3072
-        logits = np.zeros(10)
+        logits = np.zeros(self.classes)
         cap = 4096
         tr = np.zeros((cap, 4))
         rows = C.c_int()
@@ -420,7 +428,7 @@ class ResNet:
         """bka_resnet_infer_batch: images (n, 3072) on the host -> logits (n, 10); `in_flight` images at a time, one host
         thread and CUDA stream each (the reference's OpenMP image loop, infer_seal.cpp:404)."""
         imgs = np.ascontiguousarray(images, dtype=np.float64).reshape(-1, 3072)
-        logits = np.zeros((imgs.shape[0], 10))
+        logits = np.zeros((imgs.shape[0], self.classes))
         self.s.app.ck(self.s.app.L.bka_resnet_infer_batch(self.h, _dptr(imgs), imgs.shape[0], int(in_flight), _dptr(logits)))
         return logits
 

@@ -18,9 +18,10 @@ def resnet_shapes(layer_num):
     return end_num, shapes
 
 
-def random_weights(layer_num, seed=0):
+def random_weights(layer_num, seed=0, classes=10):
     """He-style convolutions and near-identity batch-norm statistics: activations stay well inside the [-B, B] = [-40, 40]
-    range the network's approximate ReLU covers."""
+    range the network's approximate ReLU covers.  classes = 100 adds the 1x1 stride-2 shortcut convolutions of the
+    CIFAR-100 network (infer_seal.cpp:108-250, :826-831)."""
     rng = np.random.default_rng(seed)
     _, shapes = resnet_shapes(layer_num)
     w = dict(conv_weight=[], bn_bias=[], bn_mean=[], bn_var=[], bn_weight=[])
@@ -30,8 +31,17 @@ def random_weights(layer_num, seed=0):
         w["bn_mean"].append(rng.normal(0, 0.1, co))
         w["bn_var"].append(rng.uniform(0.5, 1.5, co))
         w["bn_weight"].append(rng.uniform(0.5, 1.0, co))
-    w["linear_weight"] = rng.normal(0, 0.3, 640)
-    w["linear_bias"] = rng.normal(0, 0.1, 10)
+    w["linear_weight"] = rng.normal(0, 0.3, classes * 64)
+    w["linear_bias"] = rng.normal(0, 0.1, classes)
+    if classes == 100:
+        for k in ("shortcut_weight", "shortcut_bn_bias", "shortcut_bn_mean", "shortcut_bn_var", "shortcut_bn_weight"):
+            w[k] = []
+        for ci, co in ((16, 32), (32, 64)):
+            w["shortcut_weight"].append(rng.normal(0, math.sqrt(2.0 / ci), ci * co) * 0.5)
+            w["shortcut_bn_bias"].append(rng.normal(0, 0.1, co))
+            w["shortcut_bn_mean"].append(rng.normal(0, 0.1, co))
+            w["shortcut_bn_var"].append(rng.uniform(0.5, 1.5, co))
+            w["shortcut_bn_weight"].append(rng.uniform(0.5, 1.0, co))
     return w
 
 

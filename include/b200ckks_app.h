@@ -150,6 +150,16 @@ int bka_tensor_add(bka_session_t s, bka_ct_t a, bka_ct_t b, bka_ct_t *out);
 int bka_resnet_create(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias,
                       const double *bn_mean, const double *bn_var, const double *bn_weight, const double *linear_weight,
                       const double *linear_bias, bka_resnet_t *out);
+/* The CIFAR-100 network the fork has commented out (ResNet_cifar100_seal_sparse, infer_seal.cpp:585-891): B = 65, 100
+ * classes (linear_weight 100 x 64, linear_bias 100), and 1x1 stride-2 shortcut convolutions with batch norm at the two
+ * down-sampling blocks: shortcut_weight = [16*32 | 32*64] values, shortcut_bn_* = [32 | 64] values. */
+int bka_resnet_create_cifar100(bka_session_t s, int layer_num, const double *conv_weight, const double *bn_bias,
+                               const double *bn_mean, const double *bn_var, const double *bn_weight, const double *linear_weight,
+                               const double *linear_bias, const double *shortcut_weight, const double *shortcut_bn_bias,
+                               const double *shortcut_bn_mean, const double *shortcut_bn_var, const double *shortcut_bn_weight,
+                               bka_resnet_t *out);
+/* number of logits every inference call of this network writes (10 or 100) */
+int bka_resnet_classes(bka_resnet_t net, int *classes_out);
 int bka_resnet_destroy(bka_resnet_t net);
 /* image: 3*32*32 doubles (CHW).  logits_out: 10 doubles.  trace_out (may be NULL): per stage
  * {op code, remaining level, scale, milliseconds}, up to trace_cap rows; trace_rows receives the row count.

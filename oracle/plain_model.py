@@ -214,10 +214,20 @@ _sys.path.insert(0, os.path.normpath(os.path.join(os.path.dirname(os.path.abspat
 from b200ckks.synthetic import random_weights, resnet_shapes, synthetic_image  # noqa: E402,F401  (shared synthetic inputs)
 
 
+def conv1x1(x, weight, stride):
+    """x: (ci, h, w); weight: flat data[ci oc + ic] (the reference's order with fh = fw = 1)."""
+    ci = x.shape[0]
+    W = np.asarray(weight, dtype=np.float64).reshape(-1, ci)
+    return np.einsum("oi,ihw->ohw", W, x)[:, ::stride, ::stride]
+
+
 def resnet_forward(layer_num, w, image, relu=minimax_relu, collect=None):
     """Values are carried divided by B exactly like the ciphertext slots.  collect: optional list receiving
-    (op, array) after every operation in the order of the engine's trace."""
+    (op, array) after every operation in the order of the engine's trace.  Weights with "shortcut_weight" select the
+    CIFAR-100 network (B = 65, 1x1 stride-2 shortcut convolutions + batch norm, 100 logits; infer_seal.cpp:585-891)."""
     end_num, _ = resnet_shapes(layer_num)
+    cifar100 = "shortcut_weight" in w
+    B = 65.0 if cifar100 else 40.0
     x = np.asarray(image, dtype=np.float64).reshape(3, 32, 32) / B
     log = (lambda op, a: collect.append((op, a.copy()))) if collect is not None else (lambda op, a: None)
 
@@ -228,7 +238,7 @@ def resnet_forward(layer_num, w, image, relu=minimax_relu, collect=None):
 
     def bn(stage):
         nonlocal x
-        x = bn_shift(x, w["bn_bias"][stage], w["bn_mean"][stage], w["bn_var"][stage], w["bn_weight"][stage])
+        x = bn_shift(x, w["bn_bias"][stage], w["bn_mean"][stage], w["bn_var"][stage], w["bn_weight"][stage], b=B)
         log("bn", x)
 
     def act():
@@ -249,15 +259,23 @@ def resnet_forward(layer_num, w, image, relu=minimax_relu, collect=None):
             act()
             conv(stage + 1, 1)
             bn(stage + 1)
-            if j >= 1 and k == 0:
+            if j >= 1 and k == 0 and cifar100:
+                sc = j - 1
+                g = np.asarray(w["shortcut_bn_weight"][sc]) / np.sqrt(np.asarray(w["shortcut_bn_var"][sc]) + EPS)
+                short = conv1x1(short, w["shortcut_weight"][sc], 2) * g[:, None, None]
+                log("conv", short)
+                short = bn_shift(short, w["shortcut_bn_bias"][sc], w["shortcut_bn_mean"][sc], w["shortcut_bn_var"][sc],
+                                 w["shortcut_bn_weight"][sc], b=B)
+                log("bn", short)
+            elif j >= 1 and k == 0:
                 short = downsample(short)
                 log("downsample", short)
             x = short + x
             log("add", x)
             log("bootstrap", x)
             act()
-    pooled = avgpool(x)
+    pooled = avgpool(x, b=B)
     log("avgpool", pooled)
-    logits = fc(pooled, w["linear_weight"])
+    logits = fc(pooled, w["linear_weight"], q=100 if cifar100 else 10)
     log("fc", logits)
     return logits

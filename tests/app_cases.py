@@ -115,3 +115,17 @@ def case_bootstrap(sess, logn, real=True, seed=4, tol=5e-5, hoisting=None):
     err = np.abs(y - xs)
     assert err.max() < tol, err.max()           # reference log: ~1e-7 on values ~3e-2; here |x| <= 1
     return err.max()
+
+
+def case_conv1x1_shortcut(sess, k, h, w, c, co, seed=7):
+    """The CIFAR-100 shortcut: 1x1 stride-2 multiplexed convolution with folded batch-norm scale (infer_seal.cpp:826-829)."""
+    rng = np.random.default_rng(seed)
+    x, ct, parms = make_tensor(sess, rng, k, h, w, c, limbs=4)
+    wt = rng.normal(0, 0.3, c * co)
+    var, bw = rng.uniform(0.5, 1.5, co), rng.uniform(0.5, 1.0, co)
+    out, op = sess.conv(ct, parms, co, 2, wt, var, bw, fh=1, fw=1)
+    g = bw / np.sqrt(var + 1e-5)
+    want = pm.conv1x1(x, wt, 2) * g[:, None, None]
+    assert op[:4] == [k * 2, h // 2, w // 2, co]
+    for got in unpack_all(sess, out, op):
+        assert np.abs(got - want).max() < 1e-6

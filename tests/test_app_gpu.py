@@ -36,6 +36,11 @@ def test_bn_add_downsample_pool_fc(cnn_session):
     cases.case_bn_add_downsample_pool_fc(cnn_session)
 
 
+@pytest.mark.parametrize("k,h,w,c,co", [(1, 8, 8, 4, 8), (2, 4, 4, 8, 16)])
+def test_conv1x1_stride2_shortcut(cnn_session, k, h, w, c, co):
+    cases.case_conv1x1_shortcut(cnn_session, k, h, w, c, co)
+
+
 def test_relu_small(app):
     s = app.session(cases.SMALL_LOG_N, cases.RELU_BITS, hamming_weight=64)
     cases.case_relu(s)
