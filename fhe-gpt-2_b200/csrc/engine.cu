@@ -129,6 +129,14 @@ namespace bk
         BK_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
         uint64_t thresh = UINT64_MAX;
         BK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+        // $B200CKKS_POOL_NODEPS=1: never let the allocator make one stream wait for another to reuse a freed block.
+        // Measured with images in flight on their own streams (tools/in_flight_sweep.py): slower at 4 in flight (0.76 vs
+        // 0.86 images/s, fresh blocks cost more than the waits), faster at 6 (0.84 vs 0.65); the default stays.
+        if (std::getenv("B200CKKS_POOL_NODEPS"))
+        {
+            int off = 0;
+            BK_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off));
+        }
 
         // per-prime constants + twiddle tables
         h_primes.resize(n_primes);
