@@ -76,6 +76,11 @@ namespace bk
     }
 
     // ---------------------------------------------------------------------------------- Context
+    // ---- scratch arenas, one per stream a context created
+    static std::mutex g_arena_mu;
+    static std::unordered_map<cudaStream_t, ScratchArena *> g_arenas;
+    static std::atomic<uint64_t> g_arena_generation{ 1 }; // bumped whenever an arena is retired (stream handles get reused)
+
     Context::Context(int log_n_, const uint64_t *primes_, int n_primes_, int device_)
         : log_n(log_n_), n(size_t(1) << log_n_), n_primes(n_primes_), device(device_)
     {
@@ -214,7 +219,26 @@ namespace bk
             delete kv.second;
         }
         for (auto &kv : streams)
+        {
+            ScratchArena *arena = nullptr;
+            {
+                std::lock_guard<std::mutex> ga(g_arena_mu);
+                auto it = g_arenas.find(kv.second);
+                if (it != g_arenas.end())
+                {
+                    arena = it->second;
+                    g_arenas.erase(it);
+                    g_arena_generation.fetch_add(1, std::memory_order_release);
+                }
+            }
+            if (arena)
+            {
+                for (auto &ch : arena->chunks)
+                    cudaFree(ch.first);
+                delete arena;
+            }
             cudaStreamDestroy(kv.second);
+        }
         for (auto &kv : galois_tables)
             cudaFree(kv.second);
         for (auto &kv : hplans)
@@ -236,6 +260,24 @@ namespace bk
         cudaFree(d_inv);
     }
 
+    ScratchArena *arena_of(cudaStream_t s)
+    {
+        static thread_local cudaStream_t last_stream = nullptr;
+        static thread_local ScratchArena *last_arena = nullptr;
+        static thread_local uint64_t last_generation = 0;
+        const uint64_t generation = g_arena_generation.load(std::memory_order_acquire);
+        if (last_arena && last_stream == s && last_generation == generation)
+            return last_arena;
+        std::lock_guard<std::mutex> g(g_arena_mu);
+        auto it = g_arenas.find(s);
+        if (it == g_arenas.end())
+            return nullptr;
+        last_stream = s;
+        last_arena = it->second;
+        last_generation = generation;
+        return it->second;
+    }
+
     void Context::activate() const
     {
         int cur = -1;
@@ -255,6 +297,10 @@ namespace bk
         cudaStream_t s;
         BK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
         streams[id] = s;
+        {
+            std::lock_guard<std::mutex> ga(g_arena_mu);
+            g_arenas[s] = new ScratchArena();
+        }
         return s;
     }
 

@@ -3,6 +3,7 @@
 #include "../../include/b200ckks.h"
 #include "hostmath.h"
 #include "kernels.cuh"
+#include <algorithm>
 #include <atomic>
 #include <cuda_runtime.h>
 #include <map>
@@ -33,19 +34,66 @@ namespace bk
             throw bk::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));                                   \
     } while (0)
 
-    // stream-ordered scratch buffer (cudaMallocAsync pool; the pool's release threshold is
-    // raised at context creation so steady-state allocation never reaches the driver)
+    // Scratch memory of one CUDA stream: a stack of device chunks.  Scratch objects are automatic variables, so their
+    // lifetimes nest; every kernel that touches a scratch buffer is enqueued on the stream the arena belongs to, hence a
+    // block popped by one operation can be handed to the next operation on that stream without any synchronisation -
+    // and, unlike cudaMallocAsync / cudaFreeAsync per call (5 per key switch), without the allocator ordering one
+    // host thread's stream behind another's to reuse a freed block.
+    struct ScratchArena
+    {
+        std::vector<std::pair<char *, size_t>> chunks;
+        size_t cur = 0, off = 0;
+    };
+    ScratchArena *arena_of(cudaStream_t s); // engine.cu: arenas of the streams the contexts created; null for foreign streams
+
     struct Scratch
     {
         u64 *p = nullptr;
         cudaStream_t s;
+        ScratchArena *a = nullptr;
+        size_t save_cur = 0, save_off = 0;
         Scratch(cudaStream_t stream, size_t words) : s(stream)
         {
-            BK_CUDA(cudaMallocAsync((void **)&p, words * sizeof(u64), s));
+            a = arena_of(stream);
+            if (!a)
+            {
+                BK_CUDA(cudaMallocAsync((void **)&p, words * sizeof(u64), s));
+                return;
+            }
+            const size_t bytes = (words * sizeof(u64) + 255) & ~size_t(255);
+            save_cur = a->cur;
+            save_off = a->off;
+            for (;;)
+            {
+                if (a->cur < a->chunks.size() && a->off + bytes <= a->chunks[a->cur].second)
+                {
+                    p = reinterpret_cast<u64 *>(a->chunks[a->cur].first + a->off);
+                    a->off += bytes;
+                    return;
+                }
+                if (a->cur + 1 < a->chunks.size())
+                {
+                    a->cur++;
+                    a->off = 0;
+                    continue;
+                }
+                const size_t last = a->chunks.empty() ? 0 : a->chunks.back().second;
+                const size_t cap = std::max(bytes, std::max<size_t>(size_t(64) << 20, 2 * last));
+                char *chunk = nullptr;
+                BK_CUDA(cudaMalloc((void **)&chunk, cap));
+                a->chunks.emplace_back(chunk, cap);
+                a->cur = a->chunks.size() - 1;
+                a->off = 0;
+            }
         }
         ~Scratch()
         {
-            if (p)
+            if (a)
+            {
+                a->cur = save_cur;
+                a->off = save_off;
+            }
+            else if (p)
                 cudaFreeAsync(p, s);
         }
         Scratch(const Scratch &) = delete;
