@@ -550,15 +550,24 @@ namespace bk
         if (l <= 5)
             return;
         double best_cost = (double)l + (double)l * (l + 1) - l + l * (double)l / 8.0 + 2.0 + 2.0 * l / 8.0 + 2.0 * l;
+        // At the two levels below the top only one or two primes are idle; there a digit may be as large as P_S
+        // (dsize = alpha), which makes the noise that of SEAL's own top-level key switch (51-bit digits over a 51-bit
+        // special prime) instead of a prime below it, and halves / thirds the digit count.  Bootstrapping error with it:
+        // rms 4.3e-6 against 1.6e-5 on the reference-exact path and 3.0e-6 with narrow digits everywhere
+        // (tools/boot_precision.py).  $B200CKKS_HYBRID_NARROW_TOP=1 keeps dsize = alpha - 1 at every level.
+        static const bool wide_top = std::getenv("B200CKKS_HYBRID_NARROW_TOP") == nullptr;
         for (int a = 2; a <= std::min(top - l + 1, 17); a++)
         {
-            const int ds = a - 1, d = (l + ds - 1) / ds;
-            double cost = l + (double)d * (l + a) - l + d * ds * (double)l / 8.0 + 2.0 * a + 2.0 * a * l / 8.0 + 2.0 * l;
-            if (cost < best_cost - 1e-9)
+            for (int ds = a - 1; ds <= ((wide_top && l >= top - 2) ? a : a - 1); ds++)
             {
-                best_cost = cost;
-                alpha = a;
-                dsize = ds;
+                const int d = (l + ds - 1) / ds;
+                double cost = l + (double)d * (l + a) - l + d * ds * (double)l / 8.0 + 2.0 * a + 2.0 * a * l / 8.0 + 2.0 * l;
+                if (cost < best_cost - 1e-9)
+                {
+                    best_cost = cost;
+                    alpha = a;
+                    dsize = ds;
+                }
             }
         }
     }

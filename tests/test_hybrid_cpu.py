@@ -25,11 +25,11 @@ def hybrid_shape(l, top):
         return alpha, dsize
     best = l + l * (l + 1) - l + l * l / 8.0 + 2.0 + 2.0 * l / 8.0 + 2.0 * l
     for a in range(2, min(top - l + 1, 17) + 1):
-        ds = a - 1
-        d = (l + ds - 1) // ds
-        cost = l + d * (l + a) - l + d * ds * l / 8.0 + 2.0 * a + 2.0 * a * l / 8.0 + 2.0 * l
-        if cost < best - 1e-9:
-            best, alpha, dsize = cost, a, ds
+        for ds in range(a - 1, (a if l >= top - 2 else a - 1) + 1):      # wide digits only at the two levels below the top
+            d = (l + ds - 1) // ds
+            cost = l + d * (l + a) - l + d * ds * l / 8.0 + 2.0 * a + 2.0 * a * l / 8.0 + 2.0 * l
+            if cost < best - 1e-9:
+                best, alpha, dsize = cost, a, ds
     return alpha, dsize
 
 
@@ -38,6 +38,6 @@ def test_shape_rule_respects_the_chain():
         for l in range(1, top + 1):
             alpha, dsize = hybrid_shape(l, top)
             assert l + alpha - 1 <= top            # only idle primes are borrowed
-            assert dsize == max(1, alpha - 1) and 1 <= alpha <= 17
+            assert 1 <= alpha <= 17 and (dsize == max(1, alpha - 1) or (dsize == alpha and l >= top - 2))
         assert hybrid_shape(top, top) == (1, 1)    # nothing is idle at the top level: SEAL's own scheme
     assert hybrid_shape(20, 31)[0] > 2 and hybrid_shape(3, 31) == (1, 1)
