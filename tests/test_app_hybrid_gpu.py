@@ -41,7 +41,10 @@ def test_resnet20_hybrid_key_switching(hybrid_session):
     img = synthetic.synthetic_image(0)
     logits, trace = net.infer(img)
     want = pm.resnet_forward(20, w, img)
-    assert np.abs(logits - want).max() < 3e-2          # same budget as the reference path (tests/test_app_gpu.py)
+    # measured 2.4e-4 .. 3.1e-4 (tools/resnet_accuracy.py; 1.0e-3 .. 1.3e-3 on the reference-exact path): the bootstrapping
+    # error drops from 1.6e-5 rms with a key-dependent offset to 4e-6 without one (tools/boot_precision.py), because every
+    # digit below the top level is at most as large as P_S
+    assert np.abs(logits - want).max() < 5e-3
     assert int(np.argmax(logits)) == int(np.argmax(want))
     gold = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resnet20_trajectory.json")))
     assert [r["op"] for r in trace] == [r["op"] for r in gold["rows"]]
@@ -52,6 +55,6 @@ def test_resnet20_hybrid_key_switching(hybrid_session):
     together = net.infer_batch(imgs, 2)
     assert np.abs(together[0] - logits).max() < 5e-3
     kb, generated = s.key_residency()
-    # level-specific keys: ceil(l / (alpha - 1)) digits over l + alpha moduli instead of l digits over l + 1 (4x smaller
-    # at l = 20); the CoeffToSlot keys at l = 29..31, where no or few primes are idle, keep SEAL's shape and dominate
-    assert 2 ** 30 < kb < 70 * 2 ** 30, kb
+    # level-specific keys: ceil(l / dsize) digits over l + alpha moduli instead of l digits over l + 1 (4x smaller at
+    # l = 20); measured 39.8 GiB against 60.6 GiB on the reference-exact path
+    assert 2 ** 30 < kb < 50 * 2 ** 30, kb
