@@ -288,7 +288,8 @@ def run_engine(args):
         d = kernels[dom]
         roof = {"bound": "hbm", "kernel": {"fwd_cols": "k_fwd_cols (NTT column pass)", "fwd_blocks": "k_fwd_blocks (NTT block pass)",
                                             "inv_blocks": "k_inv_blocks", "inv_cols": "k_inv_cols", "ks_mac": "k_ks_mac",
-                                            "elementwise": "k_ew / k_scalar_pack", "fft": "k_fft_*", "other": "other"}[dom],
+                                            "elementwise": "k_ew / k_scalar_pack", "fft": "k_fft_*",
+                                            "other": "k_hyb_conv (basis conversion) and samplers"}[dom],
                 "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": traffic,
                 "traffic_algorithmic_bytes": traffic_algo,
                 "traffic_source": "profiles/r1_ncu_full_keyswitch_l31.md (one launch of this kernel in an l=31 key-switch chunk)",

@@ -660,7 +660,7 @@ namespace bk
     static void launch_hyb_conv(Context &c, cudaStream_t s, const HybConvArgs &a, int groups, int ds)
     {
         dim3 grid((unsigned)((c.n / 2 + 127) / 128), (unsigned)groups, (unsigned)((a.nT + HYB_CONV_TARGETS - 1) / HYB_CONV_TARGETS));
-        ProfScope ps(c, s, TAG_ELEMENTWISE, groups * a.nT);
+        ProfScope ps(c, s, TAG_OTHER, groups * a.nT);
         switch (ds)
         {
 #define BK_HYB_CONV_CASE(DS) case DS: k_hyb_conv<DS><<<grid, 128, 0, s>>>(a, c.tables); break;

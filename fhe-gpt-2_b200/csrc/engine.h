@@ -202,7 +202,7 @@ namespace bk
         TAG_KS_MAC = 4,
         TAG_ELEMENTWISE = 5,
         TAG_FFT = 6,   // encoder / decoder complex FFT passes
-        TAG_OTHER = 7, // samplers, gathers, CRT composition
+        TAG_OTHER = 7, // basis conversions of hybrid key switching (k_hyb_conv); samplers, gathers, CRT composition
         TAG_COUNT = 8
     };
     // RAII: records an event pair around one launch when its tag is being profiled
