@@ -96,6 +96,20 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
+class stdout_to_stderr:
+    """NCCL prints its version banner with printf on first use; stdout must carry the one JSON line only."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 def dist_env():
     return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
 
@@ -119,8 +133,11 @@ def run_engine(args):
     dist = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # stdout carries the one JSON line only
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        with stdout_to_stderr():
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            warm = torch.zeros(1, device="cuda")
+            dist.all_reduce(warm)                 # creates the communicator (and prints the banner) here
+            torch.cuda.synchronize()
 
     # ---- keys: one secret for the node (rank 0 samples it, NCCL broadcast), evaluation keys derived per GPU ----
     os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")
