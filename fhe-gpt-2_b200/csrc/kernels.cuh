@@ -393,29 +393,8 @@ struct StInvScaled
     }
 };
 
-// digit extension: job = eloc * dnum + d -> digit d converted to extended limb e = e0 + eloc; the digit's own limbs are
-// skipped (their NTT form is the input itself)
-struct LdHybDigit
-{
-    const u64 *y;  // [l][N] pre-scaled coefficient form
-    const u64 *w;  // [ne][dnum][dsize]  (Q_d / q_{d dsize + a}) mod p_e
-    size_t n;
-    HybDims h;
-    int e0;
-    __device__ __forceinline__ bool skip(int job) const { return h.own(e0 + job / h.dnum, job % h.dnum); }
-    __device__ __forceinline__ int prime(int job) const { return h.eprime(e0 + job / h.dnum); }
-    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
-    {
-        const int d = job % h.dnum, e = e0 + job / h.dnum;
-        const int first = d * h.dsize, cnt = min(h.dsize, h.l - first);
-        const u64 *wv = w + ((size_t)e * h.dnum + d) * h.dsize;
-        u64 lo = 0, hi = 0;
-        for (int a = 0; a < cnt; a++)
-            mac128(lo, hi, y[(size_t)(first + a) * n + idx], wv[a]);
-        return barrett128(lo, hi, pd);
-    }
-};
-
+// NTT block-pass store of the extended digits: job = eloc * dnum + d (extended limb e0 + eloc, digit d); the digit's own
+// limbs are skipped (their NTT form is the input itself)
 struct StHybDigit
 {
     static constexpr bool RAW = true;
@@ -445,26 +424,6 @@ struct LdInvSpecials
         return acc[((size_t)(job / h.alpha) * h.ne() + h.l + job % h.alpha) * n + idx];
     }
     __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
-};
-
-// ModDown source: job = p * l + i -> sum_a t[p][a] * ((P_S / p_a) mod q_i)
-struct LdHybDown
-{
-    const u64 *t;  // [2][alpha][N] pre-scaled coefficient form
-    const u64 *ws; // [l][alpha]
-    size_t n;
-    HybDims h;
-    __device__ __forceinline__ bool skip(int) const { return false; }
-    __device__ __forceinline__ int prime(int job) const { return job % h.l; }
-    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
-    {
-        const int p = job / h.l, i = job % h.l;
-        const u64 *wv = ws + (size_t)i * h.alpha;
-        u64 lo = 0, hi = 0;
-        for (int a = 0; a < h.alpha; a++)
-            mac128(lo, hi, t[((size_t)p * h.alpha + a) * n + idx], wv[a]);
-        return barrett128(lo, hi, pd);
-    }
 };
 
 // Basis conversion as its own kernel (the NTT column pass then loads plain words and keeps its register budget):
@@ -521,7 +480,7 @@ static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTable
     }
 }
 
-// column-pass loader over an already converted buffer; own-limb jobs are skipped as in LdHybDigit
+// column-pass loader over the converted buffer; own-limb jobs are skipped as in StHybDigit
 struct LdHybPlain
 {
     const u64 *src; // [nE][dnum][N]
