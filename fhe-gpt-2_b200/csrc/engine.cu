@@ -2045,6 +2045,50 @@ extern "C"
         BK_END
     }
 
+    bk_status bk_multiply_plain_sum(bk_context_t ctx, bk_ct_t dst, const bk_ct_t *cts, const bk_pt_t *pts, int count)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (count < 1)
+            throw std::invalid_argument("count must be positive");
+        if (!dst || dst->ctx != ctx)
+            throw std::invalid_argument("destination is not valid for encryption parameters");
+        for (int t = 0; t < count; t++)
+        {
+            plain_check(ctx, cts[t], pts[t]);
+            if (cts[t] == dst)
+                throw std::invalid_argument("destination must not be one of the operands");
+            if (cts[t]->size != cts[0]->size || cts[t]->limbs != cts[0]->limbs || !close_scale(cts[t]->scale, cts[0]->scale) ||
+                !close_scale(pts[t]->scale, pts[0]->scale))
+                throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
+        }
+        const double new_scale = cts[0]->scale * pts[0]->scale;
+        if (!c.scale_in_bounds(new_scale, cts[0]->limbs))
+            throw std::invalid_argument("scale out of bounds");
+        const int size = cts[0]->size, limbs = cts[0]->limbs;
+        ensure_ct(dst, size, limbs, false);
+        const size_t total2 = (size_t)size * limbs * c.n / 2;
+        for (int t0 = 0; t0 < count; t0 += MUL_SUM_TERMS)
+        {
+            MulSumArgs a{};
+            a.count = std::min(MUL_SUM_TERMS, count - t0);
+            for (int t = 0; t < a.count; t++)
+            {
+                a.ct[t] = cts[t0 + t]->d;
+                a.pt[t] = pts[t0 + t]->d;
+            }
+            ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, size * limbs * a.count);
+            if (t0 == 0)
+                k_mul_plain_sum<false><<<c.ew_grid(total2), 256, 0, c.stream()>>>(dst->d, a, c.d_primes, c.log_n, limbs, size);
+            else
+                k_mul_plain_sum<true><<<c.ew_grid(total2), 256, 0, c.stream()>>>(dst->d, a, c.d_primes, c.log_n, limbs, size);
+            c.count();
+        }
+        dst->scale = new_scale;
+        dst->ntt = true;
+        BK_END
+    }
+
     bk_status bk_transform_to_ntt_inplace(bk_context_t ctx, bk_ct_t a)
     {
         BK_TRY

@@ -650,6 +650,48 @@ __global__ void __launch_bounds__(256) k_mul_plain_acc(u64 *__restrict__ acc, co
 
 // ct x ct tensor product (ckks_multiply, evaluator.cpp:744-772): (a0,a1) x (b0,b1) ->
 // (a0 b0, a0 b1 + a1 b0, a1 b1).  out may alias neither input.
+// dst = sum_t a_t (.) pt_t over up to MUL_SUM_TERMS terms in one pass (the inner sum of a BSGS group / the taps of a
+// convolution): every operand is read once, the products are accumulated in 128 bits and reduced once - the residues
+// equal those of the term-by-term multiply_plain + add sequence.  ACCUMULATE adds the previous content of dst.
+constexpr int MUL_SUM_TERMS = 16;
+struct MulSumArgs
+{
+    const u64 *ct[MUL_SUM_TERMS];
+    const u64 *pt[MUL_SUM_TERMS];
+    int count;
+};
+template <bool ACCUMULATE>
+__global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, MulSumArgs a, const PrimeDev *primes, int log_n,
+                                                       int limbs, int polys)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = (size_t)polys * per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t e = i * 2, ep = e % per_poly;
+        const PrimeDev pd = primes[(int)(ep >> log_n)];
+        u64 lx = 0, hx = 0, ly = 0, hy = 0;
+        if (ACCUMULATE)
+        {
+            ulonglong2 vc = *reinterpret_cast<const ulonglong2 *>(dst + e);
+            lx = vc.x;
+            ly = vc.y;
+        }
+        for (int t = 0; t < a.count; t++)
+        {
+            ulonglong2 va = *reinterpret_cast<const ulonglong2 *>(a.ct[t] + e);
+            ulonglong2 vp = *reinterpret_cast<const ulonglong2 *>(a.pt[t] + ep);
+            mac128(lx, hx, va.x, vp.x);
+            mac128(ly, hy, va.y, vp.y);
+        }
+        ulonglong2 r;
+        r.x = barrett128(lx, hx, pd);
+        r.y = barrett128(ly, hy, pd);
+        *reinterpret_cast<ulonglong2 *>(dst + e) = r;
+    }
+}
+
 static __global__ void __launch_bounds__(256) k_tensor(const u64 *__restrict__ a, const u64 *__restrict__ b,
                                                 u64 *__restrict__ out, const PrimeDev *primes, int log_n, int limbs)
 {

@@ -354,16 +354,18 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
     {
         // diagonals i*gs + j, pre-rotated by the giant step so that one rotation serves the whole group
         const int jlast = (i != p.giantlast) ? p.basicstart + p.gs - 1 : totlen - i * p.gs;
-        bool giant_started = false;
+        vector<const Ciphertext *> terms;
+        vector<std::uint64_t> diags;
         for (int j = p.basicstart; j <= jlast; j++)
         {
-            const std::size_t diag = (std::size_t)(i * p.gs + j + totlen);
-            multiply_vector_named_accumulate(evaluator, giantct, giant_started, babyct[(std::size_t)(j - p.basicstart)], cache_owner,
-                                             diag, cache_variant, [&]() -> const vector<complex<double>> & {
-                                                 rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[diag], rotated);
-                                                 return rotated;
-                                             });
+            terms.push_back(&babyct[(std::size_t)(j - p.basicstart)]);
+            diags.push_back((std::uint64_t)(i * p.gs + j + totlen));
         }
+        multiply_vector_named_sum(evaluator, giantct, terms, cache_owner, diags, cache_variant,
+                                  [&](std::uint64_t diag) -> const vector<complex<double>> & {
+                                      rotation(coeff_logn, N, -i * p.gs * basicstep, fftcoeff[(std::size_t)diag], rotated);
+                                      return rotated;
+                                  });
         if (i != 0)
         {
             evaluator.rotate_vector(giantct, wrap(i * p.gs * basicstep), gal_keys, product);
@@ -410,16 +412,18 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
     for (int i = 0; i <= giantlast; i++)
     {
         const int jlast = (i != giantlast) ? gs - 1 : totlen - i * gs;
-        bool giant_started = false;
+        vector<const Ciphertext *> terms;
+        vector<std::uint64_t> diags;
         for (int j = 0; j <= jlast; j++)
         {
-            const std::size_t diag = (std::size_t)(i * gs + j);
-            multiply_vector_named_accumulate(evaluator, giantct, giant_started, babyct[(std::size_t)j], cache_owner, diag,
-                                             cache_variant, [&]() -> const vector<complex<double>> & {
-                                                 rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[diag], rotated);
-                                                 return rotated;
-                                             });
+            terms.push_back(&babyct[(std::size_t)j]);
+            diags.push_back((std::uint64_t)(i * gs + j));
         }
+        multiply_vector_named_sum(evaluator, giantct, terms, cache_owner, diags, cache_variant,
+                                  [&](std::uint64_t diag) -> const vector<complex<double>> & {
+                                      rotation(coeff_logn, N, -i * gs * basicstep, fftcoeff[(std::size_t)diag], rotated);
+                                      return rotated;
+                                  });
         if (i != 0)
         {
             evaluator.rotate_vector(giantct, wrap(i * gs * basicstep), gal_keys, product);

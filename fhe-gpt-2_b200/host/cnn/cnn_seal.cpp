@@ -207,13 +207,15 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
     for (long g = 0; g < q; g++)
     {
         // weighted sum over the filter taps
-        bool taps_started = false;
+        vector<const Ciphertext *> taps;
+        vector<std::uint64_t> tap_ids;
         for (int t = 0; t < fh * fw; t++)
         {
-            const std::size_t idx = (std::size_t)(t * q + g);
-            multiply_vector_named_accumulate(evaluator, sum, taps_started, ctxt_rot[(std::size_t)t], owner, idx, 0,
-                                             [&]() -> const vector<double> & { return P.tap_weights[idx]; });
+            taps.push_back(&ctxt_rot[(std::size_t)t]);
+            tap_ids.push_back((std::uint64_t)(t * q + g));
         }
+        multiply_vector_named_sum(evaluator, sum, taps, owner, tap_ids, 0,
+                                  [&](std::uint64_t idx) -> const vector<double> & { return P.tap_weights[(std::size_t)idx]; });
         evaluator.rescale_to_next_inplace(sum);
         var = sum;
 

@@ -8,6 +8,7 @@
 #pragma once
 #include "seal/seal.h"
 #include <cstdint>
+#include <vector>
 
 template <class Make>
 inline void multiply_vector_named(seal::Evaluator &evaluator, seal::Ciphertext &encrypted, const void *owner,
@@ -46,6 +47,31 @@ inline void multiply_vector_named_accumulate(seal::Evaluator &evaluator, seal::C
         evaluator.add_inplace_reduced_error(sum, product);
 #endif
     started = true;
+}
+
+// sum <- sum over t of terms[t] * (vector named (owner, indices[t], variant)); make_at(index) builds a term's slot vector.
+// On the engine one pass over all operands; on stock SEAL the reference's loop
+//   multiply_vector_reduced_error(x_t, v_t, tmp); if (first) sum = tmp; else add_inplace_reduced_error(sum, tmp);
+template <class MakeAt>
+inline void multiply_vector_named_sum(seal::Evaluator &evaluator, seal::Ciphertext &sum,
+                                      const std::vector<const seal::Ciphertext *> &terms, const void *owner,
+                                      const std::vector<std::uint64_t> &indices, std::uint64_t variant, MakeAt &&make_at)
+{
+#ifdef B200CKKS_FACADE
+    evaluator.multiply_vector_sum_cached(sum, terms, owner, indices, variant, make_at);
+#else
+    (void)owner;
+    (void)variant;
+    seal::Ciphertext product;
+    for (std::size_t t = 0; t < terms.size(); t++)
+    {
+        evaluator.multiply_vector_reduced_error(const_cast<seal::Ciphertext &>(*terms[t]), make_at(indices[t]), product);
+        if (t == 0)
+            sum = product;
+        else
+            evaluator.add_inplace_reduced_error(sum, product);
+    }
+#endif
 }
 
 inline void forget_named(seal::Evaluator &evaluator, const void *owner)

@@ -1699,6 +1699,58 @@ namespace seal
             detail::check(bk_multiply_plain_accumulate(h(), accumulator.handle(), encrypted.handle(), plain.handle()));
             accumulator.pull();
         }
+        // destination <- sum_t terms[t] * (vector named (owner, indices[t], variant)): all terms of a BSGS group or of a
+        // convolution's filter taps in ONE pass (bk_multiply_plain_sum) - each operand is read once and the sum is reduced
+        // once; residues and scale as the term-by-term sequence.  make_at(index) builds the slot vector of a term whose
+        // encoding is not cached yet.  Terms on different levels / scales fall back to the term-by-term path.
+        template <class MakeAt>
+        void multiply_vector_sum_cached(
+            Ciphertext &destination, const std::vector<const Ciphertext *> &terms, const void *owner,
+            const std::vector<std::uint64_t> &indices, std::uint64_t variant, MakeAt &&make_at)
+        {
+            if (terms.empty() || terms.size() != indices.size())
+                throw std::invalid_argument("terms and indices must have the same positive length");
+            bool uniform = true;
+            for (const Ciphertext *t : terms)
+            {
+                need(*t, "encrypted");
+                uniform = uniform && t != &destination && t->coeff_modulus_size() == terms[0]->coeff_modulus_size() &&
+                          t->scale() == terms[0]->scale() && t->size() == terms[0]->size();
+            }
+            if (!uniform || terms.size() == 1)
+            {
+                Ciphertext sum;
+                for (std::size_t t = 0; t < terms.size(); t++)
+                    multiply_vector_accumulate_cached(sum, *terms[t], owner, indices[t], variant,
+                                                      [&]() -> decltype(make_at(indices[t])) { return make_at(indices[t]); });
+                destination = std::move(sum);
+                return;
+            }
+            const int limbs = (int)terms[0]->coeff_modulus_size();
+            std::vector<std::unique_ptr<Plaintext>> once(terms.size());
+            std::vector<bk_ct_t> cts;
+            std::vector<bk_pt_t> pts;
+            for (std::size_t t = 0; t < terms.size(); t++)
+            {
+                const Plaintext &plain = named_plaintext(limbs, terms[0]->scale(), owner, indices[t], variant,
+                                                         [&]() -> decltype(make_at(indices[t])) { return make_at(indices[t]); },
+                                                         once[t]);
+                terms[t]->push();
+                plain.push();
+                cts.push_back(terms[t]->handle());
+                pts.push_back(plain.handle());
+            }
+            stats_.encode_vector += terms.size();
+            stats_.multiply_plain += terms.size();
+            stats_.add += terms.size() - 1;
+            for (std::size_t t = 0; t < terms.size(); t++)
+                stats_.hit(2, (std::size_t)limbs);
+            for (std::size_t t = 1; t < terms.size(); t++)
+                stats_.hit(5, (std::size_t)limbs);
+            destination.bind(context_.impl());
+            detail::check(bk_multiply_plain_sum(h(), destination.handle(), cts.data(), pts.data(), (int)cts.size()));
+            destination.pull();
+        }
         // drop every cached plaintext of `owner` (call before the owner's storage is released or rewritten)
         void forget_cached(const void *owner) const
         {

@@ -195,6 +195,10 @@ bk_status bk_multiply_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);   /
  * acc (size 0) is initialised with the product.  acc takes the product's scale (the reduced-error add overwrites
  * scales the same way, :316-321).  Residues equal those of the two separate calls. */
 bk_status bk_multiply_plain_accumulate(bk_context_t ctx, bk_ct_t acc, bk_ct_t a, bk_pt_t p);
+/* dst = sum_t cts[t] (.) pts[t]: the inner sum of a BSGS group (Bootstrapper.cpp:1995-2012) or of the filter taps of a
+ * convolution (cnn_seal.cpp:455-470) in one pass over the operands; same residues as multiply_plain + add_inplace term
+ * by term.  All operands on one level with equal scales; dst must not be an operand. */
+bk_status bk_multiply_plain_sum(bk_context_t ctx, bk_ct_t dst, const bk_ct_t *cts, const bk_pt_t *pts, int count);
 bk_status bk_transform_to_ntt_inplace(bk_context_t ctx, bk_ct_t a);            /* :2069-2118 */
 bk_status bk_transform_from_ntt_inplace(bk_context_t ctx, bk_ct_t a);
 /* fork: add_const / multiply_const (evaluator.cpp:287-302): scalar encode (ckks.cpp:77-153)
