@@ -3,6 +3,9 @@ the reference's own SEAL, oracle/_ref/libapp_ref.so) and tests/test_gpt2_gpu.py 
 through the C ABI).  Expected values come from the float64 slot model oracle/gpt2_model.py, which
 tests/test_gpt2_cpu.py pins to the expected vectors of the reference's own doctest cases (run/run_approx_test.cpp);
 level consumption is asserted next to the values.  Tolerances are stated next to each assertion."""
+import json
+import os
+
 import numpy as np
 
 import gpt2_model as gm
@@ -12,15 +15,9 @@ POLY_BITS = [49] + [46] * 22 + [60]          # 23 data limbs: one composite sign
 SHORT_BITS = [49] + [46] * 6 + [60]
 SCALE = 2.0 ** 46
 
-# expected vectors of the reference's doctest cases (gpt2_ckks/run/run_approx_test.cpp)
-KAT = {
-    "sign_f": ([-0.4, 0.5, -1, 1], [-0.80238268, 0.9021453857, -1.0, 1.0]),                    # :399-423
-    "sign_g": ([-0.4, 0.5, -1, 1], [-0.899779538, 0.7708721161, -0.998046875, 0.998046875]),   # :425-449
-    "sign": ([-0.4, 0.5, 0.01, -0.02], [-1, 1, 0.98683881, -0.9999994]),                       # :451-479
-    "gelu_p": ([-0.4, 0.5, 1, -1], [-0.3501723443, -0.7345966621, -1.036827125, -0.188669242]),  # :481-504
-    "gelu_q": ([-3, 5, 1, -1], [-0.5845409261, 13.43445935, 0.8339413477, -0.1655280783]),     # :506-529
-    "exp": ([2, -0.05, 10], [7.166276152788219, 0.9512108363005606, 10847.05214173728]),       # :589-611
-}
+# expected vectors of the reference's doctest cases (gpt2_ckks/run/run_approx_test.cpp), committed as a fixture
+_GOLDEN = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gpt2_doctest_vectors.json")))
+KAT = {k: (v["input"], v["expected"]) for k, v in _GOLDEN.items() if not k.startswith("_")}
 
 
 def pow2_steps(slots):
