@@ -64,7 +64,21 @@ def app():
 
 @pytest.fixture(scope="module")
 def poly_session(app):
-    s = app.session(cases.SMALL_LOG_N, cases.POLY_BITS, hamming_weight=64, rotation_steps=cases.pow2_steps(2048))
+    # The reference's SEAL seeds its keys from std::random_device.  One run in ~25 on this container produced a session
+    # whose every result was off by O(1) (not reproducible afterwards); a session must pass a fresh-encryption and a
+    # rotation round trip before the cases use it, and the observation is printed if it ever recurs.
+    for attempt in range(3):
+        s = app.session(cases.SMALL_LOG_N, cases.POLY_BITS, hamming_weight=64, rotation_steps=cases.pow2_steps(2048))
+        x, ct = cases.enc(s, np.linspace(-1, 1, 64))
+        fresh = np.abs(s.decrypt(ct).real - x).max()
+        s.rotate(ct, 1)
+        rotated = np.abs(s.decrypt(ct).real - np.roll(x, -1)).max()
+        if fresh < 1e-7 and rotated < 1e-6:
+            break
+        print(f"reference-SEAL session {attempt} unhealthy: fresh {fresh:.2e}, rotated {rotated:.2e}")
+        s.close()
+    else:
+        pytest.fail("three reference-SEAL sessions in a row failed the round-trip check")
     yield s
     s.close()
 
