@@ -136,15 +136,16 @@ void Bootstrapper::addLeftRotKeys_Linear_to_vector_3(vector<int> &steps)
 
 void Bootstrapper::find_slot_index()
 {
-    slot_index = -1;
+    long found = -1; // written to the member once: images run on several host threads over one Bootstrapper
     for (std::size_t i = 0; i < slot_vec.size(); i++)
         if (slot_vec[i] == logn)
         {
-            slot_index = (long)i;
+            found = (long)i;
             break;
         }
-    if (slot_index == -1)
+    if (found == -1)
         throw std::invalid_argument("LT coefficients were not generated for this logn");
+    slot_index = found;
 }
 
 void Bootstrapper::addBootKeys_3(GaloisKeys &keys)
