@@ -315,7 +315,12 @@ def run_engine(args):
                 "algorithmic_bytes_per_launch": int(d["limb_polys"] * ALGO_BYTES_PER_UNIT[dom] / d["launches"]),
                 "note": "NTT passes are integer-issue bound (ncu: 68-78 % of peak instruction throughput, DRAM 5-16 %), "
                         "see profiles/; the HBM fraction is reported because the contract asks for hbm|tensor",
-                "gpu_busy_fraction_of_step": round(total_kernel_ms / prof_ms, 4)}
+                "gpu_busy_fraction_of_step": round(total_kernel_ms / prof_ms, 4),
+                # what actually bounds the NTT passes: the IMAD half of the FMA pipe, from the committed ncu captures (static,
+                # not measured in this run)
+                "int_pipe_ncu": {"metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
+                                 "k_fwd_cols": 78.5, "k_fwd_blocks": 63.1, "k_ks_mac": 50.6,
+                                 "source": "profiles/r1_ncu_metrics_kernel_tour.md"}}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------
     cpu = None
