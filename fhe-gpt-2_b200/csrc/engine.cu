@@ -1621,6 +1621,8 @@ extern "C"
         // SEAL layout restricted to the resident part: [digits][2][klimbs+1][N], special last
         BK_TRY
         Context &c = *key->ctx;
+        if (!key->d)
+            throw std::logic_error("this key is a hybrid-mode recipe: it has no SEAL-layout data to download");
         cudaStream_t s = c.stream();
         BK_CUDA(cudaMemcpyAsync(host_out, key->d, key->words * sizeof(u64), cudaMemcpyDeviceToHost, s));
         BK_CUDA(cudaStreamSynchronize(s));
@@ -1630,6 +1632,8 @@ extern "C"
     {
         BK_TRY
         Context &c = *key->ctx;
+        if (!key->d)
+            throw std::logic_error("this key is a hybrid-mode recipe: it has no SEAL-layout data to export");
         BK_CUDA(cudaMemcpyAsync(dev_dst, key->d, key->words * sizeof(u64), cudaMemcpyDeviceToDevice, c.stream()));
         BK_CUDA(cudaStreamSynchronize(c.stream()));
         BK_END
