@@ -783,7 +783,7 @@ namespace bk
                            const u64 *base1, u64 *out, int l, bk_kskey_t key)
     {
         bk_kskey_s level_view; // hybrid mode at a level whose shape is SEAL's own: its level key is a pruned SEAL key
-        if (c.hybrid && key->sk)
+        if (key->sk && (c.hybrid || !key->d)) // a recipe generated in hybrid mode has no SEAL-layout data
         {
             if (hybrid_plan(c, l).alpha > 1)
             {
@@ -855,7 +855,7 @@ namespace bk
         const int l = in->limbs;
         std::vector<bk_kskey_s> level_views;
         std::vector<bk_kskey_t> level_keys;
-        if (c.hybrid && count > 0 && keys[0]->sk)
+        if (count > 0 && keys[0]->sk && (c.hybrid || !keys[0]->d))
         {
             if (hybrid_plan(c, l).alpha > 1)
             {
