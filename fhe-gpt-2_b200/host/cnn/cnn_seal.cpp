@@ -194,7 +194,10 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
             rotated_copy(ctxt_in, ctxt_rot[(std::size_t)(i1 * fw + i2)], ki * ki * wi * (i1 - (fh - 1) / 2) + ki * (i2 - (fw - 1) / 2),
                          evaluator, gal_keys);
 
-    // an encryption of zero at the input's scale (start value of the running sums)
+    // an encryption of zero at the input's scale: the reference's start value of its running sums (cnn_seal.cpp:433-436).
+    // Without it (default) a running sum starts from its first term - same level and scale as zero + first term.
+    const bool zero_start = encrypt_constants();
+    if (zero_start)
     {
         vector<double> zero((std::size_t)n, 0.0);
         Plaintext plain;
@@ -232,11 +235,15 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
         }
         if (c == -1)
         {
-            sum = ct_zero;
+            if (zero_start)
+                sum = ct_zero;
             for (int x = 0; x < ti; x++)
             {
                 rotated_copy(var, temp, ki * ki * hi * wi * x, evaluator, gal_keys);
-                evaluator.add_inplace_reduced_error(sum, temp);
+                if (x == 0 && !zero_start)
+                    sum = temp;
+                else
+                    evaluator.add_inplace_reduced_error(sum, temp);
             }
             var = sum;
         }
@@ -264,11 +271,15 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
 
     if (!end)
     { // replicate into po copies
-        sum = ct_zero;
+        if (zero_start)
+            sum = ct_zero;
         for (int u6 = 0; u6 < po; u6++)
         {
             rotated_copy(var, temp, (int)(-u6 * (n / po)), evaluator, gal_keys);
-            evaluator.add_inplace_reduced_error(sum, temp);
+            if (u6 == 0 && !zero_start)
+                sum = temp;
+            else
+                evaluator.add_inplace_reduced_error(sum, temp);
         }
         var = sum;
     }
@@ -323,9 +334,17 @@ void multiplexed_parallel_batch_norm_seal(const TensorCipher &cnn_in, TensorCiph
     }
     Plaintext plain;
     Ciphertext cipher_g, temp = cnn_in.cipher();
-    encoder.encode(g, temp.scale(), plain);
-    encryptor.encrypt(plain, cipher_g);
-    evaluator.sub_inplace_reduced_error(temp, cipher_g);
+    if (encrypt_constants())
+    { // the reference's sequence (cnn_seal.cpp:566-570): a fresh top-level encryption of g, walked down by the subtraction
+        encoder.encode(g, temp.scale(), plain);
+        encryptor.encrypt(plain, cipher_g);
+        evaluator.sub_inplace_reduced_error(temp, cipher_g);
+    }
+    else
+    { // g as the plaintext it is, encoded at the ciphertext's own level and scale
+        encoder.encode(g, temp.parms_id(), temp.scale(), plain);
+        evaluator.sub_plain_inplace(temp, plain);
+    }
     cnn_out = TensorCipher(logn, ki, hi, wi, ci, ti, pi, temp);
 }
 

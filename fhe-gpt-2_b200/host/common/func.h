@@ -6,6 +6,7 @@
 #pragma once
 #include "seal/seal.h"
 #include <cmath>
+#include <cstdlib>
 #include <complex>
 #include <stdexcept>
 #include <vector>
@@ -48,6 +49,18 @@ namespace minicomp
         return c;
     }
 } // namespace minicomp
+
+// The reference encrypts a handful of constants inside its hot paths (the zero accumulator of a convolution,
+// cnn_seal.cpp:433-436; the batch-norm shift, :568-569; the 1/2 of the ReLU, SEALcomp.cpp:54-55; T0 = 1 of the Chebyshev
+// basis, SEALfunc.cpp:43-45) and lets the reduced-error add walk those fresh top-level ciphertexts down to the working
+// level.  By default they are used as the plaintext constants they are (same levels, scales and values, less noise,
+// no encryption and no walk-down: SURVEY.md 8(f) rank 1); $B200CKKS_ENCRYPT_CONSTANTS=1 restores the reference's
+// call sequence.
+inline bool encrypt_constants()
+{
+    static const bool on = std::getenv("B200CKKS_ENCRYPT_CONSTANTS") != nullptr;
+    return on;
+}
 
 // baby-step size minimising ceil(M/k) + k - 1 (first minimiser, k <= 3 sqrt(M))
 inline int giantstep(int M)

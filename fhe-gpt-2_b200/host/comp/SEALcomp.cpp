@@ -68,9 +68,14 @@ void minimax_ReLU_seal(long comp_no, std::vector<int> deg, long alpha, std::vect
     std::vector<double> half(cipher_in.poly_modulus_degree() / 2, 0.5);
     Plaintext plain_half;
     Ciphertext cipher_half, sum;
-    encoder.encode(half, x.scale(), plain_half);
-    encryptor.encrypt(plain_half, cipher_half);
-    evaluator.add_reduced_error(x, cipher_half, sum);
+    if (encrypt_constants())
+    {
+        encoder.encode(half, x.scale(), plain_half);
+        encryptor.encrypt(plain_half, cipher_half);
+        evaluator.add_reduced_error(x, cipher_half, sum);
+    }
+    else
+        evaluator.add_const(x, 0.5, sum);
     evaluator.multiply_reduced_error(sum, cipher_in, relin_keys, cipher_res);
     evaluator.rescale_to_next_inplace(cipher_res);
 }

@@ -45,16 +45,24 @@ namespace seal
         evaluator.multiply_reduced_error(Tm, Tn, relin_keys, twice);
         evaluator.add_inplace_reduced_error(twice, twice);
         evaluator.rescale_to_next_inplace(twice);
-        evaluator.sub_reduced_error(twice, Tmminusn, Tmplusn);
+        if (Tmminusn.size() == 0) // T0 = 1 kept as the constant it is (geneT0T1)
+            evaluator.add_const(twice, -1.0, Tmplusn);
+        else
+            evaluator.sub_reduced_error(twice, Tmminusn, Tmplusn);
     }
 
     void geneT0T1(Encryptor &encryptor, Evaluator &, CKKSEncoder &encoder, PublicKey &, SecretKey &, RelinKeys &,
                   Ciphertext &T0, Ciphertext &T1, Ciphertext &cipher)
     {
-        std::vector<double> ones(cipher.poly_modulus_degree() / 2, 1.0);
-        Plaintext plain;
-        encoder.encode(ones, cipher.scale(), plain);
-        encryptor.encrypt(plain, T0);
+        if (encrypt_constants())
+        {
+            std::vector<double> ones(cipher.poly_modulus_degree() / 2, 1.0);
+            Plaintext plain;
+            encoder.encode(ones, cipher.scale(), plain);
+            encryptor.encrypt(plain, T0);
+        }
+        else
+            T0 = Ciphertext(); // empty: evalT subtracts the constant 1 instead
         T1 = cipher;
     }
 

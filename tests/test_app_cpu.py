@@ -48,6 +48,24 @@ def test_bn_add_downsample_pool_fc(cnn_session):
     cases.case_bn_add_downsample_pool_fc(cnn_session)
 
 
+def test_reference_constant_encryptions_give_the_same_layers():
+    """$B200CKKS_ENCRYPT_CONSTANTS=1: the reference's own sequence (fresh encryptions of zero / shift / one-half / T0 walked
+    down by the reduced-error adds) instead of the default plaintext adds - same values, levels and scales.  The switch
+    is read once per process, so the cases run in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    code = ("import sys; sys.path[:0] = [%r, %r]; import appref, app_cases as c; a = appref.app(); "
+            "s = a.session(c.SMALL_LOG_N, c.CNN_SMALL_BITS, hamming_weight=64, rotation_steps=list(range(1, 2048))); "
+            "c.case_conv(s, 1, 8, 8, 4, 8, 2); c.case_conv(s, 1, 8, 8, 3, 4, 1); c.case_bn_add_downsample_pool_fc(s); s.close(); "
+            "s = a.session(c.SMALL_LOG_N, c.RELU_BITS, hamming_weight=64); c.case_relu(s); s.close()"
+            % (os.path.dirname(os.path.abspath(__file__)), os.path.dirname(os.path.abspath(appref.__file__))))
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, B200CKKS_ENCRYPT_CONSTANTS="1"),
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("k,h,w,c,co", [(1, 8, 8, 4, 8), (2, 4, 4, 8, 16)])
 def test_conv1x1_stride2_shortcut(cnn_session, k, h, w, c, co):
     cases.case_conv1x1_shortcut(cnn_session, k, h, w, c, co)
