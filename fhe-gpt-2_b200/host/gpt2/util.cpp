@@ -1,5 +1,6 @@
 // gpt2/util.cpp - see util.h.  Follows gpt2_ckks/gpt2-ckks/single-key/gpt2/util.cpp of the reference.
 #include "gpt2/util.h"
+#include "common/cached.h"
 #include <algorithm>
 #include <chrono>
 #include <complex>
@@ -142,11 +143,21 @@ namespace gpt2
         }
     }
 
+    // util.cpp:279-287 of the reference: multiply by a 0/1 slot vector, rescale.  The matrix operators ask for the same
+    // few masks thousands of times; on the engine the encoded mask is kept per (start, length, level, scale)
+    // (common/cached.h), on stock SEAL this is the reference's multiply_vector_reduced_error.
     void mask_out(Ciphertext &cipher, Ciphertext &out, int start, int length, CKKSEncoder &encoder, Evaluator &evaluator, RelinKeys &)
     {
-        vector<double> mask(encoder.slot_count(), 0.0);
-        std::fill(mask.begin() + start, mask.begin() + start + length, 1.0);
-        evaluator.multiply_vector_reduced_error(cipher, mask, out);
+        static const char mask_owner = 0;
+        vector<double> mask;
+        if (&out != &cipher)
+            out = cipher;
+        multiply_vector_named(evaluator, out, &mask_owner, ((std::uint64_t)(std::uint32_t)start << 32) | (std::uint32_t)length, 0,
+                              [&]() -> const vector<double> & {
+                                  mask.assign(encoder.slot_count(), 0.0);
+                                  std::fill(mask.begin() + start, mask.begin() + start + length, 1.0);
+                                  return mask;
+                              });
         evaluator.rescale_to_next_inplace(out);
     }
 
