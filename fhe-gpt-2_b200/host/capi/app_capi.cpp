@@ -225,6 +225,15 @@ extern "C"
         s->context = std::make_unique<SEALContext>(s->parms, true, sec_level_type::none, device);
 #else
         (void)device;
+        // $B200CKKS_REF_SEED (reference-SEAL checker build only): a seeded factory hands every encryption the same
+        // stream (randomgen.h:440-447), so this session and one of oracle/_ref/libcnn_ref.so - the reference's own
+        // application code - produce identical keys and fresh ciphertexts, and their results can be compared limb by limb
+        if (const char *e = std::getenv("B200CKKS_REF_SEED"))
+        {
+            std::uint64_t v = std::strtoull(e, nullptr, 0);
+            prng_seed_type seed = { v, v ^ 0x9E3779B97F4A7C15ull, v + 1, v + 2, v + 3, v + 4, v + 5, v + 6 };
+            s->parms.set_random_generator(std::make_shared<Blake2xbPRNGFactory>(seed));
+        }
         s->context = std::make_unique<SEALContext>(s->parms, true, sec_level_type::none);
 #endif
         s->keygen = std::make_unique<KeyGenerator>(*s->context);
@@ -614,6 +623,41 @@ extern "C"
         Ciphertext rtn;
         b->b->mod_reducer->modular_reduction(rtn, ct->ct);
         *out = wrap(std::move(rtn));
+        BKA_END
+    }
+
+    int bka_bootstrapper_set_evalmod_heap(bka_bootstrapper_t b, const double *data, int count)
+    {
+        BKA_TRY
+        if (count < 4)
+            throw std::invalid_argument("heap data is too short");
+        auto &red = *b->b->mod_reducer;
+        auto &p = red.sin_cos_polynomial;
+        const long heaplen = (long)data[0];
+        p.heap_k = (long)data[1];
+        p.heap_m = (long)data[2];
+        p.heaplen = heaplen;
+        red.scale_inverse_coeff = data[3];
+        p.poly_heap.clear();
+        p.poly_heap.resize((std::size_t)heaplen);
+        int pos = 4;
+        for (long i = 0; i < heaplen; i++)
+        {
+            if (pos >= count)
+                throw std::invalid_argument("heap data is truncated");
+            const long deg = (long)data[pos++];
+            if (deg < 0)
+                continue;
+            if (pos + deg + 1 > count)
+                throw std::invalid_argument("heap data is truncated");
+            auto node = std::make_unique<boot::Polynomial>();
+            node->set_zero_polynomial(deg);
+            for (long j = 0; j <= deg; j++)
+                node->chebcoeff[(std::size_t)j] = data[pos++];
+            if (deg <= 3)
+                node->cheb_to_power();
+            p.poly_heap[(std::size_t)i] = std::move(node);
+        }
         BKA_END
     }
 

@@ -607,6 +607,8 @@ namespace seal
                 ntt_ = o.ntt_;
                 return *this;
             }
+            o.flush_host_view();
+            drop_host_view();
             bind(o.ctx_);
             detail::check(bk_ct_copy(h_, o.h_));
             size_ = o.size_;
@@ -669,6 +671,7 @@ namespace seal
             auto cd = context.get_context_data(parms_id);
             if (!cd)
                 throw std::invalid_argument("parms_id is not valid for encryption parameters");
+            flush_host_view();
             bind(context.impl());
             detail::check(bk_ct_resize(h_, (int)size, SEALContext::limbs_of(parms_id)));
             size_ = (int)size;
@@ -676,6 +679,7 @@ namespace seal
         }
         void release()
         {
+            drop_host_view();
             if (h_)
                 bk_ct_destroy(h_);
             h_ = nullptr;
@@ -693,11 +697,39 @@ namespace seal
         }
         SEAL_NODISCARD bk_ct_t handle() const
         {
+            flush_host_view();
             return h_;
         }
         SEAL_NODISCARD const CtxImpl &ctx() const
         {
             return ctx_;
+        }
+        // Host view of the raw words in the reference's layout [size][limbs][N] for util::iter(Ciphertext &)
+        // (the reference's Bootstrapper::modraise_inplace writes limbs directly, Bootstrapper.cpp:2928-2944).  The
+        // view is downloaded on first access and written back before the next engine call that touches this
+        // ciphertext (every such call goes through handle()).
+        SEAL_NODISCARD std::uint64_t *host_view() const
+        {
+            if (!h_ || !size_ || !limbs_)
+                throw std::logic_error("ciphertext is empty");
+            if (!view_)
+            {
+                view_ = std::make_unique<std::vector<std::uint64_t>>((std::size_t)size_ * (std::size_t)limbs_ * poly_modulus_degree());
+                detail::check(bk_ct_download(h_, view_->data()));
+            }
+            return view_->data();
+        }
+        void flush_host_view() const
+        {
+            if (!view_)
+                return;
+            auto v = std::move(view_);
+            view_.reset();
+            detail::check(bk_ct_upload(h_, v->data(), size_, limbs_, scale_, ntt_ ? 1 : 0));
+        }
+        void drop_host_view() const
+        {
+            view_.reset();
         }
         void push() const
         {
@@ -713,10 +745,12 @@ namespace seal
         // raw limbs in the reference's layout [size][limbs][N] (ciphertext.h:335-347)
         void download(std::uint64_t *host) const
         {
+            flush_host_view();
             detail::check(bk_ct_download(h_, host));
         }
         void upload(const SEALContext &context, const std::uint64_t *host, int size, int limbs, double scale, bool ntt)
         {
+            drop_host_view();
             bind(context.impl());
             detail::check(bk_ct_upload(h_, host, size, limbs, scale, ntt ? 1 : 0));
             pull();
@@ -731,12 +765,14 @@ namespace seal
             std::swap(limbs_, o.limbs_);
             std::swap(scale_, o.scale_);
             std::swap(ntt_, o.ntt_);
+            std::swap(view_, o.view_);
         }
         CtxImpl ctx_;
         bk_ct_t h_ = nullptr;
         int size_ = 0, limbs_ = 0;
         double scale_ = 1.0;
         bool ntt_ = true;
+        mutable std::unique_ptr<std::vector<std::uint64_t>> view_;
     };
 
     // --------------------------------------------------------------------------------------- keys
@@ -967,6 +1003,19 @@ namespace seal
                 elts.push_back(e);
             }
             create_galois_keys(elts, destination);
+        }
+        // fork: keygenerator.h:154,219 - keys that switch from sigma^-1(s), used only by the fork's dead
+        // `*_hoisting` bootstrapping variants (Bootstrapper.cpp:448-477).  The engine's hoisted rotations
+        // (Evaluator::rotate_vector_hoisted) work on ordinary Galois keys, so this key type is not produced.
+        inline void create_hoisted_galois_keys(const std::vector<int> &, GaloisKeys &)
+        {
+            throw std::logic_error("create_hoisted_galois_keys: the fork's hoisted key type is not supported "
+                                   "(use create_galois_keys; the engine hoists rotations on ordinary keys)");
+        }
+        inline void create_hoisted_galois_keys(
+            const std::vector<std::uint32_t> &, const std::vector<std::uint32_t> &, GaloisKeys &)
+        {
+            throw std::logic_error("create_hoisted_galois_keys: the fork's hoisted key type is not supported");
         }
         // all power-of-two rotations + conjugation (keygenerator.h:271, galois.cpp:97-133)
         inline void create_galois_keys(GaloisKeys &destination)
@@ -1962,7 +2011,69 @@ namespace seal
         {
             return v;
         }
+        // Iterators over the raw words of a ciphertext (util/iterator.h: PolyIter -> RNSIter -> CoeffIter), as far as
+        // the reference's application code uses them: iter(cipher)[poly][limb][coeff] (Bootstrapper.cpp:2928-2944) and
+        // RNSIter as a member type (Bootstrapper.h:47).  They walk the ciphertext's host view (Ciphertext::host_view).
+        struct CoeffIter
+        {
+            std::uint64_t *p = nullptr;
+            std::uint64_t &operator[](std::size_t i) const
+            {
+                return p[i];
+            }
+            std::uint64_t &operator*() const
+            {
+                return *p;
+            }
+            operator std::uint64_t *() const
+            {
+                return p;
+            }
+        };
         struct RNSIter
-        {};
+        {
+            std::uint64_t *p = nullptr;
+            std::size_t n = 0; // poly_modulus_degree
+            RNSIter() = default;
+            RNSIter(std::uint64_t *ptr, std::size_t poly_modulus_degree) : p(ptr), n(poly_modulus_degree)
+            {}
+            CoeffIter operator[](std::size_t limb) const
+            {
+                return CoeffIter{ p + limb * n };
+            }
+            CoeffIter operator*() const
+            {
+                return CoeffIter{ p };
+            }
+            SEAL_NODISCARD std::size_t poly_modulus_degree() const
+            {
+                return n;
+            }
+        };
+        struct PolyIter
+        {
+            std::uint64_t *p = nullptr;
+            std::size_t n = 0, limbs = 0;
+            RNSIter operator[](std::size_t poly) const
+            {
+                return RNSIter(p + poly * limbs * n, n);
+            }
+            RNSIter operator*() const
+            {
+                return RNSIter(p, n);
+            }
+            SEAL_NODISCARD std::size_t poly_modulus_degree() const
+            {
+                return n;
+            }
+            SEAL_NODISCARD std::size_t coeff_modulus_size() const
+            {
+                return limbs;
+            }
+        };
+        inline PolyIter iter(Ciphertext &ct)
+        {
+            return PolyIter{ ct.host_view(), ct.poly_modulus_degree(), ct.coeff_modulus_size() };
+        }
     } // namespace util
 } // namespace seal

@@ -99,6 +99,11 @@ int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int ca
 /* LT coefficients: which = 0..2 SlotToCoeff matrices 1..3, 3..5 CoeffToSlot matrices 1..3.
  * Returns the number of diagonals and their length; data_out (may be NULL) receives (re, im) pairs. */
 int bka_bootstrapper_lt_coefficients(bka_bootstrapper_t b, int which, int *n_diagonals, int *length, double *data_out);
+/* Replaces the baby-step/giant-step heap of the EvalMod polynomial (boot::Polynomial::generate_poly_heap) by given
+ * coefficients: data = {heaplen, heap_k, heap_m, scale_inverse_coeff, then per heap node: degree (-1 = absent) followed
+ * by degree + 1 Chebyshev coefficients}.  For callers that bring their own minimax polynomial (the tests feed the
+ * coefficients of the reference's own Remez run, ModularReducer.cpp:37-51, to compare bootstraps limb by limb). */
+int bka_bootstrapper_set_evalmod_heap(bka_bootstrapper_t b, const double *data, int count);
 /* bootstrap_3 (real_message = 0) / bootstrap_real_3 (real_message = 1); ct is consumed like the reference's input */
 int bka_bootstrap(bka_bootstrapper_t b, bka_ct_t ct, int real_message, bka_ct_t *out);
 /* EvalMod alone: ModularReducer::modular_reduction */
