@@ -510,6 +510,44 @@ extern "C"
         s->evaluator->add_inplace_reduced_error(a->ct, b->ct);
         BKA_END
     }
+    int bka_reduced_error_op(bka_session_t s, int which, bka_ct_t a, bka_ct_t b)
+    {
+        BKA_TRY
+        switch (which)
+        {
+        case 0: s->evaluator->add_inplace_reduced_error(a->ct, b->ct); break;
+        case 1: s->evaluator->sub_inplace_reduced_error(a->ct, b->ct); break;
+        case 2: s->evaluator->multiply_inplace_reduced_error(a->ct, b->ct, s->relin_keys); break;
+        default: throw std::invalid_argument("which must be 0 (add), 1 (sub) or 2 (multiply)");
+        }
+        BKA_END
+    }
+    int bka_ct_upload(bka_session_t s, const uint64_t *host, int size, int limbs, double scale, int is_ntt, bka_ct_t *out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        Ciphertext c;
+        c.upload(*s->context, host, size, limbs, scale, is_ntt != 0);
+        *out = wrap(std::move(c));
+#else
+        (void)s, (void)host, (void)size, (void)limbs, (void)scale, (void)is_ntt, (void)out;
+        throw std::logic_error("raw ciphertext upload is an engine-backend feature");
+#endif
+        BKA_END
+    }
+    int bka_session_import_relin_key(bka_session_t s, const uint64_t *host, int digits)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        auto k = std::make_shared<RelinKeys::Holder>();
+        seal::detail::check(bk_kskey_upload(s->context->handle(), host, digits, 0, &k->h));
+        s->relin_keys.k_ = k;
+#else
+        (void)s, (void)host, (void)digits;
+        throw std::logic_error("raw key import is an engine-backend feature");
+#endif
+        BKA_END
+    }
     int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex)
     {
         BKA_TRY

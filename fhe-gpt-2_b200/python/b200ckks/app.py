@@ -248,6 +248,23 @@ class Session:
     def add_reduced_error(self, a, b):
         self.app.ck(self.app.L.bka_add_reduced_error(self.h, a.h, b.h))
 
+    def reduced_error_op(self, which, a, b):
+        """a <- a {add, sub, multiply}_inplace_reduced_error b (evaluator.cpp:312-486)"""
+        self.app.ck(self.app.L.bka_reduced_error_op(self.h, {"add": 0, "sub": 1, "multiply": 2}[which], a.h, b.h))
+
+    def upload(self, limbs_array, scale, ntt=True):
+        """ciphertext from raw limbs [size][limbs][N] in the reference's layout"""
+        d = np.ascontiguousarray(limbs_array, dtype=np.uint64)
+        out = C.c_void_p()
+        self.app.ck(self.app.L.bka_ct_upload(self.h, d.ctypes.data_as(C.c_void_p), d.shape[0], d.shape[1], C.c_double(scale),
+                                             int(ntt), C.byref(out)))
+        return Ct(self, out)
+
+    def import_relin_key(self, key):
+        """relinearization key in SEAL's layout [digits][2][n_primes][N]"""
+        d = np.ascontiguousarray(key, dtype=np.uint64)
+        self.app.ck(self.app.L.bka_session_import_relin_key(self.h, d.ctypes.data_as(C.c_void_p), d.shape[0]))
+
     def multiply_vector_rescale(self, a, values):
         v = np.asarray(values)
         if np.iscomplexobj(v):

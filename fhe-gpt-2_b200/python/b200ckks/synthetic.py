@@ -45,6 +45,47 @@ def random_weights(layer_num, seed=0, classes=10):
     return w
 
 
+def load_pretrained(directory, layer_num):
+    """The reference's parameter files (pretrained_parameters/resnet<L>_new/*.txt) in the order
+    import_parameters_cifar10 reads them (infer_seal.cpp:3-107): whitespace-separated values, one tensor per file."""
+    import os
+
+    end_num, shapes = resnet_shapes(layer_num)
+
+    def rd(name, count):
+        with open(os.path.join(directory, name + ".txt")) as f:
+            v = np.array(f.read().split(), dtype=np.float64)
+        if v.size < count:
+            raise ValueError(f"{name}.txt holds {v.size} values, {count} expected")
+        return v[:count]
+
+    conv_names, bn_names = ["conv1"], ["bn1"]
+    for j in range(1, 4):
+        for k in range(end_num + 1):
+            conv_names += [f"layer{j}_{k}_conv1", f"layer{j}_{k}_conv2"]
+            bn_names += [f"layer{j}_{k}_bn1", f"layer{j}_{k}_bn2"]
+    w = dict(conv_weight=[], bn_bias=[], bn_mean=[], bn_var=[], bn_weight=[])
+    for (ci, co), cn, bn in zip(shapes, conv_names, bn_names):
+        w["conv_weight"].append(rd(cn + "_weight", 9 * ci * co))
+        w["bn_bias"].append(rd(bn + "_bias", co))
+        w["bn_mean"].append(rd(bn + "_running_mean", co))
+        w["bn_var"].append(rd(bn + "_running_var", co))
+        w["bn_weight"].append(rd(bn + "_weight", co))
+    w["linear_weight"] = rd("linear_weight", 10 * 64)
+    w["linear_bias"] = rd("linear_bias", 10)
+    return w
+
+
+def pretrained_dir(layer_num=20):
+    """tests/golden/pretrained_parameters/resnet<L>_new (a copy of the reference's trained parameters kept as a test
+    fixture), or None when it is not there"""
+    import os
+
+    d = os.path.normpath(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..", "tests", "golden",
+                                      "pretrained_parameters", f"resnet{layer_num}_new"))
+    return d if os.path.isdir(d) else None
+
+
 def synthetic_image(image_id):
     """3072 i.i.d. N(0,1) values clipped to [-2.5, 2.5] (normalised-CIFAR-like), seed = image id, CHW order."""
     return np.clip(np.random.default_rng(image_id).normal(0, 1, 3072), -2.5, 2.5)

@@ -83,6 +83,13 @@ int bka_rotate(bka_session_t s, bka_ct_t ct, int steps);
 int bka_multiply_relin_rescale(bka_session_t s, bka_ct_t a, bka_ct_t b); /* a <- rescale(relin(a * b)) */
 int bka_add_reduced_error(bka_session_t s, bka_ct_t a, bka_ct_t b);      /* a <- a + b */
 int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex);
+/* Evaluator::{add,sub,multiply}_inplace_reduced_error (evaluator.cpp:312-486; which = 0, 1, 2): a <- a op b, operands
+ * may sit at different levels (the higher one is walked down as the reference does); multiply relinearizes. */
+int bka_reduced_error_op(bka_session_t s, int which, bka_ct_t a, bka_ct_t b);
+/* a ciphertext from raw limbs in the reference's layout [size][limbs][N] (Ciphertext::data(), ciphertext.h:335-347) */
+int bka_ct_upload(bka_session_t s, const uint64_t *host, int size, int limbs, double scale, int is_ntt, bka_ct_t *out);
+/* replace the session's relinearization key by one in SEAL's layout [digits][2][n_primes][N] (kswitchkeys.h:340) */
+int bka_session_import_relin_key(bka_session_t s, const uint64_t *host, int digits);
 
 /* ---- bootstrapping (Bootstrapper.h) ----------------------------------------------------------------------------
  * create = constructor + prepare_mod_polynomial + slot_vec.push_back(logn) + generate_LT_coefficient_3; the

@@ -1,0 +1,159 @@
+"""Drop-in proof (north_star: "so cnn_ckks ... link against it unchanged"): the REFERENCE's application sources -
+common/*.cpp, ckks_bootstrapping/*.cpp, comp/*.cpp, cnn/*.cpp, run/run_cnn.cpp - compiled UNMODIFIED against this
+repo's seal:: facade (fhe-gpt-2_b200/host/seal/seal.h) and linked with libb200ckks.so (oracle/Makefile target
+cnn_dropin; oracle/ntl_shim stands in for NTL).  The reference's object code then runs on the B200:
+
+* its convolution / batch norm / ReLU / bootstrap against the float64 model and against the same object code on the
+  reference's own SEAL (oracle/_ref/libcnn_ref.so, CPU);
+* the Evaluator operations it issues, counted by the facade, against the restated layers in reference-sequence mode;
+* the whole program `cnn 20 10 0 0` (ResNet_cifar10_seal_sparse, infer_seal.cpp:251-584) at N = 2^16 with the
+  reference's trained parameters (pretrained_parameters/resnet20_new): result file in the reference's format, level
+  and scale trajectory equal to the reference's committed log, logits against the float64 model."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import app_cases as cases
+import cnnref
+import plain_model as pm
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+if not (cnnref.available() and cnnref.dropin_available()):  # pragma: no cover
+    pytest.skip("oracle/_ref/libcnn_dropin.so not built (needs /root/reference at build time)", allow_module_level=True)
+
+
+@pytest.fixture(scope="module")
+def dropin():
+    return cnnref.dropin_app()
+
+
+@pytest.fixture(scope="module")
+def ref_app():
+    return cnnref.app()
+
+
+def test_reference_cnn_layers_run_on_the_engine(dropin):
+    s = dropin.session(cases.SMALL_LOG_N, cases.CNN_SMALL_BITS, hamming_weight=64, rotation_steps=list(range(1, 2048)))
+    cases.case_conv(s, 1, 8, 8, 4, 8, 2)           # multiplexed_parallel_convolution_seal, cnn_seal.cpp:284
+    cases.case_conv(s, 2, 4, 4, 8, 8, 1)
+    cases.case_bn_add_downsample_pool_fc(s)        # cnn_seal.cpp:531-787
+    st = s.stats()
+    assert st["key_switch_rotate"] > 0 and st["multiply_plain"] > 0   # the facade served them: the engine did the work
+    assert s.engine().launch_count() > 0
+    s.close()
+
+
+def test_reference_relu_runs_on_the_engine(dropin):
+    with cnnref.workdir():
+        s = dropin.session(cases.SMALL_LOG_N, cases.RELU_BITS, hamming_weight=64)
+        cases.case_relu(s)                         # minimax_ReLU_seal, SEALcomp.cpp:3
+        assert s.stats(reset=True)["key_switch_relin"] == 27
+        s.close()
+
+
+def test_reference_bootstrap_runs_on_the_engine_like_on_its_own_seal(dropin, ref_app):
+    """bootstrap_real_3 (Bootstrapper.cpp:3421) incl. the reference's modraise_inplace writing raw limbs through
+    iter(cipher)[poly][limb][i] (:2928-2944) - served by the facade's host view of the ciphertext."""
+    rng = np.random.default_rng(4)
+    out = {}
+    for name, app in (("engine", dropin), ("seal", ref_app)):
+        s = app.session(cases.SMALL_LOG_N, cases.BOOT_BITS, hamming_weight=64)
+        boot = s.bootstrapper(9)                   # runs the reference's own Remez (common/Remez.cpp)
+        xs = np.tile(np.random.default_rng(4).uniform(-1, 1, 512), s.slots // 512)
+        if name == "engine":
+            s.stats(reset=True)
+        o = boot.bootstrap(s.encrypt(xs, 2.0 ** 46, limbs=1), real_message=True)
+        assert o.info() == (2, 17, 2.0 ** 46)
+        out[name] = s.decrypt(o)
+        if name == "engine":
+            st = s.stats()
+            # rotations: 3 x (baby + giant) per transform + SubSum + conjugations, relinearizations of EvalMod:
+            # identical to what the restated Bootstrapper issues in its reference-sequence mode (test below)
+            assert st["key_switch_relin"] == 18
+        assert np.abs(out[name] - xs).max() < 5e-5, name
+        s.close()
+    # same code, two libraries: results differ only by encryption and key-switching noise
+    assert np.abs(out["engine"] - out["seal"]).max() < 5e-5
+
+
+def test_reference_and_restated_layers_issue_the_same_operations():
+    """Evaluator call counts (rotations, relinearizations, rescales, ct x ct, ct x pt, encodes, additions, mod
+    switches, scalar operations) of the reference's object code and of the restated layers in reference-sequence mode,
+    both on the engine - for one convolution, one ReLU and one bootstrap."""
+    code = r'''
+import json, os, sys
+sys.path[:0] = [%r, %r]
+os.environ["B200CKKS_ENCRYPT_CONSTANTS"] = "1"; os.environ["B200CKKS_NO_HOIST"] = "1"
+import numpy as np
+import app_cases as c, cnnref
+from b200ckks.app import App
+res = {}
+with cnnref.workdir():
+    for name, a in (("reference", cnnref.dropin_app()), ("restated", App())):
+        r = {}
+        s = a.session(c.SMALL_LOG_N, c.CNN_SMALL_BITS, hamming_weight=64, rotation_steps=list(range(1, 2048)))
+        rng = np.random.default_rng(1)
+        x, ct, parms = c.make_tensor(s, rng, 1, 8, 8, 4, limbs=4)
+        s.stats(reset=True)
+        s.conv(ct, parms, 8, 2, rng.normal(0, 0.3, 9 * 4 * 8), rng.uniform(0.5, 1.5, 8), rng.uniform(0.5, 1.0, 8))
+        r["conv"] = s.stats(reset=True); s.close()
+        s = a.session(c.SMALL_LOG_N, c.RELU_BITS, hamming_weight=64)
+        ct = s.encrypt(np.random.default_rng(3).uniform(-1, 1, s.slots), 2.0 ** 46, limbs=17)
+        s.stats(reset=True); s.relu(ct); r["relu"] = s.stats(reset=True); s.close()
+        s = a.session(c.SMALL_LOG_N, c.BOOT_BITS, hamming_weight=64)
+        b = s.bootstrapper(9)
+        xs = np.tile(np.random.default_rng(4).uniform(-1, 1, 512), s.slots // 512)
+        ct = s.encrypt(xs, 2.0 ** 46, limbs=1)
+        s.stats(reset=True); b.bootstrap(ct, real_message=True); r["bootstrap"] = s.stats(reset=True); s.close()
+        res[name] = r
+print("COUNTS " + json.dumps(res))
+''' % (HERE, os.path.dirname(os.path.abspath(cnnref.__file__)))
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:]
+    counts = json.loads(r.stdout.split("COUNTS ", 1)[1])
+    for layer in ("conv", "relu", "bootstrap"):
+        ref, res = counts["reference"][layer], counts["restated"][layer]
+        # the reference decrypts and prints inside its ReLU (decrypt_and_print_part, SEALcomp.cpp:52), which costs no
+        # Evaluator call; everything the Evaluator is asked to do must agree
+        assert ref == res, (layer, ref, res)
+
+
+def test_reference_cnn_program_on_the_engine(tmp_path):
+    """`cnn 20 10 0 0`: the reference's main() (run/run_cnn.cpp) -> ResNet_cifar10_seal_sparse at N = 2^16, trained
+    parameters of pretrained_parameters/resnet20_new, on one B200."""
+    from b200ckks import synthetic
+
+    w = synthetic.load_pretrained(synthetic.pretrained_dir(20), 20)
+    image = synthetic.synthetic_image(0)       # the reference's CIFAR image file is missing from its repository
+    want = pm.resnet_forward(20, w, image)
+    label = int(np.argmax(want))
+    base = str(tmp_path)
+    build = cnnref.make_tree(base, 20, images=[image], labels=[label])
+    r = subprocess.run([cnnref.CNN_DROPIN, "20", "10", "0", "0"], cwd=build, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=3000)
+    assert r.returncode == 0, r.stdout[-3000:]
+    log = open(os.path.join(base, "FHE-GPT-2", "result", "resnet20_cifar10_image0.txt")).read()
+    from util import parse_reference_log
+
+    got = parse_reference_log(log)       # the reference's own result format (infer_seal.cpp:543-575)
+    assert got["inferred_label"] == label and got["image_label"] == label, (got["inferred_label"], label, got["logits"])
+    # operation, remaining level and scale of every stage equal the reference's committed run log
+    # (result/resnet20_cifar10_image0.txt; scales to the 6 digits it prints)
+    golden = json.load(open(os.path.join(HERE, "golden", "resnet20_trajectory.json")))
+    assert [r["op"] for r in got["rows"]] == [r["op"] for r in golden["rows"]]
+    assert [r["level"] for r in got["rows"]] == [r["level"] for r in golden["rows"]]
+    for a, b in zip(got["rows"], golden["rows"]):
+        assert abs(a["scale"] - b["scale"]) <= 1.5e-6 * b["scale"], (a, b)
+    # logits against the float64 model with the same trained parameters
+    logits = np.array(got["logits"])
+    assert logits.shape == (10,) and np.abs(logits - want).max() < 5e-2, (logits, want)
+    t = re.search(r"total time : (\d+) ms", log)
+    assert t, log[-500:]
+    print(f"reference cnn program on the engine: total time {t.group(1)} ms, logits err {np.abs(logits - want).max():.2e}")

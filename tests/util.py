@@ -44,3 +44,39 @@ def assert_ct_equal(eng_ct, ref, ct_id, what=""):
         bad = np.argwhere(got != want)
         raise AssertionError(f"{what}: {len(bad)} of {got.size} words differ, first at {bad[0]}: "
                              f"{got[tuple(bad[0])]} vs {want[tuple(bad[0])]}")
+
+
+REFERENCE_LOG_OPS = {"multiplexed parallel convolution...": "conv", "multiplexed parallel batch normalization...": "bn",
+                     "approximate ReLU...": "relu", "bootstrapping...": "bootstrap", "cipher add...": "add",
+                     "multiplexed parallel downsampling...": "downsample", "average pooling...": "avgpool",
+                     "fully connected layer...": "fc"}
+
+
+def parse_reference_log(text):
+    """A result file in the reference's format (cnn_seal.cpp:101-283 *_print wrappers, infer_seal.cpp:543-575):
+    rows of (op, ms, remaining level, scale), the ten logits, total time, image and inferred label.  Same rules as
+    tools/make_golden_trajectory.py, which made tests/golden/resnet20_trajectory.json from the reference's own log."""
+    import re
+
+    rows, cur, out = [], None, {"logits": None, "total_ms": None, "inferred_label": None, "image_label": None}
+    for line in text.splitlines():
+        line = line.strip()
+        if line in REFERENCE_LOG_OPS:
+            cur = {"op": REFERENCE_LOG_OPS[line], "ms": None, "level": None, "scale": None}
+            rows.append(cur)
+        elif line.startswith("time :") and cur is not None:
+            cur["ms"] = float(line.split()[2])
+        elif line.startswith("remaining level :") and cur is not None:
+            cur["level"] = int(line.split()[-1])
+        elif line.startswith("scale:") and cur is not None:
+            cur["scale"] = float(line.split()[-1])
+        elif line.startswith("total time"):
+            out["total_ms"] = float(line.split()[3])
+        elif line.startswith("inferred label"):
+            out["inferred_label"] = int(line.split()[-1])
+        elif line.startswith("image label"):
+            out["image_label"] = int(line.split()[-1])
+        elif line.startswith("( (") and len(re.findall(r"\(", line)) == 11:
+            out["logits"] = [float(m) for m in re.findall(r"\((-?[0-9.e+-]+),", line)]
+    out["rows"] = rows
+    return out
