@@ -6,6 +6,7 @@
 // same exception types.  There is no CPU arithmetic path: without a CUDA device
 // bk_context_create fails with BK_NO_DEVICE.
 #include "engine.h"
+#include <sys/random.h>
 #include <cmath>
 #include <algorithm>
 #include <cstdlib>
@@ -90,6 +91,24 @@ namespace bk
             throw std::invalid_argument("coeff_modulus size is invalid");
         if (const char *e = std::getenv("B200CKKS_HYBRID_KS"))
             hybrid = std::atoi(e) != 0;
+        // random generator master key (rng.cuh): the operating system's entropy unless a reproducible run is asked for
+        if (const char *e = std::getenv("B200CKKS_SEED"))
+        {
+            uint64_t v = std::strtoull(e, nullptr, 0);
+            RngKey seed_key = { { (uint32_t)v, (uint32_t)(v >> 32), 0x62323030u, 0x636b6b73u, 0, 0, 0, 0 } };
+            rng_master = derive_call_key(seed_key, 0);
+        }
+        else
+        {
+            size_t got = 0;
+            while (got < sizeof rng_master.k)
+            {
+                ssize_t r = getrandom((char *)rng_master.k + got, sizeof rng_master.k - got, 0);
+                if (r < 0)
+                    throw std::runtime_error("getrandom failed: no entropy source for key and encryption randomness");
+                got += (size_t)r;
+            }
+        }
         int dev_count = 0;
         if (cudaGetDeviceCount(&dev_count) != cudaSuccess || dev_count == 0)
             throw NoDevice("no CUDA device: this engine has no CPU path");
@@ -104,8 +123,11 @@ namespace bk
         for (int i = 0; i < n_primes; i++)
         {
             uint64_t q = primes[i];
-            if (q >> 61 || !is_prime_u64(q) || (q - 1) % (2 * n) != 0)
-                throw std::invalid_argument("coeff_modulus is not valid (need NTT-friendly primes < 2^61)");
+            // SEAL's own user limit (SEAL_USER_MOD_BIT_COUNT_MAX = 60, util/defines.h:33-40).  It also bounds the unreduced
+            // 128-bit sums of k_ks_mac / k_mul_plain_sum: at most 61 digits in [0, 4q) times keys in [0, q) stay below
+            // 61 * 4 * 2^120 < 2^128.
+            if (q >> 60 || !is_prime_u64(q) || (q - 1) % (2 * n) != 0)
+                throw std::invalid_argument("coeff_modulus is not valid (need NTT-friendly primes of at most 60 bits)");
             for (int j = 0; j < i; j++)
                 if (primes[j] == q)
                     throw std::invalid_argument("coeff_modulus primes must be distinct");
@@ -243,16 +265,7 @@ namespace bk
             cudaFree(kv.second);
         for (auto &kv : hplans)
         {
-            HybridPlan *P = kv.second;
-            cudaFree(P->d_prescale);
-            cudaFree(P->d_limb_primes);
-            cudaFree(P->d_w);
-            cudaFree(P->d_sprescale);
-            cudaFree(P->d_sprimes);
-            cudaFree(P->d_ws);
-            cudaFree(P->d_psinv);
-            cudaFree(P->d_keyfactor);
-            delete P;
+            delete kv.second;
         }
         cudaFree(d_primes);
         cudaFree(d_tw);
@@ -302,6 +315,31 @@ namespace bk
             g_arenas[s] = new ScratchArena();
         }
         return s;
+    }
+
+    cudaStream_t Context::stream_if_any()
+    {
+        std::lock_guard<std::mutex> g(mu);
+        auto it = streams.find(std::this_thread::get_id());
+        return it == streams.end() ? nullptr : it->second;
+    }
+
+    void Context::release_words(void *d, cudaStream_t owner)
+    {
+        if (!d)
+            return;
+        activate();
+        cudaStream_t cur = stream_if_any();
+        if (cur && (cur == owner || !owner))
+        {
+            cudaFreeAsync(d, cur);
+            return;
+        }
+        cudaDeviceSynchronize();
+        if (owner)
+            cudaFreeAsync(d, owner);
+        else
+            cudaFree(d);
     }
 
     char *Context::staging(size_t bytes, cudaEvent_t *done_out)
@@ -457,7 +495,7 @@ namespace bk
     }
 
     // ------------------------------------------------------------------------------- containers
-    static void realloc_words(Context &c, u64 *&d, size_t &cap, size_t words, bool keep, size_t keep_words)
+    static void realloc_words(Context &c, u64 *&d, cudaStream_t &owner, size_t &cap, size_t words, bool keep, size_t keep_words)
     {
         if (words <= cap)
             return;
@@ -468,9 +506,10 @@ namespace bk
         {
             if (keep && keep_words)
                 BK_CUDA(cudaMemcpyAsync(nd, d, keep_words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-            BK_CUDA(cudaFreeAsync(d, s));
+            c.release_words(d, owner);
         }
         d = nd;
+        owner = s;
         cap = words;
     }
 
@@ -478,7 +517,7 @@ namespace bk
     {
         Context &c = *ct->ctx;
         size_t words = (size_t)size * limbs * c.n;
-        realloc_words(c, ct->d, ct->cap, words, keep, (size_t)ct->size * ct->limbs * c.n);
+        realloc_words(c, ct->d, ct->owner, ct->cap, words, keep, (size_t)ct->size * ct->limbs * c.n);
         ct->size = size;
         ct->limbs = limbs;
     }
@@ -486,7 +525,7 @@ namespace bk
     void ensure_pt(bk_pt_t pt, int limbs)
     {
         Context &c = *pt->ctx;
-        realloc_words(c, pt->d, pt->cap, (size_t)limbs * c.n, false, 0);
+        realloc_words(c, pt->d, pt->owner, pt->cap, (size_t)limbs * c.n, false, 0);
         pt->limbs = limbs;
     }
 
@@ -494,9 +533,9 @@ namespace bk
     static void adopt(bk_ct_t ct, u64 *nd, size_t cap, int size, int limbs)
     {
         cudaStream_t s = ct->ctx->stream();
-        if (ct->d)
-            BK_CUDA(cudaFreeAsync(ct->d, s));
+        ct->ctx->release_words(ct->d, ct->owner);
         ct->d = nd;
+        ct->owner = s; // alloc_words() below allocates on the calling thread's stream
         ct->cap = cap;
         ct->size = size;
         ct->limbs = limbs;
@@ -1192,6 +1231,14 @@ extern "C"
         BK_CUDA(cudaStreamSynchronize(ctx->stream()));
         BK_END
     }
+    bk_status bk_context_set_rng_key(bk_context_t ctx, const uint8_t key[32])
+    {
+        BK_TRY
+        if (!key)
+            throw std::invalid_argument("key is null");
+        std::memcpy(ctx->rng_master.k, key, 32);
+        BK_END
+    }
     bk_status bk_context_set_hybrid(bk_context_t ctx, int on)
     {
         BK_TRY
@@ -1378,8 +1425,7 @@ extern "C"
         BK_TRY
         if (ct)
         {
-            if (ct->d)
-                cudaFreeAsync(ct->d, ct->ctx->stream());
+            ct->ctx->release_words(ct->d, ct->owner);
             delete ct;
         }
         BK_END
@@ -1487,8 +1533,7 @@ extern "C"
         BK_TRY
         if (pt)
         {
-            if (pt->d)
-                cudaFreeAsync(pt->d, pt->ctx->stream());
+            pt->ctx->release_words(pt->d, pt->owner);
             delete pt;
         }
         BK_END

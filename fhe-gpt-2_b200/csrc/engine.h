@@ -1,5 +1,6 @@
 // engine.h - host-side objects behind the C ABI (include/b200ckks.h).
 #pragma once
+#include "rng.cuh"
 #include "../../include/b200ckks.h"
 #include "hostmath.h"
 #include "kernels.cuh"
@@ -127,6 +128,20 @@ namespace bk
         u64 *d_ws = nullptr;               // [l][alpha] (P_S / p_a) mod q_i
         ulonglong2 *d_psinv = nullptr;     // [l] {P_S^-1 mod q_i, shoup}
         u64 *d_keyfactor = nullptr;        // [dnum][ne] P_S mod q_e on the digit's own limbs, 0 elsewhere
+        HybridPlan() = default;
+        HybridPlan(const HybridPlan &) = delete;
+        HybridPlan &operator=(const HybridPlan &) = delete;
+        ~HybridPlan() // owns its tables (also the copy that loses the publication race in hybrid_plan())
+        {
+            cudaFree(d_prescale);
+            cudaFree(d_limb_primes);
+            cudaFree(d_w);
+            cudaFree(d_sprescale);
+            cudaFree(d_sprimes);
+            cudaFree(d_ws);
+            cudaFree(d_psinv);
+            cudaFree(d_keyfactor);
+        }
     };
 
     struct Context
@@ -145,6 +160,9 @@ namespace bk
         NttTables tables{};
         int ks_chunk = 4;
         int sparse_slots = 0;
+        // 256-bit master key of the random generator (rng.cuh): getrandom(2), or expanded from $B200CKKS_SEED /
+        // bk_context_set_rng_key for reproducible runs
+        RngKey rng_master{};
         // hybrid key switching: generated keys are level-specific and not in SEAL's layout ($B200CKKS_HYBRID_KS=1 or
         // bk_context_set_hybrid before any key is generated)
         bool hybrid = false;
@@ -172,6 +190,13 @@ namespace bk
         Context(int log_n, const uint64_t *primes, int n_primes, int device);
         ~Context();
         cudaStream_t stream();
+        // the calling thread's stream if it has one (does not create it: a thread that only destroys objects must not
+        // acquire a stream and a scratch arena)
+        cudaStream_t stream_if_any();
+        // returns `d` to the stream-ordered pool.  `owner` is the stream the buffer was allocated on; a release from
+        // another thread cannot know who else still reads it, so it waits for the whole device first (rare: hand-over
+        // of results between threads, teardown of shared caches)
+        void release_words(void *d, cudaStream_t owner);
         // next free pinned slot of the calling thread's ring (>= bytes); *done_out must be recorded on the stream
         // after the copy that reads the slot
         char *staging(size_t bytes, cudaEvent_t *done_out);
@@ -261,6 +286,7 @@ struct bk_ct_s
 {
     bk::Context *ctx;
     u64 *d = nullptr;
+    cudaStream_t owner = nullptr; // stream `d` was allocated on
     size_t cap = 0; // words
     int size = 0, limbs = 0;
     double scale = 1.0;
@@ -271,6 +297,7 @@ struct bk_pt_s
 {
     bk::Context *ctx;
     u64 *d = nullptr;
+    cudaStream_t owner = nullptr;
     size_t cap = 0;
     int limbs = 0;
     double scale = 1.0;

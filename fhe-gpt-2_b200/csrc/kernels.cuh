@@ -132,8 +132,11 @@ struct StPlain
     }
 };
 
-// Key-switch digits: keep the lazy NTT output in [0,4q) in place (the reference multiplies
-// the lazy values straight into the key, evaluator.cpp:2407-2436).  job = iloc * l + J as in
+// Key-switch digits: keep the unreduced NTT output in place (the reference multiplies its lazy
+// values straight into the key, evaluator.cpp:2407-2436).  Range: [0,4q) from the lazy butterflies
+// (primes >= 2^57), [0,66q) from the unreduced "wide" butterflies (primes < 2^57, ntt.cuh).  Either way
+// the 128-bit sums of k_ks_mac hold: 61 * 4 * 2^120 < 2^128 and 61 * 66 * 2^114 < 2^128 (primes are
+// limited to 60 bits at context creation).  job = iloc * l + J as in
 // LdKsDigit; the I == J job is skipped (its operand is the NTT-form input itself).
 struct StKsDigit
 {
@@ -278,7 +281,7 @@ struct StInvAddHalf
 
 // ============================================================================================
 // Key-switch inner product (evaluator.cpp:2368-2463).  The digit NTTs are complete when this
-// runs (column pass LdKsDigit + block pass StKsDigit, lazy values in [0,4q)); this kernel is the
+// runs (column pass LdKsDigit + block pass StKsDigit, unreduced values); this kernel is the
 // pure stream  acc_p[I][i] = sum_J digit[I][J][i] * key[J][p][I][i]  with 128-bit accumulators
 // and one final barrett_reduce_128.  The key (2 l (l+1) limb-polys, up to 1 GiB) is the
 // dominant HBM stream of the whole key switch: 16-byte loads, two coefficients per thread,
@@ -288,7 +291,7 @@ struct StInvAddHalf
 // ============================================================================================
 struct KsMacArgs
 {
-    const u64 *digits;     // [nI][l][N] NTT form, lazy [0,4q); slot J == I unused
+    const u64 *digits;     // [nI][l][N] NTT form, unreduced (see StKsDigit); slot J == I unused
     const u64 *target_ntt; // [l][N] NTT form
     const uint32_t *perm;  // Galois table or null
     const u64 *key;        // [digits][2][klimbs+1][N], special prime's limb at index klimbs

@@ -13,11 +13,12 @@
 //
 // The arithmetic (NTT, products, rounding division) is identical to the reference's.  The
 // RANDOMNESS is not: the reference draws from a Blake2xb stream on the CPU, this engine draws
-// from a counter-based Philox4x32-10 generator on the GPU (275 GiB of key material cannot be
-// sampled on the host in reasonable time), so freshly generated keys / ciphertexts have the
-// same distribution but different bits.  Bit-exact parity tests therefore upload the
+// from ChaCha20 in counter mode on the GPU, keyed per context with 256 bits from the operating
+// system (rng.cuh; 275 GiB of key material cannot be sampled on the host in reasonable time),
+// so freshly generated keys / ciphertexts have the same distribution but different bits.  Bit-exact parity tests therefore upload the
 // reference's keys and ciphertexts (bk_kskey_upload / bk_ct_upload) instead.
 #include "engine.h"
+#include "rng.cuh"
 #include <algorithm>
 #include <cstring>
 #include <random>
@@ -28,29 +29,21 @@ namespace bk
 }
 using namespace bk;
 
-// ---- Philox4x32-10 -----------------------------------------------------------------------------
-__device__ __forceinline__ uint4 philox(uint4 ctr, uint2 key)
+// ---- ChaCha20 block -> 128 bits (rng.cuh) --------------------------------------------------------------------
+__device__ __forceinline__ uint4 rand128(const RngKey &key, unsigned c0, unsigned c1, unsigned stream, unsigned attempt)
 {
-#pragma unroll
-    for (int r = 0; r < 10; r++)
-    {
-        unsigned hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
-        unsigned hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
-        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
-        key.x += 0x9E3779B9u;
-        key.y += 0xBB67AE85u;
-    }
-    return ctr;
+    uint32_t w[4];
+    chacha20_block<4>(key, c0, c1, stream, attempt, w);
+    return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
 // uniform residue in [0,q) by rejection (sample_poly_uniform, util/rlwe.cpp:137-178)
-__device__ __forceinline__ u64 uniform_mod(u64 seed, unsigned stream, u64 index, const PrimeDev &pd)
+__device__ __forceinline__ u64 uniform_mod(const RngKey &key, unsigned stream, u64 index, const PrimeDev &pd)
 {
     const u64 max_multiple = 0xFFFFFFFFFFFFFFFFull - barrett64(0xFFFFFFFFFFFFFFFFull, pd) - 1;
-    uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
     for (unsigned attempt = 0;; attempt++)
     {
-        uint4 r = philox(make_uint4((unsigned)index, (unsigned)(index >> 32), stream, attempt), key);
+        uint4 r = rand128(key, (unsigned)index, (unsigned)(index >> 32), stream, attempt);
         u64 v = ((u64)r.x << 32) | r.y;
         if (v < max_multiple)
             return barrett64(v, pd);
@@ -62,18 +55,17 @@ __device__ __forceinline__ u64 uniform_mod(u64 seed, unsigned stream, u64 index,
 
 // small signed polynomials: mode 0 = uniform ternary (sample_poly_ternary), 1 = centred binomial
 // with sigma 3.2 (sample_poly_cbd: 21 bits minus 21 bits)
-__global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, size_t count, u64 seed, unsigned stream,
+__global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, size_t count, RngKey key, unsigned stream,
                                                       int mode)
 {
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= count)
         return;
-    uint2 key = make_uint2((unsigned)seed, (unsigned)(seed >> 32));
     if (mode == 0)
     {
         for (unsigned attempt = 0;; attempt++)
         {
-            uint4 r = philox(make_uint4((unsigned)i, (unsigned)(i >> 32), stream, attempt), key);
+            uint4 r = rand128(key, (unsigned)i, (unsigned)(i >> 32), stream, attempt);
             // uniform in {0,1,2} by rejection on 32-bit words
             unsigned w[4] = { r.x, r.y, r.z, r.w };
             bool done = false;
@@ -89,7 +81,7 @@ __global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, siz
     }
     else
     {
-        uint4 r = philox(make_uint4((unsigned)i, (unsigned)(i >> 32), stream, 0u), key);
+        uint4 r = rand128(key, (unsigned)i, (unsigned)(i >> 32), stream, 0u);
         out[i] = __popc(r.x & 0x1FFFFFu) - __popc(r.y & 0x1FFFFFu);
     }
 }
@@ -145,7 +137,7 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
                                                   const u64 *__restrict__ e_ntt /*[limbs][N]*/,
                                                   const u64 *__restrict__ newkey /*[n_primes][N] or null*/,
                                                   int add_limb, u64 factor, JobMap map, const PrimeDev *primes,
-                                                  int log_n, int limbs, u64 seed, unsigned stream,
+                                                  int log_n, int limbs, RngKey rkey, unsigned stream,
                                                   const u64 *__restrict__ factors = nullptr /*[limbs], 0 = none*/)
 {
     const size_t n = size_t(1) << log_n;
@@ -156,7 +148,7 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
         size_t idx = i & (n - 1);
         int pi = map.prime(l);
         const PrimeDev pd = primes[pi];
-        u64 a = uniform_mod(seed, stream, i, pd);
+        u64 a = uniform_mod(rkey, stream, i, pd);
         u64 s = sk[(size_t)pi * n + idx];
         u64 v = addmod(mulmod(a, s, pd), e_ntt[i], pd.q);
         v = v ? pd.q - v : 0ull;
@@ -250,6 +242,7 @@ namespace bk
         key->kind = kind;
         key->elt = elt;
         key->seed = seed;
+        const RngKey rk = derive_call_key(c.rng_master, seed);
         if (c.hybrid)
         {
             // a recipe only: the level-specific keys are generated by hybrid_key() at the levels that use them
@@ -269,14 +262,14 @@ namespace bk
         for (int j = 0; j < kl; j++)
         {
             unsigned st_e = g_stream_counter.fetch_add(2);
-            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st_e, 1);
+            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st_e, 1);
             c.count();
             ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, kl + 1, map);
             u64 factor = c.primes[sp] % c.primes[j];
             u64 *c0 = key->d + ((size_t)j * 2) * (kl + 1) * n;
             u64 *c1 = c0 + (size_t)(kl + 1) * n;
             k_sym_zero<false><<<c.ew_grid((size_t)(kl + 1) * n), 256, 0, s>>>(c0, c1, sk->d, e_ntt.p, newkey, j, factor,
-                                                                            map, c.d_primes, c.log_n, kl + 1, seed,
+                                                                            map, c.d_primes, c.log_n, kl + 1, rk,
                                                                             st_e + 1);
             c.count();
         }
@@ -330,17 +323,17 @@ namespace bk
         compute_newkey(c, s, key->sk, key->kind, key->elt, newkey.p);
         Scratch small(s, (n + 1) / 2);
         Scratch e_ntt(s, (size_t)ne * n);
-        const u64 seed = key->seed + 0x9E3779B97F4A7C15ull * (u64)(l + 1);
+        const RngKey rk = derive_call_key(c.rng_master, key->seed + 0x9E3779B97F4A7C15ull * (u64)(l + 1));
         for (int d = 0; d < P.dnum; d++)
         {
             unsigned st_e = g_stream_counter.fetch_add(2);
-            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st_e, 1);
+            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st_e, 1);
             c.count();
             ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, ne, map);
             u64 *c0 = hk->d + ((size_t)d * 2) * ne * n;
             u64 *c1 = c0 + (size_t)ne * n;
             k_sym_zero<false><<<c.ew_grid((size_t)ne * n), 256, 0, s>>>(c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map, c.d_primes,
-                                                                      c.log_n, ne, seed, st_e + 1,
+                                                                      c.log_n, ne, rk, st_e + 1,
                                                                       P.d_keyfactor + (size_t)d * ne);
             c.count();
         }
@@ -363,25 +356,50 @@ extern "C"
         if (hamming_weight < 0 || (size_t)hamming_weight > n)
             throw std::invalid_argument("hamming_weight is invalid");
         std::vector<int> small(n, 0);
-        std::mt19937_64 rng(seed ? seed : std::random_device{}());
+        // host-side words of ChaCha20(call key, counter = block number, nonce = "sk")
+        struct HostStream
+        {
+            RngKey key;
+            uint32_t buf[16];
+            uint64_t block = 0;
+            int pos = 16;
+            uint32_t next()
+            {
+                if (pos == 16)
+                {
+                    chacha20_block<16>(key, (uint32_t)block, (uint32_t)(block >> 32), 0x6b73u, 0u, buf);
+                    block++;
+                    pos = 0;
+                }
+                return buf[pos++];
+            }
+            // uniform in [0, bound) by rejection
+            uint32_t below(uint32_t bound)
+            {
+                const uint32_t limit = 0xFFFFFFFFu - (0xFFFFFFFFu % bound + 1u) % bound;
+                for (;;)
+                {
+                    uint32_t v = next();
+                    if (v <= limit)
+                        return v % bound;
+                }
+            }
+        } rng{ derive_call_key(c.rng_master, seed) };
         if (hamming_weight == 0)
         {
-            std::uniform_int_distribution<int> d(0, 2);
             for (auto &v : small)
-                v = d(rng) - 1;
+                v = (int)rng.below(3) - 1;
         }
         else
         {
             // sample_poly_sparse_ternary (rlwe.cpp:40-70): h distinct positions, each +-1
-            std::uniform_int_distribution<size_t> pos(0, n - 1);
-            std::uniform_int_distribution<int> sign(0, 1);
             int w = 0;
             while (w < hamming_weight)
             {
-                size_t i = pos(rng);
+                size_t i = rng.below((uint32_t)n);
                 if (small[i])
                     continue;
-                small[i] = sign(rng) ? 1 : -1;
+                small[i] = (rng.next() & 1u) ? 1 : -1;
                 w++;
             }
         }
@@ -435,6 +453,7 @@ extern "C"
         BK_TRY
         // keygenerator.cpp:99-131: encrypt_zero_symmetric at the key level, NTT form
         Context &c = *ctx;
+        const RngKey rk = derive_call_key(c.rng_master, seed);
         if (!sk || sk->ctx != ctx)
             throw std::logic_error("cannot generate public key for unspecified secret key");
         cudaStream_t s = c.stream();
@@ -444,12 +463,12 @@ extern "C"
         Scratch small(s, (n + 1) / 2);
         Scratch e_ntt(s, (size_t)L * n);
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st, 1);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st, 1);
         c.count();
         ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, L, limb_map(L));
         k_sym_zero<false><<<c.ew_grid((size_t)L * n), 256, 0, s>>>(pk_out->d, pk_out->d + (size_t)L * n, sk->d,
                                                                    e_ntt.p, nullptr, -1, 0, limb_map(L), c.d_primes,
-                                                                   c.log_n, L, seed, st + 1);
+                                                                   c.log_n, L, rk, st + 1);
         c.count();
         pk_out->scale = 1.0;
         pk_out->ntt = true;
@@ -500,6 +519,7 @@ extern "C"
         // encrypt zero with l+1 limbs (the next prime up, or the special prime at the top level),
         // divide by that prime with rounding, add the plaintext to c0.
         Context &c = *ctx;
+        const RngKey rk = derive_call_key(c.rng_master, seed);
         if (!pk || pk->ctx != ctx || pk->size != 2 || pk->limbs != c.n_primes)
             throw std::logic_error("public key is not set");
         if (!pt || pt->ctx != ctx || !pt->d)
@@ -512,8 +532,8 @@ extern "C"
         Scratch small(s, (3 * n + 1) / 2);
         int *d_small = (int *)small.p;
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_small, n, seed, st, 0);
-        k_sample_small<<<(unsigned)((2 * n + 255) / 256), 256, 0, s>>>(d_small + n, 2 * n, seed, st + 1, 1);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_small, n, rk, st, 0);
+        k_sample_small<<<(unsigned)((2 * n + 255) / 256), 256, 0, s>>>(d_small + n, 2 * n, rk, st + 1, 1);
         c.count(2);
         Scratch u_ntt(s, (size_t)l1 * n);
         Scratch e_ntt(s, (size_t)2 * l1 * n);
@@ -532,9 +552,9 @@ extern "C"
         rescale_core(c, &tmp);
         k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(tmp.d, pt->d, c.d_primes, c.log_n, l, 1, 1);
         c.count();
-        if (out->d)
-            BK_CUDA(cudaFreeAsync(out->d, s));
+        c.release_words(out->d, out->owner);
         out->d = tmp.d;
+        out->owner = tmp.owner ? tmp.owner : s;
         out->cap = tmp.cap;
         out->size = 2;
         out->limbs = l;
@@ -547,6 +567,7 @@ extern "C"
     {
         BK_TRY
         Context &c = *ctx;
+        const RngKey rk = derive_call_key(c.rng_master, seed);
         if (!sk || sk->ctx != ctx)
             throw std::logic_error("secret key is not set");
         if (!pt || pt->ctx != ctx || !pt->d)
@@ -558,12 +579,12 @@ extern "C"
         Scratch small(s, (n + 1) / 2);
         Scratch e_ntt(s, (size_t)l * n);
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, seed, st, 1);
+        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st, 1);
         c.count();
         ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, l, limb_map(l));
         k_sym_zero<false><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(out->d, out->d + (size_t)l * n, sk->d, e_ntt.p,
                                                                    nullptr, -1, 0, limb_map(l), c.d_primes, c.log_n, l,
-                                                                   seed, st + 1);
+                                                                   rk, st + 1);
         k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(out->d, pt->d, c.d_primes, c.log_n, l, 1, 1);
         c.count(2);
         out->scale = pt->scale;

@@ -41,6 +41,7 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <random>
 #include <set>
 #include <shared_mutex>
 #include <stdexcept>
@@ -69,12 +70,18 @@ namespace seal
             default: throw std::runtime_error(msg);
             }
         }
+        // Nonce handed to the engine's sampling calls (keys, encryptions).  The randomness itself comes from the
+        // engine's ChaCha20 generator under a 256-bit per-context key from the operating system (include/b200ckks.h,
+        // bk_context_set_rng_key); this value only separates the streams of different calls.  $B200CKKS_SEED makes
+        // both reproducible (tests, benchmarks) and must not be set in production.
         inline std::uint64_t next_seed()
         {
             static std::atomic<std::uint64_t> ctr{ 0 };
             static const std::uint64_t base = [] {
-                const char *e = std::getenv("B200CKKS_SEED");
-                return e ? std::strtoull(e, nullptr, 0) : 0x5EA1C0DEull;
+                if (const char *e = std::getenv("B200CKKS_SEED"))
+                    return (std::uint64_t)std::strtoull(e, nullptr, 0);
+                std::random_device rd;
+                return ((std::uint64_t)rd() << 32) ^ (std::uint64_t)rd();
             }();
             return base + 0x9E3779B97F4A7C15ull * (ctr.fetch_add(1) + 1);
         }

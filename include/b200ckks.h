@@ -81,6 +81,12 @@ bk_status bk_stream(bk_context_t ctx, void **stream_out);
  * primes above the level joining the special prime as temporary special moduli.  Decrypted results equal those of
  * Evaluator::switch_key_inplace (evaluator.cpp:2281-2525) up to key-switching noise; ciphertext limbs do not, and the
  * keys are not in SEAL's layout.  Uploaded keys (bk_kskey_upload) always take SEAL's path. */
+/* Randomness (replaces randomgen.h: the Blake2xb/SHAKE PRNG factories): key generation and encryption draw from
+ * ChaCha20 in counter mode on the device.  Each context owns a 256-bit master key taken from the operating system
+ * (getrandom) when the context is created; $B200CKKS_SEED or this call replace it for REPRODUCIBLE runs (tests,
+ * benchmarks) - never set either in production.  The `seed` argument of the sampling calls below is a nonce that
+ * separates the streams of different calls; 0 is as good as any other value. */
+bk_status bk_context_set_rng_key(bk_context_t ctx, const uint8_t key[32]);
 bk_status bk_context_set_hybrid(bk_context_t ctx, int on);
 bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys);
 /* block until every stream of the device has drained (before an object other host threads may be reading is freed). */

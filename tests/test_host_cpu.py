@@ -96,3 +96,32 @@ def test_product_path_never_touches_the_oracle():
                 src = open(os.path.join(dp, f), errors="ignore").read()
                 for word in ("refseal", "ckks_port", "libseal_ref", "appref", "libapp_ref", "plain_model"):
                     assert word not in src, (f, word)
+
+
+def test_chacha20_block_matches_rfc8439(tmp_path):
+    """csrc/rng.cuh is the generator behind key generation and encryption; its block function against the test vector of
+    RFC 8439 section 2.3.2 (key 00..1f, block counter 1, nonce 00:00:00:09:00:00:00:4a:00:00:00:00)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include "rng.cuh"
+int main() {
+    bk::RngKey k;
+    for (int i = 0; i < 8; i++) k.k[i] = (4u*i) | ((4u*i+1) << 8) | ((4u*i+2) << 16) | ((4u*i+3) << 24);
+    uint32_t out[16];
+    bk::chacha20_block<16>(k, 1u, 0x09000000u, 0x4a000000u, 0u, out);
+    for (int i = 0; i < 16; i++) printf("%08x ", out[i]);
+    printf("\n");
+    bk::RngKey d1 = bk::derive_call_key(k, 1), d2 = bk::derive_call_key(k, 2);
+    printf("%d\n", d1.k[0] != d2.k[0] || d1.k[1] != d2.k[1]);
+}''')
+    exe = str(tmp_path / "t")
+    subprocess.run(["g++", "-std=c++17", "-D__host__=", "-D__device__=", "-D__forceinline__=inline",
+                    "-I" + os.path.join(root, "fhe-gpt-2_b200", "csrc"), str(src), "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, stdout=subprocess.PIPE, text=True).stdout.split("\n")
+    assert out[0].split() == ["e4e7f110", "15593bd1", "1fdd0f50", "c47120a3", "c7f4d1c7", "0368c033", "9aaa2204", "4e6cd4c3",
+                              "466482d2", "09aa9f07", "05d7c214", "a2028bd9", "d19c12b5", "b94e16de", "e883d0cb", "4e3c50a2"]
+    assert out[1] == "1"
