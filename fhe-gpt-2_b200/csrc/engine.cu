@@ -1661,6 +1661,46 @@ extern "C"
             *device_bytes = key->words * sizeof(u64);
         BK_END
     }
+    // ---- key plans: evaluation keys generated up front, evaluation without the secret key ------------------------
+    bk_status bk_kskey_levels(bk_kskey_t key, int *levels_out, int cap, int *count_out)
+    {
+        BK_TRY
+        std::lock_guard<std::mutex> g(key->hmu);
+        int n = 0;
+        if (key->d)
+        {
+            if (n < cap && levels_out)
+                levels_out[n] = key->klimbs;
+            n++;
+        }
+        for (auto &kv : key->hyb)
+        {
+            if (n < cap && levels_out)
+                levels_out[n] = kv.first;
+            n++;
+        }
+        if (count_out)
+            *count_out = n;
+        BK_END
+    }
+    bk_status bk_kskey_prepare_level(bk_kskey_t key, int limbs)
+    {
+        BK_TRY
+        Context &c = *key->ctx;
+        if (limbs < 1 || limbs > c.top_limbs())
+            throw std::invalid_argument("limbs is out of range");
+        if (!c.hybrid || key->d)
+            throw std::logic_error("only recipes of the level-aware hybrid mode have level-specific keys");
+        hybrid_key(c, key, limbs);
+        BK_END
+    }
+    bk_status bk_kskey_drop_secret(bk_kskey_t key)
+    {
+        BK_TRY
+        std::lock_guard<std::mutex> g(key->hmu);
+        key->sk = nullptr;
+        BK_END
+    }
     bk_status bk_kskey_download(bk_kskey_t key, uint64_t *host_out)
     {
         // SEAL layout restricted to the resident part: [digits][2][klimbs+1][N], special last
@@ -1732,6 +1772,14 @@ extern "C"
         }
         else
             gk->keys[galois_elt] = key;
+        BK_END
+    }
+    bk_status bk_gkeys_get(bk_gkeys_t gk, uint32_t galois_elt, bk_kskey_t *key_out)
+    {
+        BK_TRY
+        *key_out = find_gkey(gk, galois_elt);
+        if (!*key_out)
+            throw std::invalid_argument("Galois key not present");
         BK_END
     }
     bk_status bk_gkeys_has(bk_gkeys_t gk, uint32_t galois_elt, int *has_out)

@@ -304,7 +304,9 @@ namespace bk
         if (it != key->hyb.end())
             return it->second;
         if (!key->sk || !key->kind)
-            throw std::invalid_argument("kswitch_keys is not valid for encryption parameters (no recipe for a level key)");
+            throw std::invalid_argument(key->kind ? "key switching key not present for this level (the keys were generated from a "
+                                                    "plan and the secret key has been detached)"
+                                                  : "kswitch_keys is not valid for encryption parameters (no recipe for a level key)");
         const HybridPlan &P = hybrid_plan(c, l);
         cudaStream_t s = c.stream();
         const size_t n = c.n;

@@ -385,6 +385,41 @@ extern "C"
         BKA_END
     }
 
+    int bka_session_key_plan(bka_session_t s, char *text_out, int cap, int *length_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        s->ensure_keys();
+        std::string t = KeyPlan::capture(*s->context, s->relin_keys, s->gal_keys).to_string();
+        if (length_out)
+            *length_out = (int)t.size();
+        if (text_out && cap > 0)
+        {
+            std::size_t n = std::min<std::size_t>(t.size(), (std::size_t)cap - 1);
+            std::memcpy(text_out, t.data(), n);
+            text_out[n] = 0;
+        }
+#else
+        (void)s, (void)text_out, (void)cap, (void)length_out;
+        throw std::logic_error("key plans are an engine-backend feature (the reference generates every key in full)");
+#endif
+        BKA_END
+    }
+    int bka_session_apply_key_plan(bka_session_t s, const char *text, int detach_secret)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        s->ensure_keys();
+        KeyPlan::from_string(text).generate(*s->context, s->relin_keys, s->gal_keys);
+        if (detach_secret)
+            KeyPlan::detach_secret(s->relin_keys, s->gal_keys);
+#else
+        (void)s, (void)text, (void)detach_secret;
+        throw std::logic_error("key plans are an engine-backend feature (the reference generates every key in full)");
+#endif
+        BKA_END
+    }
+
     int bka_session_plain_cache(bka_session_t s, uint64_t *bytes_out, uint64_t *hits_out, uint64_t *misses_out)
     {
         BKA_TRY

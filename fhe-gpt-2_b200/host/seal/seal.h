@@ -36,6 +36,7 @@
 #include <cmath>
 #include <complex>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <map>
@@ -797,6 +798,22 @@ namespace seal
         };
     } // namespace detail
 
+    namespace detail
+    {
+        inline std::vector<int> kskey_levels(bk_kskey_t k)
+        {
+            std::vector<int> v;
+            if (!k)
+                return v;
+            int n = 0;
+            check(bk_kskey_levels(k, nullptr, 0, &n));
+            v.resize((std::size_t)n);
+            if (n)
+                check(bk_kskey_levels(k, v.data(), n, &n));
+            return v;
+        }
+    } // namespace detail
+
     class SecretKey
     {
     public:
@@ -855,6 +872,18 @@ namespace seal
         {
             return k_ ? k_->h : nullptr;
         }
+        // ---- engine access: key plans (see KeyPlan below)
+        SEAL_NODISCARD std::vector<int> levels() const
+        {
+            return detail::kskey_levels(handle());
+        }
+        void drop_secret_key()
+        {
+            if (!k_)
+                return;
+            detail::check(bk_kskey_drop_secret(k_->h));
+            k_->sk.reset();
+        }
         std::shared_ptr<Holder> k_;
     };
 
@@ -874,6 +903,7 @@ namespace seal
             std::uint64_t seed = 0;
             std::shared_mutex mu;
             std::uint64_t bytes = 0, generated = 0;
+            bool sealed = false; // keys were generated from a plan and the secret key is gone: never generate again
             ~State()
             {
                 if (h)
@@ -923,6 +953,9 @@ namespace seal
             auto it = s.resident.find(elt);
             if (it != s.resident.end() && it->second >= limbs)
                 return;
+            if (s.sealed || !s.sk)
+                throw std::invalid_argument("Galois key not present for this level (the keys were generated from a plan and "
+                                            "the secret key has been detached)");
             int top = s.ctx->n_primes - 1;
             bk_kskey_t key = nullptr;
             detail::check(bk_galois_key_generate(
@@ -946,7 +979,139 @@ namespace seal
         {
             return st_ ? st_->h : nullptr;
         }
+        // ---- engine access: key plans (see KeyPlan below).  (element, limbs) pairs the keys cover so far: one pair per
+        // element in SEAL's key layout (the largest level it was used at), one per level key in hybrid mode.
+        SEAL_NODISCARD std::vector<std::pair<std::uint32_t, int>> coverage() const
+        {
+            std::vector<std::pair<std::uint32_t, int>> v;
+            if (!st_)
+                return v;
+            std::shared_lock<std::shared_mutex> rl(st_->mu);
+            int hybrid = 0;
+            bk_context_hybrid(st_->ctx->h, &hybrid, nullptr, nullptr);
+            for (auto &kv : st_->resident)
+            {
+                if (!hybrid)
+                {
+                    v.emplace_back(kv.first, kv.second);
+                    continue;
+                }
+                bk_kskey_t k = nullptr;
+                detail::check(bk_gkeys_get(st_->h, kv.first, &k));
+                for (int l : detail::kskey_levels(k))
+                    v.emplace_back(kv.first, l);
+            }
+            return v;
+        }
+        // generate the key of `elt` for ciphertexts of `limbs` limbs now
+        void prepare(std::uint32_t elt, int limbs) const
+        {
+            if (!has_key(elt))
+                throw std::invalid_argument("Galois key not present");
+            ensure(elt, limbs);
+            int hybrid = 0;
+            bk_context_hybrid(st_->ctx->h, &hybrid, nullptr, nullptr);
+            if (hybrid)
+            {
+                bk_kskey_t k = nullptr;
+                detail::check(bk_gkeys_get(st_->h, elt, &k));
+                detail::check(bk_kskey_prepare_level(k, limbs));
+            }
+        }
+        void drop_secret_key()
+        {
+            if (!st_)
+                return;
+            std::unique_lock<std::shared_mutex> wl(st_->mu);
+            for (auto &kv : st_->resident)
+            {
+                bk_kskey_t k = nullptr;
+                detail::check(bk_gkeys_get(st_->h, kv.first, &k));
+                detail::check(bk_kskey_drop_secret(k));
+            }
+            st_->sk.reset();
+            st_->sealed = true;
+        }
         std::shared_ptr<State> st_;
+    };
+
+    // KeyPlan - which evaluation keys, at which levels, a workload touches.  The reference generates every Galois key
+    // in full up front (infer_seal.cpp:379: 284 keys, 275 GiB) and evaluates without the secret key.  This engine
+    // prunes keys to the levels they are used at, which it learns on first use - and generating on first use needs
+    // the secret key at evaluation time.  A plan removes that: run the workload once under any throw-away key
+    // (the set of (element, level) pairs does not depend on the data or the key), capture(), then for the real key
+    // generate() everything up front and detach_secret(); afterwards a rotation outside the plan throws
+    // std::invalid_argument("Galois key not present ...") exactly like a missing key in the reference.
+    struct KeyPlan
+    {
+        bool hybrid = false;
+        std::vector<std::pair<std::uint32_t, int>> galois; // (Galois element, limbs)
+        std::vector<int> relin;                            // limbs (hybrid mode only; SEAL's layout has one full key)
+
+        static KeyPlan capture(const SEALContext &context, const RelinKeys &rk, const GaloisKeys &gk)
+        {
+            KeyPlan p;
+            int hybrid = 0;
+            bk_context_hybrid(context.handle(), &hybrid, nullptr, nullptr);
+            p.hybrid = hybrid != 0;
+            p.galois = gk.coverage();
+            if (p.hybrid)
+                p.relin = rk.levels();
+            return p;
+        }
+        // the keys must come from create_relin_keys / create_galois_keys of a KeyGenerator that still has its secret
+        void generate(const SEALContext &context, RelinKeys &rk, GaloisKeys &gk) const
+        {
+            int hybrid = 0;
+            bk_context_hybrid(context.handle(), &hybrid, nullptr, nullptr);
+            if ((hybrid != 0) != this->hybrid)
+                throw std::invalid_argument("the plan was captured in the other key-switching mode");
+            for (auto &e : galois)
+                gk.prepare(e.first, e.second);
+            for (int l : relin)
+                detail::check(bk_kskey_prepare_level(rk.handle(), l));
+            detail::check(bk_sync_device(context.handle()));
+        }
+        static void detach_secret(RelinKeys &rk, GaloisKeys &gk)
+        {
+            rk.drop_secret_key();
+            gk.drop_secret_key();
+        }
+        // text form: "hybrid 0|1", then "g <element> <limbs>" and "r <limbs>" lines
+        SEAL_NODISCARD std::string to_string() const
+        {
+            std::string s = std::string("hybrid ") + (hybrid ? "1" : "0") + "\n";
+            for (auto &e : galois)
+                s += "g " + std::to_string(e.first) + " " + std::to_string(e.second) + "\n";
+            for (int l : relin)
+                s += "r " + std::to_string(l) + "\n";
+            return s;
+        }
+        static KeyPlan from_string(const std::string &text)
+        {
+            KeyPlan p;
+            std::size_t pos = 0;
+            while (pos < text.size())
+            {
+                std::size_t end = text.find('\n', pos);
+                if (end == std::string::npos)
+                    end = text.size();
+                std::string line = text.substr(pos, end - pos);
+                pos = end + 1;
+                if (line.empty())
+                    continue;
+                unsigned long a = 0, b = 0;
+                if (std::sscanf(line.c_str(), "hybrid %lu", &a) == 1)
+                    p.hybrid = a != 0;
+                else if (std::sscanf(line.c_str(), "g %lu %lu", &a, &b) == 2)
+                    p.galois.emplace_back((std::uint32_t)a, (int)b);
+                else if (std::sscanf(line.c_str(), "r %lu", &a) == 1)
+                    p.relin.push_back((int)a);
+                else
+                    throw std::invalid_argument("malformed key plan line: " + line);
+            }
+            return p;
+        }
     };
 
     class KeyGenerator

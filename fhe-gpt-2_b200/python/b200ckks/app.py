@@ -213,6 +213,18 @@ class Session:
         self.app.ck(self.app.L.bka_session_key_residency(self.h, C.byref(b), C.byref(g)))
         return b.value, g.value
 
+    def key_plan(self):
+        """text of the (Galois element, level) pairs and relinearization levels the keys cover so far"""
+        n = C.c_int()
+        self.app.ck(self.app.L.bka_session_key_plan(self.h, None, 0, C.byref(n)))
+        buf = C.create_string_buffer(n.value + 1)
+        self.app.ck(self.app.L.bka_session_key_plan(self.h, buf, n.value + 1, C.byref(n)))
+        return buf.value.decode()
+
+    def apply_key_plan(self, text, detach_secret=True):
+        """generate exactly the keys of a plan now; detach_secret: the evaluation keys forget the secret key"""
+        self.app.ck(self.app.L.bka_session_apply_key_plan(self.h, text.encode(), int(detach_secret)))
+
     def plain_cache(self):
         b, h, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
         self.app.ck(self.app.L.bka_session_plain_cache(self.h, C.byref(b), C.byref(h), C.byref(m)))

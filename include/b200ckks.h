@@ -151,6 +151,15 @@ bk_status bk_pt_mod_switch_to(bk_pt_t pt, int limbs);
 bk_status bk_kskey_upload(bk_context_t ctx, const uint64_t *host, int digits, int max_limbs, bk_kskey_t *out);
 bk_status bk_kskey_destroy(bk_kskey_t key);
 bk_status bk_kskey_info(bk_kskey_t key, int *digits, int *limbs, uint64_t *device_bytes);
+/* Key plans.  The reference materialises every evaluation key up front (KeyGenerator::create_galois_keys,
+ * infer_seal.cpp:379) and evaluates without the secret key.  In the level-aware hybrid mode a generated key is a
+ * recipe that makes one key per level on first use - which needs the secret key at evaluation time.  To evaluate
+ * WITHOUT it: learn the levels a workload uses (bk_kskey_levels after a dry run under any throw-away key; the set
+ * is data independent), generate exactly those keys up front (bk_kskey_prepare_level), then detach the secret
+ * (bk_kskey_drop_secret): from then on a missing level is BK_INVALID_ARGUMENT instead of a key generation. */
+bk_status bk_kskey_levels(bk_kskey_t key, int *levels_out, int cap, int *count_out);
+bk_status bk_kskey_prepare_level(bk_kskey_t key, int limbs);
+bk_status bk_kskey_drop_secret(bk_kskey_t key);
 /* resident part in SEAL's order: [digits][2][limbs+1][N], the special prime's limb last. */
 bk_status bk_kskey_download(bk_kskey_t key, uint64_t *host_out);
 /* device-to-device export/import of the resident key ([digits][2][limbs+1][N] words, engine
@@ -161,6 +170,8 @@ bk_status bk_gkeys_create(bk_context_t ctx, bk_gkeys_t *out);
 bk_status bk_gkeys_destroy(bk_gkeys_t gk);                      /* destroys the keys it owns */
 bk_status bk_gkeys_set(bk_gkeys_t gk, uint32_t galois_elt, bk_kskey_t key); /* takes ownership */
 bk_status bk_gkeys_has(bk_gkeys_t gk, uint32_t galois_elt, int *has_out);
+/* the key of one element (still owned by the set), for the key-plan calls above */
+bk_status bk_gkeys_get(bk_gkeys_t gk, uint32_t galois_elt, bk_kskey_t *key_out);
 
 /* Native key generation (keygenerator.cpp:64-76,164-233,384-417; util/rlwe.cpp:21-70,294-409).
  * The secret key is a device-resident plaintext-shaped object [n_primes][N] in NTT form. */

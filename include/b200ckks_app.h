@@ -61,6 +61,13 @@ int bka_session_sync(bka_session_t s);
 int bka_session_stats(bka_session_t s, uint64_t counts_out[9], int reset);
 /* bytes of Galois keys resident in HBM and number of key generations so far (engine backend; 0 otherwise) */
 int bka_session_key_residency(bka_session_t s, uint64_t *bytes_out, uint64_t *generated_out);
+/* Key plans (host/seal/seal.h KeyPlan; include/b200ckks.h bk_kskey_levels ...): the (Galois element, level) pairs and
+ * relinearization levels the session's keys cover so far, as text; and the reverse - generate exactly the keys of a
+ * plan now and, with detach_secret != 0, drop every reference the evaluation keys hold on the secret key, after which
+ * the Evaluator can no longer generate keys (a rotation outside the plan fails like a missing key in the reference).
+ * A plan is data- and key-independent: capture it once from a dry run under a throw-away key. */
+int bka_session_key_plan(bka_session_t s, char *text_out, int cap, int *length_out);
+int bka_session_apply_key_plan(bka_session_t s, const char *text, int detach_secret);
 /* encoded plaintext operands kept resident in HBM (bootstrapping diagonals, convolution weight masks; see
  * host/common/cached.h): bytes, and hits / misses of the cache since the session was created */
 int bka_session_plain_cache(bka_session_t s, uint64_t *bytes_out, uint64_t *hits_out, uint64_t *misses_out);
