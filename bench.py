@@ -8,13 +8,18 @@ and random-init weights of that architecture.  One step = one image per GPU.  Im
 to rank i mod G, no data-path collective (weak scaling); rank 0 samples the secret key and broadcasts it with NCCL,
 every rank derives its evaluation keys from it on its own GPU.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--layers 20]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl engine|reference] [--layers 20|110]
 
   value  images/s with the encrypted image already resident in HBM (device-timed, CUDA events, max over ranks)
   e2e    images/s through the C ABI call a user makes (bka_resnet_infer: host image in, host logits out; packing,
          encoding, encryption, every host->device copy of plaintext operands, decryption and decoding inside the
          timed region)
-  roofline      the kernel family with the largest share of the step, timed live with CUDA events
+  roofline      the kernel family with the largest share of the step, timed live with CUDA events; int_roofline inside
+                it is the same kernel against the integer multiply-add peak measured on this GPU in this run
+  exact         the same workload with every tolerance-mode path switched off (key switching decomposed one digit per
+                prime, rotations one by one, constants encrypted on the hot path: the reference's exact operation
+                sequence, the mode the limb-level parity tests cover), measured in a child process of the same run
+  key_switch_us rotate_vector at N = 2^16 and 31 / 17 / 3 limbs: this engine (both modes) and the reference per thread
   cpu_baseline  the reference's own SEAL (oracle/_ref/libseal_ref.so) on this host's cores: per-operation times
                 measured per level on all cores, composed with the operation histogram of one inference
                 (the full CPU run needs NTL, ~384 GB of RAM and ~2200 s per image: reference README / result log)
@@ -35,8 +40,46 @@ CNN_BITS = [51] + [46] * 16 + [51] * 14 + [51]   # infer_seal.cpp:288-311
 LIMB_BYTES = (1 << LOG_N) * 8
 METRIC = "ResNet-20 CIFAR-10 homomorphic inference throughput (bootstrapped, N=2^16)"
 UNIT = "images/s"
-HIST_PATH = os.path.join(ROOT, "tests", "golden", "resnet20_op_histogram.json")
 HIST_KEYS = ["key_switch", "rescale", "multiply_vector", "multiply", "scalar", "add"]
+NTT_BUTTERFLIES_PER_PASS = (1 << LOG_N) // 2 * 8      # a pass = 8 of the 16 stages of one limb-polynomial
+IMAD_PER_BUTTERFLY = 9                                # 32-bit multiplies of one 64-bit Shoup butterfly (ntt.cuh ct_bfly_wide)
+
+
+def hist_path(layers):
+    return os.path.join(ROOT, "tests", "golden", f"resnet{layers}_op_histogram.json")
+
+
+def metric_name(layers):
+    return METRIC if layers == 20 else METRIC.replace("ResNet-20", f"ResNet-{layers}")
+
+
+def load_weights(layers):
+    """the reference's trained parameters when the fixture is there (tests/golden/pretrained_parameters/resnet20_new,
+    a copy of the reference's pretrained_parameters/resnet20_new), else random-init weights of the architecture"""
+    from b200ckks import synthetic
+
+    d = synthetic.pretrained_dir(layers)
+    if d:
+        return synthetic.load_pretrained(d, layers), f"trained parameters pretrained_parameters/resnet{layers}_new"
+    return synthetic.random_weights(layers, seed=0), "random-init weights of the architecture"
+
+
+def make_config(args):
+    """identical for both arms (the driver compares the two config objects)"""
+    from b200ckks import synthetic
+
+    K = max(1, args.in_flight)
+    weights = (f"trained parameters pretrained_parameters/resnet{args.layers}_new" if synthetic.pretrained_dir(args.layers)
+               else "random-init weights of the architecture")
+    return {"workload": f"ResNet-{args.layers} CIFAR-10 with bootstrapping (reference: ./cnn {args.layers} 10 i j); logN=16 RNS-CKKS, "
+                        "primes 51|46x16|51x14|51, Hamming weight 192, scale 2^46",
+            "log_n": LOG_N, "layers": args.layers, "images_per_step_per_unit": K,
+            "images": "synthetic: N(0,1) clipped to [-2.5, 2.5], seed = image id (the reference's CIFAR image file is missing)",
+            "weights": weights,
+            "l2": "working set larger than L2: every bootstrap streams tens of GiB of evaluation keys and 31-limb "
+                  "ciphertexts (31 MiB each) against a 126 MB L2",
+            "parallelism": f"{args.gpus} unit(s), independent images dealt round-robin, no data-path exchange"}
+
 
 # algorithmic bytes per limb-polynomial and kernel family (DESIGN.md 3; SURVEY.md 8d): an NTT reads and writes a limb
 # once (2 N w) and is executed as two passes, so each pass owns N w; the key-switch inner product streams one key limb
@@ -140,10 +183,39 @@ def run_engine(args):
             torch.cuda.synchronize()
 
     # ---- keys: one secret for the node (rank 0 samples it, NCCL broadcast), evaluation keys derived per GPU ----
-    os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")
+    os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")      # reproducible benchmark randomness (never set in production)
     hybrid = not args.no_hybrid
     os.environ["B200CKKS_HYBRID_KS"] = "1" if hybrid else "0"
     app = App()
+    weights, weights_name = load_weights(args.layers)
+    image_of = lambda step: synthetic.synthetic_image(rank + world * step)
+
+    # Key plan (host/seal/seal.h KeyPlan): which (Galois element, level) keys the network touches.  It depends on the
+    # network and the key-switching mode only, so it is read from fhe-gpt-2_b200/plans/ when committed there, else
+    # learnt from one inference under a THROW-AWAY secret key.  The real session then generates exactly those keys up
+    # front and detaches the secret key from every evaluation key: the timed region evaluates without it, as the
+    # reference does after create_galois_keys (infer_seal.cpp:379).
+    mode_name = "hybrid" if hybrid else "exact"
+    plan_path = os.path.join(ROOT, "fhe-gpt-2_b200", "plans", f"resnet{args.layers}_{mode_name}.plan")
+    t_plan = time.perf_counter()
+    if args.lazy_keys:
+        plan, plan_source = None, "none (--lazy-keys: keys generated on first use from the resident secret key)"
+    elif os.path.exists(plan_path):
+        plan, plan_source = open(plan_path).read(), os.path.relpath(plan_path, ROOT)
+    else:
+        dry = app.session(LOG_N, CNN_BITS, hamming_weight=192, device=local)
+        dry_net = dry.resnet(args.layers, weights)
+        dry_net.infer(image_of(0), trace=False)
+        if args.in_flight > 1:      # the batch path takes the same rotations; run it once so nothing is missed
+            dry_net.infer_batch(np.stack([image_of(0)] * 2), 2)
+        plan, plan_source = dry.key_plan(), "dry run under a throw-away key"
+        del dry_net
+        dry.close()
+        if rank == 0 and args.write_plan:
+            os.makedirs(os.path.dirname(args.write_plan), exist_ok=True)
+            open(args.write_plan, "w").write(plan)
+    plan_s = time.perf_counter() - t_plan
+
     t_setup = time.perf_counter()
     sk_words = len(CNN_BITS) * (1 << LOG_N)
     if world > 1:
@@ -160,9 +232,12 @@ def run_engine(args):
     else:
         sess = app.session(LOG_N, CNN_BITS, hamming_weight=192, device=local)
     eng = sess.engine()
-    weights = synthetic.random_weights(args.layers, seed=0)
     net = sess.resnet(args.layers, weights)
-    image_of = lambda step: synthetic.synthetic_image(rank + world * step)
+    t_gen = time.perf_counter()
+    if plan is not None:
+        sess.apply_key_plan(plan, detach_secret=True)
+    gen_s = time.perf_counter() - t_gen
+    keys_after_plan = sess.key_residency()[1]
 
     def barrier():
         sess.sync()
@@ -179,6 +254,9 @@ def run_engine(args):
             first_logits = logits
     setup_s = time.perf_counter() - t_setup
     key_bytes, key_gens = sess.key_residency()
+    if plan is not None and key_gens != keys_after_plan:
+        raise SystemExit(f"rank {rank}: {key_gens - keys_after_plan} key(s) were generated during evaluation although the "
+                         "keys come from a plan")
     barrier()
 
     # ---- value: encrypted images resident in HBM, device-timed -----------------------------------------------
@@ -313,14 +391,22 @@ def run_engine(args):
                 "peak_source": which, "launches_per_step": d["launches"], "ms_per_launch": round(d["ms"] / d["launches"], 5),
                 "kernel_share_of_step": round(d["ms"] / prof_ms, 4),
                 "algorithmic_bytes_per_launch": int(d["limb_polys"] * ALGO_BYTES_PER_UNIT[dom] / d["launches"]),
-                "note": "NTT passes are integer-issue bound (ncu: 68-78 % of peak instruction throughput, DRAM 5-16 %), "
-                        "see profiles/; the HBM fraction is reported because the contract asks for hbm|tensor",
-                "gpu_busy_fraction_of_step": round(total_kernel_ms / prof_ms, 4),
-                # what actually bounds the NTT passes: the IMAD half of the FMA pipe, from the committed ncu captures (static,
-                # not measured in this run)
-                "int_pipe_ncu": {"metric": "sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active",
-                                 "k_fwd_cols": 78.5, "k_fwd_blocks": 63.1, "k_ks_mac": 50.6,
-                                 "source": "profiles/r1_ncu_metrics_kernel_tour.md"}}
+                "note": "the NTT passes are bound by the integer multiply-add pipe, not by HBM (ncu captures in profiles/); the "
+                        "HBM fraction is reported because the contract asks for hbm|tensor, int_roofline is the bound that applies",
+                "gpu_busy_fraction_of_step": round(total_kernel_ms / prof_ms, 4)}
+        # Integer roofline, measured in this run: peak 32-bit multiply-add rate of this GPU (bk_measure_imad_peak) against
+        # the multiplies the NTT passes of one image need (9 per 64-bit Shoup butterfly, 2^15 x 8 butterflies per pass and
+        # limb-polynomial, limb-polynomials from the engine's kernel counters) over their live-timed duration.
+        imad_peak = eng.imad_peak()
+        int_roof = {"peak_imad_per_s": imad_peak, "peak_source": "bk_measure_imad_peak: 8 independent mad.lo.u32 chains per thread, "
+                    "this GPU, this run", "multiplies_per_butterfly": IMAD_PER_BUTTERFLY, "butterflies_per_limb_poly_pass": NTT_BUTTERFLIES_PER_PASS}
+        for fam in ("fwd_cols", "fwd_blocks", "inv_blocks", "inv_cols"):
+            if fam in kernels and kernels[fam]["ms"] > 0:
+                rate = kernels[fam]["limb_polys"] * NTT_BUTTERFLIES_PER_PASS * IMAD_PER_BUTTERFLY / (kernels[fam]["ms"] * 1e-3)
+                int_roof[fam] = {"achieved_imad_per_s": rate, "frac": round(rate / imad_peak, 4)}
+        if dom in int_roof:
+            int_roof["frac"] = int_roof[dom]["frac"]
+        roof["int_roofline"] = int_roof
 
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------
     cpu = None
@@ -328,25 +414,35 @@ def run_engine(args):
         per_image = {k: [c / args.steps for c in v] for k, v in hist.items()}
         cpu = cpu_baseline(per_image, reps=1)
 
+    # ---- key-switch microseconds and the exact mode (rank 0, N = 1 only): the main session is closed first ------
+    ks_us, exact = None, None
+    plain_cache = sess.plain_cache()
+    if rank == 0 and world == 1 and not args.no_exact:
+        del net
+        sess.close()
+        ks_us = {"engine_hybrid" if hybrid else "engine_exact": key_switch_us(app, local)}
+        if cpu and cpu.get("key_switch_seconds_per_thread"):
+            ks_us["reference_per_thread"] = {str(l): round(v * 1e6, 1) for l, v in cpu["key_switch_seconds_per_thread"].items()
+                                             if int(l) in (31, 17, 3)}
+        if hybrid:
+            exact = run_exact_child(args)
+            if exact and "key_switch_us" in exact:
+                ks_us["engine_exact"] = exact.pop("key_switch_us")
+
     if rank == 0:
         total_images = world * args.steps * K
         line = {
-            "metric": METRIC, "value": total_images / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "metric": metric_name(args.layers), "value": total_images / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": f"ResNet-{args.layers} CIFAR-10 with bootstrapping (reference: ./cnn {args.layers} 10 i j), {K} image(s) in "
-                                   "flight per GPU per step; logN=16 RNS-CKKS, primes 51|46x16|51x14|51, Hamming weight 192, scale 2^46; synthetic "
-                                   "images (N(0,1) clipped, seed = image id), random-init weights of the architecture",
-                       "images_per_step_per_gpu": K, "images_in_flight_per_gpu": K,
-                       "key_switching": ("level-aware hybrid (idle primes above the level as temporary special moduli; decrypted "
-                                         "values equal the reference's, limbs do not)" if hybrid
-                                         else "one digit per prime as in the reference (bit-exact limbs)"),
-                       "log_n": LOG_N, "layers": args.layers,
-                       "l2": "working set larger than L2: every bootstrap streams ~60 GiB of level-pruned Galois keys and "
-                             "31-limb ciphertexts (31 MiB each) against a 126 MB L2",
-                       "parallelism": f"dp{world}: image i -> rank i mod {world}; secret key broadcast once over NCCL, evaluation "
-                                      f"keys derived per GPU; no data-path collective; per GPU {K} host threads / CUDA streams, "
-                                      "one image each, over shared keys (the reference's OpenMP image loop)"},
+            "vs_baseline": None, "dtype": "u64", "data": f"synthetic images; {weights_name}",
+            "config": make_config(args),
+            "engine": {"images_in_flight_per_gpu": K,
+                       "mode": ("tolerance mode: level-aware hybrid key switching, hoisted baby-step rotations, constants as "
+                                "plaintexts (decrypted values equal the reference's, limbs do not)" if hybrid
+                                else "key switching decomposed one digit per prime as in the reference"),
+                       "parallelism": f"dp{world}: image i -> rank i mod {world}; secret key broadcast once over NCCL, evaluation keys "
+                                      f"generated per GPU; no data-path collective; per GPU {K} host threads / CUDA streams, one "
+                                      "image each, over shared keys (the reference's OpenMP image loop, infer_seal.cpp:404)"},
             "seconds_per_image": ms * 1e-3 / (args.steps * K),
             "latency": {"seconds_per_image": latency_ms * 1e-3 / args.steps, "images_in_flight": 1,
                         "note": "one image alone on the GPU, device-timed over `steps` images"},
@@ -354,11 +450,15 @@ def run_engine(args):
                     "h2d_bytes_per_step": (h2d1 - h2d0) // e2e_steps, "d2h_bytes_per_step": (d2h1 - d2h0) // e2e_steps,
                     "call": ("bka_resnet_infer_batch(net, images[n][3072] on the host, in_flight) -> logits[n][10] on the host" if K > 1
                              else "bka_resnet_infer(net, image[3072] on the host) -> logits[10] on the host")},
+            "exact": exact, "key_switch_us": ks_us,
             "gpu_launches": int(launches_tp), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "ops_per_image": {k: v // args.steps for k, v in stats.items()},
-            "galois_keys": {"resident_gib": round(key_bytes / 2 ** 30, 2), "generated": key_gens,
-                            "setup_and_warmup_seconds": round(setup_s, 1)},
-            "plaintext_cache": {k: (round(v / 2 ** 30, 2) if k == "bytes" else v) for k, v in sess.plain_cache().items()},
+            "keys": {"plan": plan_source, "plan_seconds": round(plan_s, 1), "generate_seconds": round(gen_s, 1),
+                     "secret_key_detached_from_evaluation_keys": plan is not None,
+                     "resident_gib": round(key_bytes / 2 ** 30, 2), "generated": key_gens,
+                     "generated_during_evaluation": (key_gens - keys_after_plan) if plan is not None else key_gens,
+                     "setup_and_warmup_seconds": round(setup_s, 1)},
+            "plaintext_cache": {k: (round(v / 2 ** 30, 2) if k == "bytes" else v) for k, v in plain_cache.items()},
             "check": {"logits_image0": [round(float(x), 4) for x in first_logits],
                       "max_logit_difference_between_timed_paths": drift},
         }
@@ -368,6 +468,86 @@ def run_engine(args):
     if dist:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def key_switch_us(app, device, reps=10):
+    """rotate_vector(step 1) at N = 2^16 and 31 / 17 / 3 limbs, microseconds (CUDA events, mean of `reps` after 3 warm-ups),
+    in the key-switching mode of the current environment"""
+    import numpy as np
+
+    s = app.session(LOG_N, CNN_BITS, hamming_weight=192, device=device, rotation_steps=[1])
+    eng = s.engine()
+    out = {}
+    x = np.linspace(-1, 1, s.slots)
+    for limbs in (31, 17, 3):
+        ct = s.encrypt(x, 2.0 ** 46, limbs=limbs)
+        for _ in range(3):
+            s.rotate(ct, 1)
+        s.sync()
+        eng.timer_begin()
+        for _ in range(reps):
+            s.rotate(ct, 1)
+        out[str(limbs)] = round(eng.timer_end() * 1e3 / reps, 1)
+    s.close()
+    return out
+
+
+def run_exact_child(args):
+    """the exact mode in a process of its own (its switches are read once per process)"""
+    env = dict(os.environ, B200CKKS_HYBRID_KS="0", B200CKKS_NO_HOIST="1", B200CKKS_ENCRYPT_CONSTANTS="1")
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "exact-child", "--layers", str(args.layers), "--steps", str(min(args.steps, 3)),
+           "--in-flight", str(args.in_flight)]
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=1500)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(lines[-1])
+    except Exception as e:      # the headline must not die with the side measurement
+        return {"error": repr(e)}
+
+
+def run_exact_child_body(args):
+    """ResNet with every tolerance-mode path off: one digit per prime, rotations one by one, constants encrypted on the
+    hot path - the reference's exact operation sequence (the limb-level parity tests cover this mode)"""
+    import numpy as np
+    from b200ckks import synthetic
+    from b200ckks.app import App
+
+    app = App()
+    os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")
+    weights, _ = load_weights(args.layers)
+    sess = app.session(LOG_N, CNN_BITS, hamming_weight=192)
+    eng = sess.engine()
+    net = sess.resnet(args.layers, weights)
+    img = lambda k: synthetic.synthetic_image(k)
+    first = net.infer(img(0), trace=False)[0]          # warm-up: materialises the level-pruned keys
+    enc = [net.encrypt_image(img(1 + k)) for k in range(args.steps)]
+    sess.sync()
+    eng.timer_begin()
+    outs = [net.infer_encrypted(c)[0] for c in enc]
+    alone_ms = eng.timer_end()
+    K = max(1, args.in_flight)
+    batch = [enc[k % args.steps].clone() for k in range(K * 2)]
+    net.infer_encrypted_batch(batch[:K], K)
+    sess.sync()
+    eng.timer_begin()
+    net.infer_encrypted_batch(batch, K)
+    tp_ms = eng.timer_end()
+    key_bytes, key_gens = sess.key_residency()
+    logits = net.decrypt_logits(outs[0])
+    if not (np.isfinite(logits).all() and np.abs(logits).max() < 1e3):
+        raise SystemExit("exact mode produced non-finite logits")
+    del net, outs, enc, batch
+    sess.close()
+    res = {"mode": "reference operation sequence: key switching one digit per prime, rotations one by one, constants encrypted "
+                   "(B200CKKS_HYBRID_KS=0 B200CKKS_NO_HOIST=1 B200CKKS_ENCRYPT_CONSTANTS=1)",
+           "value": (K * 2) / (tp_ms * 1e-3), "unit": UNIT, "images_in_flight": K,
+           "seconds_per_image": tp_ms * 1e-3 / (K * 2), "latency_seconds_per_image": alone_ms * 1e-3 / args.steps,
+           "galois_keys_resident_gib": round(key_bytes / 2 ** 30, 2),
+           "logits_image0": [round(float(x), 4) for x in first],
+           "key_switch_us": key_switch_us(app, 0)}
+    print(json.dumps(res), flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------- CPU arm
@@ -439,11 +619,12 @@ def cpu_baseline(hist, reps=1, threads=None):
     sec, parts = compose_seconds_per_image(per_op, hist)
     return {"value": T / sec, "unit": UNIT, "cores": T, "kind": "reference", "seconds_per_image_per_thread": sec,
             "seconds_by_operation": {k: round(v, 1) for k, v in parts.items()},
+            "key_switch_seconds_per_thread": {str(l): v for l, v in per_op["key_switch"].items()},
             "sample": f"the reference's modified SEAL 3.6.6 (compiled in place, -O2, no HEXL): rotate / rescale / multiply_vector / "
                       f"multiply / multiply_const / add timed at 3-5 levels with {T} OpenMP threads each on its own ciphertext "
-                      f"({reps} call(s) per thread and level), composed with the per-level operation counts of one ResNet-20 "
-                      f"inference; the reference's own single-thread log reports 2188.8 s per image "
-                      f"(result/resnet20_cifar10_image0.txt) and its full run needs NTL and ~384 GB of RAM"}
+                      f"({reps} call(s) per thread and level), composed with the per-level operation counts of one "
+                      f"inference of this run; the reference's own single-thread log reports 2188.8 s per image for ResNet-20 "
+                      f"(result/resnet20_cifar10_image0.txt) and its full run needs ~384 GB of RAM"}
 
 
 def run_reference(args):
@@ -456,10 +637,10 @@ def run_reference(args):
     if not refseal.available():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libseal_ref.so is not built"}))
         return
-    if args.layers != 20 or not os.path.exists(HIST_PATH):
+    if not os.path.exists(hist_path(args.layers)):
         print(json.dumps({"impl": "reference", "unavailable": "no committed operation histogram for this depth"}))
         return
-    hist = json.load(open(HIST_PATH))
+    hist = json.load(open(hist_path(args.layers)))
     T = host_threads()
     for _ in range(args.warmup):
         measure_reference_ops(T, 1)
@@ -473,12 +654,12 @@ def run_reference(args):
     sample = (f"each step measures the reference's modified SEAL 3.6.6 operations (rotate, rescale, multiply_vector, multiply, "
               f"multiply_const, add) at 3-5 levels of the CNN chain with {T} OpenMP threads, one ciphertext per thread, and "
               f"composes them with the committed per-level operation counts of one ResNet-20 inference "
-              f"(tests/golden/resnet20_op_histogram.json); value = {T} concurrent images / composed seconds per image")
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+              f"(tests/golden/resnet{args.layers}_op_histogram.json); value = {T} concurrent images / composed seconds per image")
+    weights_name = make_config(args)["weights"]
+    line = {"impl": "reference", "metric": metric_name(args.layers), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": wall * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "ResNet-20 CIFAR-10 with bootstrapping (./cnn 20 10 i i), logN=16 RNS-CKKS, primes 51|46x16|51x14|51",
-                       "log_n": LOG_N, "layers": args.layers, "threads": T},
+            "vs_baseline": None, "dtype": "u64", "data": f"synthetic images; {weights_name}",
+            "config": make_config(args), "threads": T,
             "seconds_per_image": sec / T, "seconds_per_image_per_thread": sec,
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": T, "kind": "reference", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -490,17 +671,24 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--impl", default="engine", choices=["engine", "reference", "exact-child"])
     ap.add_argument("--layers", type=int, default=20)
     ap.add_argument("--no-hybrid", action="store_true",
                     help="key switching exactly as the reference decomposes it (one digit per prime); default: level-aware "
                          "hybrid key switching (tolerance mode)")
     ap.add_argument("--in-flight", type=int, default=4, help="images in flight per GPU (a step = that many images per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-exact", action="store_true", help="skip the exact-mode child run and the key-switch timings")
+    ap.add_argument("--lazy-keys", action="store_true",
+                    help="round-1 behaviour: evaluation keys generated on first use from the resident secret key instead of "
+                         "up front from a key plan")
+    ap.add_argument("--write-plan", default=None, help="write the key plan learnt from the dry run to this file")
     ap.add_argument("--dump-histogram", default=None, help="write the per-level operation counts of one inference (JSON)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "exact-child":
+        run_exact_child_body(args)
     else:
         args.warmup = max(args.warmup, 3)
         run_engine(args)

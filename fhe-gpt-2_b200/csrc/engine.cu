@@ -13,6 +13,24 @@
 #include <cstring>
 #include <limits>
 
+// 8 independent chains of 32-bit multiply-adds per thread (bk_measure_imad_peak)
+static __global__ void __launch_bounds__(256) k_imad_peak(unsigned *sink, int iters, unsigned m)
+{
+    unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+#pragma unroll 8
+    for (int i = 0; i < iters; i++)
+    {
+        asm volatile("mad.lo.u32 %0, %0, %8, %0;\n\tmad.lo.u32 %1, %1, %8, %1;\n\tmad.lo.u32 %2, %2, %8, %2;\n\t"
+                     "mad.lo.u32 %3, %3, %8, %3;\n\tmad.lo.u32 %4, %4, %8, %4;\n\tmad.lo.u32 %5, %5, %8, %5;\n\t"
+                     "mad.lo.u32 %6, %6, %8, %6;\n\tmad.lo.u32 %7, %7, %8, %7;"
+                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
+                     : "r"(m));
+    }
+    unsigned r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u && iters < 0)
+        *sink = r;
+}
+
 namespace bk
 {
     static thread_local std::string g_err;
@@ -425,13 +443,34 @@ namespace bk
     default: { constexpr int LOGR = 8; __VA_ARGS__; } break;                                                                  \
     }
 
+    // Launches of a few limb-polynomials (special limbs of a ModDown, last limb of a rescale, key switches at 2-3
+    // limbs) would occupy 16 CTAs per limb-polynomial - a fraction of the 148 SMs; they run with narrower column
+    // tiles (8 columns: 32 CTAs per limb-polynomial) and 64-thread block-pass CTAs (64 per limb-polynomial).
+    static bool small_launch(const Context &c, int jobs)
+    {
+        return jobs * 16 < 2 * c.sm_count;
+    }
     template <class Load>
     static void launch_fwd_cols(Context &c, cudaStream_t s, const Load &ld, u64 *out, int jobs)
     {
         if (jobs <= 0)
             return;
-        dim3 grid(16, jobs);
         ProfScope ps(c, s, TAG_FWD_COLS, jobs);
+        if (small_launch(c, jobs))
+        {
+            dim3 grid(32, jobs);
+            if (c.tables.wide)
+            {
+                BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            }
+            else
+            {
+                BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            }
+            c.count();
+            return;
+        }
+        dim3 grid(16, jobs);
         if (c.tables.wide)
         {
             BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
@@ -447,12 +486,13 @@ namespace bk
     {
         if (jobs <= 0)
             return;
-        dim3 grid((unsigned)(c.n >> 12), jobs);
+        const unsigned threads = small_launch(c, jobs) ? 64 : 256;
+        dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
         if (c.tables.wide)
-            k_fwd_blocks<Store, true><<<grid, 256, 0, s>>>(in, st, c.tables);
+            k_fwd_blocks<Store, true><<<grid, threads, 0, s>>>(in, st, c.tables);
         else
-            k_fwd_blocks<Store, false><<<grid, 256, 0, s>>>(in, st, c.tables);
+            k_fwd_blocks<Store, false><<<grid, threads, 0, s>>>(in, st, c.tables);
         c.count();
     }
     template <class Load>
@@ -460,9 +500,10 @@ namespace bk
     {
         if (jobs <= 0)
             return;
-        dim3 grid((unsigned)(c.n >> 12), jobs);
+        const unsigned threads = small_launch(c, jobs) ? 64 : 256;
+        dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_INV_BLOCKS, jobs);
-        k_inv_blocks<Load><<<grid, 256, 0, s>>>(ld, out, c.tables);
+        k_inv_blocks<Load><<<grid, threads, 0, s>>>(ld, out, c.tables);
         c.count();
     }
     template <class Store>
@@ -470,9 +511,17 @@ namespace bk
     {
         if (jobs <= 0)
             return;
-        dim3 grid(16, jobs);
         ProfScope ps(c, s, TAG_INV_COLS, jobs);
-        BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
+        if (small_launch(c, jobs))
+        {
+            dim3 grid(32, jobs);
+            BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
+        }
+        else
+        {
+            dim3 grid(16, jobs);
+            BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
+        }
         c.count();
     }
 
@@ -1408,6 +1457,40 @@ extern "C"
         static const size_t words = (size_t)192 << 17; // 192 MiB
         Scratch junk(ctx->stream(), words);
         BK_CUDA(cudaMemsetAsync(junk.p, 0x5a, words * sizeof(u64), ctx->stream()));
+        BK_END
+    }
+
+    // Peak of the pipe that bounds the NTT passes, measured on this GPU at its current clocks: 32-bit integer
+    // multiply-add (IMAD) thread-instructions per second from a kernel of independent dependent-chains - the
+    // denominator of bench.py's integer roofline (a 64-bit Shoup butterfly needs 9 of them, ntt.cuh ct_bfly_wide).
+    bk_status bk_measure_imad_peak(bk_context_t ctx, double *imad_per_second_out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        cudaStream_t s = c.stream();
+        Scratch sink(s, 1);
+        const int iters = 4096, chains = 8;
+        dim3 grid((unsigned)c.sm_count * 8);
+        cudaEvent_t e0, e1;
+        BK_CUDA(cudaEventCreate(&e0));
+        BK_CUDA(cudaEventCreate(&e1));
+        double best = 0;
+        for (int rep = 0; rep < 4; rep++)
+        {
+            BK_CUDA(cudaEventRecord(e0, s));
+            k_imad_peak<<<grid, 256, 0, s>>>((unsigned *)sink.p, iters, 0x9E3779B9u);
+            BK_CUDA(cudaEventRecord(e1, s));
+            BK_CUDA(cudaEventSynchronize(e1));
+            float ms = 0;
+            BK_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+            double rate = (double)grid.x * 256.0 * iters * chains / (ms * 1e-3);
+            if (rep > 0 && rate > best)
+                best = rate;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        c.count(4);
+        *imad_per_second_out = best;
         BK_END
     }
 

@@ -148,14 +148,24 @@ __device__ __forceinline__ int swz(int e)
     return e ^ ((e >> 4) & 15);
 }
 
+// shared-memory offset of a row of the column-pass tile.  With 8 columns the four row groups a warp touches in the
+// transposed phase (rows 16 apart) would fall on the same 16 banks; odd groups are shifted by 64 bytes.
+template <int COLS>
+__device__ __forceinline__ int cols_idx(int row)
+{
+    return row * COLS + (COLS == 8 ? ((row >> 4) & 1) * 8 : 0);
+}
+
 // ============================================================================================
-// Column pass, forward (first LOGR stages).  grid = (16, jobs), block = 16 * (R/16) threads.
-// CTA tile: all R rows x 16 consecutive columns (one 128-byte line per row).
+// Column pass, forward (first LOGR stages).  grid = (256 / COLS, jobs), block = COLS * (R/16) threads.
+// CTA tile: all R rows x COLS consecutive columns: COLS = 16 is one 128-byte line per row; launches of a few
+// limb-polynomials (the special limbs of a ModDown, the last limb of a rescale, key switches at 2-3 limbs) use
+// COLS = 8 so that twice as many CTAs spread over the 148 SMs.
 //   Load:  int prime(int job);  bool skip(int job);  u64 load(int job, int idx, const PrimeDev&)
 //          (must return a value < 4q of prime(job)).
 // Output: lazy values in [0,4q) at out[job*N + idx].
 // ============================================================================================
-template <int LOGR, class Load, bool WIDE = false>
+template <int LOGR, class Load, bool WIDE = false, int COLS = 16>
 __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out, NttTables T)
 {
     constexpr int R = 1 << LOGR;
@@ -163,14 +173,14 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
     constexpr int LOG2 = LOGR - 4; // stages in the second phase
     constexpr int S2 = 1 << LOG2;  // = TR
     constexpr int G = 16 / S2;     // groups per thread in the second phase
-    __shared__ u64 sm[R * 16];
+    __shared__ u64 sm[R * COLS + 8];
 
     const int job = blockIdx.y;
     if (ld.skip(job))
         return;
-    const int c = threadIdx.x & 15;
-    const int t = threadIdx.x >> 4;
-    const int col = blockIdx.x * 16 + c;
+    const int c = threadIdx.x % COLS;
+    const int t = threadIdx.x / COLS;
+    const int col = blockIdx.x * COLS + c;
     const int pi = ld.prime(job);
     const PrimeDev pd = T.primes[pi];
     const size_t n = size_t(1) << T.log_n;
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
     {
 #pragma unroll
         for (int k = 0; k < 16; k++)
-            sm[(t + TR * k) * 16 + c] = x[k];
+            sm[cols_idx<COLS>(t + TR * k) + c] = x[k];
         __syncthreads();
         // phase 2: G groups; group g covers rows u*S2 + k', u = t*G + g (top 4 bits), k' < S2
 #pragma unroll
@@ -200,7 +210,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
             const int u = t * G + g;
 #pragma unroll
             for (int k = 0; k < S2; k++)
-                x[g * S2 + k] = sm[(u * S2 + k) * 16 + c];
+                x[g * S2 + k] = sm[cols_idx<COLS>(u * S2 + k) + c];
         }
 #pragma unroll
         for (int g = 0; g < G; g++)
@@ -230,8 +240,9 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 }
 
 // ============================================================================================
-// Block pass, forward (last 8 stages).  grid = (N/4096, jobs), block = 256 threads:
-// 16 blocks of 256 coefficients per CTA, one half-warp per block (only __syncwarp needed).
+// Block pass, forward (last 8 stages).  grid = (N / (16 blockDim.x), jobs), block = 256 (or 64) threads:
+// blockDim.x / 16 blocks of 256 coefficients per CTA, one half-warp per block (only __syncwarp needed); small
+// launches use 64-thread CTAs so that four times as many CTAs spread over the SMs.
 //   Store: int prime(int job);  bool skip(int job);
 //          u64  pre (int job, int blk, int t, int k, u64 v, const PrimeDev&)   - register layout
 //               e = 16t + k, v in [0,4q); returns the value to be staged;
@@ -246,7 +257,7 @@ __global__ void __launch_bounds__(256, WIDE ? 3 : 2) k_fwd_blocks(const u64 *__r
         return;
     const int t = threadIdx.x & 15;
     const int lb = threadIdx.x >> 4;         // local block 0..15
-    const int blk = blockIdx.x * 16 + lb;    // 256-block index within the limb
+    const int blk = blockIdx.x * (int)(blockDim.x >> 4) + lb; // 256-block index within the limb
     const int pi = st.prime(job);
     const PrimeDev pd = T.primes[pi];
     const size_t n = size_t(1) << T.log_n;
@@ -312,7 +323,7 @@ __global__ void __launch_bounds__(256) k_inv_blocks(Load ld, u64 *__restrict__ o
     const int job = blockIdx.y;
     const int t = threadIdx.x & 15;
     const int lb = threadIdx.x >> 4;
-    const int blk = blockIdx.x * 16 + lb;
+    const int blk = blockIdx.x * (int)(blockDim.x >> 4) + lb;
     const int pi = ld.prime(job);
     const PrimeDev pd = T.primes[pi];
     const size_t n = size_t(1) << T.log_n;
@@ -357,7 +368,7 @@ __global__ void __launch_bounds__(256) k_inv_blocks(Load ld, u64 *__restrict__ o
 // Column pass, inverse (last LOGR GS stages, N^-1 folded into the final one).
 //   Store: int prime(int job); void store(int job, int idx, u64 v /* [0,2q) */, const PrimeDev&)
 // ============================================================================================
-template <int LOGR, class Store>
+template <int LOGR, class Store, int COLS = 16>
 __global__ void __launch_bounds__(256) k_inv_cols(const u64 *__restrict__ in, Store st, NttTables T)
 {
     constexpr int R = 1 << LOGR;
@@ -365,12 +376,12 @@ __global__ void __launch_bounds__(256) k_inv_cols(const u64 *__restrict__ in, St
     constexpr int LOG2 = LOGR - 4;
     constexpr int S2 = 1 << LOG2;
     constexpr int G = 16 / S2;
-    __shared__ u64 sm[R * 16];
+    __shared__ u64 sm[R * COLS + 8];
 
     const int job = blockIdx.y;
-    const int c = threadIdx.x & 15;
-    const int t = threadIdx.x >> 4;
-    const int col = blockIdx.x * 16 + c;
+    const int c = threadIdx.x % COLS;
+    const int t = threadIdx.x / COLS;
+    const int col = blockIdx.x * COLS + c;
     const int pi = st.prime(job);
     const PrimeDev pd = T.primes[pi];
     const size_t n = size_t(1) << T.log_n;
@@ -397,12 +408,12 @@ __global__ void __launch_bounds__(256) k_inv_cols(const u64 *__restrict__ in, St
             const int u = t * G + g;
 #pragma unroll
             for (int k = 0; k < S2; k++)
-                sm[(u * S2 + k) * 16 + c] = x[g * S2 + k];
+                sm[cols_idx<COLS>(u * S2 + k) + c] = x[g * S2 + k];
         }
         __syncthreads();
 #pragma unroll
         for (int k = 0; k < 16; k++)
-            x[k] = sm[(t + TR * k) * 16 + c];
+            x[k] = sm[cols_idx<COLS>(t + TR * k) + c];
     }
     else
     {

@@ -74,6 +74,11 @@ class EngineView:
         self._ck(self.L.bk_timer_end(self.h, C.byref(ms)))
         return ms.value
 
+    def imad_peak(self):
+        v = C.c_double()
+        self._ck(self.L.bk_measure_imad_peak(self.h, C.byref(v)))
+        return v.value
+
     def flush_l2(self):
         self._ck(self.L.bk_flush_l2(self.h))
 

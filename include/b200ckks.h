@@ -119,6 +119,9 @@ bk_status bk_kernel_counters(bk_context_t ctx, uint64_t launches_out[8], uint64_
 bk_status bk_transfer_bytes(bk_context_t ctx, uint64_t *h2d_out, uint64_t *d2h_out);
 /* overwrite a 192 MiB scratch buffer (> the 126 MB L2) on the caller's stream. */
 bk_status bk_flush_l2(bk_context_t ctx);
+/* measured peak of 32-bit integer multiply-add thread-instructions per second on this GPU (the pipe that bounds the
+ * NTT butterflies): the denominator of the benchmark's integer roofline */
+bk_status bk_measure_imad_peak(bk_context_t ctx, double *imad_per_second_out);
 
 /* ---- ciphertext container (ciphertext.h) -------------------------------------------------- */
 bk_status bk_ct_create(bk_context_t ctx, bk_ct_t *out);

@@ -58,3 +58,43 @@ def test_resnet20_hybrid_key_switching(hybrid_session):
     # level-specific keys: ceil(l / dsize) digits over l + alpha moduli instead of l digits over l + 1 (4x smaller at
     # l = 20); measured 39.8 GiB against 60.6 GiB on the reference-exact path
     assert 2 ** 30 < kb < 50 * 2 ** 30, kb
+
+
+def test_resnet20_with_the_references_trained_parameters(hybrid_session):
+    """BASELINE config 1 as written: pretrained_parameters/resnet20_new (a copy is kept under tests/golden) read in the
+    order of import_parameters_cifar10 (infer_seal.cpp:3-107).  Trained batch-norm statistics are a different numeric
+    regime from random-init ones (ReLU input range, B = 40 scaling): logits and prediction against the float64 model."""
+    from b200ckks import synthetic
+
+    d = synthetic.pretrained_dir(20)
+    assert d is not None, "tests/golden/pretrained_parameters/resnet20_new is part of the repository"
+    w = synthetic.load_pretrained(d, 20)
+    assert [len(a) for a in w["conv_weight"][:3]] == [9 * 3 * 16, 9 * 16 * 16, 9 * 16 * 16] and len(w["linear_weight"]) == 640
+    net = hybrid_session.resnet(20, w)
+    for image_id in (0, 1):
+        img = synthetic.synthetic_image(image_id)
+        logits, _ = net.infer(img, trace=False)
+        want = pm.resnet_forward(20, w, img)
+        assert np.abs(want).max() > 5.0                      # trained network: confident logits (random-init: < 1)
+        assert np.abs(logits - want).max() < 2e-2, np.abs(logits - want).max()
+        assert int(np.argmax(logits)) == int(np.argmax(want))
+
+
+def test_resnet110_deepest_bootstrapping_chain(hybrid_session):
+    """BASELINE config 4 (./cnn 110 10 0 0): 109 convolutions, 108 bootstraps - where a per-bootstrap error compounds.
+    Logits against the float64 model and the operation trace of the network."""
+    from b200ckks import synthetic
+
+    w = synthetic.random_weights(110, seed=0)
+    net = hybrid_session.resnet(110, w)
+    img = synthetic.synthetic_image(0)
+    logits, trace = net.infer(img)
+    want = pm.resnet_forward(110, w, img)
+    assert np.abs(logits - want).max() < 2e-2, np.abs(logits - want).max()     # measured 5e-3 .. 7e-3 on the exact path in round 1
+    assert int(np.argmax(logits)) == int(np.argmax(want))
+    ops = [r["op"] for r in trace]
+    assert ops.count("bootstrap") == 108 and ops.count("conv") == 109 and ops.count("relu") == 109
+    assert ops.count("downsample") == 2 and ops.count("add") == 54 and ops[-2:] == ["avgpool", "fc"]
+    # every bootstrap returns to remaining level 16 at scale 2^46, every ReLU leaves at level 2 (the reference's log)
+    assert all(r["level"] == 16 and r["scale"] == 2.0 ** 46 for r in trace if r["op"] == "bootstrap")
+    assert all(r["level"] == 2 for r in trace if r["op"] == "relu")
