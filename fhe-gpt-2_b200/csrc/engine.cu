@@ -7,6 +7,8 @@
 // bk_context_create fails with BK_NO_DEVICE.
 #include "engine.h"
 #include <sys/random.h>
+#include <execinfo.h>
+#include <cstdio>
 #include <cmath>
 #include <algorithm>
 #include <cstdlib>
@@ -109,6 +111,8 @@ namespace bk
             throw std::invalid_argument("coeff_modulus size is invalid");
         if (const char *e = std::getenv("B200CKKS_HYBRID_KS"))
             hybrid = std::atoi(e) != 0;
+        if (const char *e = std::getenv("B200CKKS_DEBUG_SYNC"))
+            debug_sync = std::atoi(e) != 0;
         // random generator master key (rng.cuh): the operating system's entropy unless a reproducible run is asked for
         if (const char *e = std::getenv("B200CKKS_SEED"))
         {
@@ -335,6 +339,18 @@ namespace bk
         return s;
     }
 
+    void Context::debug_check()
+    {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e == cudaSuccess)
+            return;
+        std::fprintf(stderr, "b200ckks: launch #%llu failed: %s\n", (unsigned long long)launches.load(), cudaGetErrorString(e));
+        void *frames[24];
+        int n = backtrace(frames, 24);
+        backtrace_symbols_fd(frames, n, 2);
+        std::abort();
+    }
+
     cudaStream_t Context::stream_if_any()
     {
         std::lock_guard<std::mutex> g(mu);
@@ -448,7 +464,8 @@ namespace bk
     // tiles (8 columns: 32 CTAs per limb-polynomial) and 64-thread block-pass CTAs (64 per limb-polynomial).
     static bool small_launch(const Context &c, int jobs)
     {
-        return jobs * 16 < 2 * c.sm_count;
+        static const bool off = std::getenv("B200CKKS_NO_SMALL_LAUNCH") != nullptr;
+        return !off && jobs * 16 < 2 * c.sm_count;
     }
     template <class Load>
     static void launch_fwd_cols(Context &c, cudaStream_t s, const Load &ld, u64 *out, int jobs)
@@ -871,7 +888,7 @@ namespace bk
                            const u64 *base1, u64 *out, int l, bk_kskey_t key)
     {
         bk_kskey_s level_view; // hybrid mode at a level whose shape is SEAL's own: its level key is a pruned SEAL key
-        if (key->sk && (c.hybrid || !key->d)) // a recipe generated in hybrid mode has no SEAL-layout data
+        if (key->recipe) // a recipe generated in hybrid mode has no SEAL-layout data
         {
             if (hybrid_plan(c, l).alpha > 1)
             {
@@ -943,7 +960,7 @@ namespace bk
         const int l = in->limbs;
         std::vector<bk_kskey_s> level_views;
         std::vector<bk_kskey_t> level_keys;
-        if (count > 0 && keys[0]->sk && (c.hybrid || !keys[0]->d))
+        if (count > 0 && keys[0]->recipe)
         {
             if (hybrid_plan(c, l).alpha > 1)
             {
@@ -1772,7 +1789,7 @@ extern "C"
         Context &c = *key->ctx;
         if (limbs < 1 || limbs > c.top_limbs())
             throw std::invalid_argument("limbs is out of range");
-        if (!c.hybrid || key->d)
+        if (!key->recipe)
             throw std::logic_error("only recipes of the level-aware hybrid mode have level-specific keys");
         hybrid_key(c, key, limbs);
         BK_END

@@ -204,7 +204,13 @@ namespace bk
         void count(int k = 1)
         {
             launches.fetch_add((uint64_t)k, std::memory_order_relaxed);
+            if (debug_sync)
+                debug_check();
         }
+        // $B200CKKS_DEBUG_SYNC=1: wait for the device after every launch and report the first failing one with a host
+        // backtrace (compute-sanitizer is not available on the GPU pool)
+        bool debug_sync = false;
+        void debug_check();
         int top_limbs() const
         {
             return n_primes - 1;
@@ -318,7 +324,8 @@ struct bk_kskey_s
     size_t words = 0;
     // hybrid mode: the key is a recipe (secret key, what it switches from, seed) and one level-specific key per level
     // it has been used at, generated on first use
-    bk_sk_s *sk = nullptr;
+    bk_sk_s *sk = nullptr; // null once detached (bk_kskey_drop_secret): only the level keys made so far remain usable
+    bool recipe = false;   // generated in hybrid mode: no SEAL-layout data, level keys in `hyb`
     int kind = 0;       // 0 uploaded / SEAL layout only, 1 relinearization (s^2), 2 Galois (elt)
     uint32_t elt = 0;
     uint64_t seed = 0;

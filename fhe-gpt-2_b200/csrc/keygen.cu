@@ -246,6 +246,7 @@ namespace bk
         if (c.hybrid)
         {
             // a recipe only: the level-specific keys are generated by hybrid_key() at the levels that use them
+            key->recipe = true;
             key->digits = top;
             key->klimbs = top;
             return key;

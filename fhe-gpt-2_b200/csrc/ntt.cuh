@@ -149,11 +149,12 @@ __device__ __forceinline__ int swz(int e)
 }
 
 // shared-memory offset of a row of the column-pass tile.  With 8 columns the four row groups a warp touches in the
-// transposed phase (rows 16 apart) would fall on the same 16 banks; odd groups are shifted by 64 bytes.
+// transposed phase (rows 16 apart) would fall on the same 16 banks; every group of 16 rows is shifted by a further
+// 64 bytes (tile size R * COLS + R / 16 * 8 words).
 template <int COLS>
 __device__ __forceinline__ int cols_idx(int row)
 {
-    return row * COLS + (COLS == 8 ? ((row >> 4) & 1) * 8 : 0);
+    return row * COLS + (COLS == 8 ? (row >> 4) * 8 : 0);
 }
 
 // ============================================================================================
@@ -173,7 +174,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
     constexpr int LOG2 = LOGR - 4; // stages in the second phase
     constexpr int S2 = 1 << LOG2;  // = TR
     constexpr int G = 16 / S2;     // groups per thread in the second phase
-    __shared__ u64 sm[R * COLS + 8];
+    __shared__ u64 sm[R * COLS + (R / 16 + 1) * 8];
 
     const int job = blockIdx.y;
     if (ld.skip(job))
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(256) k_inv_cols(const u64 *__restrict__ in, St
     constexpr int LOG2 = LOGR - 4;
     constexpr int S2 = 1 << LOG2;
     constexpr int G = 16 / S2;
-    __shared__ u64 sm[R * COLS + 8];
+    __shared__ u64 sm[R * COLS + (R / 16 + 1) * 8];
 
     const int job = blockIdx.y;
     const int c = threadIdx.x % COLS;
