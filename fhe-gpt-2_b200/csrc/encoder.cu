@@ -410,8 +410,9 @@ struct LdEncode
     const double *re; // [N]
     size_t n;
     int limbs;
+    int special_pos = -1, special_prime = 0; // extended encodes: the last job is the special prime
     __device__ __forceinline__ bool skip(int) const { return false; }
-    __device__ __forceinline__ int prime(int job) const { return job; }
+    __device__ __forceinline__ int prime(int job) const { return job == special_pos ? special_prime : job; }
     __device__ __forceinline__ u64 load(int, int idx, const PrimeDev &pd) const
     {
         return real_to_residue(re[idx], pd);
@@ -531,8 +532,10 @@ namespace bk
     // device-resident values -> plaintext.  d_vals: n_values complex on the device.
     // check_limbs: level whose bit count bounds the scale / coefficient checks (the reference's
     // 2-argument encode works at the top level and the caller then drops limbs).
+    // ext > 0: `ext` further limbs after the first `limbs` - primes limbs .. limbs + ext - 2 and the special prime (the
+    // special moduli of the level-aware key switch at that level), for operands multiplied in the extended basis.
     void encode_device(Context &c, cudaStream_t s, const cplx *d_vals, int n_values, int limbs, int check_limbs,
-                       double scale, bk_pt_t out)
+                       double scale, bk_pt_t out, int ext = 0)
     {
         EncoderState &e = encoder(c);
         const size_t n = c.n;
@@ -583,14 +586,27 @@ namespace bk
             if (max_coeff_bit_count >= c.total_bits[check_limbs])
                 throw std::invalid_argument("encoded values are too large");
         }
-        ensure_pt(out, limbs);
+        const int jobs = limbs + ext;
+        if (ext < 0 || limbs + std::max(ext - 1, 0) > c.top_limbs())
+            throw std::invalid_argument("extended limbs are out of range");
+        ensure_pt(out, jobs);
+        out->limbs = limbs;
+        out->ext = ext;
         // RNS decomposition fused into the first NTT pass (ckks.h:536-634)
         {
-            Scratch tmp(s, (size_t)limbs * n);
-            LdEncode ld{ (const double *)re.p, n, limbs };
-            dim3 grid(16, limbs);
+            Scratch tmp(s, (size_t)jobs * n);
+            LdEncode ld{ (const double *)re.p, n, jobs };
+            JobMap map = limb_map(jobs);
+            if (ext > 0)
             {
-            ProfScope ps(c, s, TAG_FWD_COLS, limbs);
+                ld.special_pos = jobs - 1;
+                ld.special_prime = c.n_primes - 1;
+                map.special_pos = jobs - 1;
+                map.special_prime = c.n_primes - 1;
+            }
+            dim3 grid(16, jobs);
+            {
+            ProfScope ps(c, s, TAG_FWD_COLS, jobs);
             switch (c.log_n)
             {
             case 12: k_fwd_cols<4, LdEncode><<<grid, 16, 0, s>>>(ld, tmp.p, c.tables); break;
@@ -601,10 +617,10 @@ namespace bk
             }
             }
             c.count();
-            StPlain st{ out->d, limb_map(limbs), n };
-            dim3 grid2((unsigned)(n >> 12), limbs);
+            StPlain st{ out->d, map, n };
+            dim3 grid2((unsigned)(n >> 12), jobs);
             {
-                ProfScope ps(c, s, TAG_FWD_BLOCKS, limbs);
+                ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
                 k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
             }
             c.count();
@@ -616,7 +632,7 @@ namespace bk
 extern "C"
 {
     static void encode_host(bk_context_t ctx, const double *values, int n_values, int is_complex, int limbs,
-                            int check_limbs, double scale, bk_pt_t out)
+                            int check_limbs, double scale, bk_pt_t out, int ext = 0)
     {
         Context &c = *ctx;
         if (!values && n_values > 0)
@@ -639,7 +655,7 @@ extern "C"
             BK_CUDA(cudaEventRecord(done, s));
             c.h2d_bytes += (size_t)n_values * sizeof(cplx);
         }
-        encode_device(c, s, (const cplx *)dv.p, n_values, limbs, check_limbs, scale, out);
+        encode_device(c, s, (const cplx *)dv.p, n_values, limbs, check_limbs, scale, out, ext);
     }
 
     bk_status bk_encode(bk_context_t ctx, const double *values, int n_values, int is_complex, int limbs, double scale,
@@ -655,6 +671,17 @@ extern "C"
     {
         BK_TRY
         encode_host(ctx, values, n_values, is_complex, limbs, ctx->top_limbs(), scale, out);
+        BK_END
+    }
+
+    bk_status bk_encode_ext(bk_context_t ctx, const double *values, int n_values, int is_complex, int limbs, double scale,
+                            bk_pt_t out)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        if (limbs < 1 || limbs > c.top_limbs())
+            throw std::invalid_argument("parms_id is not valid for encryption parameters");
+        encode_host(ctx, values, n_values, is_complex, limbs, c.top_limbs(), scale, out, hybrid_plan(c, limbs).alpha);
         BK_END
     }
 

@@ -801,12 +801,25 @@ namespace bk
             launch_fwd_cols(c, s, ld, inter, nE * P.dnum);
             StHybDigit st{ inter, n, h, e0 };
             launch_fwd_blocks(c, s, inter, st, nE * P.dnum);
-            for (int k = 0; k < count; k++)
+            for (int k0 = 0; k0 < count; k0 += HYB_MAC_BATCH)
             {
-                HybMacArgs a{ inter, target_ntt, perms[k], keys[k]->d, acc + (size_t)k * 2 * P.ne * n, n, h, e0, gather };
-                dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE);
+                const int nk = std::min(HYB_MAC_BATCH, count - k0);
+                HybMacArgs a{};
+                a.digits = inter;
+                a.target_ntt = target_ntt;
+                for (int k = 0; k < nk; k++)
                 {
-                    ProfScope ps(c, s, TAG_KS_MAC, nE * 2 * P.dnum);
+                    a.perm[k] = perms[k0 + k];
+                    a.key[k] = keys[k0 + k]->d;
+                }
+                a.acc = acc + (size_t)k0 * 2 * P.ne * n;
+                a.n = n;
+                a.h = h;
+                a.e0 = e0;
+                a.gather_digits = gather;
+                dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE, nk);
+                {
+                    ProfScope ps(c, s, TAG_KS_MAC, nE * 2 * P.dnum * nk);
                     k_ks_mac_hyb<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
                 }
                 c.count();
@@ -1309,6 +1322,19 @@ extern "C"
     {
         BK_TRY
         ctx->hybrid = on != 0;
+        BK_END
+    }
+    bk_status bk_context_hybrid_shape(bk_context_t ctx, int limbs, int *alpha_out, int *dsize_out)
+    {
+        BK_TRY
+        if (limbs < 1 || limbs > ctx->top_limbs())
+            throw std::invalid_argument("limbs is out of range");
+        int a = 1, d = 1;
+        hybrid_shape(limbs, ctx->top_limbs(), a, d);
+        if (alpha_out)
+            *alpha_out = a;
+        if (dsize_out)
+            *dsize_out = d;
         BK_END
     }
     bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys)
@@ -2144,6 +2170,180 @@ extern "C"
             adopt(outs[k], bufs[k], words, 2, l);
             outs[k]->scale = in->scale;
             outs[k]->ntt = true;
+        }
+        BK_END
+    }
+    // Double-hoisted inner sums of a baby-step / giant-step linear transform (Bossuat, Mouchet, Troncoso-Pastoriza,
+    // Hubaux: "Efficient bootstrapping for approximate homomorphic encryption with non-sparse keys", Alg. 6), for the
+    // level-aware hybrid key switching of this engine.  The reference computes, per giant step g,
+    //     sum_k  rotate(ct, baby_k) (.) pt[g][k]                      (Bootstrapper.cpp:1969-2012)
+    // with one full key switch (incl. its division by the special modulus) per baby rotation.  Here the input is
+    // decomposed once, every baby rotation stops after the inner product with its key - an accumulator over the
+    // EXTENDED basis Q_l * P_S - the plaintexts are multiplied in that basis, and the division by P_S (ModDown) is done
+    // once per giant step on the sum.  The c0 halves need no key switch at all: rotate(ct)_0 = perm(c0) + ModDown(acc_0),
+    // and ModDown(P_S x) = x, so sum_k perm_k(c0) pt[g][k] is added after the ModDown.  Decrypted values equal the
+    // reference's up to key-switching noise (one rounding per giant step instead of one per baby step).
+    //   elts[k]: Galois element of baby step k, 1 = no rotation.  pts[g * n_baby + k]: extended plaintext
+    //   (bk_encode_ext at the ciphertext's level) or NULL where the group has no such term.  outs[g]: the giant step's
+    //   ciphertext at the input's level, scale = ct scale * plaintext scale.
+    bk_status bk_bsgs_inner_sums(bk_context_t ctx, bk_ct_t in, const uint32_t *elts, int n_baby, bk_gkeys_t gk,
+                                 const bk_pt_t *pts, int n_giant, bk_ct_t *outs)
+    {
+        BK_TRY
+        Context &c = *ctx;
+        check_ct(ctx, in, "encrypted");
+        if (!gk || gk->ctx != ctx)
+            throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+        if (in->size != 2 || !in->ntt)
+            throw std::invalid_argument("encrypted must be a size-2 ciphertext in NTT form");
+        if (n_baby < 1 || n_baby > 64 || n_giant < 1 || n_giant > 64)
+            throw std::invalid_argument("count is out of range");
+        if (!c.hybrid)
+            throw std::logic_error("double-hoisted inner sums need the level-aware hybrid key switching mode");
+        const int l = in->limbs;
+        const size_t n = c.n;
+        const HybridPlan &P = hybrid_plan(c, l);
+        const HybDims h{ l, P.alpha, P.dsize, P.dnum, c.n_primes - 1 };
+        const int ne = P.ne;
+        cudaStream_t s = c.stream();
+
+        // rotating babies: keys, tables
+        std::vector<int> rot_of((size_t)n_baby, -1);
+        std::vector<const uint32_t *> perms;
+        std::vector<bk_hybkey_s *> hks;
+        for (int k = 0; k < n_baby; k++)
+        {
+            if (elts[k] == 1)
+                continue;
+            if (!(elts[k] & 1) || elts[k] >= 2 * n)
+                throw std::invalid_argument("Galois element is not valid");
+            bk_kskey_t key = find_gkey(gk, elts[k]);
+            if (!key)
+                throw std::invalid_argument("Galois key not present");
+            if (!key->recipe)
+                throw std::logic_error("double-hoisted inner sums need keys generated in hybrid mode");
+            rot_of[(size_t)k] = (int)perms.size();
+            perms.push_back(c.galois_table(elts[k]));
+            hks.push_back(hybrid_key(c, key, l));
+        }
+        double pt_scale = 0;
+        for (int i = 0; i < n_giant * n_baby; i++)
+        {
+            bk_pt_t p = pts[i];
+            if (!p)
+                continue;
+            if (p->ctx != ctx || !p->d || p->limbs != l || p->ext != P.alpha)
+                throw std::invalid_argument("plain is not an extended plaintext of the ciphertext's level");
+            if (pt_scale == 0)
+                pt_scale = p->scale;
+            else if (!close_scale(p->scale, pt_scale))
+                throw std::invalid_argument("scale mismatch");
+        }
+        if (pt_scale == 0)
+            throw std::invalid_argument("no plaintext operands");
+        const double new_scale = in->scale * pt_scale;
+        if (!c.scale_in_bounds(new_scale, l))
+            throw std::invalid_argument("scale out of bounds");
+        for (int g = 0; g < n_giant; g++)
+            if (!outs[g] || outs[g]->ctx != ctx || outs[g] == in)
+                throw std::invalid_argument("destination is not valid");
+
+        const u64 *c0 = in->d, *c1 = in->d + (size_t)l * n;
+        const int count = (int)perms.size();
+        Scratch y(s, (size_t)l * n);
+        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
+        Scratch acc(s, (size_t)std::max(count, 1) * 2 * ne * n);
+        Scratch tl(s, (size_t)2 * P.alpha * n);
+        Scratch sum(s, (size_t)2 * ne * n);
+        Scratch base0(s, (size_t)l * n), base1(s, (size_t)l * n);
+        if (count > 0)
+        {
+            LdInvPlain ld{ c1, limb_map(l), n, nullptr };
+            launch_inv_blocks(c, s, ld, inter.p, l);
+            StInvScaled st{ y.p, n, P.d_prescale, P.d_limb_primes };
+            launch_inv_cols(c, s, inter.p, st, l);
+            hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, c1, count, perms.data(), hks.data(), acc.p, 1);
+        }
+        for (int g = 0; g < n_giant; g++)
+        {
+            const bk_pt_t *row = pts + (size_t)g * n_baby;
+            ensure_ct(outs[g], 2, l, false);
+            // (1) the key-switched halves, summed in the extended basis
+            int ext_terms = 0;
+            for (int k0 = 0; k0 < n_baby;)
+            {
+                MulSumArgs a{};
+                a.count = 0;
+                int k = k0;
+                for (; k < n_baby && a.count < MUL_SUM_TERMS; k++)
+                    if (row[k] && rot_of[(size_t)k] >= 0)
+                    {
+                        a.ct[a.count] = acc.p + (size_t)rot_of[(size_t)k] * 2 * ne * n;
+                        a.pt[a.count] = row[k]->d;
+                        a.count++;
+                    }
+                k0 = k;
+                if (!a.count)
+                    continue;
+                const size_t total2 = (size_t)2 * ne * n / 2;
+                ProfScope ps_ew(c, s, TAG_ELEMENTWISE, 2 * ne * a.count);
+                if (ext_terms == 0)
+                    k_mul_plain_sum<false><<<c.ew_grid(total2), 256, 0, s>>>(sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
+                else
+                    k_mul_plain_sum<true><<<c.ew_grid(total2), 256, 0, s>>>(sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
+                c.count();
+                ext_terms += a.count;
+            }
+            // (2) the c0 halves: permutations of the input's c0 (and c1 for the unrotated term), in the ordinary basis
+            int plain_terms = 0;
+            const bk_pt_s *identity = nullptr;
+            for (int k0 = 0; k0 < n_baby;)
+            {
+                GatherSumArgs a{};
+                a.count = 0;
+                int k = k0;
+                for (; k < n_baby && a.count < GATHER_SUM_TERMS; k++)
+                    if (row[k])
+                    {
+                        a.perm[a.count] = rot_of[(size_t)k] >= 0 ? perms[(size_t)rot_of[(size_t)k]] : nullptr;
+                        a.pt[a.count] = row[k]->d;
+                        a.count++;
+                        if (rot_of[(size_t)k] < 0)
+                            identity = row[k];
+                    }
+                k0 = k;
+                if (!a.count)
+                    continue;
+                ProfScope ps_ew(c, s, TAG_ELEMENTWISE, l * a.count);
+                if (plain_terms == 0)
+                    k_gather_mul_sum<false><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(base0.p, c0, a, c.d_primes, c.log_n, l);
+                else
+                    k_gather_mul_sum<true><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(base0.p, c0, a, c.d_primes, c.log_n, l);
+                c.count();
+                plain_terms += a.count;
+            }
+            if (!plain_terms)
+                throw std::invalid_argument("a giant step has no terms");
+            if (identity)
+            {
+                MulSumArgs a{};
+                a.count = 1;
+                a.ct[0] = c1;
+                a.pt[0] = identity->d;
+                ProfScope ps_ew(c, s, TAG_ELEMENTWISE, l);
+                k_mul_plain_sum<false><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(base1.p, a, c.d_primes, c.log_n, l, 1);
+                c.count();
+            }
+            if (ext_terms)
+                hyb_mod_down(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr, nullptr);
+            else
+            { // only the unrotated term: (c0 pt, c1 pt)
+                BK_CUDA(cudaMemcpyAsync(outs[g]->d, base0.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+                BK_CUDA(cudaMemcpyAsync(outs[g]->d + (size_t)l * n, base1.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            }
+            outs[g]->scale = new_scale;
+            outs[g]->ntt = true;
         }
         BK_END
     }

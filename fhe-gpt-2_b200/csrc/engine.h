@@ -306,6 +306,7 @@ struct bk_pt_s
     cudaStream_t owner = nullptr;
     size_t cap = 0;
     int limbs = 0;
+    int ext = 0; // > 0: `ext` further limbs follow the first `limbs` (bk_encode_ext): the special moduli of that level
     double scale = 1.0;
 };
 

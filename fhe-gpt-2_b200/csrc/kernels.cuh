@@ -307,6 +307,23 @@ __device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p)
     asm volatile("ld.global.nc.L1::no_allocate.v2.u64 {%0,%1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p));
     return v;
 }
+// Evaluation keys are read exactly once per key switch while the digits they are multiplied with are re-read for every
+// key (every baby rotation of a hoisted group) and every output modulus: key loads carry an L2 evict-first policy so
+// that hundreds of megabytes of key do not push the digit buffer out of the 126 MB L2.
+__device__ __forceinline__ u64 l2_evict_first_policy()
+{
+    u64 p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p, u64 policy)
+{
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+                 : "=l"(v.x), "=l"(v.y)
+                 : "l"(p), "l"(policy));
+    return v;
+}
 
 static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
 {
@@ -324,6 +341,7 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
     const u64 *k0 = a.key + (size_t)kl * n + e;
 
     u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
+    const u64 key_policy = l2_evict_first_policy();
 #pragma unroll 4
     for (int J = 0; J < a.l; J++)
     {
@@ -347,8 +365,8 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
         }
         else
             x = *reinterpret_cast<const ulonglong2 *>(dig + (size_t)J * n);
-        ulonglong2 w0 = ldg_stream2(k0 + (size_t)J * 2 * kstride);
-        ulonglong2 w1 = ldg_stream2(k0 + (size_t)J * 2 * kstride + kstride);
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)J * 2 * kstride, key_policy);
+        ulonglong2 w1 = ldg_stream2(k0 + (size_t)J * 2 * kstride + kstride, key_policy);
         mac128(l0x, h0x, x.x, w0.x);
         mac128(l0y, h0y, x.y, w0.y);
         mac128(l1x, h1x, x.x, w1.x);
@@ -495,20 +513,23 @@ struct LdHybPlain
     __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &) const { return src[(size_t)job * n + idx]; }
 };
 
+constexpr int HYB_MAC_BATCH = 32;
 struct HybMacArgs
 {
     const u64 *digits;     // [nE][dnum][N] NTT form, lazy; own-limb slots unused
     const u64 *target_ntt; // [l][N] NTT form
-    const uint32_t *perm;  // Galois table or null
-    const u64 *key;        // [dnum][2][ne][N]
-    u64 *acc;              // [2][ne][N]
+    const uint32_t *perm[HYB_MAC_BATCH]; // per rotation of a hoisted group (blockIdx.z): Galois table or null
+    const u64 *key[HYB_MAC_BATCH];       // per rotation: [dnum][2][ne][N]
+    u64 *acc;              // [rotations][2][ne][N]
     size_t n;
     HybDims h;
     int e0;
     int gather_digits;
 };
 
-// acc_p[e] = sum_d ext_d[e] * key[d][p][e]; grid = (ceil(N / 2 / threads), nE)
+// acc_p[e] = sum_d ext_d[e] * key[d][p][e]; grid = (ceil(N / 2 / threads), nE, rotations): all rotations of a hoisted
+// group in one launch - the digits of a chunk are shared by them and stay in L2, and one launch of thousands of CTAs
+// fills the machine where one launch per rotation left a ramp and a tail every 30 microseconds.
 static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTables T)
 {
     const int eloc = blockIdx.y;
@@ -520,18 +541,28 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
     const PrimeDev pd = T.primes[a.h.eprime(e)];
     const int ne = a.h.ne();
     const size_t kstride = (size_t)ne * n;
-    const u64 *k0 = a.key + (size_t)e * n + i;
+    const int rot = blockIdx.z;
+    const uint32_t *perm = a.perm[rot];
+    u64 *acc = a.acc + (size_t)rot * 2 * ne * n;
+    const u64 *k0 = a.key[rot] + (size_t)e * n + i;
     u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
-    for (int d = 0; d < a.h.dnum; d++)
+    const u64 key_policy = l2_evict_first_policy();
+    // gather indices are the same for every digit
+    size_t gx = i, gy = i + 1;
+    if (perm)
     {
+        gx = perm[i];
+        gy = perm[i + 1];
+    }
+    auto load_digit = [&](int d) -> ulonglong2 {
         ulonglong2 x;
         if (a.h.own(e, d))
         {
             const u64 *src = a.target_ntt + (size_t)e * n;
-            if (a.perm)
+            if (perm)
             {
-                x.x = src[a.perm[i]];
-                x.y = src[a.perm[i + 1]];
+                x.x = src[gx];
+                x.y = src[gy];
             }
             else
                 x = *reinterpret_cast<const ulonglong2 *>(src + i);
@@ -541,14 +572,37 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
             const u64 *src = a.digits + ((size_t)eloc * a.h.dnum + d) * n;
             if (a.gather_digits)
             {
-                x.x = src[a.perm[i]];
-                x.y = src[a.perm[i + 1]];
+                x.x = src[gx];
+                x.y = src[gy];
             }
             else
                 x = *reinterpret_cast<const ulonglong2 *>(src + i);
         }
-        ulonglong2 w0 = ldg_stream2(k0 + (size_t)d * 2 * kstride);
-        ulonglong2 w1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride);
+        return x;
+    };
+    // two digits per iteration: six independent loads in flight per thread before the first multiply
+    int d = 0;
+    for (; d + 1 < a.h.dnum; d += 2)
+    {
+        ulonglong2 xa = load_digit(d), xb = load_digit(d + 1);
+        ulonglong2 wa0 = ldg_stream2(k0 + (size_t)d * 2 * kstride, key_policy);
+        ulonglong2 wa1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride, key_policy);
+        ulonglong2 wb0 = ldg_stream2(k0 + (size_t)(d + 1) * 2 * kstride, key_policy);
+        ulonglong2 wb1 = ldg_stream2(k0 + (size_t)(d + 1) * 2 * kstride + kstride, key_policy);
+        mac128(l0x, h0x, xa.x, wa0.x);
+        mac128(l0y, h0y, xa.y, wa0.y);
+        mac128(l1x, h1x, xa.x, wa1.x);
+        mac128(l1y, h1y, xa.y, wa1.y);
+        mac128(l0x, h0x, xb.x, wb0.x);
+        mac128(l0y, h0y, xb.y, wb0.y);
+        mac128(l1x, h1x, xb.x, wb1.x);
+        mac128(l1y, h1y, xb.y, wb1.y);
+    }
+    if (d < a.h.dnum)
+    {
+        ulonglong2 x = load_digit(d);
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)d * 2 * kstride, key_policy);
+        ulonglong2 w1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride, key_policy);
         mac128(l0x, h0x, x.x, w0.x);
         mac128(l0y, h0y, x.y, w0.y);
         mac128(l1x, h1x, x.x, w1.x);
@@ -559,8 +613,8 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
     r0.y = barrett128(l0y, h0y, pd);
     r1.x = barrett128(l1x, h1x, pd);
     r1.y = barrett128(l1y, h1y, pd);
-    *reinterpret_cast<ulonglong2 *>(a.acc + (size_t)e * n + i) = r0;
-    *reinterpret_cast<ulonglong2 *>(a.acc + ((size_t)ne + e) * n + i) = r1;
+    *reinterpret_cast<ulonglong2 *>(acc + (size_t)e * n + i) = r0;
+    *reinterpret_cast<ulonglong2 *>(acc + ((size_t)ne + e) * n + i) = r1;
 }
 
 // ============================================================================================
@@ -663,9 +717,11 @@ struct MulSumArgs
     const u64 *pt[MUL_SUM_TERMS];
     int count;
 };
+// special_pos >= 0: limb `special_pos` of every polynomial belongs to prime `special_prime` (operands in the extended
+// basis of a key switch, whose last limb is the special prime).
 template <bool ACCUMULATE>
 __global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, MulSumArgs a, const PrimeDev *primes, int log_n,
-                                                       int limbs, int polys)
+                                                       int limbs, int polys, int special_pos = -1, int special_prime = 0)
 {
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
@@ -673,7 +729,8 @@ __global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, Mu
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     {
         const size_t e = i * 2, ep = e % per_poly;
-        const PrimeDev pd = primes[(int)(ep >> log_n)];
+        const int limb = (int)(ep >> log_n);
+        const PrimeDev pd = primes[limb == special_pos ? special_prime : limb];
         u64 lx = 0, hx = 0, ly = 0, hy = 0;
         if (ACCUMULATE)
         {
@@ -692,6 +749,37 @@ __global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, Mu
         r.x = barrett128(lx, hx, pd);
         r.y = barrett128(ly, hy, pd);
         *reinterpret_cast<ulonglong2 *>(dst + e) = r;
+    }
+}
+
+// dst[limbs][N] (+)= sum_t src[.][perm_t[x]] * pt_t[.][x]: the part of a double-hoisted BSGS inner sum that needs no key
+// switch (the c0 halves of the rotated ciphertexts are plain permutations of the input's c0).  perm_t == null: identity.
+constexpr int GATHER_SUM_TERMS = 16;
+struct GatherSumArgs
+{
+    const uint32_t *perm[GATHER_SUM_TERMS];
+    const u64 *pt[GATHER_SUM_TERMS];
+    int count;
+};
+template <bool ACCUMULATE>
+__global__ void __launch_bounds__(256) k_gather_mul_sum(u64 *__restrict__ dst, const u64 *__restrict__ src, GatherSumArgs a,
+                                                        const PrimeDev *primes, int log_n, int limbs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t total = (size_t)limbs * n;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const int limb = (int)(i >> log_n);
+        const size_t x = i & (n - 1);
+        const PrimeDev pd = primes[limb];
+        const u64 *row = src + (size_t)limb * n;
+        u64 lo = ACCUMULATE ? dst[i] : 0ull, hi = 0;
+        for (int t = 0; t < a.count; t++)
+        {
+            const size_t sx = a.perm[t] ? (size_t)a.perm[t][x] : x;
+            mac128(lo, hi, row[sx], a.pt[t][i]);
+        }
+        dst[i] = barrett128(lo, hi, pd);
     }
 }
 

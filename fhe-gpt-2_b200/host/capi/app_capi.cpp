@@ -385,6 +385,17 @@ extern "C"
         BKA_END
     }
 
+    int bka_session_double_hoisted_groups(bka_session_t s, uint64_t *count_out)
+    {
+        BKA_TRY
+#ifdef B200CKKS_FACADE
+        *count_out = s->evaluator->stats().double_hoisted_groups.load();
+#else
+        (void)s;
+        *count_out = 0;
+#endif
+        BKA_END
+    }
     int bka_session_key_plan(bka_session_t s, char *text_out, int cap, int *length_out)
     {
         BKA_TRY
@@ -632,9 +643,10 @@ extern "C"
     {
         BKA_TRY
         if (previous)
-            *previous = b->b->hoisting ? 1 : 0;
+            *previous = (b->b->hoisting ? 1 : 0) | ((b->b->hoisting && !b->b->double_hoisting) ? 2 : 0);
 #ifdef B200CKKS_FACADE
-        b->b->hoisting = on != 0;
+        b->b->hoisting = (on & 1) != 0;
+        b->b->double_hoisting = (on & 2) == 0;
 #else
         (void)on; // stock SEAL has no hoisted rotation
 #endif

@@ -18,9 +18,9 @@ namespace
     struct SignedPlan
     {
         int gs, basicstart, giantfirst, giantlast;
-        explicit SignedPlan(int totlen)
+        explicit SignedPlan(int totlen, int width = 0)
         {
-            gs = giantstep(2 * totlen + 1);
+            gs = width > 0 ? width : giantstep(2 * totlen + 1);
             basicstart = -totlen + gs * (totlen / gs);
             giantfirst = -(totlen / gs);
             giantlast = (2 * totlen) / gs + giantfirst;
@@ -47,8 +47,15 @@ Bootstrapper::Bootstrapper(long _loge, long _logn, long _logNh, long _L, double 
     Nh = 1L << logNh;
 #ifdef B200CKKS_FACADE
     hoisting = std::getenv("B200CKKS_NO_HOIST") == nullptr;
+    double_hoisting = std::getenv("B200CKKS_NO_DOUBLE_HOIST") == nullptr;
+    {
+        int hybrid = 0;
+        bk_context_hybrid(context.handle(), &hybrid, nullptr, nullptr);
+        wide_babies = hoisting && double_hoisting && hybrid != 0;
+    }
 #else
     hoisting = false;
+    double_hoisting = false;
 #endif
     mod_reducer = new ModularReducer(boundary_K, (double)loge, sin_cos_deg, scale_factor, inverse_deg, context, encoder,
                                      encryptor, evaluator, relin_keys, decryptor);
@@ -132,6 +139,39 @@ void Bootstrapper::addLeftRotKeys_Linear_to_vector_3(vector<int> &steps)
     for (int i = p3.giantfirst; i <= p3.giantlast; i++)
         if (i != 0)
             push_unique(steps, wrap(i * p3.gs * s.basicstep[2]));
+    if (!wide_babies)
+        return;
+    // the baby-step splits of double hoisting (bsgs_width picks the width from the level the transform runs at): every
+    // stage of both directions, signed and rotated form, every width up to the cap.  Declaring a key costs nothing on
+    // the engine - keys are generated for the (element, level) pairs that are used.
+    const Split both[2] = { split_encode(logn), split_decode(logn) };
+    const char *cap_env = std::getenv("B200CKKS_BSGS_MAX_BABY");
+    const int cap = cap_env ? std::max(2, std::atoi(cap_env)) : 32;
+    for (const Split &sp : both)
+        for (int st = 0; st < 3; st++)
+        {
+            const int t = sp.totlen[st], b = sp.basicstep[st];
+            for (int k = 1; k <= cap; k++)
+            {
+                if (k <= 2 * t + 1)
+                {
+                    const SignedPlan ps(t, k);
+                    for (int i = ps.basicstart; i < ps.basicstart + ps.gs; i++)
+                        if (i != 0)
+                            push_unique(steps, wrap(i * b));
+                    for (int i = ps.giantfirst; i <= ps.giantlast; i++)
+                        if (i != 0)
+                            push_unique(steps, wrap(i * ps.gs * b));
+                }
+                if (k <= t + 1)
+                {
+                    for (int i = 1; i < k; i++)
+                        push_unique(steps, wrap(i * b));
+                    for (int i = 1; i <= t / k; i++)
+                        push_unique(steps, wrap(i * k * b));
+                }
+            }
+        }
 }
 
 void Bootstrapper::find_slot_index()
@@ -320,11 +360,56 @@ namespace
     }
 } // namespace
 
+// Baby-step count of a transform over M diagonals on a ciphertext of `limbs` limbs.  The reference balances baby and
+// giant rotations (giantstep(), common/func.cpp:203-213: both cost a full key switch there).  With double-hoisted
+// inner sums a baby rotation is only the inner product with its key, a giant step costs a ModDown plus (beyond the
+// first) a full key switch, so the optimum moves towards more babies and fewer giants - how far depends on the level:
+// near the top few primes are idle, keys have many digits and the inner product (a stream over the whole key) is not
+// cheap.  Costs in forward-NTT equivalents (about 1 us at N = 2^16 on B200), from the shape of the level-aware key
+// switch (alpha special moduli, dnum digits, ne = limbs + alpha extended limbs):
+//   baby    b = 0.2 * 2 dnum ne                         (key stream at ~2.5 TB/s)
+//   ModDown m = 2 alpha + 2 alpha limbs / 8 + 2 limbs
+//   switch  g = dnum ne + dnum dsize limbs / 8 + m + b   (decomposition + ModDown + inner product)
+// minimise (k - 1) b + ceil(M / k) m + (ceil(M / k) - 1) g over k <= $B200CKKS_BSGS_MAX_BABY (default 32).
+int Bootstrapper::bsgs_width(int M, int limbs) const
+{
+    if (!wide_babies)
+        return giantstep(M);
+#ifdef B200CKKS_FACADE
+    static const int cap = [] {
+        const char *e = std::getenv("B200CKKS_BSGS_MAX_BABY");
+        return e ? std::max(2, std::atoi(e)) : 32;
+    }();
+    int alpha = 1, dsize = 1;
+    bk_context_hybrid_shape(context.handle(), limbs, &alpha, &dsize);
+    const double dnum = (limbs + dsize - 1) / dsize, ne = limbs + alpha;
+    const double b = 0.2 * 2 * dnum * ne;
+    const double m = 2.0 * alpha + 2.0 * alpha * limbs / 8.0 + 2.0 * limbs;
+    const double g = dnum * ne + dnum * dsize * limbs / 8.0 + m + b;
+    double best = 1e300;
+    int arg = 1;
+    for (int k = 1; k <= std::min(M, cap); k++)
+    {
+        const int giants = (M + k - 1) / k;
+        const double cost = (k - 1) * b + giants * m + (giants - 1) * g;
+        if (cost < best - 1e-9)
+        {
+            best = cost;
+            arg = k;
+        }
+    }
+    return arg;
+#else
+    (void)limbs;
+    return giantstep(M);
+#endif
+}
+
 void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
                                          int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
                                          std::uint64_t cache_variant)
 {
-    const SignedPlan p(totlen);
+    const SignedPlan p(totlen, bsgs_width(2 * totlen + 1, (int)cipher.coeff_modulus_size()));
     const int N = (int)Nh;
     auto wrap = [N](int step) { return ((step % N) + N) % N; };
 
@@ -336,6 +421,45 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
         vector<int> steps;
         for (int i = p.basicstart; i < p.basicstart + p.gs; i++)
             steps.push_back(i == 0 ? 0 : wrap(i * basicstep));
+        if (double_hoisting)
+        {
+            // all inner sums in one call: the baby rotations stay in the extended basis, one ModDown per giant step
+            vector<vector<std::pair<int, std::uint64_t>>> groups;
+            vector<int> giant_of;
+            for (int i = p.giantfirst; i <= p.giantlast; i++)
+            {
+                const int jlast = (i != p.giantlast) ? p.basicstart + p.gs - 1 : totlen - i * p.gs;
+                groups.emplace_back();
+                giant_of.push_back(i);
+                for (int j = p.basicstart; j <= jlast; j++)
+                    groups.back().emplace_back(j - p.basicstart, (std::uint64_t)(i * p.gs + j + totlen));
+            }
+            vector<Ciphertext> giants;
+            vector<complex<double>> rot;
+            if (evaluator.bsgs_inner_sums_cached(cipher, steps, gal_keys, groups, cache_owner, cache_variant,
+                                                 [&](std::size_t g, std::uint64_t diag) -> const vector<complex<double>> & {
+                                                     rotation(coeff_logn, N, -giant_of[g] * p.gs * basicstep, fftcoeff[(std::size_t)diag], rot);
+                                                     return rot;
+                                                 },
+                                                 giants))
+            {
+                Ciphertext total, product;
+                bool total_started = false;
+                for (std::size_t g = 0; g < giants.size(); g++)
+                {
+                    const int i = giant_of[g];
+                    if (i != 0)
+                    {
+                        evaluator.rotate_vector(giants[g], wrap(i * p.gs * basicstep), gal_keys, product);
+                        accumulate(evaluator, total, total_started, product);
+                    }
+                    else
+                        accumulate(evaluator, total, total_started, giants[g]);
+                }
+                rtncipher = total;
+                return;
+            }
+        }
         evaluator.rotate_vector_hoisted(cipher, steps, gal_keys, babyct);
         babies_done = true;
     }
@@ -382,7 +506,7 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
                                                  int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
                                                  std::uint64_t cache_variant)
 {
-    const int gs = giantstep(totlen + 1);
+    const int gs = bsgs_width(totlen + 1, (int)cipher.coeff_modulus_size());
     const int giantlast = totlen / gs;
     const int N = (int)Nh;
     auto wrap = [N](int step) { return ((step % N) + N) % N; };
@@ -395,6 +519,41 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
         vector<int> steps;
         for (int i = 0; i < gs; i++)
             steps.push_back(i == 0 ? 0 : wrap(i * basicstep));
+        if (double_hoisting)
+        {
+            vector<vector<std::pair<int, std::uint64_t>>> groups;
+            for (int i = 0; i <= giantlast; i++)
+            {
+                const int jlast = (i != giantlast) ? gs - 1 : totlen - i * gs;
+                groups.emplace_back();
+                for (int j = 0; j <= jlast; j++)
+                    groups.back().emplace_back(j, (std::uint64_t)(i * gs + j));
+            }
+            vector<Ciphertext> giants;
+            vector<complex<double>> rot;
+            if (evaluator.bsgs_inner_sums_cached(cipher, steps, gal_keys, groups, cache_owner, cache_variant,
+                                                 [&](std::size_t g, std::uint64_t diag) -> const vector<complex<double>> & {
+                                                     rotation(coeff_logn, N, -(int)g * gs * basicstep, fftcoeff[(std::size_t)diag], rot);
+                                                     return rot;
+                                                 },
+                                                 giants))
+            {
+                Ciphertext total, product;
+                bool total_started = false;
+                for (std::size_t g = 0; g < giants.size(); g++)
+                {
+                    if (g != 0)
+                    {
+                        evaluator.rotate_vector(giants[g], wrap((int)g * gs * basicstep), gal_keys, product);
+                        accumulate(evaluator, total, total_started, product);
+                    }
+                    else
+                        accumulate(evaluator, total, total_started, giants[g]);
+                }
+                rtncipher = total;
+                return;
+            }
+        }
         evaluator.rotate_vector_hoisted(cipher, steps, gal_keys, babyct);
         babies_done = true;
     }

@@ -55,6 +55,15 @@ public:
     // limbs than the reference's one-by-one rotations.  Off = the reference's exact operation sequence.  Default: on,
     // unless $B200CKKS_NO_HOIST is set; always off on stock SEAL.
     bool hoisting;
+    // With hoisting on and the engine in level-aware hybrid mode, the inner sums of a transform are double-hoisted
+    // (Evaluator::bsgs_inner_sums_cached): the baby rotations stay in the extended basis of the key switch and every
+    // giant step pays one division by the special modulus instead of one per baby rotation.  Default: on, unless
+    // $B200CKKS_NO_DOUBLE_HOIST is set.
+    bool double_hoisting;
+    // fixed at construction (it decides the rotation keys): double hoisting available -> transforms use bsgs_width()
+    // baby steps instead of the reference's balanced giantstep() split
+    bool wide_babies = false;
+    int bsgs_width(int M, int limbs) const;
 
     Bootstrapper(long _loge, long _logn, long _logNh, long _L, double _final_scale, long _boundary_K, long _sin_cos_deg,
                  long _scale_factor, long _inverse_deg, seal::SEALContext &_context, seal::KeyGenerator &_keygen,

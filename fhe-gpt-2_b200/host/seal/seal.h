@@ -1282,6 +1282,21 @@ namespace seal
         {
             encode_at(values.data(), values.size(), limbs, scale, destination, true);
         }
+        // the same plus the special moduli of the level-aware key switch at that level (bk_encode_ext): the operand
+        // format of Evaluator::bsgs_inner_sums_cached
+        void encode_ext(const std::vector<double> &values, int limbs, double scale, Plaintext &destination) const
+        {
+            destination.bind(context_.impl());
+            detail::check(bk_encode_ext(context_.handle(), values.data(), (int)values.size(), 0, limbs, scale, destination.handle()));
+            destination.pull();
+        }
+        void encode_ext(const std::vector<std::complex<double>> &values, int limbs, double scale, Plaintext &destination) const
+        {
+            destination.bind(context_.impl());
+            detail::check(bk_encode_ext(context_.handle(), reinterpret_cast<const double *>(values.data()), (int)values.size(), 1,
+                                        limbs, scale, destination.handle()));
+            destination.pull();
+        }
 
     private:
         void encode_at(const double *v, std::size_t n, int limbs, double scale, Plaintext &dst, bool top_dropped) const
@@ -1371,6 +1386,7 @@ namespace seal
         std::atomic<std::uint64_t> key_switch_rotate{ 0 }, key_switch_relin{ 0 }, rescale{ 0 }, multiply{ 0 },
             multiply_plain{ 0 }, encode_vector{ 0 }, add{ 0 }, mod_switch{ 0 }, scalar_op{ 0 };
         std::atomic<std::uint64_t> cache_hits{ 0 }, cache_misses{ 0 }; // multiply_vector_inplace_cached
+        std::atomic<std::uint64_t> double_hoisted_groups{ 0 };         // giant steps served by bsgs_inner_sums_cached
         std::atomic<std::uint64_t> hoisted_rotations{ 0 };             // rotate_vector_hoisted (also counted as rotations)
         // the same events by coeff_modulus_size of the ciphertext operand: [0] key switches (rotate + relinearize),
         // [1] rescales, [2] vector encode + multiply_plain, [3] ct x ct multiplications, [4] scalar ops, [5] add/sub
@@ -1972,6 +1988,89 @@ namespace seal
             detail::check(bk_multiply_plain_sum(h(), destination.handle(), cts.data(), pts.data(), (int)cts.size()));
             destination.pull();
         }
+        // Double-hoisted inner sums of a baby-step / giant-step linear transform (bk_bsgs_inner_sums):
+        //   giants[g] = sum over (k, index) in groups[g] of rotate_vector(encrypted, baby_steps[k]) * (vector named
+        //   (owner, index, variant)),   baby_steps[k] == 0 meaning "no rotation".
+        // The input is decomposed once, the baby rotations stay in the extended basis of the key switch, the (cached,
+        // extended) plaintexts are multiplied there and each giant step pays one division by the special modulus
+        // instead of one per baby rotation.  Returns false - nothing done - where that path does not apply (level-aware
+        // hybrid mode off, a baby step without a declared key); the caller then takes rotate_vector_hoisted +
+        // multiply_vector_sum_cached.  Tolerance mode: values equal the rotation-by-rotation sequence up to
+        // key-switching noise.  make_at(g, index) builds the slot vector of a term that is not cached yet.
+        template <class MakeAt>
+        bool bsgs_inner_sums_cached(
+            const Ciphertext &encrypted, const std::vector<int> &baby_steps, const GaloisKeys &galois_keys,
+            const std::vector<std::vector<std::pair<int, std::uint64_t>>> &groups, const void *owner, std::uint64_t variant,
+            MakeAt &&make_at, std::vector<Ciphertext> &giants)
+        {
+            int hybrid = 0;
+            bk_context_hybrid(h(), &hybrid, nullptr, nullptr);
+            if (!hybrid || !galois_keys.handle() || groups.empty() || baby_steps.empty())
+                return false;
+            need(encrypted, "encrypted");
+            if (encrypted.size() != 2)
+                return false;
+            const int limbs = (int)encrypted.coeff_modulus_size();
+            std::vector<std::uint32_t> elts(baby_steps.size(), 1);
+            for (std::size_t k = 0; k < baby_steps.size(); k++)
+            {
+                if (baby_steps[k] == 0)
+                    continue;
+                detail::check(bk_galois_elt_from_step(context_.impl()->log_n, baby_steps[k], &elts[k]));
+                if (!galois_keys.has_key(elts[k]))
+                    return false;
+            }
+            for (std::size_t k = 0; k < baby_steps.size(); k++)
+                if (elts[k] != 1)
+                    galois_keys.ensure(elts[k], limbs);
+            const std::size_t nb = baby_steps.size(), ng = groups.size();
+            std::vector<std::unique_ptr<Plaintext>> once;
+            std::vector<bk_pt_t> pts(ng * nb, nullptr);
+            std::size_t terms = 0, rotating = 0;
+            for (std::size_t g = 0; g < ng; g++)
+                for (auto &term : groups[g])
+                {
+                    once.emplace_back();
+                    const std::uint64_t index = term.second;
+                    const Plaintext &plain = named_plaintext(limbs, encrypted.scale(), owner, index, variant,
+                                                             [&]() -> decltype(make_at(g, index)) { return make_at(g, index); },
+                                                             once.back(), true);
+                    plain.push();
+                    pts[g * nb + (std::size_t)term.first] = plain.handle();
+                    terms++;
+                }
+            for (std::size_t k = 0; k < nb; k++)
+                rotating += elts[k] != 1;
+            giants.resize(ng);
+            std::vector<bk_ct_t> outs;
+            for (auto &c : giants)
+            {
+                c.bind(context_.impl());
+                outs.push_back(c.handle());
+            }
+            encrypted.push();
+            {
+                std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
+                detail::check(bk_bsgs_inner_sums(h(), encrypted.handle(), elts.data(), (int)nb, galois_keys.handle(), pts.data(),
+                                                 (int)ng, outs.data()));
+            }
+            for (auto &c : giants)
+                c.pull();
+            // counted as what the rotation-by-rotation sequence would have done
+            stats_.key_switch_rotate += rotating;
+            stats_.hoisted_rotations += rotating;
+            stats_.double_hoisted_groups += ng;
+            for (std::size_t k = 0; k < rotating; k++)
+                stats_.hit(0, (std::size_t)limbs);
+            stats_.encode_vector += terms;
+            stats_.multiply_plain += terms;
+            stats_.add += terms - ng;
+            for (std::size_t t = 0; t < terms; t++)
+                stats_.hit(2, (std::size_t)limbs);
+            for (std::size_t t = ng; t < terms; t++)
+                stats_.hit(5, (std::size_t)limbs);
+            return true;
+        }
         // drop every cached plaintext of `owner` (call before the owner's storage is released or rewritten)
         void forget_cached(const void *owner) const
         {
@@ -1979,7 +2078,7 @@ namespace seal
             for (auto it = plain_cache_.begin(); it != plain_cache_.end();)
                 if (it->first.owner == owner)
                 {
-                    cache_bytes_ -= (std::uint64_t)it->first.limbs * (8ull << context_.impl()->log_n);
+                    cache_bytes_ -= (std::uint64_t)std::abs(it->first.limbs) * (8ull << context_.impl()->log_n);
                     it = plain_cache_.erase(it);
                 }
                 else
@@ -2126,18 +2225,27 @@ namespace seal
         // budget allows; otherwise handed back through `once`, which then owns it)
         template <class Make>
         const Plaintext &named_plaintext(int limbs, double scale, const void *owner, std::uint64_t index, std::uint64_t variant,
-                                         Make &&make, std::unique_ptr<Plaintext> &once) const
+                                         Make &&make, std::unique_ptr<Plaintext> &once, bool ext = false) const
         {
+            auto encode = [&](Plaintext &dst) {
+                if (ext)
+                    encoder_.encode_ext(make(), limbs, scale, dst);
+                else
+                    encoder_.encode_top_dropped(make(), limbs, scale, dst);
+            };
             if (!owner || !cache_budget_bytes())
             {
                 once = std::make_unique<Plaintext>();
-                encoder_.encode_top_dropped(make(), limbs, scale, *once);
+                encode(*once);
                 return *once;
             }
             std::uint64_t scale_bits;
             static_assert(sizeof(double) == sizeof(std::uint64_t), "");
             std::memcpy(&scale_bits, &scale, sizeof(scale));
-            PlainKey key{ owner, index, variant, scale_bits, limbs };
+            int ext_limbs = 0;
+            if (ext)
+                detail::check(bk_context_hybrid_shape(h(), limbs, &ext_limbs, nullptr));
+            PlainKey key{ owner, index, variant, scale_bits, ext ? -(limbs + ext_limbs) : limbs };
             {
                 std::shared_lock<std::shared_mutex> rl(cache_mu_);
                 auto it = plain_cache_.find(key);
@@ -2148,8 +2256,8 @@ namespace seal
                 }
             }
             auto plain = std::make_unique<Plaintext>();
-            encoder_.encode_top_dropped(make(), limbs, scale, *plain);
-            std::uint64_t bytes = (std::uint64_t)limbs * (8ull << context_.impl()->log_n);
+            encode(*plain);
+            std::uint64_t bytes = (std::uint64_t)(limbs + ext_limbs) * (8ull << context_.impl()->log_n);
             std::unique_lock<std::shared_mutex> wl(cache_mu_);
             if (cache_bytes_ + bytes > cache_budget_bytes())
             { // over budget: use it once, do not keep it

@@ -218,6 +218,11 @@ class Session:
         self.app.ck(self.app.L.bka_session_key_residency(self.h, C.byref(b), C.byref(g)))
         return b.value, g.value
 
+    def double_hoisted_groups(self):
+        n = C.c_uint64()
+        self.app.ck(self.app.L.bka_session_double_hoisted_groups(self.h, C.byref(n)))
+        return n.value
+
     def key_plan(self):
         """text of the (Galois element, level) pairs and relinearization levels the keys cover so far"""
         n = C.c_int()
@@ -369,10 +374,11 @@ class Bootstrapper:
             self.s.app.L.bka_bootstrapper_destroy(self.h)
             self.h = None
 
-    def set_hoisting(self, on):
+    def set_hoisting(self, on, double=True):
+        """hoisted baby steps on / off; double=False keeps one ModDown per baby rotation (no double hoisting)"""
         prev = C.c_int()
-        self.s.app.ck(self.s.app.L.bka_bootstrapper_set_hoisting(self.h, int(on), C.byref(prev)))
-        return bool(prev.value)
+        self.s.app.ck(self.s.app.L.bka_bootstrapper_set_hoisting(self.h, (1 if on else 0) | (0 if double else 2), C.byref(prev)))
+        return bool(prev.value & 1)
 
     def rotation_steps(self):
         buf = np.zeros(4096, dtype=np.int32)

@@ -89,6 +89,9 @@ bk_status bk_stream(bk_context_t ctx, void **stream_out);
 bk_status bk_context_set_rng_key(bk_context_t ctx, const uint8_t key[32]);
 bk_status bk_context_set_hybrid(bk_context_t ctx, int on);
 bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys);
+/* shape of the level-aware key switch at `limbs` limbs: alpha special moduli (alpha - 1 idle primes + the special
+ * prime), digits of dsize primes */
+bk_status bk_context_hybrid_shape(bk_context_t ctx, int limbs, int *alpha_out, int *dsize_out);
 /* block until every stream of the device has drained (before an object other host threads may be reading is freed). */
 bk_status bk_sync_device(bk_context_t ctx);
 /* Hand-over points between host threads (the reference runs one image per OpenMP thread over shared keys,
@@ -208,6 +211,19 @@ bk_status bk_complex_conjugate_inplace(bk_context_t ctx, bk_ct_t a, bk_gkeys_t g
  * of BSGS linear transforms.  outs[k] must be distinct ciphertext objects different from `in`. */
 bk_status bk_apply_galois_hoisted(bk_context_t ctx, bk_ct_t in, const uint32_t *galois_elts, int count, bk_gkeys_t gk,
                                   bk_ct_t *outs);
+/* Double-hoisted inner sums of a baby-step / giant-step linear transform (Bootstrapper::bsgs_linear_transform,
+ * Bootstrapper.cpp:1952-2016, inner loop :1995-2012): outs[g] = sum_k rotate(ct, baby_k) (.) pts[g * n_baby + k].
+ * The input is decomposed once, the baby rotations stay in the extended basis Q_l * P_S, the plaintexts (extended,
+ * bk_encode_ext) are multiplied there, and the division by P_S is done once per giant step instead of once per baby
+ * rotation.  elts[k] = 1 means "no rotation"; NULL plaintexts are skipped.  Level-aware hybrid mode only
+ * (BK_LOGIC_ERROR otherwise); tolerance mode: decrypted values equal the rotation-by-rotation sequence up to
+ * key-switching noise. */
+bk_status bk_bsgs_inner_sums(bk_context_t ctx, bk_ct_t in, const uint32_t *elts, int n_baby, bk_gkeys_t gk,
+                             const bk_pt_t *pts, int n_giant, bk_ct_t *outs);
+/* CKKSEncoder::encode at `limbs` limbs plus the special moduli the level-aware key switch uses at that level (the
+ * operand format of bk_bsgs_inner_sums); usable as an ordinary plaintext of that level as well. */
+bk_status bk_encode_ext(bk_context_t ctx, const double *values, int n_values, int is_complex, int limbs, double scale,
+                        bk_pt_t out);
 bk_status bk_add_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);        /* :1578-1650 */
 bk_status bk_sub_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);        /* :1652-1724 */
 bk_status bk_multiply_plain_inplace(bk_context_t ctx, bk_ct_t a, bk_pt_t p);   /* :1726-1761,1891-1930 */

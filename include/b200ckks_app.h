@@ -108,6 +108,10 @@ int bka_bootstrapper_destroy(bka_bootstrapper_t b);
 /* baby-step rotations through one shared decomposition (engine; default on unless $B200CKKS_NO_HOIST) or one by one
  * exactly as the reference issues them (0).  Returns the previous setting in *previous (may be NULL). */
 int bka_bootstrapper_set_hoisting(bka_bootstrapper_t b, int on, int *previous);
+/* `on` above: bit 0 = hoisted baby steps; bit 1 set = WITHOUT the double-hoisted inner sums (one ModDown per giant step,
+ * Evaluator::bsgs_inner_sums_cached; level-aware hybrid mode), which are otherwise used together with hoisting unless
+ * $B200CKKS_NO_DOUBLE_HOIST is set.  bka_session_double_hoisted_groups: giant steps served that way so far. */
+int bka_session_double_hoisted_groups(bka_session_t s, uint64_t *count_out);
 /* steps of addLeftRotKeys_Linear_to_vector_3 for this logn, appended to steps_out (capacity cap) */
 int bka_bootstrapper_rotation_steps(bka_bootstrapper_t b, int *steps_out, int cap, int *count_out);
 /* LT coefficients: which = 0..2 SlotToCoeff matrices 1..3, 3..5 CoeffToSlot matrices 1..3.

@@ -68,3 +68,40 @@ def test_hybrid_key_switch_decrypts_like_the_reference_path(log_n, bits, levels)
     # l <= 5 use in hybrid mode; in between, digits are one prime smaller than P_S and the error is ~2e-8
     for op, errs in worst.items():
         assert max(errs) < 3e-6, (op, errs)
+
+
+@pytest.mark.parametrize("log_n,logn", [(12, 9), (16, 14)])
+def test_double_hoisted_bootstrap_matches_single_hoisting(log_n, logn):
+    """Double hoisting (one division by the special modulus per giant step: bk_bsgs_inner_sums) against the hoisted and
+    the rotation-by-rotation bootstraps on the same input: same level, scale and values within the bootstrapping error."""
+    import os
+    import sys
+
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__)))
+    import app_cases as cases
+    from b200ckks.app import App
+
+    old = os.environ.get("B200CKKS_HYBRID_KS")
+    os.environ["B200CKKS_HYBRID_KS"] = "1"
+    try:
+        s = App().session(log_n, cases.BOOT_BITS, hamming_weight=64 if log_n < 16 else 192)
+    finally:
+        if old is None:
+            del os.environ["B200CKKS_HYBRID_KS"]
+        else:
+            os.environ["B200CKKS_HYBRID_KS"] = old
+    n = 1 << logn
+    xs = np.tile(np.random.default_rng(4).uniform(-1, 1, n), s.slots // n)
+    boot = s.bootstrapper(logn)
+    out = {}
+    for name, (on, double) in {"one by one": (False, False), "hoisted": (True, False), "double hoisted": (True, True)}.items():
+        boot.set_hoisting(on, double=double)
+        before = s.double_hoisted_groups()
+        ct = boot.bootstrap(s.encrypt(xs, 2.0 ** 46, limbs=1), real_message=True)
+        assert ct.info() == (2, 17, 2.0 ** 46)
+        used = s.double_hoisted_groups() - before
+        assert (used > 0) == (name == "double hoisted"), (name, used)
+        out[name] = s.decrypt(ct)
+        assert np.abs(out[name] - xs).max() < 5e-5, name
+    assert np.abs(out["double hoisted"] - out["hoisted"]).max() < 5e-5
+    s.close()
