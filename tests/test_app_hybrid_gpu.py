@@ -56,8 +56,9 @@ def test_resnet20_hybrid_key_switching(hybrid_session):
     assert np.abs(together[0] - logits).max() < 5e-3
     kb, generated = s.key_residency()
     # level-specific keys: ceil(l / dsize) digits over l + alpha moduli instead of l digits over l + 1 (4x smaller at
-    # l = 20); measured 39.8 GiB against 60.6 GiB on the reference-exact path
-    assert 2 ** 30 < kb < 50 * 2 ** 30, kb
+    # l = 20); measured 39.8 GiB against 60.6 GiB on the reference-exact path.  Double-hoisted transforms use more baby
+    # steps (up to 32 per stage, each with its own key at that level): 52.8 GiB.
+    assert 2 ** 30 < kb < 70 * 2 ** 30, kb
 
 
 def test_resnet20_with_the_references_trained_parameters(hybrid_session):
