@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <condition_variable>
 #include <cstring>
+#include <fstream>
 #include <functional>
 #include <memory>
 #include <mutex>
@@ -588,10 +589,65 @@ extern "C"
         auto k = std::make_shared<RelinKeys::Holder>();
         seal::detail::check(bk_kskey_upload(s->context->handle(), host, digits, 0, &k->h));
         s->relin_keys.k_ = k;
+        s->relin_keys.ctx_ = s->context->impl();
 #else
         (void)s, (void)host, (void)digits;
         throw std::logic_error("raw key import is an engine-backend feature");
 #endif
+        BKA_END
+    }
+    // SEAL's wire format through files.  what: 0 ciphertext, 2 relinearization keys, 3 Galois keys, 4 secret key,
+    // 5 public key
+    int bka_save(bka_session_t s, int what, bka_ct_t ct, const char *path)
+    {
+        BKA_TRY
+        std::ofstream f(path, std::ios::binary);
+        if (!f)
+            throw std::runtime_error("cannot open file");
+        switch (what)
+        {
+        case 0: ct->ct.save(f, compr_mode_type::none); break;
+        case 2: s->relin_keys.save(f, compr_mode_type::none); break;
+        case 3:
+            s->ensure_keys();
+            s->gal_keys.save(f, compr_mode_type::none);
+            break;
+        case 4: s->secret_key.save(f, compr_mode_type::none); break;
+        case 5: s->public_key.save(f, compr_mode_type::none); break;
+        default: throw std::invalid_argument("what must be 0, 2, 3, 4 or 5");
+        }
+        BKA_END
+    }
+    int bka_load(bka_session_t s, int what, const char *path, bka_ct_t *ct_out)
+    {
+        BKA_TRY
+        std::ifstream f(path, std::ios::binary);
+        if (!f)
+            throw std::runtime_error("cannot open file");
+        switch (what)
+        {
+        case 0:
+        {
+            Ciphertext c;
+            c.load(*s->context, f);
+            *ct_out = wrap(std::move(c));
+            break;
+        }
+        case 2: s->relin_keys.load(*s->context, f); break;
+        case 3:
+            s->gal_keys.load(*s->context, f);
+            s->keys_ready = true; // loaded keys are complete: nothing is generated afterwards
+            break;
+        case 4:
+            s->secret_key.load(*s->context, f);
+            s->decryptor = std::make_unique<Decryptor>(*s->context, s->secret_key);
+            break;
+        case 5:
+            s->public_key.load(*s->context, f);
+            s->encryptor = std::make_unique<Encryptor>(*s->context, s->public_key);
+            break;
+        default: throw std::invalid_argument("what must be 0, 2, 3, 4 or 5");
+        }
         BKA_END
     }
     int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex)

@@ -39,6 +39,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <iosfwd>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -105,6 +106,16 @@ namespace seal
     {
         mm_default = 0
     };
+    // serialization.h: the reference's SEAL is built without zlib / zstd here, so is this
+    enum class compr_mode_type : std::uint8_t
+    {
+        none = 0
+    };
+    struct Serialization
+    {
+        static constexpr compr_mode_type compr_mode_default = compr_mode_type::none;
+    };
+    class SEALContext;
 
     // memory pools are a host-allocator concept of the reference; kept as an ignorable handle so
     // that call sites passing a pool still compile
@@ -563,6 +574,13 @@ namespace seal
         {
             return ctx_;
         }
+        // SEAL's wire format (seal/serialization.h; plaintext.cpp:204-300)
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff load(const SEALContext &context, std::istream &stream);
+        std::streamoff unsafe_load(const SEALContext &context, std::istream &stream)
+        {
+            return load(context, stream);
+        }
 
     private:
         void release()
@@ -763,6 +781,11 @@ namespace seal
             detail::check(bk_ct_upload(h_, host, size, limbs, scale, ntt ? 1 : 0));
             pull();
         }
+        // SEAL's wire format (seal/serialization.h; ciphertext.cpp:183-360)
+        std::streamoff save_size(compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff unsafe_load(const SEALContext &context, std::istream &stream);
+        std::streamoff load(const SEALContext &context, std::istream &stream);
 
     private:
         void swap(Ciphertext &o) noexcept
@@ -836,6 +859,8 @@ namespace seal
             sk.sk_ = h;
             return sk;
         }
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff load(const SEALContext &context, std::istream &stream);
         std::shared_ptr<detail::SkHolder> sk_;
     };
 
@@ -846,6 +871,8 @@ namespace seal
         {
             return ct_;
         }
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff load(const SEALContext &context, std::istream &stream);
         Ciphertext ct_;
     };
 
@@ -884,7 +911,11 @@ namespace seal
             detail::check(bk_kskey_drop_secret(k_->h));
             k_->sk.reset();
         }
+        // SEAL's wire format (seal/serialization.h; kswitchkeys.cpp:42-145): full-size keys in SEAL's layout only
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff load(const SEALContext &context, std::istream &stream);
         std::shared_ptr<Holder> k_;
+        CtxImpl ctx_;
     };
 
     // Galois keys: the set of elements is fixed by create_galois_keys (galoiskeys.h:48-74); each key is
@@ -1018,6 +1049,10 @@ namespace seal
                 detail::check(bk_kskey_prepare_level(k, limbs));
             }
         }
+        // SEAL's wire format (seal/serialization.h; kswitchkeys.cpp:42-145, galoiskeys.h): save needs every declared key
+        // at full size in SEAL's layout (generated now if necessary); loaded keys are complete and need no secret key
+        std::streamoff save(std::ostream &stream, compr_mode_type compr_mode = Serialization::compr_mode_default) const;
+        std::streamoff load(const SEALContext &context, std::istream &stream);
         void drop_secret_key()
         {
             if (!st_)
@@ -1144,6 +1179,7 @@ namespace seal
             detail::check(bk_relin_key_generate(context_.handle(), sk_.handle(), detail::next_seed(), 0, &k->h));
             k->sk = sk_.sk_;
             destination.k_ = k;
+            destination.ctx_ = context_.impl();
         }
         // keygenerator.h:148 / :213.  The set of keys is fixed here; generation is on first use.
         inline void create_galois_keys(const std::vector<std::uint32_t> &galois_elts, GaloisKeys &destination)
@@ -2357,3 +2393,5 @@ namespace seal
         }
     } // namespace util
 } // namespace seal
+
+#include "serialization.h"

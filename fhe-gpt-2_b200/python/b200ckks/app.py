@@ -287,6 +287,17 @@ class Session:
         d = np.ascontiguousarray(key, dtype=np.uint64)
         self.app.ck(self.app.L.bka_session_import_relin_key(self.h, d.ctypes.data_as(C.c_void_p), d.shape[0]))
 
+    WHAT = dict(ciphertext=0, relin_keys=2, galois_keys=3, secret_key=4, public_key=5)
+
+    def save(self, what, path, ct=None):
+        """SEAL 3.6 wire format (compr_mode none) of a ciphertext or of the session's keys, into a file"""
+        self.app.ck(self.app.L.bka_save(self.h, self.WHAT[what], ct.h if ct is not None else None, path.encode()))
+
+    def load(self, what, path):
+        out = C.c_void_p()
+        self.app.ck(self.app.L.bka_load(self.h, self.WHAT[what], path.encode(), C.byref(out)))
+        return Ct(self, out) if what == "ciphertext" else None
+
     def multiply_vector_rescale(self, a, values):
         v = np.asarray(values)
         if np.iscomplexobj(v):

@@ -90,6 +90,13 @@ int bka_rotate(bka_session_t s, bka_ct_t ct, int steps);
 int bka_multiply_relin_rescale(bka_session_t s, bka_ct_t a, bka_ct_t b); /* a <- rescale(relin(a * b)) */
 int bka_add_reduced_error(bka_session_t s, bka_ct_t a, bka_ct_t b);      /* a <- a + b */
 int bka_multiply_vector_rescale(bka_session_t s, bka_ct_t a, const double *values, int n_values, int is_complex);
+/* SEAL 3.6's binary wire format (Ciphertext / RelinKeys / GaloisKeys / SecretKey / PublicKey ::save and ::load,
+ * seal/serialization.h, compr_mode_type::none) through files, interchangeable with the reference's own SEAL.
+ * what: 0 ciphertext (ct / ct_out), 2 relinearization keys, 3 Galois keys, 4 secret key, 5 public key of the session.
+ * Keys are saved at full size in SEAL's layout (not available for level-aware hybrid keys); loaded keys are complete,
+ * so nothing is generated afterwards. */
+int bka_save(bka_session_t s, int what, bka_ct_t ct, const char *path);
+int bka_load(bka_session_t s, int what, const char *path, bka_ct_t *ct_out);
 /* Evaluator::{add,sub,multiply}_inplace_reduced_error (evaluator.cpp:312-486; which = 0, 1, 2): a <- a op b, operands
  * may sit at different levels (the higher one is walked down as the reference does); multiply relinearizes. */
 int bka_reduced_error_op(bka_session_t s, int which, bka_ct_t a, bka_ct_t b);

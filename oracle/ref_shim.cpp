@@ -12,6 +12,7 @@
 #include "seal/seal.h"
 #include <chrono>
 #include <cstring>
+#include <fstream>
 #include <map>
 #include <memory>
 #include <omp.h>
@@ -555,6 +556,55 @@ extern "C"
         for (double x : acc)
             s += x;
         *mean_op_s = s / (double(threads) * reps);
+        REF_CATCH
+    }
+
+    // ---- SEAL's own serialization (save / load members of the reference's classes), through files.
+    // what: 0 ciphertext `id`, 1 plaintext `id`, 2 relinearization keys, 3 Galois keys, 4 secret key, 5 public key
+    int ref_save(void *h, int what, int id, const char *path)
+    {
+        REF_TRY
+        Ref *r = (Ref *)h;
+        std::ofstream f(path, std::ios::binary);
+        if (!f)
+            throw runtime_error("cannot open file");
+        switch (what)
+        {
+        case 0: r->cts.at(id).save(f, compr_mode_type::none); break;
+        case 1: r->pts.at(id).save(f, compr_mode_type::none); break;
+        case 2:
+            if (!r->have_rk)
+            {
+                r->keygen->create_relin_keys(r->rk);
+                r->have_rk = true;
+            }
+            r->rk.save(f, compr_mode_type::none);
+            break;
+        case 3: r->gk.save(f, compr_mode_type::none); break;
+        case 4: r->keygen->secret_key().save(f, compr_mode_type::none); break;
+        case 5: r->pk.save(f, compr_mode_type::none); break;
+        default: throw invalid_argument("what");
+        }
+        REF_CATCH
+    }
+    int ref_load(void *h, int what, int id, const char *path)
+    {
+        REF_TRY
+        Ref *r = (Ref *)h;
+        std::ifstream f(path, std::ios::binary);
+        if (!f)
+            throw runtime_error("cannot open file");
+        switch (what)
+        {
+        case 0: r->cts[id].load(*r->ctx, f); break;
+        case 1: r->pts[id].load(*r->ctx, f); break;
+        case 2:
+            r->rk.load(*r->ctx, f);
+            r->have_rk = true;
+            break;
+        case 3: r->gk.load(*r->ctx, f); break;
+        default: throw invalid_argument("what");
+        }
         REF_CATCH
     }
 

@@ -211,5 +211,14 @@ class RefSeal:
                                     C.byref(wall), C.byref(mean)))
         return wall.value, mean.value
 
+    WHAT = dict(ciphertext=0, plaintext=1, relin_keys=2, galois_keys=3, secret_key=4, public_key=5)
+
+    def save(self, what, path, ident=0):
+        """the reference's own save() (compr_mode_type::none) of an object into a file"""
+        self._ck(self.L.ref_save(self.h, self.WHAT[what], ident, path.encode()))
+
+    def load(self, what, path, ident=0):
+        self._ck(self.L.ref_load(self.h, self.WHAT[what], ident, path.encode()))
+
     def max_threads(self):
         return self.L.ref_max_threads()
