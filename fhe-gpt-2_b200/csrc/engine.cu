@@ -817,10 +817,23 @@ namespace bk
                 a.h = h;
                 a.e0 = e0;
                 a.gather_digits = gather;
-                dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE, nk);
+                // key stream through the bulk-copy engine (cp.async.bulk + mbarrier ring) unless $B200CKKS_MAC_BULK=0
+                static const bool bulk = [] {
+                    const char *e = std::getenv("B200CKKS_MAC_BULK");
+                    return !e || std::atoi(e) != 0;
+                }();
                 {
                     ProfScope ps(c, s, TAG_KS_MAC, nE * 2 * P.dnum * nk);
-                    k_ks_mac_hyb<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                    if (bulk && n % KS_BULK_TILE == 0)
+                    {
+                        dim3 grid((unsigned)(n / KS_BULK_TILE), nE, nk);
+                        k_ks_mac_hyb_bulk<<<grid, 128, 0, s>>>(a, c.tables);
+                    }
+                    else
+                    {
+                        dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE, nk);
+                        k_ks_mac_hyb<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                    }
                 }
                 c.count();
             }

@@ -617,6 +617,163 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
     *reinterpret_cast<ulonglong2 *>(acc + ((size_t)ne + e) * n + i) = r1;
 }
 
+// ---- the same inner product with every operand streamed by the bulk-copy engine (TMA 1-D: cp.async.bulk) ---------
+// The key is the HBM stream of a key switch (2 dnum ne limb-polynomials, read once); the threads of the kernel above
+// keep at most two digits' worth of it in flight in registers and fetch the digits of a hoisted rotation through the
+// Galois table with scattered 8-byte loads.  Here one elected thread hands whole tiles to the copy engine - a ring of
+// KS_BULK_STAGES digits, per digit 4 KB of each key polynomial and the two 2 KB blocks of the digit, completion
+// signalled on one mbarrier per stage with complete_tx byte counting, L2 evict-first policy on the key - while all
+// threads multiply the stage that has landed.
+// The digit needs no scattered global loads: in NTT (bit-reversed) order a Galois automorphism maps every aligned
+// block of 256 coefficients ONTO one aligned block of 256 (index i <-> exponent 2 brev(i) + 1; multiplying the exponent
+// by the Galois element acts on its low bits, i.e. on the HIGH bits of i, independently of the rest).  So the source
+// of a 256-coefficient half tile is one contiguous 2 KB block, copied in bulk; the permutation inside the block is
+// applied when the threads read shared memory.
+// grid = (N / 512, nE, rotations), block = 128: thread t owns coefficients 2t, 2t+1 and 256 + 2t, 256 + 2t + 1 of the
+// tile (two conflict-free 16-byte shared-memory reads per key polynomial).
+constexpr int KS_BULK_TILE = 512;
+constexpr int KS_BULK_STAGES = 3;
+
+__device__ __forceinline__ unsigned smem_u32(const void *p)
+{
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(u64 *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64 *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, u64 *bar, u64 policy)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_plain(void *dst, const void *src, unsigned bytes, u64 *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bounded: a barrier that never completes traps (kernel error) instead of hanging the device
+__device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity)
+{
+    for (unsigned spin = 0; spin < (1u << 26); spin++)
+    {
+        unsigned ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok)
+                     : "r"(smem_u32(bar)), "r"(parity)
+                     : "memory");
+        if (ok)
+            return;
+    }
+    __trap();
+}
+
+static __global__ void __launch_bounds__(128) k_ks_mac_hyb_bulk(HybMacArgs a, NttTables T)
+{
+    __shared__ __align__(128) u64 sk[KS_BULK_STAGES][2][KS_BULK_TILE];
+    __shared__ __align__(128) u64 sd[KS_BULK_STAGES][KS_BULK_TILE];
+    __shared__ __align__(8) u64 full[KS_BULK_STAGES];
+    const int eloc = blockIdx.y;
+    const int e = a.e0 + eloc;
+    const int rot = blockIdx.z;
+    const size_t n = a.n;
+    const size_t base = (size_t)blockIdx.x * KS_BULK_TILE;
+    const int dnum = a.h.dnum, ne = a.h.ne();
+    const PrimeDev pd = T.primes[a.h.eprime(e)];
+    const size_t kstride = (size_t)ne * n;
+    const u64 *k0 = a.key[rot] + (size_t)e * n + base;
+    const uint32_t *perm = a.perm[rot];
+    u64 *acc = a.acc + (size_t)rot * 2 * ne * n;
+    const unsigned t = threadIdx.x;
+    constexpr unsigned TILE_BYTES = KS_BULK_TILE * (unsigned)sizeof(u64), HALF_BYTES = TILE_BYTES / 2;
+
+    if (t == 0)
+    {
+        for (int s = 0; s < KS_BULK_STAGES; s++)
+            mbar_init(&full[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    const u64 policy = l2_evict_first_policy();
+    // source blocks of the two half tiles under this rotation's automorphism, and of the unpermuted tile
+    const size_t blk_a = perm ? ((size_t)perm[base] & ~(size_t)255) : base;
+    const size_t blk_b = perm ? ((size_t)perm[base + 256] & ~(size_t)255) : base + 256;
+    auto issue = [&](int d) {
+        const int s = d % KS_BULK_STAGES;
+        const bool own = a.h.own(e, d);
+        const u64 *src = own ? a.target_ntt + (size_t)e * n : a.digits + ((size_t)eloc * dnum + d) * n;
+        const bool gather = own ? perm != nullptr : a.gather_digits != 0;
+        mbar_expect_tx(&full[s], 3 * TILE_BYTES);
+        bulk_g2s(&sk[s][0][0], k0 + (size_t)d * 2 * kstride, TILE_BYTES, &full[s], policy);
+        bulk_g2s(&sk[s][1][0], k0 + (size_t)d * 2 * kstride + kstride, TILE_BYTES, &full[s], policy);
+        bulk_g2s_plain(&sd[s][0], src + (gather ? blk_a : base), HALF_BYTES, &full[s]);
+        bulk_g2s_plain(&sd[s][256], src + (gather ? blk_b : base + 256), HALF_BYTES, &full[s]);
+    };
+    if (t == 0)
+        for (int d = 0; d < dnum && d < KS_BULK_STAGES; d++)
+            issue(d);
+
+    // coefficients of this thread: two pairs, 256 apart; where they sit inside the source blocks
+    const size_t ia = base + 2 * t, ib = base + 256 + 2 * t;
+    unsigned pa0 = 2 * t, pa1 = 2 * t + 1, pb0 = 256 + 2 * t, pb1 = 256 + 2 * t + 1;
+    unsigned qa0 = pa0, qa1 = pa1, qb0 = pb0, qb1 = pb1;
+    if (perm)
+    {
+        qa0 = perm[ia] & 255u;
+        qa1 = perm[ia + 1] & 255u;
+        qb0 = 256u + (perm[ib] & 255u);
+        qb1 = 256u + (perm[ib + 1] & 255u);
+    }
+    u64 lo[2][4] = {}, hi[2][4] = {}; // [key polynomial][coefficient]
+    for (int d = 0; d < dnum; d++)
+    {
+        const int s = d % KS_BULK_STAGES;
+        const bool own = a.h.own(e, d);
+        const bool gather = own ? perm != nullptr : a.gather_digits != 0;
+        mbar_wait(&full[s], (unsigned)(d / KS_BULK_STAGES) & 1u);
+        u64 x[4];
+        x[0] = sd[s][gather ? qa0 : pa0];
+        x[1] = sd[s][gather ? qa1 : pa1];
+        x[2] = sd[s][gather ? qb0 : pb0];
+        x[3] = sd[s][gather ? qb1 : pb1];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+        {
+            const ulonglong2 wa = *reinterpret_cast<const ulonglong2 *>(&sk[s][p][2 * t]);
+            const ulonglong2 wb = *reinterpret_cast<const ulonglong2 *>(&sk[s][p][256 + 2 * t]);
+            mac128(lo[p][0], hi[p][0], x[0], wa.x);
+            mac128(lo[p][1], hi[p][1], x[1], wa.y);
+            mac128(lo[p][2], hi[p][2], x[2], wb.x);
+            mac128(lo[p][3], hi[p][3], x[3], wb.y);
+        }
+        __syncthreads(); // every thread is done with stage s
+        if (t == 0 && d + KS_BULK_STAGES < dnum)
+        {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); // generic-proxy reads before the async-proxy refill
+            issue(d + KS_BULK_STAGES);
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+    {
+        ulonglong2 ra, rb;
+        ra.x = barrett128(lo[p][0], hi[p][0], pd);
+        ra.y = barrett128(lo[p][1], hi[p][1], pd);
+        rb.x = barrett128(lo[p][2], hi[p][2], pd);
+        rb.y = barrett128(lo[p][3], hi[p][3], pd);
+        u64 *dst = acc + ((size_t)p * ne + e) * n;
+        *reinterpret_cast<ulonglong2 *>(dst + ia) = ra;
+        *reinterpret_cast<ulonglong2 *>(dst + ib) = rb;
+    }
+}
+
 // ============================================================================================
 // Element-wise limb kernels.  Data = [polys][limbs][N]; grid-stride over polys*limbs*N with the
 // prime taken from the limb index.  2 coefficients (16 bytes) per thread per step.
