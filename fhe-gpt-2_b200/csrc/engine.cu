@@ -15,21 +15,38 @@
 #include <cstring>
 #include <limits>
 
-// 8 independent chains of 32-bit multiply-adds per thread (bk_measure_imad_peak)
-static __global__ void __launch_bounds__(256) k_imad_peak(unsigned *sink, int iters, unsigned m)
+// 8 independent chains of 32-bit multiply-adds per thread (bk_measure_imad_peak).  KIND 0: mad.lo.u32 (32-bit result),
+// 1: mad.wide.u32 (64-bit result), 2: mad.hi.u32
+template <int KIND>
+static __global__ void __launch_bounds__(256) k_imad_peak(unsigned long long *sink, int iters, unsigned m)
 {
-    unsigned a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
-#pragma unroll 8
+    unsigned a[8];
+    unsigned long long w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+    {
+        a[j] = threadIdx.x + j;
+        w[j] = threadIdx.x + j;
+    }
+#pragma unroll 4
     for (int i = 0; i < iters; i++)
     {
-        asm volatile("mad.lo.u32 %0, %0, %8, %0;\n\tmad.lo.u32 %1, %1, %8, %1;\n\tmad.lo.u32 %2, %2, %8, %2;\n\t"
-                     "mad.lo.u32 %3, %3, %8, %3;\n\tmad.lo.u32 %4, %4, %8, %4;\n\tmad.lo.u32 %5, %5, %8, %5;\n\t"
-                     "mad.lo.u32 %6, %6, %8, %6;\n\tmad.lo.u32 %7, %7, %8, %7;"
-                     : "+r"(a0), "+r"(a1), "+r"(a2), "+r"(a3), "+r"(a4), "+r"(a5), "+r"(a6), "+r"(a7)
-                     : "r"(m));
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+        {
+            if (KIND == 0)
+                asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[j]) : "r"(m));
+            else if (KIND == 1)
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a[j]), "r"(m));
+            else
+                asm volatile("mad.hi.u32 %0, %0, %1, %0;" : "+r"(a[j]) : "r"(m));
+        }
     }
-    unsigned r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
-    if (r == 0x12345678u && iters < 0)
+    unsigned long long r = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+        r ^= a[j] ^ w[j];
+    if (r == 0x12345678ull && iters < 0)
         *sink = r;
 }
 
@@ -1519,10 +1536,8 @@ extern "C"
     // Peak of the pipe that bounds the NTT passes, measured on this GPU at its current clocks: 32-bit integer
     // multiply-add (IMAD) thread-instructions per second from a kernel of independent dependent-chains - the
     // denominator of bench.py's integer roofline (a 64-bit Shoup butterfly needs 9 of them, ntt.cuh ct_bfly_wide).
-    bk_status bk_measure_imad_peak(bk_context_t ctx, double *imad_per_second_out)
+    static double imad_rate(Context &c, int kind)
     {
-        BK_TRY
-        Context &c = *ctx;
         cudaStream_t s = c.stream();
         Scratch sink(s, 1);
         const int iters = 4096, chains = 8;
@@ -1534,7 +1549,12 @@ extern "C"
         for (int rep = 0; rep < 4; rep++)
         {
             BK_CUDA(cudaEventRecord(e0, s));
-            k_imad_peak<<<grid, 256, 0, s>>>((unsigned *)sink.p, iters, 0x9E3779B9u);
+            if (kind == 0)
+                k_imad_peak<0><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
+            else if (kind == 1)
+                k_imad_peak<1><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
+            else
+                k_imad_peak<2><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
             BK_CUDA(cudaEventRecord(e1, s));
             BK_CUDA(cudaEventSynchronize(e1));
             float ms = 0;
@@ -1546,7 +1566,19 @@ extern "C"
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
         c.count(4);
-        *imad_per_second_out = best;
+        return best;
+    }
+    bk_status bk_measure_imad_peak(bk_context_t ctx, double *imad_per_second_out)
+    {
+        BK_TRY
+        *imad_per_second_out = imad_rate(*ctx, 0);
+        BK_END
+    }
+    bk_status bk_measure_int_pipe(bk_context_t ctx, double rates_out[3])
+    {
+        BK_TRY
+        for (int k = 0; k < 3; k++)
+            rates_out[k] = imad_rate(*ctx, k);
         BK_END
     }
 

@@ -79,6 +79,12 @@ class EngineView:
         self._ck(self.L.bk_measure_imad_peak(self.h, C.byref(v)))
         return v.value
 
+    def int_pipe_rates(self):
+        """thread-instructions per second of mad.lo.u32 / mad.wide.u32 / mad.hi.u32 on this GPU"""
+        v = (C.c_double * 3)()
+        self._ck(self.L.bk_measure_int_pipe(self.h, v))
+        return dict(zip(("mad_lo", "mad_wide", "mad_hi"), (float(x) for x in v)))
+
     def flush_l2(self):
         self._ck(self.L.bk_flush_l2(self.h))
 

@@ -125,6 +125,9 @@ bk_status bk_flush_l2(bk_context_t ctx);
 /* measured peak of 32-bit integer multiply-add thread-instructions per second on this GPU (the pipe that bounds the
  * NTT butterflies): the denominator of the benchmark's integer roofline */
 bk_status bk_measure_imad_peak(bk_context_t ctx, double *imad_per_second_out);
+/* the same for the three multiply-add forms a 64-bit modular butterfly is made of: rates_out = thread-instructions per
+ * second of mad.lo.u32, mad.wide.u32 and mad.hi.u32 */
+bk_status bk_measure_int_pipe(bk_context_t ctx, double rates_out[3]);
 
 /* ---- ciphertext container (ciphertext.h) -------------------------------------------------- */
 bk_status bk_ct_create(bk_context_t ctx, bk_ct_t *out);
