@@ -621,7 +621,7 @@ namespace bk
             dim3 grid2((unsigned)(n >> 12), jobs);
             {
                 ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
-                k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
+                k_fwd_blocks<StPlain><<<grid2, 256, 256 * 128, s>>>(tmp.p, st, c.tables);
             }
             c.count();
         }

@@ -260,8 +260,8 @@ namespace bk
         tables.log_n = log_n;
         tables.wide = 1;
         for (uint64_t q : primes)
-            if (q >> 57)
-                tables.wide = 0; // the unreduced forward butterflies need 66 q < 2^64
+            if ((q >> 57) || !(q >> 32))
+                tables.wide = 0; // the unreduced forward butterflies need 66 q < 2^64 (and reduce with barrett64_r32)
         if (std::getenv("B200CKKS_CLASSIC_NTT"))
             tables.wide = 0;
     }
@@ -476,13 +476,13 @@ namespace bk
     default: { constexpr int LOGR = 8; __VA_ARGS__; } break;                                                                  \
     }
 
-    // Launches of a few limb-polynomials (special limbs of a ModDown, last limb of a rescale, key switches at 2-3
-    // limbs) would occupy 16 CTAs per limb-polynomial - a fraction of the 148 SMs; they run with narrower column
-    // tiles (8 columns: 32 CTAs per limb-polynomial) and 64-thread block-pass CTAs (64 per limb-polynomial).
-    static bool small_launch(const Context &c, int jobs)
+    // Launch geometry (measured with tools/lab/ntt_lab.cu, profiles/r2_ntt_lab.md): the passes are bound by the
+    // integer multiplier and by how evenly the CTAs tile the 148 SMs, so small CTAs win at every size - column tiles
+    // of 8 columns (128 threads, 32 CTAs per limb-polynomial) and block-pass CTAs of 128 threads (8 blocks of 256
+    // coefficients), 64 threads when the whole launch would otherwise leave SMs empty.
+    static unsigned block_pass_threads(const Context &c, int jobs)
     {
-        static const bool off = std::getenv("B200CKKS_NO_SMALL_LAUNCH") != nullptr;
-        return !off && jobs * 16 < 2 * c.sm_count;
+        return (long)jobs * 32 < 2L * c.sm_count ? 64u : 128u;
     }
     template <class Load>
     static void launch_fwd_cols(Context &c, cudaStream_t s, const Load &ld, u64 *out, int jobs)
@@ -490,28 +490,14 @@ namespace bk
         if (jobs <= 0)
             return;
         ProfScope ps(c, s, TAG_FWD_COLS, jobs);
-        if (small_launch(c, jobs))
-        {
-            dim3 grid(32, jobs);
-            if (c.tables.wide)
-            {
-                BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
-            }
-            else
-            {
-                BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
-            }
-            c.count();
-            return;
-        }
-        dim3 grid(16, jobs);
+        dim3 grid(32, jobs);
         if (c.tables.wide)
         {
-            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
         }
         else
         {
-            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
         }
         c.count();
     }
@@ -520,13 +506,13 @@ namespace bk
     {
         if (jobs <= 0)
             return;
-        const unsigned threads = small_launch(c, jobs) ? 64 : 256;
+        const unsigned threads = block_pass_threads(c, jobs);
         dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
         if (c.tables.wide)
-            k_fwd_blocks<Store, true><<<grid, threads, 0, s>>>(in, st, c.tables);
+            k_fwd_blocks<Store, true><<<grid, threads, threads * 128, s>>>(in, st, c.tables);
         else
-            k_fwd_blocks<Store, false><<<grid, threads, 0, s>>>(in, st, c.tables);
+            k_fwd_blocks<Store, false><<<grid, threads, threads * 128, s>>>(in, st, c.tables);
         c.count();
     }
     template <class Load>
@@ -534,10 +520,10 @@ namespace bk
     {
         if (jobs <= 0)
             return;
-        const unsigned threads = small_launch(c, jobs) ? 64 : 256;
+        const unsigned threads = block_pass_threads(c, jobs);
         dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_INV_BLOCKS, jobs);
-        k_inv_blocks<Load><<<grid, threads, 0, s>>>(ld, out, c.tables);
+        k_inv_blocks<Load><<<grid, threads, threads * 128, s>>>(ld, out, c.tables);
         c.count();
     }
     template <class Store>
@@ -546,16 +532,8 @@ namespace bk
         if (jobs <= 0)
             return;
         ProfScope ps(c, s, TAG_INV_COLS, jobs);
-        if (small_launch(c, jobs))
-        {
-            dim3 grid(32, jobs);
-            BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
-        }
-        else
-        {
-            dim3 grid(16, jobs);
-            BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store><<<grid, 16 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
-        }
+        dim3 grid(32, jobs);
+        BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
         c.count();
     }
 
@@ -1146,7 +1124,7 @@ namespace bk
         if (scale <= 0 || ((int)std::log2(scale) >= c.total_bits[top]))
             throw std::invalid_argument("scale out of bounds");
         value *= scale;
-        int coeff_bit_count = (int)std::log2(std::fabs(value)) + 2;
+        int coeff_bit_count = value == 0 ? 0 : (int)std::log2(std::fabs(value)) + 2;
         if (coeff_bit_count >= c.total_bits[top])
             throw std::invalid_argument("encoded value is too large");
         double coeffd = std::round(value);
@@ -1235,6 +1213,55 @@ __global__ void __launch_bounds__(256) k_scalar_pack(u64 *__restrict__ a, Scalar
             va.y = addmod(va.y, f.x, q);
         }
         *reinterpret_cast<ulonglong2 *>(a + e) = va;
+    }
+}
+
+// dst = sum_j scalar_j * ct_j (+ a constant on c0): the leaves of a Chebyshev evaluation tree in one pass, see
+// bk_scalar_linear_combination.  Sources may carry more limbs than dst (only the first `limbs` are read).
+constexpr int LINCOMB_TERMS = 8;
+struct LinCombArgs
+{
+    const u64 *src[LINCOMB_TERMS];
+    int limbs_in[LINCOMB_TERMS];
+    int terms;
+    ulonglong2 c[LINCOMB_TERMS][62];
+};
+__global__ void __launch_bounds__(256) k_scalar_lincomb(u64 *__restrict__ dst, const __grid_constant__ LinCombArgs a,
+                                                        const __grid_constant__ ScalarPack addc, const PrimeDev *primes,
+                                                        int log_n, int limbs)
+{
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = per_poly; // two polynomials, two words per step
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t e = i * 2;
+        const int p = e >= per_poly;
+        const size_t r = e - (size_t)p * per_poly;
+        const int limb = (int)(r >> log_n);
+        const size_t x = r & (n - 1);
+        const PrimeDev pd = primes[limb];
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+#pragma unroll
+        for (int j = 0; j < LINCOMB_TERMS; j++)
+        {
+            if (j < a.terms)
+            {
+                const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(a.src[j] + ((size_t)p * a.limbs_in[j] + limb) * n + x));
+                const u64 f = a.c[j][limb].x;
+                mac128(lo0, hi0, v.x, f);
+                mac128(lo1, hi1, v.y, f);
+            }
+        }
+        ulonglong2 o;
+        o.x = barrett128(lo0, hi0, pd);
+        o.y = barrett128(lo1, hi1, pd);
+        if (p == 0)
+        {
+            o.x = addmod(o.x, addc.c[limb].x, pd.q);
+            o.y = addmod(o.y, addc.c[limb].x, pd.q);
+        }
+        *reinterpret_cast<ulonglong2 *>(dst + e) = o;
     }
 }
 
@@ -2586,6 +2613,49 @@ extern "C"
             a->d, sp, c.d_primes, c.log_n, a->limbs, a->size);
         c.count();
         a->scale = new_scale;
+        BK_END
+    }
+
+    bk_status bk_scalar_linear_combination(bk_context_t ctx, bk_ct_t dst, const bk_ct_t *cts, const double *values,
+                                           int count, double constant, double target_scale)
+    {
+        BK_TRY
+        // tolerance-mode replacement for the multiply_const + rescale + add_reduced_error chains with which the
+        // reference builds each leaf of a polynomial evaluation tree (common/Polynomial.cpp:438-456,
+        // comp/SEALfunc.cpp): dst = constant + sum_j values[j] * cts[j] at the lowest level among the sources and at
+        // scale target_scale - term j's scalar is encoded at target_scale / cts[j]->scale, so sources at different
+        // scales line up exactly - leaving ONE rescale for the caller instead of one per term.
+        Context &c = *ctx;
+        if (!cts || !values || count < 1 || count > LINCOMB_TERMS)
+            throw std::invalid_argument("between 1 and 8 terms are supported");
+        int limbs = 1 << 30;
+        for (int j = 0; j < count; j++)
+        {
+            check_ct(ctx, cts[j], "encrypted");
+            if (!cts[j]->ntt || cts[j]->size != 2)
+                throw std::invalid_argument("encrypted must be of size 2 and in NTT form");
+            if (cts[j] == dst)
+                throw std::invalid_argument("destination must not be one of the sources");
+            limbs = std::min(limbs, cts[j]->limbs);
+        }
+        if (!c.scale_in_bounds(target_scale, limbs))
+            throw std::invalid_argument("scale out of bounds");
+        LinCombArgs a{};
+        a.terms = count;
+        for (int j = 0; j < count; j++)
+        {
+            a.src[j] = cts[j]->d;
+            a.limbs_in[j] = cts[j]->limbs;
+            scalar_residues(c, values[j], target_scale / cts[j]->scale, limbs, a.c[j]);
+        }
+        ScalarPack addc{};
+        scalar_residues(c, constant, target_scale, limbs, addc.c);
+        ensure_ct(dst, 2, limbs, false);
+        ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, 2 * limbs * count);
+        k_scalar_lincomb<<<c.ew_grid((size_t)limbs * c.n), 256, 0, c.stream()>>>(dst->d, a, addc, c.d_primes, c.log_n, limbs);
+        c.count();
+        dst->scale = target_scale;
+        dst->ntt = true;
         BK_END
     }
 

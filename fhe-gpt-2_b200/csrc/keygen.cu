@@ -122,7 +122,7 @@ namespace bk
         c.count();
         StPlain st{ out, map, c.n };
         dim3 grid2((unsigned)(c.n >> 12), jobs);
-        k_fwd_blocks<StPlain><<<grid2, 256, 0, s>>>(tmp.p, st, c.tables);
+        k_fwd_blocks<StPlain><<<grid2, 256, 256 * 128, s>>>(tmp.p, st, c.tables);
         c.count();
     }
 }

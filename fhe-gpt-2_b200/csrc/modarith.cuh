@@ -40,6 +40,16 @@ __device__ __forceinline__ u64 barrett64(u64 x, const PrimeDev &p)
     return csub(r, p.q);
 }
 
+// The same for moduli above 2^32: the high word of floor(2^128 / q) then fits in 32 bits, and two 32-bit multiplies
+// give the same floor(x r1 / 2^64) as the four of __umul64hi.
+__device__ __forceinline__ u64 barrett64_r32(u64 x, const PrimeDev &p)
+{
+    const unsigned r1 = (unsigned)p.r1;
+    u64 t = ((u64)(unsigned)(x >> 32) * r1 + __umulhi((unsigned)x, r1)) >> 32;
+    u64 r = x - t * p.q;
+    return csub(r, p.q);
+}
+
 // (hi:lo) mod q, hi:lo < 2^128 arbitrary as long as q < 2^63 (here q < 2^61).
 __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
 {

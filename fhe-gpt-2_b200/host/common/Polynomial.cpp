@@ -311,6 +311,28 @@ namespace boot
                 continue;
             auto cc = [p](long j) { return static_cast<double>(p->chebcoeff[(std::size_t)j]); };
             set[(std::size_t)i] = true;
+#ifdef B200CKKS_FACADE
+            if (fused_leaves())
+            {
+                // all terms in one pass at the level of the lowest baby, one rescale for the leaf
+                std::vector<const Ciphertext *> terms;
+                std::vector<double> values;
+                for (long j = 1; j <= p->deg; j++)
+                    if (j == 1 || !(std::fabs(cc(j)) <= zero))
+                    {
+                        terms.push_back(j < k ? &baby[(std::size_t)j] : &giant[0]);
+                        values.push_back(cc(j));
+                    }
+                const Ciphertext *lowest = terms[0];
+                for (const Ciphertext *t : terms)
+                    if (t->coeff_modulus_size() < lowest->coeff_modulus_size())
+                        lowest = t;
+                evaluator.scalar_linear_combination(terms, values, std::fabs(cc(1)) <= zero ? 0.0 : cc(0),
+                                                    lowest->scale() * lowest->scale(), node[(std::size_t)i]);
+                evaluator.rescale_to_next_inplace(node[(std::size_t)i]);
+                continue;
+            }
+#endif
             evaluator.multiply_const(baby[1], cc(1), node[(std::size_t)i]);
             evaluator.rescale_to_next_inplace(node[(std::size_t)i]);
             if (!(std::fabs(cc(1)) <= zero))

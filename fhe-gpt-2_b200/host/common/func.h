@@ -62,6 +62,22 @@ inline bool encrypt_constants()
     return on;
 }
 
+// The reference builds every leaf of a polynomial evaluation tree term by term: multiply_const, rescale_to_next and a
+// reduced-error add that walks the higher-level operand down (common/Polynomial.cpp:438-456, comp/SEALfunc.cpp) -
+// ten rescales per degree-7 leaf.  By default (engine only) a leaf is one pass over its terms with the scalars encoded
+// so that all terms meet at one scale, and ONE rescale (Evaluator::scalar_linear_combination); same level out, same
+// value up to rounding.  $B200CKKS_TERMWISE_LEAVES=1 (or the reference's constants, above) restores the reference's
+// sequence.
+inline bool fused_leaves()
+{
+#ifdef B200CKKS_FACADE
+    static const bool off = std::getenv("B200CKKS_TERMWISE_LEAVES") != nullptr || encrypt_constants();
+    return !off;
+#else
+    return false;
+#endif
+}
+
 // baby-step size minimising ceil(M/k) + k - 1 (first minimiser, k <= 3 sqrt(M))
 inline int giantstep(int M)
 {

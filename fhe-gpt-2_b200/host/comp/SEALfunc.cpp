@@ -109,6 +109,27 @@ namespace seal
                     continue;
                 long idx = first_coeff[(std::size_t)j];
                 Ciphertext &acc = part[j];
+#ifdef B200CKKS_FACADE
+                if (fused_leaves())
+                {
+                    // one pass over the odd basis elements at the level of the lowest one (the reference walks the
+                    // accumulator down with one multiply_const + rescale per level it meets)
+                    std::vector<const Ciphertext *> terms;
+                    std::vector<double> values;
+                    for (long k = 1; k <= degree[(std::size_t)j]; k += 2, idx += 2)
+                    {
+                        terms.push_back(&basis(k));
+                        values.push_back(decomp_coeff[(std::size_t)idx]);
+                    }
+                    const Ciphertext *lowest = terms[0];
+                    for (const Ciphertext *t : terms)
+                        if (t->coeff_modulus_size() < lowest->coeff_modulus_size())
+                            lowest = t;
+                    evaluator.scalar_linear_combination(terms, values, 0.0, lowest->scale() * lowest->scale(), acc);
+                    evaluator.rescale_to_next_inplace(acc);
+                    continue;
+                }
+#endif
                 evaluator.multiply_const(basis(1), decomp_coeff[(std::size_t)idx], acc);
                 idx += 2;
                 for (long k = 3; k <= degree[(std::size_t)j]; k += 2, idx += 2)

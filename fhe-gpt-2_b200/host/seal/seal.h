@@ -1771,6 +1771,30 @@ namespace seal
             destination = encrypted;
             multiply_const_inplace(destination, value);
         }
+        // engine extension (tolerance mode): destination = constant + sum_j values[j] * terms[j] at the lowest level
+        // among the terms and at scale target_scale, in one pass (bk_scalar_linear_combination).  Replaces the
+        // multiply_const + rescale_to_next + add_reduced_error chain per term of the reference's polynomial
+        // evaluation leaves (common/Polynomial.cpp:438-456); the caller rescales once.
+        void scalar_linear_combination(const std::vector<const Ciphertext *> &terms, const std::vector<double> &values,
+                                       double constant, double target_scale, Ciphertext &destination) const
+        {
+            if (terms.empty() || terms.size() != values.size())
+                throw std::invalid_argument("terms and values must have the same non-zero size");
+            std::vector<bk_ct_t> hs;
+            std::size_t limbs = terms[0]->coeff_modulus_size();
+            for (const Ciphertext *t : terms)
+            {
+                t->push();
+                hs.push_back(t->handle());
+                limbs = std::min(limbs, t->coeff_modulus_size());
+            }
+            stats_.scalar_op += terms.size();
+            stats_.hit(4, limbs);
+            destination.bind(context_.impl());
+            detail::check(bk_scalar_linear_combination(h(), destination.handle(), hs.data(), values.data(), (int)hs.size(),
+                                                       constant, target_scale));
+            destination.pull();
+        }
         template <typename T>
         void multiply_vector_inplace(Ciphertext &encrypted, const std::vector<T> &value) const
         {

@@ -238,6 +238,12 @@ bk_status bk_multiply_plain_accumulate(bk_context_t ctx, bk_ct_t acc, bk_ct_t a,
  * convolution (cnn_seal.cpp:455-470) in one pass over the operands; same residues as multiply_plain + add_inplace term
  * by term.  All operands on one level with equal scales; dst must not be an operand. */
 bk_status bk_multiply_plain_sum(bk_context_t ctx, bk_ct_t dst, const bk_ct_t *cts, const bk_pt_t *pts, int count);
+/* dst = constant + sum_j values[j] * cts[j] (1 <= count <= 8) at the lowest level among the sources and at scale
+ * target_scale: term j's scalar is encoded at target_scale / scale(cts[j]).  Tolerance-mode replacement for the
+ * multiply_const + rescale_to_next + add_reduced_error chains of the reference's polynomial evaluation leaves
+ * (cnn_ckks/common/Polynomial.cpp:438-456): one rescale per leaf is left to the caller instead of one per term. */
+bk_status bk_scalar_linear_combination(bk_context_t ctx, bk_ct_t dst, const bk_ct_t *cts, const double *values, int count,
+                                       double constant, double target_scale);
 bk_status bk_transform_to_ntt_inplace(bk_context_t ctx, bk_ct_t a);            /* :2069-2118 */
 bk_status bk_transform_from_ntt_inplace(bk_context_t ctx, bk_ct_t a);
 /* fork: add_const / multiply_const (evaluator.cpp:287-302): scalar encode (ckks.cpp:77-153)
