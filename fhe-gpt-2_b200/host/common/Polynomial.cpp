@@ -253,6 +253,17 @@ namespace boot
             else
             {
                 evaluator.multiply_reduced_error(Ta, Tb, relin_keys, out);
+#ifdef B200CKKS_FACADE
+                if (fused_leaves() && Tdiff->coeff_modulus_size() >= out.coeff_modulus_size())
+                {
+                    // 2 Ta Tb - T|a-b| before the rescale (the subtrahend joins at the product's scale)
+                    Ciphertext sum;
+                    evaluator.scalar_linear_combination({ &out, Tdiff }, { 2.0, -1.0 }, 0.0, out.scale(), sum);
+                    evaluator.rescale_to_next_inplace(sum);
+                    out = std::move(sum);
+                    return;
+                }
+#endif
                 evaluator.rescale_to_next_inplace(out);
                 evaluator.double_inplace(out);
                 evaluator.sub_reduced_error(out, *Tdiff, out);
@@ -360,6 +371,18 @@ namespace boot
                 else
                 {
                     evaluator.multiply_reduced_error(node[quo], giant[(std::size_t)gindex], relin_keys, node[(std::size_t)i]);
+#ifdef B200CKKS_FACADE
+                    if (fused_leaves() && node[rem].coeff_modulus_size() >= node[(std::size_t)i].coeff_modulus_size())
+                    {
+                        // quotient * giant + remainder before the rescale
+                        Ciphertext sum;
+                        evaluator.scalar_linear_combination({ &node[(std::size_t)i], &node[rem] }, { 1.0, 1.0 }, 0.0,
+                                                            node[(std::size_t)i].scale(), sum);
+                        evaluator.rescale_to_next_inplace(sum);
+                        node[(std::size_t)i] = std::move(sum);
+                        continue;
+                    }
+#endif
                     evaluator.rescale_to_next_inplace(node[(std::size_t)i]);
                     evaluator.add_reduced_error(node[(std::size_t)i], node[rem], node[(std::size_t)i]);
                 }

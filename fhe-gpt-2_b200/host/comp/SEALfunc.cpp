@@ -43,6 +43,16 @@ namespace seal
     {
         Ciphertext twice;
         evaluator.multiply_reduced_error(Tm, Tn, relin_keys, twice);
+#ifdef B200CKKS_FACADE
+        if (fused_leaves() && Tmminusn.size() != 0 && Tmminusn.coeff_modulus_size() >= twice.coeff_modulus_size())
+        {
+            // 2 Tm Tn - T(m-n) before the rescale: the subtrahend joins at the product's scale (one pass) instead
+            // of being walked down with its own multiply_const + rescale afterwards
+            evaluator.scalar_linear_combination({ &twice, &Tmminusn }, { 2.0, -1.0 }, 0.0, twice.scale(), Tmplusn);
+            evaluator.rescale_to_next_inplace(Tmplusn);
+            return;
+        }
+#endif
         evaluator.add_inplace_reduced_error(twice, twice);
         evaluator.rescale_to_next_inplace(twice);
         if (Tmminusn.size() == 0) // T0 = 1 kept as the constant it is (geneT0T1)
@@ -153,6 +163,17 @@ namespace seal
                     evaluator.multiply_reduced_error(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), relin_keys, term);
                     evaluator.add_inplace_reduced_error(acc, term);
                 }
+#ifdef B200CKKS_FACADE
+                if (fused_leaves() && part.at(k).coeff_modulus_size() >= acc.coeff_modulus_size())
+                {
+                    // the remainder joins the sum of products before its rescale
+                    Ciphertext sum;
+                    evaluator.scalar_linear_combination({ &acc, &part.at(k) }, { 1.0, 1.0 }, 0.0, acc.scale(), sum);
+                    evaluator.rescale_to_next_inplace(sum);
+                    acc = std::move(sum);
+                    continue;
+                }
+#endif
                 evaluator.rescale_to_next_inplace(acc);
                 evaluator.add_inplace_reduced_error(acc, part.at(k));
             }
