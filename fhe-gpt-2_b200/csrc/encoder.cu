@@ -220,6 +220,7 @@ constexpr int FFT_B = 1 << FFT_LB;
 __global__ void k_enc_scatter(const cplx *__restrict__ vals, int n_values, const uint32_t *__restrict__ map,
                               cplx *__restrict__ out, int slots)
 {
+    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_values)
         return;
@@ -232,6 +233,7 @@ __global__ void k_enc_scatter(const cplx *__restrict__ vals, int n_values, const
 // Stage with gap g has m = n/(2g) groups; group i uses roots[n - 2m + 1 + i].
 __global__ void __launch_bounds__(256) k_ifft_block(cplx *__restrict__ data, const cplx *__restrict__ roots, int log_n)
 {
+    pdl_prologue();
     __shared__ cplx sm[FFT_B];
     const size_t n = size_t(1) << log_n;
     cplx *base = data + (size_t)blockIdx.x * FFT_B;
@@ -265,6 +267,7 @@ __global__ void __launch_bounds__(256) k_ifft_cols(const cplx *__restrict__ data
                                                    double fix, double *__restrict__ re_out,
                                                    unsigned long long *__restrict__ max_bits, int log_n)
 {
+    pdl_prologue();
     constexpr int S = 1 << LOGS;
     const size_t n = size_t(1) << log_n;
     const int c = blockIdx.x * blockDim.x + threadIdx.x; // column 0..2047
@@ -323,6 +326,7 @@ __global__ void __launch_bounds__(256) k_ifft_cols(const cplx *__restrict__ data
 template <int LOGS>
 __global__ void __launch_bounds__(256) k_fft_cols(cplx *__restrict__ data, const cplx *__restrict__ roots)
 {
+    pdl_prologue();
     constexpr int S = 1 << LOGS;
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     cplx x[S];
@@ -353,6 +357,7 @@ __global__ void __launch_bounds__(256) k_fft_cols(cplx *__restrict__ data, const
 
 __global__ void __launch_bounds__(256) k_fft_block(cplx *__restrict__ data, const cplx *__restrict__ roots, int log_n)
 {
+    pdl_prologue();
     __shared__ cplx sm[FFT_B];
     const size_t n = size_t(1) << log_n;
     cplx *base = data + (size_t)blockIdx.x * FFT_B;
@@ -428,6 +433,7 @@ __global__ void __launch_bounds__(128) k_dec_compose(const u64 *__restrict__ coe
                                                      const u64 *__restrict__ total, const u64 *__restrict__ half,
                                                      int log_n, int l, int P, double inv_scale, int sparsity)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= n)
@@ -509,6 +515,7 @@ __global__ void __launch_bounds__(128) k_dec_compose(const u64 *__restrict__ coe
 __global__ void k_dec_gather(const cplx *__restrict__ res, const uint32_t *__restrict__ map, cplx *__restrict__ out,
                              int count)
 {
+    pdl_prologue();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < count)
         out[i] = res[map[i]];
@@ -556,16 +563,16 @@ namespace bk
         BK_CUDA(cudaMemsetAsync(d_max, 0, sizeof(unsigned long long), s));
         if (n_values > 0)
         {
-            k_enc_scatter<<<(n_values + 255) / 256, 256, 0, s>>>(d_vals, n_values, e.d_index_map, cv, slots);
+            launch_pdl(k_enc_scatter, (n_values + 255) / 256, 256, 0, s, d_vals, n_values, e.d_index_map, cv, slots);
             c.count();
         }
         double fix = scale / static_cast<double>(n);
         const int logs = c.log_n - FFT_LB;
         {
             ProfScope ps(c, s, TAG_FFT, 2);
-            k_ifft_block<<<(unsigned)(n >> FFT_LB), 256, 0, s>>>(cv, e.d_inv_roots, c.log_n);
+            launch_pdl(k_ifft_block, (unsigned)(n >> FFT_LB), 256, 0, s, cv, e.d_inv_roots, c.log_n);
             dispatch_cols(logs, [&](auto L) {
-                k_ifft_cols<decltype(L)::value><<<FFT_B / 256, 256, 0, s>>>(cv, e.d_inv_roots, fix, (double *)re.p, d_max,
+                launch_pdl(k_ifft_cols<decltype(L)::value>, FFT_B / 256, 256, 0, s, cv, e.d_inv_roots, fix, (double *)re.p, d_max,
                                                                             c.log_n);
             });
         }
@@ -609,11 +616,11 @@ namespace bk
             ProfScope ps(c, s, TAG_FWD_COLS, jobs);
             switch (c.log_n)
             {
-            case 12: k_fwd_cols<4, LdEncode><<<grid, 16, 0, s>>>(ld, tmp.p, c.tables); break;
-            case 13: k_fwd_cols<5, LdEncode><<<grid, 32, 0, s>>>(ld, tmp.p, c.tables); break;
-            case 14: k_fwd_cols<6, LdEncode><<<grid, 64, 0, s>>>(ld, tmp.p, c.tables); break;
-            case 15: k_fwd_cols<7, LdEncode><<<grid, 128, 0, s>>>(ld, tmp.p, c.tables); break;
-            default: k_fwd_cols<8, LdEncode><<<grid, 256, 0, s>>>(ld, tmp.p, c.tables); break;
+            case 12: launch_pdl(k_fwd_cols<4, LdEncode>, grid, 16, 0, s, ld, tmp.p, c.tables); break;
+            case 13: launch_pdl(k_fwd_cols<5, LdEncode>, grid, 32, 0, s, ld, tmp.p, c.tables); break;
+            case 14: launch_pdl(k_fwd_cols<6, LdEncode>, grid, 64, 0, s, ld, tmp.p, c.tables); break;
+            case 15: launch_pdl(k_fwd_cols<7, LdEncode>, grid, 128, 0, s, ld, tmp.p, c.tables); break;
+            default: launch_pdl(k_fwd_cols<8, LdEncode>, grid, 256, 0, s, ld, tmp.p, c.tables); break;
             }
             }
             c.count();
@@ -621,7 +628,7 @@ namespace bk
             dim3 grid2((unsigned)(n >> 12), jobs);
             {
                 ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
-                k_fwd_blocks<StPlain><<<grid2, 256, 256 * 128, s>>>(tmp.p, st, c.tables);
+                launch_pdl(k_fwd_blocks<StPlain>, grid2, 256, 256 * 128, s, tmp.p, st, c.tables);
             }
             c.count();
         }
@@ -751,20 +758,20 @@ extern "C"
         Scratch res(s, 2 * n);
         cplx *rv = (cplx *)res.p;
         double inv_scale = double(1.0) / pt->scale;
-        k_dec_compose<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(copy.p, rv, c.d_primes, e.d_garner_inv, e.d_prodmod,
+        launch_pdl(k_dec_compose, (unsigned)((n + 127) / 128), 128, 0, s, copy.p, rv, c.d_primes, e.d_garner_inv, e.d_prodmod,
                                                                   e.d_prodwords, e.d_total, e.d_half, c.log_n, l,
                                                                   c.n_primes, inv_scale, slots / sparse);
         c.count();
         const int logs = c.log_n - FFT_LB;
         dispatch_cols(logs, [&](auto L) {
-            k_fft_cols<decltype(L)::value><<<FFT_B / 256, 256, 0, s>>>(rv, e.d_roots);
+            launch_pdl(k_fft_cols<decltype(L)::value>, FFT_B / 256, 256, 0, s, rv, e.d_roots);
         });
         c.count();
-        k_fft_block<<<(unsigned)(n >> FFT_LB), 256, 0, s>>>(rv, e.d_roots, c.log_n);
+        launch_pdl(k_fft_block, (unsigned)(n >> FFT_LB), 256, 0, s, rv, e.d_roots, c.log_n);
         c.count();
         Scratch outv(s, (size_t)2 * slots);
         BK_CUDA(cudaMemsetAsync(outv.p, 0, (size_t)slots * sizeof(cplx), s));
-        k_dec_gather<<<(sparse + 255) / 256, 256, 0, s>>>(rv, e.d_index_map, (cplx *)outv.p, sparse);
+        launch_pdl(k_dec_gather, (sparse + 255) / 256, 256, 0, s, rv, e.d_index_map, (cplx *)outv.p, sparse);
         c.count();
         BK_CUDA(cudaMemcpyAsync(out_complex, outv.p, (size_t)slots * sizeof(cplx), cudaMemcpyDeviceToHost, s));
         c.d2h_bytes += (size_t)slots * sizeof(cplx);

@@ -20,6 +20,7 @@
 template <int KIND>
 static __global__ void __launch_bounds__(256) k_imad_peak(unsigned long long *sink, int iters, unsigned m)
 {
+    pdl_prologue();
     unsigned a[8];
     unsigned long long w[8];
 #pragma unroll
@@ -266,6 +267,12 @@ namespace bk
             tables.wide = 0;
     }
 
+    bool pdl_enabled()
+    {
+        static const bool on = std::getenv("B200CKKS_NO_PDL") == nullptr;
+        return on;
+    }
+
     Context::~Context()
     {
         cudaSetDevice(device);
@@ -493,11 +500,11 @@ namespace bk
         dim3 grid(32, jobs);
         if (c.tables.wide)
         {
-            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, true, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, true, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
         }
         else
         {
-            BK_DISPATCH_LOGR(c.log_n, k_fwd_cols<LOGR, Load, false, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, false, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
         }
         c.count();
     }
@@ -510,9 +517,9 @@ namespace bk
         dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
         if (c.tables.wide)
-            k_fwd_blocks<Store, true><<<grid, threads, threads * 128, s>>>(in, st, c.tables);
+            launch_pdl(k_fwd_blocks<Store, true>, grid, threads, threads * 128, s, in, st, c.tables);
         else
-            k_fwd_blocks<Store, false><<<grid, threads, threads * 128, s>>>(in, st, c.tables);
+            launch_pdl(k_fwd_blocks<Store, false>, grid, threads, threads * 128, s, in, st, c.tables);
         c.count();
     }
     template <class Load>
@@ -523,7 +530,7 @@ namespace bk
         const unsigned threads = block_pass_threads(c, jobs);
         dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_INV_BLOCKS, jobs);
-        k_inv_blocks<Load><<<grid, threads, threads * 128, s>>>(ld, out, c.tables);
+        launch_pdl(k_inv_blocks<Load>, grid, threads, threads * 128, s, ld, out, c.tables);
         c.count();
     }
     template <class Store>
@@ -533,7 +540,7 @@ namespace bk
             return;
         ProfScope ps(c, s, TAG_INV_COLS, jobs);
         dim3 grid(32, jobs);
-        BK_DISPATCH_LOGR(c.log_n, k_inv_cols<LOGR, Store, 8><<<grid, 8 * ((1 << LOGR) / 16), 0, s>>>(in, st, c.tables));
+        BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_inv_cols<LOGR, Store, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, in, st, c.tables));
         c.count();
     }
 
@@ -763,7 +770,7 @@ namespace bk
         ProfScope ps(c, s, TAG_OTHER, groups * a.nT);
         switch (ds)
         {
-#define BK_HYB_CONV_CASE(DS) case DS: k_hyb_conv<DS><<<grid, 128, 0, s>>>(a, c.tables); break;
+#define BK_HYB_CONV_CASE(DS) case DS: launch_pdl(k_hyb_conv<DS>, grid, 128, 0, s, a, c.tables); break;
             BK_HYB_CONV_CASE(1) BK_HYB_CONV_CASE(2) BK_HYB_CONV_CASE(3) BK_HYB_CONV_CASE(4) BK_HYB_CONV_CASE(5)
             BK_HYB_CONV_CASE(6) BK_HYB_CONV_CASE(7) BK_HYB_CONV_CASE(8) BK_HYB_CONV_CASE(9) BK_HYB_CONV_CASE(10)
             BK_HYB_CONV_CASE(11) BK_HYB_CONV_CASE(12) BK_HYB_CONV_CASE(13) BK_HYB_CONV_CASE(14) BK_HYB_CONV_CASE(15)
@@ -822,12 +829,12 @@ namespace bk
                     if (bulk && n % KS_BULK_TILE == 0)
                     {
                         dim3 grid((unsigned)(n / KS_BULK_TILE), nE, nk);
-                        k_ks_mac_hyb_bulk<<<grid, 128, 0, s>>>(a, c.tables);
+                        launch_pdl(k_ks_mac_hyb_bulk, grid, 128, 0, s, a, c.tables);
                     }
                     else
                     {
                         dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nE, nk);
-                        k_ks_mac_hyb<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                        launch_pdl(k_ks_mac_hyb, grid, KS_MAC_THREADS, 0, s, a, c.tables);
                     }
                 }
                 c.count();
@@ -953,7 +960,7 @@ namespace bk
             dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
             {
                 ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
-                k_ks_mac<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                launch_pdl(k_ks_mac, grid, KS_MAC_THREADS, 0, s, a, c.tables);
             }
             c.count();
         }
@@ -1031,7 +1038,7 @@ namespace bk
                 dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
                 {
                     ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
-                    k_ks_mac<<<grid, KS_MAC_THREADS, 0, s>>>(a, c.tables);
+                    launch_pdl(k_ks_mac, grid, KS_MAC_THREADS, 0, s, a, c.tables);
                 }
                 c.count();
             }
@@ -1192,6 +1199,7 @@ template <bool MUL>
 __global__ void __launch_bounds__(256) k_scalar_pack(u64 *__restrict__ a, ScalarPack sp, const PrimeDev *primes,
                                                      int log_n, int limbs, int polys)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = (size_t)polys * per_poly / 2;
@@ -1230,6 +1238,7 @@ __global__ void __launch_bounds__(256) k_scalar_lincomb(u64 *__restrict__ dst, c
                                                         const __grid_constant__ ScalarPack addc, const PrimeDev *primes,
                                                         int log_n, int limbs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = per_poly; // two polynomials, two words per step
@@ -1577,11 +1586,11 @@ extern "C"
         {
             BK_CUDA(cudaEventRecord(e0, s));
             if (kind == 0)
-                k_imad_peak<0><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
+                launch_pdl(k_imad_peak<0>, grid, 256, 0, s, (unsigned long long *)sink.p, iters, 0x9E3779B9u);
             else if (kind == 1)
-                k_imad_peak<1><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
+                launch_pdl(k_imad_peak<1>, grid, 256, 0, s, (unsigned long long *)sink.p, iters, 0x9E3779B9u);
             else
-                k_imad_peak<2><<<grid, 256, 0, s>>>((unsigned long long *)sink.p, iters, 0x9E3779B9u);
+                launch_pdl(k_imad_peak<2>, grid, 256, 0, s, (unsigned long long *)sink.p, iters, 0x9E3779B9u);
             BK_CUDA(cudaEventRecord(e1, s));
             BK_CUDA(cudaEventSynchronize(e1));
             float ms = 0;
@@ -2010,9 +2019,9 @@ extern "C"
         {
             ProfScope ps_ew(c, s, TAG_ELEMENTWISE, mn * l);
             if (sub)
-                k_ew<EW_SUB><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+                launch_pdl(k_ew<EW_SUB>, grid, 256, 0, s, a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
             else
-                k_ew<EW_ADD><<<grid, 256, 0, s>>>(a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
+                launch_pdl(k_ew<EW_ADD>, grid, 256, 0, s, a->d, b->d, c.d_primes, c.log_n, l, mn, mn);
         }
         c.count();
         if (a_size < b->size)
@@ -2023,7 +2032,7 @@ extern "C"
             if (sub)
             {
                 ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-                k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, s>>>(a->d + (size_t)a_size * per_poly, nullptr,
+                launch_pdl(k_ew<EW_NEG>, c.ew_grid(words / 2), 256, 0, s, a->d + (size_t)a_size * per_poly, nullptr,
                                                                   c.d_primes, c.log_n, l, b->size - a_size, 0);
                 c.count();
             }
@@ -2049,7 +2058,7 @@ extern "C"
         check_ct(ctx, a, "encrypted");
         size_t words = (size_t)a->size * a->limbs * c.n;
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-        k_ew<EW_NEG><<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, nullptr, c.d_primes, c.log_n, a->limbs,
+        launch_pdl(k_ew<EW_NEG>, c.ew_grid(words / 2), 256, 0, c.stream(), a->d, nullptr, c.d_primes, c.log_n, a->limbs,
                                                                    a->size, 0);
         c.count();
         BK_END
@@ -2077,9 +2086,9 @@ extern "C"
         {
             ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, 3 * l);
             if (a == b)
-                k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
+                launch_pdl(k_square, c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream(), a->d, out, c.d_primes, c.log_n, l);
             else
-                k_tensor<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, b->d, out, c.d_primes, c.log_n, l);
+                launch_pdl(k_tensor, c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream(), a->d, b->d, out, c.d_primes, c.log_n, l);
         }
         c.count();
         adopt(a, out, words, 3, l);
@@ -2103,7 +2112,7 @@ extern "C"
         size_t words = (size_t)3 * l * c.n;
         u64 *out = alloc_words(c, words);
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-        k_square<<<c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream()>>>(a->d, out, c.d_primes, c.log_n, l);
+        launch_pdl(k_square, c.ew_grid((size_t)l * c.n / 2), 256, 0, c.stream(), a->d, out, c.d_primes, c.log_n, l);
         c.count();
         adopt(a, out, words, 3, l);
         a->scale = new_scale;
@@ -2153,7 +2162,7 @@ extern "C"
         size_t words = (size_t)a->size * limbs * c.n;
         u64 *out = alloc_words(c, words);
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * limbs);
-        k_drop_limbs<<<c.ew_grid(words / 2), 256, 0, c.stream()>>>(a->d, out, c.log_n, a->limbs, limbs, a->size);
+        launch_pdl(k_drop_limbs, c.ew_grid(words / 2), 256, 0, c.stream(), a->d, out, c.log_n, a->limbs, limbs, a->size);
         c.count();
         adopt(a, out, words, a->size, limbs);
     }
@@ -2361,9 +2370,9 @@ extern "C"
                 const size_t total2 = (size_t)2 * ne * n / 2;
                 ProfScope ps_ew(c, s, TAG_ELEMENTWISE, 2 * ne * a.count);
                 if (ext_terms == 0)
-                    k_mul_plain_sum<false><<<c.ew_grid(total2), 256, 0, s>>>(sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
+                    launch_pdl(k_mul_plain_sum<false>, c.ew_grid(total2), 256, 0, s, sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
                 else
-                    k_mul_plain_sum<true><<<c.ew_grid(total2), 256, 0, s>>>(sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
+                    launch_pdl(k_mul_plain_sum<true>, c.ew_grid(total2), 256, 0, s, sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
                 c.count();
                 ext_terms += a.count;
             }
@@ -2389,9 +2398,9 @@ extern "C"
                     continue;
                 ProfScope ps_ew(c, s, TAG_ELEMENTWISE, l * a.count);
                 if (plain_terms == 0)
-                    k_gather_mul_sum<false><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(base0.p, c0, a, c.d_primes, c.log_n, l);
+                    launch_pdl(k_gather_mul_sum<false>, c.ew_grid((size_t)l * n), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
                 else
-                    k_gather_mul_sum<true><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(base0.p, c0, a, c.d_primes, c.log_n, l);
+                    launch_pdl(k_gather_mul_sum<true>, c.ew_grid((size_t)l * n), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
                 c.count();
                 plain_terms += a.count;
             }
@@ -2404,7 +2413,7 @@ extern "C"
                 a.ct[0] = c1;
                 a.pt[0] = identity->d;
                 ProfScope ps_ew(c, s, TAG_ELEMENTWISE, l);
-                k_mul_plain_sum<false><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(base1.p, a, c.d_primes, c.log_n, l, 1);
+                launch_pdl(k_mul_plain_sum<false>, c.ew_grid((size_t)l * n / 2), 256, 0, s, base1.p, a, c.d_primes, c.log_n, l, 1, -1, 0);
                 c.count();
             }
             if (ext_terms)
@@ -2444,7 +2453,7 @@ extern "C"
         if (!close_scale(a->scale, p->scale))
             throw std::invalid_argument("scale mismatch");
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-        k_ew<EW_ADD><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
+        launch_pdl(k_ew<EW_ADD>, c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream(), a->d, p->d, c.d_primes, c.log_n,
                                                                                     a->limbs, 1, 1);
         c.count();
         BK_END
@@ -2457,7 +2466,7 @@ extern "C"
         if (!close_scale(a->scale, p->scale))
             throw std::invalid_argument("scale mismatch");
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-        k_ew<EW_SUB><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, p->d, c.d_primes, c.log_n,
+        launch_pdl(k_ew<EW_SUB>, c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream(), a->d, p->d, c.d_primes, c.log_n,
                                                                                     a->limbs, 1, 1);
         c.count();
         BK_END
@@ -2471,7 +2480,7 @@ extern "C"
         if (!c.scale_in_bounds(new_scale, a->limbs))
             throw std::invalid_argument("scale out of bounds");
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
-        k_ew<EW_MUL><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
+        launch_pdl(k_ew<EW_MUL>, c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream(), 
             a->d, p->d, c.d_primes, c.log_n, a->limbs, a->size, 1);
         c.count();
         a->scale = new_scale;
@@ -2503,10 +2512,10 @@ extern "C"
         const size_t total2 = (size_t)a->size * a->limbs * c.n / 2;
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
         if (first)
-            k_mul_plain_acc<true><<<c.ew_grid(total2), 256, 0, c.stream()>>>(acc->d, a->d, p->d, c.d_primes, c.log_n,
+            launch_pdl(k_mul_plain_acc<true>, c.ew_grid(total2), 256, 0, c.stream(), acc->d, a->d, p->d, c.d_primes, c.log_n,
                                                                                   a->limbs, a->size);
         else
-            k_mul_plain_acc<false><<<c.ew_grid(total2), 256, 0, c.stream()>>>(acc->d, a->d, p->d, c.d_primes, c.log_n,
+            launch_pdl(k_mul_plain_acc<false>, c.ew_grid(total2), 256, 0, c.stream(), acc->d, a->d, p->d, c.d_primes, c.log_n,
                                                                                    a->limbs, a->size);
         c.count();
         acc->scale = new_scale;
@@ -2548,9 +2557,9 @@ extern "C"
             }
             ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, size * limbs * a.count);
             if (t0 == 0)
-                k_mul_plain_sum<false><<<c.ew_grid(total2), 256, 0, c.stream()>>>(dst->d, a, c.d_primes, c.log_n, limbs, size);
+                launch_pdl(k_mul_plain_sum<false>, c.ew_grid(total2), 256, 0, c.stream(), dst->d, a, c.d_primes, c.log_n, limbs, size, -1, 0);
             else
-                k_mul_plain_sum<true><<<c.ew_grid(total2), 256, 0, c.stream()>>>(dst->d, a, c.d_primes, c.log_n, limbs, size);
+                launch_pdl(k_mul_plain_sum<true>, c.ew_grid(total2), 256, 0, c.stream(), dst->d, a, c.d_primes, c.log_n, limbs, size, -1, 0);
             c.count();
         }
         dst->scale = new_scale;
@@ -2590,7 +2599,7 @@ extern "C"
         ScalarPack sp;
         scalar_residues(c, value, a->scale, a->limbs, sp.c);
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE);
-        k_scalar_pack<false><<<c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream()>>>(a->d, sp, c.d_primes,
+        launch_pdl(k_scalar_pack<false>, c.ew_grid((size_t)a->limbs * c.n / 2), 256, 0, c.stream(), a->d, sp, c.d_primes,
                                                                                             c.log_n, a->limbs, 1);
         c.count();
         BK_END
@@ -2609,7 +2618,7 @@ extern "C"
         if (!c.scale_in_bounds(new_scale, a->limbs))
             throw std::invalid_argument("scale out of bounds");
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, a->size * a->limbs);
-        k_scalar_pack<true><<<c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream()>>>(
+        launch_pdl(k_scalar_pack<true>, c.ew_grid((size_t)a->size * a->limbs * c.n / 2), 256, 0, c.stream(), 
             a->d, sp, c.d_primes, c.log_n, a->limbs, a->size);
         c.count();
         a->scale = new_scale;
@@ -2652,7 +2661,7 @@ extern "C"
         scalar_residues(c, constant, target_scale, limbs, addc.c);
         ensure_ct(dst, 2, limbs, false);
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, 2 * limbs * count);
-        k_scalar_lincomb<<<c.ew_grid((size_t)limbs * c.n), 256, 0, c.stream()>>>(dst->d, a, addc, c.d_primes, c.log_n, limbs);
+        launch_pdl(k_scalar_lincomb, c.ew_grid((size_t)limbs * c.n), 256, 0, c.stream(), dst->d, a, addc, c.d_primes, c.log_n, limbs);
         c.count();
         dst->scale = target_scale;
         dst->ntt = true;

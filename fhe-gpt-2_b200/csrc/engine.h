@@ -35,6 +35,28 @@ namespace bk
             throw bk::CudaError(std::string(#expr) + ": " + cudaGetErrorString(_e));                                   \
     } while (0)
 
+    // Every kernel launch of the engine: cudaLaunchKernelEx with programmatic stream serialization, so that the next
+    // kernel of a stream is set up (and its CTAs scheduled, parked at griddepcontrol.wait - pdl_prologue() in
+    // modarith.cuh) while the previous one still runs.  Between two dependent launches of a few limb-polynomials this
+    // hides 4-5 of the ~12 microseconds (tools/lab/ntt_lab.cu, profiles/r2_ntt_lab.md).  $B200CKKS_NO_PDL=1 launches
+    // without the attribute.
+    bool pdl_enabled();
+    template <class... KArgs, class... Args>
+    inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+    {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = pdl_enabled() ? 1 : 0;
+        BK_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    }
+
     // Scratch memory of one CUDA stream: a stack of device chunks.  Scratch objects are automatic variables, so their
     // lifetimes nest; every kernel that touches a scratch buffer is enqueued on the stream the arena belongs to, hence a
     // block popped by one operation can be handed to the next operation on that stream without any synchronisation -

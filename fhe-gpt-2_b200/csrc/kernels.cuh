@@ -326,6 +326,7 @@ __device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p, u64 policy)
 
 static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
 {
+    pdl_prologue();
     const int iloc = blockIdx.y;
     const int I = a.I0 + iloc;
     const int pi = I == a.l ? a.special_prime : I;
@@ -464,6 +465,7 @@ constexpr int HYB_CONV_TARGETS = 8;
 template <int DS>
 static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTables T)
 {
+    pdl_prologue();
     const size_t n = a.n;
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i >= n)
@@ -531,6 +533,7 @@ struct HybMacArgs
 // fills the machine where one launch per rotation left a ramp and a tail every 30 microseconds.
 static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTables T)
 {
+    pdl_prologue();
     const int eloc = blockIdx.y;
     const int e = a.e0 + eloc;
     const size_t n = a.n;
@@ -676,6 +679,7 @@ __device__ __forceinline__ void mbar_wait(u64 *bar, unsigned parity)
 
 static __global__ void __launch_bounds__(128) k_ks_mac_hyb_bulk(HybMacArgs a, NttTables T)
 {
+    pdl_prologue();
     __shared__ __align__(128) u64 sk[KS_BULK_STAGES][2][KS_BULK_TILE];
     __shared__ __align__(128) u64 sd[KS_BULK_STAGES][KS_BULK_TILE];
     __shared__ __align__(8) u64 full[KS_BULK_STAGES];
@@ -792,6 +796,7 @@ template <int OP>
 __global__ void __launch_bounds__(256) k_ew(u64 *__restrict__ a, const u64 *__restrict__ b, const PrimeDev *primes,
                                             int log_n, int limbs, int a_polys, int b_polys)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = (size_t)a_polys * per_poly / 2;
@@ -839,6 +844,7 @@ __global__ void __launch_bounds__(256) k_mul_plain_acc(u64 *__restrict__ acc, co
                                                        const u64 *__restrict__ pt, const PrimeDev *primes, int log_n,
                                                        int limbs, int polys)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = (size_t)polys * per_poly / 2;
@@ -879,6 +885,7 @@ template <bool ACCUMULATE>
 __global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, MulSumArgs a, const PrimeDev *primes, int log_n,
                                                        int limbs, int polys, int special_pos = -1, int special_prime = 0)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = (size_t)polys * per_poly / 2;
@@ -921,6 +928,7 @@ template <bool ACCUMULATE>
 __global__ void __launch_bounds__(256) k_gather_mul_sum(u64 *__restrict__ dst, const u64 *__restrict__ src, GatherSumArgs a,
                                                         const PrimeDev *primes, int log_n, int limbs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t total = (size_t)limbs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -942,6 +950,7 @@ __global__ void __launch_bounds__(256) k_gather_mul_sum(u64 *__restrict__ dst, c
 static __global__ void __launch_bounds__(256) k_tensor(const u64 *__restrict__ a, const u64 *__restrict__ b,
                                                 u64 *__restrict__ out, const PrimeDev *primes, int log_n, int limbs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = per_poly / 2;
@@ -978,6 +987,7 @@ static __global__ void __launch_bounds__(256) k_tensor(const u64 *__restrict__ a
 static __global__ void __launch_bounds__(256) k_square(const u64 *__restrict__ a, u64 *__restrict__ out,
                                                 const PrimeDev *primes, int log_n, int limbs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
     const size_t total = per_poly / 2;
@@ -1006,6 +1016,7 @@ static __global__ void __launch_bounds__(256) k_square(const u64 *__restrict__ a
 static __global__ void __launch_bounds__(256) k_permute(const u64 *__restrict__ src, u64 *__restrict__ dst,
                                                  const uint32_t *__restrict__ perm, int log_n, int jobs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t total = (size_t)jobs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -1020,6 +1031,7 @@ static __global__ void __launch_bounds__(256) k_permute(const u64 *__restrict__ 
 static __global__ void __launch_bounds__(256) k_drop_limbs(const u64 *__restrict__ src, u64 *__restrict__ dst, int log_n,
                                                     int limbs_in, int limbs_out, int polys)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_out = (size_t)limbs_out * n;
     const size_t total = (size_t)polys * per_out / 2;

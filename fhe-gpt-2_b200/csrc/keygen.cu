@@ -58,6 +58,7 @@ __device__ __forceinline__ u64 uniform_mod(const RngKey &key, unsigned stream, u
 __global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, size_t count, RngKey key, unsigned stream,
                                                       int mode)
 {
+    pdl_prologue();
     size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
     if (i >= count)
         return;
@@ -113,16 +114,16 @@ namespace bk
         dim3 grid(16, jobs);
         switch (c.log_n)
         {
-        case 12: k_fwd_cols<4, LdSmall><<<grid, 16, 0, s>>>(ld, tmp.p, c.tables); break;
-        case 13: k_fwd_cols<5, LdSmall><<<grid, 32, 0, s>>>(ld, tmp.p, c.tables); break;
-        case 14: k_fwd_cols<6, LdSmall><<<grid, 64, 0, s>>>(ld, tmp.p, c.tables); break;
-        case 15: k_fwd_cols<7, LdSmall><<<grid, 128, 0, s>>>(ld, tmp.p, c.tables); break;
-        default: k_fwd_cols<8, LdSmall><<<grid, 256, 0, s>>>(ld, tmp.p, c.tables); break;
+        case 12: launch_pdl(k_fwd_cols<4, LdSmall>, grid, 16, 0, s, ld, tmp.p, c.tables); break;
+        case 13: launch_pdl(k_fwd_cols<5, LdSmall>, grid, 32, 0, s, ld, tmp.p, c.tables); break;
+        case 14: launch_pdl(k_fwd_cols<6, LdSmall>, grid, 64, 0, s, ld, tmp.p, c.tables); break;
+        case 15: launch_pdl(k_fwd_cols<7, LdSmall>, grid, 128, 0, s, ld, tmp.p, c.tables); break;
+        default: launch_pdl(k_fwd_cols<8, LdSmall>, grid, 256, 0, s, ld, tmp.p, c.tables); break;
         }
         c.count();
         StPlain st{ out, map, c.n };
         dim3 grid2((unsigned)(c.n >> 12), jobs);
-        k_fwd_blocks<StPlain><<<grid2, 256, 256 * 128, s>>>(tmp.p, st, c.tables);
+        launch_pdl(k_fwd_blocks<StPlain>, grid2, 256, 256 * 128, s, tmp.p, st, c.tables);
         c.count();
     }
 }
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
                                                   int log_n, int limbs, RngKey rkey, unsigned stream,
                                                   const u64 *__restrict__ factors = nullptr /*[limbs], 0 = none*/)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t total = (size_t)limbs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -179,6 +181,7 @@ __global__ void __launch_bounds__(256) k_asym_zero(u64 *__restrict__ out /*[2][l
                                                    const u64 *__restrict__ e_ntt /*[2][limbs][N]*/,
                                                    const PrimeDev *primes, int log_n, int limbs, int n_primes)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per = (size_t)limbs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < 2 * per; i += (size_t)gridDim.x * blockDim.x)
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256) k_decrypt(const u64 *__restrict__ ct, con
                                                  u64 *__restrict__ out, const PrimeDev *primes, int log_n, int limbs,
                                                  int size)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per = (size_t)limbs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < per; i += (size_t)gridDim.x * blockDim.x)
@@ -215,6 +219,7 @@ __global__ void __launch_bounds__(256) k_decrypt(const u64 *__restrict__ ct, con
 __global__ void __launch_bounds__(256) k_permute_limbs(const u64 *__restrict__ src, u64 *__restrict__ dst,
                                                        const uint32_t *__restrict__ perm, int log_n, int jobs)
 {
+    pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t total = (size_t)jobs * n;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
@@ -263,15 +268,15 @@ namespace bk
         for (int j = 0; j < kl; j++)
         {
             unsigned st_e = g_stream_counter.fetch_add(2);
-            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st_e, 1);
+            launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, (int *)small.p, n, rk, st_e, 1);
             c.count();
             ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, kl + 1, map);
             u64 factor = c.primes[sp] % c.primes[j];
             u64 *c0 = key->d + ((size_t)j * 2) * (kl + 1) * n;
             u64 *c1 = c0 + (size_t)(kl + 1) * n;
-            k_sym_zero<false><<<c.ew_grid((size_t)(kl + 1) * n), 256, 0, s>>>(c0, c1, sk->d, e_ntt.p, newkey, j, factor,
+            launch_pdl(k_sym_zero<false>, c.ew_grid((size_t)(kl + 1) * n), 256, 0, s, c0, c1, sk->d, e_ntt.p, newkey, j, factor,
                                                                             map, c.d_primes, c.log_n, kl + 1, rk,
-                                                                            st_e + 1);
+                                                                            st_e + 1, (const u64 *)nullptr);
             c.count();
         }
         BK_CUDA(cudaStreamSynchronize(s));
@@ -285,12 +290,12 @@ namespace bk
         if (kind == 1)
         {
             BK_CUDA(cudaMemcpyAsync(out, sk->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-            k_ew<EW_MUL><<<c.ew_grid(words / 2), 256, 0, s>>>(out, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
+            launch_pdl(k_ew<EW_MUL>, c.ew_grid(words / 2), 256, 0, s, out, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
         }
         else
         {
             const uint32_t *perm = c.galois_table(elt);
-            k_permute_limbs<<<c.ew_grid(words), 256, 0, s>>>(sk->d, out, perm, c.log_n, c.n_primes);
+            launch_pdl(k_permute_limbs, c.ew_grid(words), 256, 0, s, sk->d, out, perm, c.log_n, c.n_primes);
         }
         c.count();
     }
@@ -330,12 +335,12 @@ namespace bk
         for (int d = 0; d < P.dnum; d++)
         {
             unsigned st_e = g_stream_counter.fetch_add(2);
-            k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st_e, 1);
+            launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, (int *)small.p, n, rk, st_e, 1);
             c.count();
             ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, ne, map);
             u64 *c0 = hk->d + ((size_t)d * 2) * ne * n;
             u64 *c1 = c0 + (size_t)ne * n;
-            k_sym_zero<false><<<c.ew_grid((size_t)ne * n), 256, 0, s>>>(c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map, c.d_primes,
+            launch_pdl(k_sym_zero<false>, c.ew_grid((size_t)ne * n), 256, 0, s, c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map, c.d_primes,
                                                                       c.log_n, ne, rk, st_e + 1,
                                                                       P.d_keyfactor + (size_t)d * ne);
             c.count();
@@ -466,12 +471,12 @@ extern "C"
         Scratch small(s, (n + 1) / 2);
         Scratch e_ntt(s, (size_t)L * n);
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st, 1);
+        launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, (int *)small.p, n, rk, st, 1);
         c.count();
         ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, L, limb_map(L));
-        k_sym_zero<false><<<c.ew_grid((size_t)L * n), 256, 0, s>>>(pk_out->d, pk_out->d + (size_t)L * n, sk->d,
-                                                                   e_ntt.p, nullptr, -1, 0, limb_map(L), c.d_primes,
-                                                                   c.log_n, L, rk, st + 1);
+        launch_pdl(k_sym_zero<false>, c.ew_grid((size_t)L * n), 256, 0, s, pk_out->d, pk_out->d + (size_t)L * n, sk->d,
+                                                                   e_ntt.p, (const u64 *)nullptr, -1, 0, limb_map(L), c.d_primes,
+                                                                   c.log_n, L, rk, st + 1, (const u64 *)nullptr);
         c.count();
         pk_out->scale = 1.0;
         pk_out->ntt = true;
@@ -489,7 +494,7 @@ extern "C"
         size_t words = (size_t)c.n_primes * c.n;
         Scratch sq(s, words);
         BK_CUDA(cudaMemcpyAsync(sq.p, sk->d, words * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-        k_ew<EW_MUL><<<c.ew_grid(words / 2), 256, 0, s>>>(sq.p, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
+        launch_pdl(k_ew<EW_MUL>, c.ew_grid(words / 2), 256, 0, s, sq.p, sk->d, c.d_primes, c.log_n, c.n_primes, 1, 1);
         c.count();
         *out = make_kskey(c, sk, sq.p, seed, max_limbs, 1, 0);
         BK_END
@@ -509,7 +514,7 @@ extern "C"
         size_t words = (size_t)c.n_primes * c.n;
         Scratch rot(s, words);
         const uint32_t *perm = c.galois_table(galois_elt);
-        k_permute_limbs<<<c.ew_grid(words), 256, 0, s>>>(sk->d, rot.p, perm, c.log_n, c.n_primes);
+        launch_pdl(k_permute_limbs, c.ew_grid(words), 256, 0, s, sk->d, rot.p, perm, c.log_n, c.n_primes);
         c.count();
         *out = make_kskey(c, sk, rot.p, seed, max_limbs, 2, galois_elt);
         BK_END
@@ -535,8 +540,8 @@ extern "C"
         Scratch small(s, (3 * n + 1) / 2);
         int *d_small = (int *)small.p;
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(d_small, n, rk, st, 0);
-        k_sample_small<<<(unsigned)((2 * n + 255) / 256), 256, 0, s>>>(d_small + n, 2 * n, rk, st + 1, 1);
+        launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, d_small, n, rk, st, 0);
+        launch_pdl(k_sample_small, (unsigned)((2 * n + 255) / 256), 256, 0, s, d_small + n, 2 * n, rk, st + 1, 1);
         c.count(2);
         Scratch u_ntt(s, (size_t)l1 * n);
         Scratch e_ntt(s, (size_t)2 * l1 * n);
@@ -545,7 +550,7 @@ extern "C"
         bk_ct_s tmp;
         tmp.ctx = ctx;
         ensure_ct(&tmp, 2, l1, false);
-        k_asym_zero<<<c.ew_grid((size_t)2 * l1 * n), 256, 0, s>>>(tmp.d, pk->d, u_ntt.p, e_ntt.p, c.d_primes, c.log_n, l1,
+        launch_pdl(k_asym_zero, c.ew_grid((size_t)2 * l1 * n), 256, 0, s, tmp.d, pk->d, u_ntt.p, e_ntt.p, c.d_primes, c.log_n, l1,
                                                                   c.n_primes);
         c.count();
         tmp.ntt = true;
@@ -553,7 +558,7 @@ extern "C"
         // divide_and_round_q_last_ntt_inplace by prime index l (the special prime when l is the top level:
         // there prime index l == n_primes - 1)
         rescale_core(c, &tmp);
-        k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(tmp.d, pt->d, c.d_primes, c.log_n, l, 1, 1);
+        launch_pdl(k_ew<EW_ADD>, c.ew_grid((size_t)l * n / 2), 256, 0, s, tmp.d, pt->d, c.d_primes, c.log_n, l, 1, 1);
         c.count();
         c.release_words(out->d, out->owner);
         out->d = tmp.d;
@@ -582,13 +587,13 @@ extern "C"
         Scratch small(s, (n + 1) / 2);
         Scratch e_ntt(s, (size_t)l * n);
         unsigned st = g_stream_counter.fetch_add(2);
-        k_sample_small<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((int *)small.p, n, rk, st, 1);
+        launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, (int *)small.p, n, rk, st, 1);
         c.count();
         ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, l, limb_map(l));
-        k_sym_zero<false><<<c.ew_grid((size_t)l * n), 256, 0, s>>>(out->d, out->d + (size_t)l * n, sk->d, e_ntt.p,
-                                                                   nullptr, -1, 0, limb_map(l), c.d_primes, c.log_n, l,
-                                                                   rk, st + 1);
-        k_ew<EW_ADD><<<c.ew_grid((size_t)l * n / 2), 256, 0, s>>>(out->d, pt->d, c.d_primes, c.log_n, l, 1, 1);
+        launch_pdl(k_sym_zero<false>, c.ew_grid((size_t)l * n), 256, 0, s, out->d, out->d + (size_t)l * n, sk->d, e_ntt.p,
+                                                                   (const u64 *)nullptr, -1, 0, limb_map(l), c.d_primes, c.log_n, l,
+                                                                   rk, st + 1, (const u64 *)nullptr);
+        launch_pdl(k_ew<EW_ADD>, c.ew_grid((size_t)l * n / 2), 256, 0, s, out->d, pt->d, c.d_primes, c.log_n, l, 1, 1);
         c.count(2);
         out->scale = pt->scale;
         out->ntt = true;
@@ -607,7 +612,7 @@ extern "C"
             throw std::invalid_argument("encrypted must be in NTT form");
         const int l = ct->limbs;
         ensure_pt(out, l);
-        k_decrypt<<<c.ew_grid((size_t)l * c.n), 256, 0, c.stream()>>>(ct->d, sk->d, out->d, c.d_primes, c.log_n, l,
+        launch_pdl(k_decrypt, c.ew_grid((size_t)l * c.n), 256, 0, c.stream(), ct->d, sk->d, out->d, c.d_primes, c.log_n, l,
                                                                       ct->size);
         c.count();
         out->scale = ct->scale;

@@ -11,6 +11,17 @@
 
 typedef unsigned long long u64;
 
+// Programmatic dependent launch: every kernel of the engine begins with this.  `wait` blocks until the grids this
+// launch depends on have completed and flushed (a no-op when the launch carries no programmatic dependency);
+// `launch_dependents` lets the next kernel of the stream be set up and its CTAs be scheduled while this one still
+// runs - they stop at their own `wait`, so no kernel touches memory before its predecessors are done, but the launch
+// latency between two dependent kernels is hidden (see launch_pdl in engine.h).
+__device__ __forceinline__ void pdl_prologue()
+{
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // Per-prime constants resident in HBM (one entry per modulus of the key-level chain).
 struct PrimeDev
 {

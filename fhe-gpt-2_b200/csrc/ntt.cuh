@@ -170,6 +170,7 @@ __device__ __forceinline__ int cols_idx(int row)
 template <int LOGR, class Load, bool WIDE = false, int COLS = 16>
 __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out, NttTables T)
 {
+    pdl_prologue();
     constexpr int R = 1 << LOGR;
     constexpr int TR = R / 16;     // threads along rows
     constexpr int LOG2 = LOGR - 4; // stages in the second phase
@@ -253,6 +254,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 template <class Store, bool WIDE = false>
 __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ in, Store st, NttTables T)
 {
+    pdl_prologue();
     extern __shared__ __align__(16) u64 sm[]; // 256 words per half-warp: blockDim.x * 16 words
     const int job = blockIdx.y;
     if (st.skip(job))
@@ -321,6 +323,7 @@ __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ i
 template <class Load>
 __global__ void __launch_bounds__(256) k_inv_blocks(Load ld, u64 *__restrict__ out, NttTables T)
 {
+    pdl_prologue();
     extern __shared__ __align__(16) u64 sm[]; // 256 words per half-warp: blockDim.x * 16 words
     const int job = blockIdx.y;
     const int t = threadIdx.x & 15;
@@ -373,6 +376,7 @@ __global__ void __launch_bounds__(256) k_inv_blocks(Load ld, u64 *__restrict__ o
 template <int LOGR, class Store, int COLS = 16>
 __global__ void __launch_bounds__(256) k_inv_cols(const u64 *__restrict__ in, Store st, NttTables T)
 {
+    pdl_prologue();
     constexpr int R = 1 << LOGR;
     constexpr int TR = R / 16;
     constexpr int LOG2 = LOGR - 4;

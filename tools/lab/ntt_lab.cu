@@ -260,6 +260,57 @@ int main(int argc, char **argv)
         float k = jobs <= 36 ? time_us([&] { k_inv_fused<LabInvLd, LabInvSt><<<dim3(8, jobs), FUSED_THREADS, FUSED_SMEM>>>(ild, ist2, T); }) : 0.f;
         printf("%5d | %8.2f %8.2f %8.2f %8.2f %8.2f | %8.2f | %8.2f %8.2f %8.2f %8.2f | %8.2f\n", jobs, a, b, c, c2, d, e, f, g, hh, i, k);
     }
+    // programmatic dependent launch: the same pair with the launch of the second pass (and of the next pair) set up
+    // while the previous kernel runs
+    {
+        auto pdl = [&](auto kern, dim3 grid, unsigned threads, size_t smem, auto... args) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = grid;
+            cfg.blockDim = dim3(threads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = 0;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            CK(cudaLaunchKernelEx(&cfg, kern, args...));
+        };
+        printf("\npairs back to back, plain launches against programmatic dependent launches, microseconds\n%5s | %10s %10s | %10s %10s\n", "jobs", "fwd", "fwd pdl", "inv", "inv pdl");
+        for (int jobs : { 1, 2, 4, 8, 16, 31, 62 })
+        {
+            const unsigned bt = jobs * 32 < 296 ? 64u : 128u;
+            float a = time_us([&] {
+                k_fwd_cols<8, LabLd, true, 8><<<dim3(32, jobs), 128>>>(ld, d_tmp, T);
+                k_fwd_blocks<LabSt, true><<<dim3(4096 / bt, jobs), bt, bt * 128>>>(d_tmp, st, T);
+            });
+            float b = time_us([&] {
+                pdl(k_fwd_cols<8, LabLd, true, 8>, dim3(32, jobs), 128u, (size_t)0, ld, d_tmp, T);
+                pdl(k_fwd_blocks<LabSt, true>, dim3(4096 / bt, jobs), bt, (size_t)bt * 128, (const u64 *)d_tmp, st, T);
+            });
+            float c = time_us([&] {
+                k_inv_blocks<LabInvLd><<<dim3(4096 / bt, jobs), bt, bt * 128>>>(ild, d_tmp, T);
+                k_inv_cols<8, LabInvSt, 8><<<dim3(32, jobs), 128>>>(d_tmp, ist, T);
+            });
+            float d = time_us([&] {
+                pdl(k_inv_blocks<LabInvLd>, dim3(4096 / bt, jobs), bt, (size_t)bt * 128, ild, d_tmp, T);
+                pdl(k_inv_cols<8, LabInvSt, 8>, dim3(32, jobs), 128u, (size_t)0, (const u64 *)d_tmp, ist, T);
+            });
+            printf("%5d | %10.2f %10.2f | %10.2f %10.2f\n", jobs, a, b, c, d);
+        }
+        // equality of the PDL chain with the plain one
+        CK(cudaMemset(d_out, 0, h.size() * 8));
+        CK(cudaMemset(d_out2, 0xff, h.size() * 8));
+        k_fwd_cols<8, LabLd, true, 8><<<dim3(32, 5), 128>>>(ld, d_tmp, T);
+        k_fwd_blocks<LabSt, true><<<dim3(32, 5), 128, 16384>>>(d_tmp, st, T);
+        CK(cudaDeviceSynchronize());
+        for (int rep = 0; rep < 20; rep++)
+        {
+            pdl(k_fwd_cols<8, LabLd, true, 8>, dim3(32, 5), 128u, (size_t)0, ld, d_tmp, T);
+            pdl(k_fwd_blocks<LabSt, true>, dim3(32, 5), 128u, (size_t)16384, (const u64 *)d_tmp, st2, T);
+        }
+        ok &= compare("PDL chain vs plain launches", 5);
+    }
     // pairs back to back (what the engine does today) against the fused kernel
     printf("\npairs back to back (two launches) against one fused launch, microseconds\n%5s | %10s %10s | %10s %10s\n", "jobs", "fwd 2pass", "fwd fused", "inv 2pass", "inv fused");
     for (int jobs : { 1, 2, 4, 8, 12, 16, 18, 24, 31 })
