@@ -58,6 +58,43 @@ namespace
         memory_save_rotate(dst, dst, steps, evaluator, gal_keys);
     }
 
+    // dst[i] = src rotated by steps[i].  The reference rotates one by one (rotated_copy); on the engine the rotations
+    // of ONE ciphertext share the decomposition of its c1 (Evaluator::rotate_vector_hoisted; tolerance mode, off with
+    // $B200CKKS_NO_HOIST or the reference's constants) - steps that memory_save_rotate splits in two keep that path.
+    void rotated_copies(const Ciphertext &src, const vector<int> &steps, vector<Ciphertext> &dst, Evaluator &evaluator,
+                        GaloisKeys &gal_keys)
+    {
+        dst.resize(steps.size());
+#ifdef B200CKKS_FACADE
+        static const bool hoist = std::getenv("B200CKKS_NO_HOIST") == nullptr && !encrypt_constants();
+        if (hoist && steps.size() > 1)
+        {
+            const long n = (long)src.poly_modulus_degree() / 2;
+            vector<int> hs;
+            vector<std::size_t> where;
+            for (std::size_t i = 0; i < steps.size(); i++)
+            {
+                const int st = (int)(((steps[i] % n) + n) % n);
+                const bool split = (34 <= st && st <= 55) || (57 <= st && st <= 61);
+                if (split)
+                    rotated_copy(src, dst[i], steps[i], evaluator, gal_keys);
+                else
+                {
+                    hs.push_back(st);
+                    where.push_back(i);
+                }
+            }
+            vector<Ciphertext> out;
+            evaluator.rotate_vector_hoisted(src, hs, gal_keys, out);
+            for (std::size_t k = 0; k < where.size(); k++)
+                dst[where[k]] = std::move(out[k]);
+            return;
+        }
+#endif
+        for (std::size_t i = 0; i < steps.size(); i++)
+            rotated_copy(src, dst[i], steps[i], evaluator, gal_keys);
+    }
+
     int copies_that_fit(long n, long used)
     {
         return (int)pow2(floor_to_int(std::log(static_cast<double>(n) / static_cast<double>(used)) / std::log(2.0)));
@@ -188,11 +225,14 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
     Ciphertext ctxt_in = cnn_in.cipher(), ct_zero, temp, sum, total_sum, var;
 
     // the fh x fw shifted copies of the input
-    vector<Ciphertext> ctxt_rot((std::size_t)(fh * fw));
-    for (int i1 = 0; i1 < fh; i1++)
-        for (int i2 = 0; i2 < fw; i2++)
-            rotated_copy(ctxt_in, ctxt_rot[(std::size_t)(i1 * fw + i2)], ki * ki * wi * (i1 - (fh - 1) / 2) + ki * (i2 - (fw - 1) / 2),
-                         evaluator, gal_keys);
+    vector<Ciphertext> ctxt_rot;
+    {
+        vector<int> tap_steps;
+        for (int i1 = 0; i1 < fh; i1++)
+            for (int i2 = 0; i2 < fw; i2++)
+                tap_steps.push_back(ki * ki * wi * (i1 - (fh - 1) / 2) + ki * (i2 - (fw - 1) / 2));
+        rotated_copies(ctxt_in, tap_steps, ctxt_rot, evaluator, gal_keys);
+    }
 
     // an encryption of zero at the input's scale: the reference's start value of its running sums (cnn_seal.cpp:433-436).
     // Without it (default) a running sum starts from its first term - same level and scale as zero + first term.
@@ -255,14 +295,19 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
             }
 
         // move every output channel of this group to its place in the output layout and mask it
+        vector<int> move_steps;
         for (int i8 = 0; i8 < pi && pi * g + i8 < co; i8++)
         {
             const int j4 = (int)(pi * g) + i8;
-            rotated_copy(var, temp,
-                         (int)((n / pi) * (j4 % pi) - j4 % ko - (long)(j4 / (ko * ko)) * ko * ko * ho * wo -
-                               (long)((j4 % (ko * ko)) / ko) * ko * wo),
-                         evaluator, gal_keys);
-            multiply_vector_named_accumulate(evaluator, total_sum, total_started, temp, owner, (std::size_t)j4, 1,
+            move_steps.push_back((int)((n / pi) * (j4 % pi) - j4 % ko - (long)(j4 / (ko * ko)) * ko * ko * ho * wo -
+                                       (long)((j4 % (ko * ko)) / ko) * ko * wo));
+        }
+        vector<Ciphertext> moved;
+        rotated_copies(var, move_steps, moved, evaluator, gal_keys);
+        for (std::size_t i8 = 0; i8 < move_steps.size(); i8++)
+        {
+            const int j4 = (int)(pi * g) + (int)i8;
+            multiply_vector_named_accumulate(evaluator, total_sum, total_started, moved[i8], owner, (std::size_t)j4, 1,
                                              [&]() -> const vector<double> & { return P.select_one_vec[(std::size_t)j4]; });
         }
     }
@@ -273,13 +318,17 @@ void multiplexed_parallel_convolution_planned(const TensorCipher &cnn_in, Tensor
     { // replicate into po copies
         if (zero_start)
             sum = ct_zero;
+        vector<int> copy_steps;
+        for (int u6 = 0; u6 < po; u6++)
+            copy_steps.push_back((int)(-u6 * (n / po)));
+        vector<Ciphertext> copies;
+        rotated_copies(var, copy_steps, copies, evaluator, gal_keys);
         for (int u6 = 0; u6 < po; u6++)
         {
-            rotated_copy(var, temp, (int)(-u6 * (n / po)), evaluator, gal_keys);
             if (u6 == 0 && !zero_start)
-                sum = temp;
+                sum = copies[(std::size_t)u6];
             else
-                evaluator.add_inplace_reduced_error(sum, temp);
+                evaluator.add_inplace_reduced_error(sum, copies[(std::size_t)u6]);
         }
         var = sum;
     }
