@@ -42,7 +42,6 @@ METRIC = "ResNet-20 CIFAR-10 homomorphic inference throughput (bootstrapped, N=2
 UNIT = "images/s"
 HIST_KEYS = ["key_switch", "rescale", "multiply_vector", "multiply", "scalar", "add"]
 NTT_BUTTERFLIES_PER_PASS = (1 << LOG_N) // 2 * 8      # a pass = 8 of the 16 stages of one limb-polynomial
-IMAD_PER_BUTTERFLY = 9                                # 32-bit multiplies of one 64-bit Shoup butterfly (ntt.cuh ct_bfly_wide)
 
 
 def hist_path(layers):
@@ -394,16 +393,24 @@ def run_engine(args):
                 "note": "the NTT passes are bound by the integer multiply-add pipe, not by HBM (ncu captures in profiles/); the "
                         "HBM fraction is reported because the contract asks for hbm|tensor, int_roofline is the bound that applies",
                 "gpu_busy_fraction_of_step": round(total_kernel_ms / prof_ms, 4)}
-        # Integer roofline, measured in this run: peak 32-bit multiply-add rate of this GPU (bk_measure_imad_peak) against
-        # the multiplies the NTT passes of one image need (9 per 64-bit Shoup butterfly, 2^15 x 8 butterflies per pass and
-        # limb-polynomial, limb-polynomials from the engine's kernel counters) over their live-timed duration.
-        imad_peak = eng.imad_peak()
-        int_roof = {"peak_imad_per_s": imad_peak, "peak_source": "bk_measure_imad_peak: 8 independent mad.lo.u32 chains per thread, "
-                    "this GPU, this run", "multiplies_per_butterfly": IMAD_PER_BUTTERFLY, "butterflies_per_limb_poly_pass": NTT_BUTTERFLIES_PER_PASS}
+        # Integer roofline, measured in this run.  The multiplier pipe of an SM issues the three forms a 64-bit Shoup
+        # butterfly is made of at different rates (bk_measure_int_pipe: dependent chains of mad.lo / mad.wide / mad.hi
+        # on this GPU); the unreduced forward butterfly (ntt.cuh ct_bfly_wide) compiles to 4 IMAD + 3 IMAD.WIDE +
+        # 2 IMAD.HI, the Gentleman-Sande butterfly of the inverse (exact 64-bit high product) to 4 + 6 + 0 (executed
+        # instruction mix of the ncu captures in profiles/r2_ntt_lab.md).  frac = multiplier-pipe seconds those instructions need at the measured rates /
+        # live-timed seconds of the family (2^15 x 8 butterflies per pass and limb-polynomial, limb-polynomials from
+        # the engine's kernel counters).  1.0 would be a pass that issues nothing but its butterflies' multiplies.
+        rates = eng.int_pipe_rates()
+        mix = {"fwd": {"mad_lo": 4, "mad_wide": 3, "mad_hi": 2}, "inv": {"mad_lo": 4, "mad_wide": 6, "mad_hi": 0}}
+        pipe_s = {k: sum(n / rates[f] for f, n in m.items()) for k, m in mix.items()}   # thread-seconds per butterfly
+        int_roof = {"rates_per_s": {k: round(v) for k, v in rates.items()},
+                    "rates_source": "bk_measure_int_pipe: 8 independent dependent chains per thread of each form, this GPU, this run",
+                    "instructions_per_butterfly": mix, "butterflies_per_limb_poly_pass": NTT_BUTTERFLIES_PER_PASS,
+                    "peak_butterflies_per_s": {k: round(1.0 / v) for k, v in pipe_s.items()}}
         for fam in ("fwd_cols", "fwd_blocks", "inv_blocks", "inv_cols"):
             if fam in kernels and kernels[fam]["ms"] > 0:
-                rate = kernels[fam]["limb_polys"] * NTT_BUTTERFLIES_PER_PASS * IMAD_PER_BUTTERFLY / (kernels[fam]["ms"] * 1e-3)
-                int_roof[fam] = {"achieved_imad_per_s": rate, "frac": round(rate / imad_peak, 4)}
+                bf = kernels[fam]["limb_polys"] * NTT_BUTTERFLIES_PER_PASS / (kernels[fam]["ms"] * 1e-3)
+                int_roof[fam] = {"achieved_butterflies_per_s": round(bf), "frac": round(bf * pipe_s[fam[:3]], 4)}
         if dom in int_roof:
             int_roof["frac"] = int_roof[dom]["frac"]
         roof["int_roofline"] = int_roof

@@ -38,7 +38,7 @@ static __global__ void __launch_bounds__(256) k_imad_peak(unsigned long long *si
             if (KIND == 0)
                 asm volatile("mad.lo.u32 %0, %0, %1, %0;" : "+r"(a[j]) : "r"(m));
             else if (KIND == 1)
-                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"(a[j]), "r"(m));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[j]) : "r"((unsigned)w[j]), "r"(m)); // operand from the chain: not loop-invariant
             else
                 asm volatile("mad.hi.u32 %0, %0, %1, %0;" : "+r"(a[j]) : "r"(m));
         }
