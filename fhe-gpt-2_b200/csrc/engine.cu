@@ -2398,9 +2398,9 @@ extern "C"
                     continue;
                 ProfScope ps_ew(c, s, TAG_ELEMENTWISE, l * a.count);
                 if (plain_terms == 0)
-                    launch_pdl(k_gather_mul_sum<false>, c.ew_grid((size_t)l * n), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
+                    launch_pdl(k_gather_mul_sum<false>, c.ew_grid((size_t)l * n / 2), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
                 else
-                    launch_pdl(k_gather_mul_sum<true>, c.ew_grid((size_t)l * n), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
+                    launch_pdl(k_gather_mul_sum<true>, c.ew_grid((size_t)l * n / 2), 256, 0, s, base0.p, c0, a, c.d_primes, c.log_n, l);
                 c.count();
                 plain_terms += a.count;
             }

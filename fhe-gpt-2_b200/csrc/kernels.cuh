@@ -120,6 +120,7 @@ struct LdModRaise
 struct StPlain
 {
     static constexpr bool RAW = false;
+    static constexpr bool BATCH = false;
     __device__ __forceinline__ bool skip(int) const { return false; }
     u64 *dst;
     JobMap map;
@@ -141,6 +142,7 @@ struct StPlain
 struct StKsDigit
 {
     static constexpr bool RAW = true; // k_ks_mac multiplies whatever 64-bit representative it is given
+    static constexpr bool BATCH = false;
     u64 *dst;
     size_t n;
     int l, I0, special_prime;
@@ -161,6 +163,7 @@ struct StKsDigit
 struct StRescale
 {
     static constexpr bool RAW = false;
+    static constexpr bool BATCH = true; // post_all: the 16 loads of a thread in flight together
     __device__ __forceinline__ bool skip(int) const { return false; }
     const u64 *x;  // [polys][limbs_in][N]
     u64 *dst;      // [polys][limbs_out][N]
@@ -169,13 +172,23 @@ struct StRescale
     int limbs_in, limbs_out;
     __device__ __forceinline__ int prime(int job) const { return job % limbs_out; }
     __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
-    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &pd) const
+    // coefficients base + t + 16 k, k < 16, their transform values at s[swz(t + 16 k)] (in [0,4q))
+    __device__ __forceinline__ void post_all(int job, int base, int t, const u64 *s, const PrimeDev &pd) const
     {
-        int p = job / limbs_out, i = job % limbs_out;
-        u64 r = x[((size_t)p * limbs_in + i) * n + idx];
-        u64 d = r + 2 * pd.two_q - v; // v in [0,4q)
-        ulonglong2 f = inv[i];
-        dst[(size_t)job * n + idx] = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+        const int p = job / limbs_out, i = job % limbs_out;
+        const u64 *src = x + ((size_t)p * limbs_in + i) * n + base + t;
+        u64 *out = dst + (size_t)job * n + base + t;
+        const ulonglong2 f = __ldg(inv + i);
+        u64 r[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            r[k] = __ldg(src + 16 * k);
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            u64 d = r[k] + 2 * pd.two_q - s[swz(t + 16 * k)];
+            out[16 * k] = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+        }
     }
 };
 
@@ -187,6 +200,7 @@ struct StRescale
 struct StModDown
 {
     static constexpr bool RAW = false;
+    static constexpr bool BATCH = true; // post_all: three dependent loads per coefficient, 16 coefficients in flight
     __device__ __forceinline__ bool skip(int) const { return false; }
     const u64 *acc;  // [2][l+1][N]
     u64 *dst;        // [2][l][N]
@@ -199,23 +213,56 @@ struct StModDown
     int acc_limbs = 0;     // limbs per polynomial of acc; 0 = l + 1 (one special prime)
     __device__ __forceinline__ int prime(int job) const { return job % l; }
     __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
-    // everything happens in the coalesced order of the store: acc is read as full 128-byte lines (reading it in the
-    // register layout, coefficient 16t + k per lane, touched one line per lane: 5x the DRAM bytes in the ncu capture)
-    __device__ __forceinline__ void post(int job, int idx, u64 v, const PrimeDev &pd) const
+    // Coefficients base + t + 16 k, k < 16, in the coalesced order of the store (acc, base and dst as full lines),
+    // their transform values at s[swz(t + 16 k)].  The loads are issued in three batches - Galois indices,
+    // accumulator, base - so that a thread waits for three DRAM latencies, not for 48 (the per-coefficient form did:
+    // 100 us for 58 limb-polynomials at 18 % of DRAM bandwidth, profiles/r2_ncu_full_moddown.md).  acc / base never
+    // overlap dst (the callers of a rotation write to a fresh buffer), hence the read-only loads.
+    __device__ __forceinline__ void post_all(int job, int base, int t, const u64 *s, const PrimeDev &pd) const
     {
-        int p = job / l, i = job % l;
-        int al = acc_limbs ? acc_limbs : l + 1;
-        u64 r = acc[((size_t)p * al + i) * n + idx];
-        u64 d = r + 2 * pd.two_q - v; // v in [0,4q)
-        ulonglong2 f = inv[i];
-        v = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+        const int p = job / l, i = job % l;
+        const int al = acc_limbs ? acc_limbs : l + 1;
+        const u64 *a = acc + ((size_t)p * al + i) * n + base + t;
         const u64 *b = p == 0 ? base0 : base1;
+        u64 *out = dst + (size_t)job * n + base + t;
+        const ulonglong2 f = __ldg(inv + i);
+        int src[16];
+        if (p == 0 && perm)
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                src[k] = (int)__ldg(perm + base + t + 16 * k);
+        }
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                src[k] = base + t + 16 * k;
+        }
+        u64 r[16], add[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+            r[k] = __ldg(a + 16 * k);
         if (b)
         {
-            int src = (p == 0 && perm) ? (int)perm[idx] : idx;
-            v = addmod(v, b[(size_t)i * n + src], pd.q);
+            b += (size_t)i * n;
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                add[k] = __ldg(b + src[k]);
         }
-        dst[(size_t)job * n + idx] = v;
+        else
+        {
+#pragma unroll
+            for (int k = 0; k < 16; k++)
+                add[k] = 0;
+        }
+#pragma unroll
+        for (int k = 0; k < 16; k++)
+        {
+            u64 d = r[k] + 2 * pd.two_q - s[swz(t + 16 * k)]; // transform value in [0,4q)
+            u64 v = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+            out[16 * k] = addmod(v, add[k], pd.q);
+        }
     }
 };
 
@@ -419,6 +466,7 @@ struct StInvScaled
 struct StHybDigit
 {
     static constexpr bool RAW = true;
+    static constexpr bool BATCH = false;
     u64 *dst;
     size_t n;
     HybDims h;
@@ -925,25 +973,59 @@ struct GatherSumArgs
     int count;
 };
 template <bool ACCUMULATE>
-__global__ void __launch_bounds__(256) k_gather_mul_sum(u64 *__restrict__ dst, const u64 *__restrict__ src, GatherSumArgs a,
-                                                        const PrimeDev *primes, int log_n, int limbs)
+__global__ void __launch_bounds__(256) k_gather_mul_sum(u64 *__restrict__ dst, const u64 *__restrict__ src,
+                                                        const __grid_constant__ GatherSumArgs a, const PrimeDev *primes,
+                                                        int log_n, int limbs)
 {
     pdl_prologue();
     const size_t n = size_t(1) << log_n;
-    const size_t total = (size_t)limbs * n;
+    const size_t total = (size_t)limbs * n / 2; // two coefficients per step
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     {
-        const int limb = (int)(i >> log_n);
-        const size_t x = i & (n - 1);
+        const size_t e = i * 2;
+        const int limb = (int)(e >> log_n);
+        const size_t x = e & (n - 1);
         const PrimeDev pd = primes[limb];
         const u64 *row = src + (size_t)limb * n;
-        u64 lo = ACCUMULATE ? dst[i] : 0ull, hi = 0;
-        for (int t = 0; t < a.count; t++)
+        u64 lo0 = 0, hi0 = 0, lo1 = 0, hi1 = 0;
+        if (ACCUMULATE)
         {
-            const size_t sx = a.perm[t] ? (size_t)a.perm[t][x] : x;
-            mac128(lo, hi, row[sx], a.pt[t][i]);
+            const ulonglong2 d = *reinterpret_cast<const ulonglong2 *>(dst + e);
+            lo0 = d.x;
+            lo1 = d.y;
         }
-        dst[i] = barrett128(lo, hi, pd);
+        // four terms at a time: their Galois indices and plaintext words are requested together, then the gathers
+        // (the input's c0 limb stays in L2), then the multiplies - one DRAM latency per four terms instead of two per term
+        for (int t0 = 0; t0 < a.count; t0 += 4)
+        {
+            uint2 sx[4];
+            ulonglong2 pw[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                const int t = min(t0 + u, a.count - 1);
+                sx[u] = a.perm[t] ? __ldg(reinterpret_cast<const uint2 *>(a.perm[t] + x)) : make_uint2((unsigned)x, (unsigned)x + 1);
+                pw[u] = __ldcs(reinterpret_cast<const ulonglong2 *>(a.pt[t] + e));
+            }
+            u64 v0[4], v1[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+            {
+                v0[u] = __ldg(row + sx[u].x);
+                v1[u] = __ldg(row + sx[u].y);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                if (t0 + u < a.count)
+                {
+                    mac128(lo0, hi0, v0[u], pw[u].x);
+                    mac128(lo1, hi1, v1[u], pw[u].y);
+                }
+        }
+        ulonglong2 o;
+        o.x = barrett128(lo0, hi0, pd);
+        o.y = barrett128(lo1, hi1, pd);
+        *reinterpret_cast<ulonglong2 *>(dst + e) = o;
     }
 }
 

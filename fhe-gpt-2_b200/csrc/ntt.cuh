@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 //   Store: int prime(int job);  bool skip(int job);
 //          u64  pre (int job, int blk, int t, int k, u64 v, const PrimeDev&)   - register layout
 //               e = 16t + k, v in [0,4q); returns the value to be staged;
-//          void post(int job, int idx, u64 v, const PrimeDev&)                  - coalesced order.
+//          void post(int job, int idx, u64 v, const PrimeDev&)                  - coalesced order;
+//          or, with BATCH: void post_all(int job, int base, int t, const u64 *s, const PrimeDev&) for all 16
+//          coefficients base + t + 16 k of the thread at once (values at s[swz(t + 16 k)]).
 // ============================================================================================
 template <class Store, bool WIDE = false>
 __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ in, Store st, NttTables T)
@@ -308,9 +310,14 @@ __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ i
     for (int k = 0; k < 16; k++)
         s[swz(16 * t + k)] = x[k];
     __syncwarp();
+    if constexpr (Store::BATCH)
+        st.post_all(job, blk * 256, t, s, pd);
+    else
+    {
 #pragma unroll
-    for (int k = 0; k < 16; k++)
-        st.post(job, blk * 256 + t + 16 * k, s[swz(t + 16 * k)], pd);
+        for (int k = 0; k < 16; k++)
+            st.post(job, blk * 256 + t + 16 * k, s[swz(t + 16 * k)], pd);
+    }
 }
 
 // ============================================================================================

@@ -24,6 +24,7 @@ struct LabLd
 struct LabSt
 {
     static constexpr bool RAW = false;
+    static constexpr bool BATCH = false;
     u64 *dst;
     int np = 1;
     __device__ __forceinline__ bool skip(int) const { return false; }
