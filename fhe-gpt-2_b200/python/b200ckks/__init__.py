@@ -512,6 +512,15 @@ class Context:
     def modraise_inplace(self, a):
         _ck(_L.bk_modraise_inplace(self.h, a.h))
 
+    def scalar_linear_combination(self, cts, values, constant, target_scale):
+        """constant + sum_j values[j] * cts[j] at the lowest level among cts and at scale target_scale (one pass;
+        term j's scalar is encoded at target_scale / cts[j].scale) - bk_scalar_linear_combination"""
+        out = Ciphertext(self)
+        hs = (C.c_void_p * len(cts))(*[c.h for c in cts])
+        vs = (C.c_double * len(cts))(*[float(v) for v in values])
+        _ck(_L.bk_scalar_linear_combination(self.h, out.h, hs, vs, len(cts), C.c_double(constant), C.c_double(target_scale)))
+        return out
+
     # -- raw kernels
     def ntt_limbs_host(self, data, prime_idx, inverse=False):
         d = np.ascontiguousarray(data, dtype=np.uint64).copy()

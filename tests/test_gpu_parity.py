@@ -238,6 +238,41 @@ def test_const_ops(small):
     assert_ct_equal(ea, ref, a, "rescale after multiply_const")
 
 
+def test_scalar_linear_combination(small):
+    """bk_scalar_linear_combination (the one-pass leaves of the polynomial evaluation trees).  With all terms at one
+    level and scale it must equal, limb by limb, the reference's sequence multiply_const per term + add + add_const
+    (same integer scalars: round(v * scale) mod q); with terms at different levels and scales every limb must equal
+    sum_j round(v_j * target / scale_j) * ct_j + round(c * target) computed in exact integer arithmetic."""
+    ref, eng, rk, gk = small
+    vals = (0.37, -1.5e-3, 2.25)
+    cts = [_pair(small, 4, 50 + j)[0] for j in range(3)]
+    ecs = [to_engine(eng, ref, c) for c in cts]
+    scale = ecs[0].scale
+    got = eng.scalar_linear_combination(ecs, vals, -0.625, scale * scale)
+    for c, v in zip(cts, vals):
+        ref.op("multiply_const", c, darg=v)
+    ref.op("add", cts[0], cts[1])
+    ref.op("add", cts[0], cts[2])
+    ref.op("add_const", cts[0], darg=-0.625)
+    assert_ct_equal(got, ref, cts[0], "linear combination vs multiply_const / add / add_const")
+
+    # mismatched levels and scales: exact integers
+    primes = [int(q) for q in eng.primes]
+    a = to_engine(eng, ref, _pair(small, 5, 60)[0])
+    b = to_engine(eng, ref, _pair(small, 3, 61, scale=2.0 ** 38)[0])
+    target = 2.0 ** 79
+    out = eng.scalar_linear_combination([a, b], (0.75, -0.2), 0.125, target)
+    assert out.info()[:3] == (2, 3, target)
+    da, db, do = a.download(), b.download(), out.download()
+    for i in range(3):
+        q = primes[i]
+        ra, rb = round(0.75 * target / a.scale) % q, round(-0.2 * target / b.scale) % q
+        rc = round(0.125 * target) % q
+        for p in range(2):
+            want = (da[p, i].astype(object) * ra + db[p, i].astype(object) * rb + (rc if p == 0 else 0)) % q
+            assert np.array_equal(do[p, i].astype(object), want), (p, i)
+
+
 def test_multiply_vector_reduced_error_path(small):
     """evaluator.h:1270-1278: encode at the top level, drop to the ciphertext level, multiply."""
     ref, eng, rk, gk = small
