@@ -4,7 +4,7 @@
 Workload (config.workload): the reference's `./cnn 20 10 i i` (ResNet_cifar10_seal_sparse, cnn_ckks/cpu-ckks/single-key/
 cnn/infer_seal.cpp:251-584) at its own parameters - N = 2^16, primes 51 | 46x16 | 51x14 | 51, Hamming weight 192,
 scale 2^46, 18 sparse-slot bootstraps, 19 multiplexed convolutions, 19 alpha=13 minimax ReLUs - on synthetic images
-and random-init weights of that architecture.  One step = one image per GPU.  Images are independent: image i goes
+with the reference's trained parameters.  One step = `--in-flight` images per GPU.  Images are independent: image i goes
 to rank i mod G, no data-path collective (weak scaling); rank 0 samples the secret key and broadcasts it with NCCL,
 every rank derives its evaluation keys from it on its own GPU.
 
@@ -185,6 +185,8 @@ def run_engine(args):
     os.environ.setdefault("B200CKKS_SEED", "0x5EA1C0DE")      # reproducible benchmark randomness (never set in production)
     hybrid = not args.no_hybrid
     os.environ["B200CKKS_HYBRID_KS"] = "1" if hybrid else "0"
+    if args.compress_keys:
+        os.environ["B200CKKS_COMPRESS_KEYS"] = "1"
     app = App()
     weights, weights_name = load_weights(args.layers)
     image_of = lambda step: synthetic.synthetic_image(rank + world * step)
@@ -462,7 +464,7 @@ def run_engine(args):
             "ops_per_image": {k: v // args.steps for k, v in stats.items()},
             "keys": {"plan": plan_source, "plan_seconds": round(plan_s, 1), "generate_seconds": round(gen_s, 1),
                      "secret_key_detached_from_evaluation_keys": plan is not None,
-                     "resident_gib": round(key_bytes / 2 ** 30, 2), "generated": key_gens,
+                     "resident_gib": round(key_bytes / 2 ** 30, 2), "seed_compressed": bool(args.compress_keys), "generated": key_gens,
                      "generated_during_evaluation": (key_gens - keys_after_plan) if plan is not None else key_gens,
                      "setup_and_warmup_seconds": round(setup_s, 1)},
             "plaintext_cache": {k: (round(v / 2 ** 30, 2) if k == "bytes" else v) for k, v in plain_cache.items()},
@@ -686,6 +688,9 @@ def main():
     ap.add_argument("--in-flight", type=int, default=4, help="images in flight per GPU (a step = that many images per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-mode child run and the key-switch timings")
+    ap.add_argument("--compress-keys", action="store_true",
+                    help="seed-compressed evaluation keys: the uniform half of every level key is regenerated from its public "
+                         "seed when the key is used instead of being resident (half the key bytes in HBM)")
     ap.add_argument("--lazy-keys", action="store_true",
                     help="round-1 behaviour: evaluation keys generated on first use from the resident secret key instead of "
                          "up front from a key plan")

@@ -129,6 +129,8 @@ namespace bk
             throw std::invalid_argument("coeff_modulus size is invalid");
         if (const char *e = std::getenv("B200CKKS_HYBRID_KS"))
             hybrid = std::atoi(e) != 0;
+        if (const char *e = std::getenv("B200CKKS_COMPRESS_KEYS"))
+            compress_keys = std::atoi(e) != 0;
         if (const char *e = std::getenv("B200CKKS_DEBUG_SYNC"))
             debug_sync = std::atoi(e) != 0;
         // random generator master key (rng.cuh): the operating system's entropy unless a reproducible run is asked for
@@ -803,16 +805,32 @@ namespace bk
             launch_fwd_cols(c, s, ld, inter, nE * P.dnum);
             StHybDigit st{ inter, n, h, e0 };
             launch_fwd_blocks(c, s, inter, st, nE * P.dnum);
-            for (int k0 = 0; k0 < count; k0 += HYB_MAC_BATCH)
+            // seed-compressed keys (all keys of a context are, or none): the uniform halves of this chunk's limbs are
+            // regenerated into scratch first, a few rotations at a time to bound the scratch
+            const bool compressed = keys[0]->compressed;
+            const int batch = compressed ? 4 : HYB_MAC_BATCH;
+            const size_t kstride = (size_t)P.ne * n;
+            Scratch halves(s, compressed ? (size_t)std::min(batch, count) * P.dnum * nE * n : 0);
+            for (int k0 = 0; k0 < count; k0 += batch)
             {
-                const int nk = std::min(HYB_MAC_BATCH, count - k0);
+                const int nk = std::min(batch, count - k0);
                 HybMacArgs a{};
                 a.digits = inter;
                 a.target_ntt = target_ntt;
+                a.dstride0 = compressed ? kstride : 2 * kstride;
+                a.dstride1 = compressed ? (size_t)nE * n : 2 * kstride;
                 for (int k = 0; k < nk; k++)
                 {
                     a.perm[k] = perms[k0 + k];
                     a.key[k] = keys[k0 + k]->d;
+                    if (compressed)
+                    {
+                        u64 *buf = halves.p + (size_t)k * P.dnum * nE * n;
+                        expand_public_halves(c, s, keys[k0 + k], e0, nE, buf);
+                        a.key1[k] = buf - (size_t)e0 * n; // the kernels add e * N with e = e0 + local limb
+                    }
+                    else
+                        a.key1[k] = keys[k0 + k]->d + kstride;
                 }
                 a.acc = acc + (size_t)k0 * 2 * P.ne * n;
                 a.n = n;
@@ -855,6 +873,25 @@ namespace bk
         launch_fwd_cols(c, s, LdPlain{ conv, limb_map(P.l), n }, inter, 2 * P.l);
         StModDown st2{ acc, out, base0, base1, perm, P.d_psinv, n, P.l, P.ne };
         launch_fwd_blocks(c, s, inter, st2, 2 * P.l);
+    }
+
+    // polynomial-1 pointer and digit strides of a SEAL-shaped key for k_ks_mac; a seed-compressed level key gets its
+    // uniform halves for output moduli [I0, I0 + nI) expanded into `halves` first
+    static void classic_key_halves(Context &c, cudaStream_t s, const bk_kskey_s *key, int I0, int nI, u64 *halves, KsMacArgs &a)
+    {
+        const size_t kstride = (size_t)(key->klimbs + 1) * c.n;
+        if (key->view_of && key->view_of->compressed)
+        {
+            expand_public_halves(c, s, key->view_of, I0, nI, halves);
+            a.key1 = halves - (size_t)I0 * c.n;
+            a.dstride0 = kstride;
+            a.dstride1 = (size_t)nI * c.n;
+        }
+        else
+        {
+            a.key1 = key->d + kstride;
+            a.dstride0 = a.dstride1 = 2 * kstride;
+        }
     }
 
     // Same contract as key_switch below; the key is the level-l hybrid key of `key`'s recipe.
@@ -926,6 +963,7 @@ namespace bk
             bk_hybkey_s *hk = hybrid_key(c, key, l);
             level_view.ctx = key->ctx;
             level_view.d = hk->d;
+            level_view.view_of = hk;
             level_view.digits = level_view.klimbs = l;
             key = &level_view;
         }
@@ -957,6 +995,9 @@ namespace bk
             StKsDigit st{ inter.p, n, l, I0, sp };
             launch_fwd_blocks(c, s, inter.p, st, nI * l);
             KsMacArgs a{ inter.p, target, perm, key->d, acc.p, n, l, I0, sp, key->klimbs, 0 };
+            const bool comp = key->view_of && key->view_of->compressed;
+            Scratch halves(s, comp ? (size_t)l * nI * n : 0);
+            classic_key_halves(c, s, key, I0, nI, halves.p, a);
             dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
             {
                 ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
@@ -1001,6 +1042,7 @@ namespace bk
                 bk_hybkey_s *hk = hybrid_key(c, keys[k], l);
                 level_views[(size_t)k].ctx = keys[k]->ctx;
                 level_views[(size_t)k].d = hk->d;
+                level_views[(size_t)k].view_of = hk;
                 level_views[(size_t)k].digits = level_views[(size_t)k].klimbs = l;
                 level_keys.push_back(&level_views[(size_t)k]);
             }
@@ -1035,6 +1077,9 @@ namespace bk
             {
                 KsMacArgs a{ inter.p, c1, perms[k], keys[k]->d, acc.p + (size_t)k * 2 * (l + 1) * n, n, l, I0, sp,
                              keys[k]->klimbs, 1 };
+                const bool comp = keys[k]->view_of && keys[k]->view_of->compressed;
+                Scratch halves(s, comp ? (size_t)l * nI * n : 0);
+                classic_key_halves(c, s, keys[k], I0, nI, halves.p, a);
                 dim3 grid((unsigned)((n / 2 + KS_MAC_THREADS - 1) / KS_MAC_THREADS), nI);
                 {
                     ProfScope ps(c, s, TAG_KS_MAC, nI * (2 * l + 2));
@@ -1388,6 +1433,12 @@ extern "C"
     {
         BK_TRY
         ctx->hybrid = on != 0;
+        BK_END
+    }
+    bk_status bk_context_set_key_compression(bk_context_t ctx, int on)
+    {
+        BK_TRY
+        ctx->compress_keys = on != 0;
         BK_END
     }
     bk_status bk_context_hybrid_shape(bk_context_t ctx, int limbs, int *alpha_out, int *dsize_out)

@@ -188,6 +188,10 @@ namespace bk
         // hybrid key switching: generated keys are level-specific and not in SEAL's layout ($B200CKKS_HYBRID_KS=1 or
         // bk_context_set_hybrid before any key is generated)
         bool hybrid = false;
+        // seed-compressed level keys ($B200CKKS_COMPRESS_KEYS=1 or bk_context_set_key_compression before keys are
+        // generated): only polynomial 0 of every digit is resident, the uniform polynomial is regenerated from its
+        // public ChaCha8 key when the key is used
+        bool compress_keys = false;
         std::map<int, HybridPlan *> hplans;
         std::atomic<uint64_t> hybrid_key_bytes{ 0 }, hybrid_keys{ 0 };
         std::atomic<uint64_t> launches{ 0 };
@@ -336,9 +340,17 @@ struct bk_sk_s;
 struct bk_hybkey_s
 {
     u64 *d = nullptr; // [dnum][2][l + alpha][N]: limbs 0 .. l + alpha - 2, then the special prime
+                      // compressed: [dnum][l + alpha][N], polynomial 0 only - polynomial 1 is (akey, astream0 + digit)
     int l = 0, alpha = 0, dsize = 0, dnum = 0;
     size_t words = 0;
+    bool compressed = false;
+    bk::RngKey akey{};     // PUBLIC key of the uniform halves (keygen.cu: public_uniform8)
+    unsigned astream0 = 0;
 };
+namespace bk
+{
+    void expand_public_halves(Context &c, cudaStream_t s, const bk_hybkey_s *hk, int limb0, int nlimbs, u64 *out);
+}
 struct bk_kskey_s
 {
     bk::Context *ctx;
@@ -354,6 +366,7 @@ struct bk_kskey_s
     uint64_t seed = 0;
     std::mutex hmu;
     std::map<int, bk_hybkey_s *> hyb;
+    const bk_hybkey_s *view_of = nullptr; // a transient SEAL-shaped view of this level key (key_switch): may be compressed
 };
 
 struct bk_gkeys_s

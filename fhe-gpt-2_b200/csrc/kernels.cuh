@@ -345,6 +345,10 @@ struct KsMacArgs
     size_t n;
     int l, I0, special_prime, klimbs;
     int gather_digits;     // hoisted rotations: the digits were computed before the automorphism, read them through perm
+    // polynomial 1 of digit J, limb kl at key1 + J * dstride1 + kl * N (polynomial 0: key + J * dstride0 + kl * N): the
+    // same array, or a buffer expanded from the key's seed just before (seed-compressed level keys)
+    const u64 *key1;
+    size_t dstride0, dstride1;
 };
 
 __device__ __forceinline__ ulonglong2 ldg_stream2(const u64 *p)
@@ -383,9 +387,9 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
     if (e >= n)
         return;
     const PrimeDev pd = T.primes[pi];
-    const size_t kstride = (size_t)(a.klimbs + 1) * n; // one key poly
     const u64 *dig = a.digits + (size_t)iloc * a.l * n + e;
     const u64 *k0 = a.key + (size_t)kl * n + e;
+    const u64 *k1 = a.key1 + (size_t)kl * n + e;
 
     u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
     const u64 key_policy = l2_evict_first_policy();
@@ -412,8 +416,8 @@ static __global__ void __launch_bounds__(256) k_ks_mac(KsMacArgs a, NttTables T)
         }
         else
             x = *reinterpret_cast<const ulonglong2 *>(dig + (size_t)J * n);
-        ulonglong2 w0 = ldg_stream2(k0 + (size_t)J * 2 * kstride, key_policy);
-        ulonglong2 w1 = ldg_stream2(k0 + (size_t)J * 2 * kstride + kstride, key_policy);
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)J * a.dstride0, key_policy);
+        ulonglong2 w1 = ldg_stream2(k1 + (size_t)J * a.dstride1, key_policy);
         mac128(l0x, h0x, x.x, w0.x);
         mac128(l0y, h0y, x.y, w0.y);
         mac128(l1x, h1x, x.x, w1.x);
@@ -568,7 +572,11 @@ struct HybMacArgs
     const u64 *digits;     // [nE][dnum][N] NTT form, lazy; own-limb slots unused
     const u64 *target_ntt; // [l][N] NTT form
     const uint32_t *perm[HYB_MAC_BATCH]; // per rotation of a hoisted group (blockIdx.z): Galois table or null
-    const u64 *key[HYB_MAC_BATCH];       // per rotation: [dnum][2][ne][N]
+    const u64 *key[HYB_MAC_BATCH];       // per rotation: polynomial 0 of digit d, limb e at key[rot] + d * dstride0 + e * N
+    const u64 *key1[HYB_MAC_BATCH];      // polynomial 1 (the uniform half) at key1[rot] + d * dstride1 + e * N: inside the
+                                         // same [dnum][2][ne][N] array, or a buffer expanded from its seed just before
+                                         // (seed-compressed keys, keygen.cu)
+    size_t dstride0, dstride1;
     u64 *acc;              // [rotations][2][ne][N]
     size_t n;
     HybDims h;
@@ -590,11 +598,11 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
         return;
     const PrimeDev pd = T.primes[a.h.eprime(e)];
     const int ne = a.h.ne();
-    const size_t kstride = (size_t)ne * n;
     const int rot = blockIdx.z;
     const uint32_t *perm = a.perm[rot];
     u64 *acc = a.acc + (size_t)rot * 2 * ne * n;
     const u64 *k0 = a.key[rot] + (size_t)e * n + i;
+    const u64 *k1 = a.key1[rot] + (size_t)e * n + i;
     u64 l0x = 0, h0x = 0, l0y = 0, h0y = 0, l1x = 0, h1x = 0, l1y = 0, h1y = 0;
     const u64 key_policy = l2_evict_first_policy();
     // gather indices are the same for every digit
@@ -635,10 +643,10 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
     for (; d + 1 < a.h.dnum; d += 2)
     {
         ulonglong2 xa = load_digit(d), xb = load_digit(d + 1);
-        ulonglong2 wa0 = ldg_stream2(k0 + (size_t)d * 2 * kstride, key_policy);
-        ulonglong2 wa1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride, key_policy);
-        ulonglong2 wb0 = ldg_stream2(k0 + (size_t)(d + 1) * 2 * kstride, key_policy);
-        ulonglong2 wb1 = ldg_stream2(k0 + (size_t)(d + 1) * 2 * kstride + kstride, key_policy);
+        ulonglong2 wa0 = ldg_stream2(k0 + (size_t)d * a.dstride0, key_policy);
+        ulonglong2 wa1 = ldg_stream2(k1 + (size_t)d * a.dstride1, key_policy);
+        ulonglong2 wb0 = ldg_stream2(k0 + (size_t)(d + 1) * a.dstride0, key_policy);
+        ulonglong2 wb1 = ldg_stream2(k1 + (size_t)(d + 1) * a.dstride1, key_policy);
         mac128(l0x, h0x, xa.x, wa0.x);
         mac128(l0y, h0y, xa.y, wa0.y);
         mac128(l1x, h1x, xa.x, wa1.x);
@@ -651,8 +659,8 @@ static __global__ void __launch_bounds__(256) k_ks_mac_hyb(HybMacArgs a, NttTabl
     if (d < a.h.dnum)
     {
         ulonglong2 x = load_digit(d);
-        ulonglong2 w0 = ldg_stream2(k0 + (size_t)d * 2 * kstride, key_policy);
-        ulonglong2 w1 = ldg_stream2(k0 + (size_t)d * 2 * kstride + kstride, key_policy);
+        ulonglong2 w0 = ldg_stream2(k0 + (size_t)d * a.dstride0, key_policy);
+        ulonglong2 w1 = ldg_stream2(k1 + (size_t)d * a.dstride1, key_policy);
         mac128(l0x, h0x, x.x, w0.x);
         mac128(l0y, h0y, x.y, w0.y);
         mac128(l1x, h1x, x.x, w1.x);
@@ -738,8 +746,8 @@ static __global__ void __launch_bounds__(128) k_ks_mac_hyb_bulk(HybMacArgs a, Nt
     const size_t base = (size_t)blockIdx.x * KS_BULK_TILE;
     const int dnum = a.h.dnum, ne = a.h.ne();
     const PrimeDev pd = T.primes[a.h.eprime(e)];
-    const size_t kstride = (size_t)ne * n;
     const u64 *k0 = a.key[rot] + (size_t)e * n + base;
+    const u64 *k1 = a.key1[rot] + (size_t)e * n + base;
     const uint32_t *perm = a.perm[rot];
     u64 *acc = a.acc + (size_t)rot * 2 * ne * n;
     const unsigned t = threadIdx.x;
@@ -762,8 +770,8 @@ static __global__ void __launch_bounds__(128) k_ks_mac_hyb_bulk(HybMacArgs a, Nt
         const u64 *src = own ? a.target_ntt + (size_t)e * n : a.digits + ((size_t)eloc * dnum + d) * n;
         const bool gather = own ? perm != nullptr : a.gather_digits != 0;
         mbar_expect_tx(&full[s], 3 * TILE_BYTES);
-        bulk_g2s(&sk[s][0][0], k0 + (size_t)d * 2 * kstride, TILE_BYTES, &full[s], policy);
-        bulk_g2s(&sk[s][1][0], k0 + (size_t)d * 2 * kstride + kstride, TILE_BYTES, &full[s], policy);
+        bulk_g2s(&sk[s][0][0], k0 + (size_t)d * a.dstride0, TILE_BYTES, &full[s], policy);
+        bulk_g2s(&sk[s][1][0], k1 + (size_t)d * a.dstride1, TILE_BYTES, &full[s], policy);
         bulk_g2s_plain(&sd[s][0], src + (gather ? blk_a : base), HALF_BYTES, &full[s]);
         bulk_g2s_plain(&sd[s][256], src + (gather ? blk_b : base + 256), HALF_BYTES, &full[s]);
     };

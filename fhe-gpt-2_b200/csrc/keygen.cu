@@ -53,6 +53,64 @@ __device__ __forceinline__ u64 uniform_mod(const RngKey &key, unsigned stream, u
     }
 }
 
+// ---- the uniform halves `a` of level keys: PUBLIC randomness -----------------------------------------------------
+// `a` is published with the key (SEAL ships it as a seed, keygenerator.cpp:384-417 / rlwe.cpp:294-409), so it comes
+// from its own 256-bit key `akey` - never from the key that samples the errors - through ChaCha8, eight 64-bit words
+// per block: word i of a digit's [ne][N] index space is word i % 8 of block i / 8 (nonce = (astream, 0)).  A word at or
+// above the largest multiple of q (probability < 2^-13) is replaced by rejection sampling on blocks keyed by the word
+// index (nonce = (astream | 2^31, attempt)).  Storing (akey, astream) instead of `a` is the seed-compressed form of a
+// key: k_expand_public_a regenerates exactly the words keygen used.
+__device__ __forceinline__ u64 public_uniform_retry(const RngKey &akey, unsigned astream, u64 index, u64 max_multiple, const PrimeDev &pd)
+{
+    for (unsigned attempt = 1;; attempt++)
+    {
+        uint32_t w[4];
+        chacha_block<4, 4>(akey, (unsigned)index, (unsigned)(index >> 32), astream | 0x80000000u, attempt, w);
+        u64 v = ((u64)w[0] << 32) | w[1];
+        if (v < max_multiple)
+            return barrett64(v, pd);
+        v = ((u64)w[2] << 32) | w[3];
+        if (v < max_multiple)
+            return barrett64(v, pd);
+    }
+}
+__device__ __forceinline__ void public_uniform8(const RngKey &akey, unsigned astream, u64 block, const PrimeDev &pd, u64 *out)
+{
+    const u64 max_multiple = 0xFFFFFFFFFFFFFFFFull - barrett64(0xFFFFFFFFFFFFFFFFull, pd) - 1;
+    uint32_t w[16];
+    chacha_block<16, 4>(akey, (unsigned)block, (unsigned)(block >> 32), astream, 0u, w);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+    {
+        const u64 v = ((u64)w[2 * k] << 32) | w[2 * k + 1];
+        out[k] = v < max_multiple ? barrett64(v, pd) : public_uniform_retry(akey, astream, block * 8 + k, max_multiple, pd);
+    }
+}
+
+// out[d][j][N] for digits d < dnum and limbs limb0 + j, j < nlimbs, of a key over ne limbs; one thread per block of 8 words
+__global__ void __launch_bounds__(256) k_expand_public_a(u64 *__restrict__ out, JobMap map, const PrimeDev *primes, int log_n,
+                                                         int ne, int limb0, int nlimbs, int dnum, RngKey akey, unsigned astream0)
+{
+    pdl_prologue();
+    const size_t n = size_t(1) << log_n;
+    const size_t per_limb = n / 8, total = (size_t)dnum * nlimbs * per_limb;
+    for (size_t b = blockIdx.x * (size_t)blockDim.x + threadIdx.x; b < total; b += (size_t)gridDim.x * blockDim.x)
+    {
+        const int d = (int)(b / ((size_t)nlimbs * per_limb));
+        const size_t r = b % ((size_t)nlimbs * per_limb);
+        const int j = (int)(r / per_limb);
+        const size_t within = r % per_limb;
+        const int limb = limb0 + j;
+        const PrimeDev pd = primes[map.prime(limb)];
+        u64 v[8];
+        public_uniform8(akey, astream0 + (unsigned)d, (size_t)limb * per_limb + within, pd, v);
+        ulonglong2 *o = reinterpret_cast<ulonglong2 *>(out + ((size_t)d * nlimbs + j) * n + within * 8);
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+            o[k] = make_ulonglong2(v[2 * k], v[2 * k + 1]);
+    }
+}
+
 // small signed polynomials: mode 0 = uniform ternary (sample_poly_ternary), 1 = centred binomial
 // with sigma 3.2 (sample_poly_cbd: 21 bits minus 21 bits)
 __global__ void __launch_bounds__(256) k_sample_small(int *__restrict__ out, size_t count, RngKey key, unsigned stream,
@@ -132,7 +190,7 @@ namespace bk
 //   c1 = a (uniform, sampled directly in NTT form), c0 = -(a*s + e)      (rlwe.cpp:340-371)
 // optional: c0[limb == add_limb] += factor * newkey      (keygenerator.cpp:406-416)
 // TRANSPOSED: write in the key's transposed-block layout.
-template <bool TRANSPOSED>
+template <bool TRANSPOSED, bool PUBLIC_A = false>
 __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__restrict__ c1,
                                                   const u64 *__restrict__ sk /*[n_primes][N]*/,
                                                   const u64 *__restrict__ e_ntt /*[limbs][N]*/,
@@ -150,7 +208,15 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
         size_t idx = i & (n - 1);
         int pi = map.prime(l);
         const PrimeDev pd = primes[pi];
-        u64 a = uniform_mod(rkey, stream, i, pd);
+        u64 a;
+        if (PUBLIC_A)
+        { // (akey, astream) ride in (rkey, stream): see hybrid_key
+            u64 blockw[8];
+            public_uniform8(rkey, stream, i >> 3, pd, blockw);
+            a = blockw[i & 7];
+        }
+        else
+            a = uniform_mod(rkey, stream, i, pd);
         u64 s = sk[(size_t)pi * n + idx];
         u64 v = addmod(mulmod(a, s, pd), e_ntt[i], pd.q);
         v = v ? pd.q - v : 0ull;
@@ -171,7 +237,8 @@ __global__ void __launch_bounds__(256) k_sym_zero(u64 *__restrict__ c0, u64 *__r
             o = ((size_t)l << log_n) + (blk << 8) + (size_t)(k * 16 + t);
         }
         c0[o] = v;
-        c1[o] = a;
+        if (c1)
+            c1[o] = a;
     }
 }
 
@@ -322,7 +389,14 @@ namespace bk
         hk->alpha = P.alpha;
         hk->dsize = P.dsize;
         hk->dnum = P.dnum;
-        hk->words = (size_t)P.dnum * 2 * ne * n;
+        // The uniform halves come from a PUBLIC 256-bit key of their own (never the key the errors are sampled with):
+        // with key compression on, only (akey, astream0) is kept and the halves are regenerated when the key is used
+        // (hyb_extend_and_mac, engine.cu) - SEAL's seeded keys (keygenerator.cpp:384-417), resident in half the bytes.
+        hk->compressed = c.compress_keys;
+        hk->akey = derive_call_key(c.rng_master, key->seed + 0xA5A5A5A5DEADBEEFull + 0x9E3779B97F4A7C15ull * (u64)(l + 1));
+        hk->astream0 = g_stream_counter.fetch_add((unsigned)P.dnum);
+        const int polys = hk->compressed ? 1 : 2;
+        hk->words = (size_t)P.dnum * polys * ne * n;
         BK_CUDA(cudaMalloc((void **)&hk->d, hk->words * sizeof(u64)));
         JobMap map = limb_map(ne);
         map.special_pos = ne - 1;
@@ -338,11 +412,10 @@ namespace bk
             launch_pdl(k_sample_small, (unsigned)((n + 255) / 256), 256, 0, s, (int *)small.p, n, rk, st_e, 1);
             c.count();
             ntt_fwd_small(c, s, (const int *)small.p, e_ntt.p, 1, ne, map);
-            u64 *c0 = hk->d + ((size_t)d * 2) * ne * n;
-            u64 *c1 = c0 + (size_t)ne * n;
-            launch_pdl(k_sym_zero<false>, c.ew_grid((size_t)ne * n), 256, 0, s, c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map, c.d_primes,
-                                                                      c.log_n, ne, rk, st_e + 1,
-                                                                      P.d_keyfactor + (size_t)d * ne);
+            u64 *c0 = hk->d + ((size_t)d * polys) * ne * n;
+            u64 *c1 = hk->compressed ? nullptr : c0 + (size_t)ne * n;
+            launch_pdl(k_sym_zero<false, true>, c.ew_grid((size_t)ne * n), 256, 0, s, c0, c1, key->sk->d, e_ntt.p, newkey.p, -1, 0, map,
+                       c.d_primes, c.log_n, ne, hk->akey, hk->astream0 + (unsigned)d, P.d_keyfactor + (size_t)d * ne);
             c.count();
         }
         BK_CUDA(cudaStreamSynchronize(s)); // complete before other host threads (streams) can pick it up
@@ -351,6 +424,22 @@ namespace bk
         bk_hybkey_s *raw = hk.release();
         key->hyb[l] = raw;
         return raw;
+    }
+}
+
+namespace bk
+{
+    // the uniform halves of a seed-compressed level key for limbs [limb0, limb0 + nlimbs): out[dnum][nlimbs][N]
+    void expand_public_halves(Context &c, cudaStream_t s, const bk_hybkey_s *hk, int limb0, int nlimbs, u64 *out)
+    {
+        const int ne = hk->l + hk->alpha;
+        JobMap map = limb_map(ne);
+        map.special_pos = ne - 1;
+        map.special_prime = c.n_primes - 1;
+        ProfScope ps(c, s, TAG_OTHER, hk->dnum * nlimbs);
+        launch_pdl(k_expand_public_a, c.ew_grid((size_t)hk->dnum * nlimbs * c.n / 8), 256, 0, s, out, map, c.d_primes, c.log_n, ne, limb0,
+                   nlimbs, hk->dnum, hk->akey, hk->astream0);
+        c.count();
     }
 }
 

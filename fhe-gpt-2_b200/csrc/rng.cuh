@@ -27,16 +27,18 @@ namespace bk
     c += d; b ^= c; b = rotl32(b, 7);
 
     // out[0..words) of the ChaCha20 block with this key, 64-bit block counter (c0, c1) and 64-bit nonce (n0, n1)
-    template <int WORDS>
-    __host__ __device__ __forceinline__ void chacha20_block(const RngKey &key, uint32_t c0, uint32_t c1, uint32_t n0, uint32_t n1,
-                                                            uint32_t *out)
+    // DOUBLE_ROUNDS = 10 is ChaCha20; 4 (ChaCha8) is used only for PUBLIC values - the uniform halves `a` of
+    // evaluation keys, which are published with the key and have to look uniform, not stay secret (keygen.cu)
+    template <int WORDS, int DOUBLE_ROUNDS = 10>
+    __host__ __device__ __forceinline__ void chacha_block(const RngKey &key, uint32_t c0, uint32_t c1, uint32_t n0, uint32_t n1,
+                                                          uint32_t *out)
     {
         uint32_t x0 = 0x61707865u, x1 = 0x3320646eu, x2 = 0x79622d32u, x3 = 0x6b206574u;
         uint32_t x4 = key.k[0], x5 = key.k[1], x6 = key.k[2], x7 = key.k[3], x8 = key.k[4], x9 = key.k[5], x10 = key.k[6],
                  x11 = key.k[7];
         uint32_t x12 = c0, x13 = c1, x14 = n0, x15 = n1;
 #pragma unroll
-        for (int r = 0; r < 10; r++)
+        for (int r = 0; r < DOUBLE_ROUNDS; r++)
         {
             BK_CHACHA_QR(x0, x4, x8, x12)
             BK_CHACHA_QR(x1, x5, x9, x13)
@@ -56,6 +58,12 @@ namespace bk
             out[i] = v[i];
     }
 #undef BK_CHACHA_QR
+    template <int WORDS>
+    __host__ __device__ __forceinline__ void chacha20_block(const RngKey &key, uint32_t c0, uint32_t c1, uint32_t n0, uint32_t n1,
+                                                            uint32_t *out)
+    {
+        chacha_block<WORDS, 10>(key, c0, c1, n0, n1, out);
+    }
 
     // the 256-bit key of one sampling call: ChaCha20(master, counter = seed)
     inline RngKey derive_call_key(const RngKey &master, uint64_t seed)

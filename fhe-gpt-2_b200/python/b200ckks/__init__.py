@@ -332,6 +332,10 @@ class Context:
         """Level-aware hybrid key switching for keys generated from now on (tolerance mode, include/b200ckks.h)."""
         _ck(_L.bk_context_set_hybrid(self.h, int(bool(on))))
 
+    def set_key_compression(self, on=True):
+        """level keys generated afterwards keep only their non-uniform halves resident (bk_context_set_key_compression)"""
+        _ck(_L.bk_context_set_key_compression(self.h, int(bool(on))))
+
     def hybrid_info(self):
         on, nbytes, keys = C.c_int(), C.c_uint64(), C.c_uint64()
         _ck(_L.bk_context_hybrid(self.h, C.byref(on), C.byref(nbytes), C.byref(keys)))

@@ -88,6 +88,11 @@ bk_status bk_stream(bk_context_t ctx, void **stream_out);
  * separates the streams of different calls; 0 is as good as any other value. */
 bk_status bk_context_set_rng_key(bk_context_t ctx, const uint8_t key[32]);
 bk_status bk_context_set_hybrid(bk_context_t ctx, int on);
+/* seed-compressed evaluation keys (SEAL ships the uniform half of a key as a seed, keygenerator.cpp:384-417,
+ * util/rlwe.cpp:294-409; here the compressed form is what stays RESIDENT): level keys generated after this call keep only
+ * polynomial 0 of every digit in HBM and regenerate the uniform polynomial from its public 256-bit ChaCha8 key each time
+ * the key is used - half the key bytes for one expansion kernel per use.  Hybrid mode only.  $B200CKKS_COMPRESS_KEYS=1. */
+bk_status bk_context_set_key_compression(bk_context_t ctx, int on);
 bk_status bk_context_hybrid(bk_context_t ctx, int *on, uint64_t *key_bytes, uint64_t *keys);
 /* shape of the level-aware key switch at `limbs` limbs: alpha special moduli (alpha - 1 idle primes + the special
  * prime), digits of dsize primes */

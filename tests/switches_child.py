@@ -15,9 +15,11 @@ mode = sys.argv[1]
 if mode == "limbs":
     import b200ckks as bk
 
-    primes = bk.coeff_modulus_create(13, [50, 40, 40, 40, 40, 50])
+    hybrid = len(sys.argv) > 2 and sys.argv[2] == "hybrid"
+    # the hybrid chain is long enough for levels with temporary special moduli (alpha > 1 below the top, above 5 limbs)
+    primes = bk.coeff_modulus_create(13, [50] + [40] * 10 + [50] if hybrid else [50, 40, 40, 40, 40, 50])
     eng = bk.Context(13, primes, device=0)
-    if len(sys.argv) > 2 and sys.argv[2] == "hybrid":
+    if hybrid:
         eng.set_hybrid(True)
     sk = eng.generate_secret_key(64, seed=1)
     pk = eng.create_public_key(sk)
@@ -25,8 +27,9 @@ if mode == "limbs":
     gk = eng.create_galois_keys(sk, [1, 5])
     rng = np.random.default_rng(0)
     x, y = rng.uniform(-1, 1, eng.slots), rng.uniform(-1, 1, eng.slots)
-    a = eng.encrypt(pk, eng.encode(x, 5, 2.0 ** 40))
-    b = eng.encrypt(pk, eng.encode(y, 5, 2.0 ** 40))
+    top = len(primes) - 1
+    a = eng.encrypt(pk, eng.encode(x, top, 2.0 ** 40))
+    b = eng.encrypt(pk, eng.encode(y, top, 2.0 ** 40))
     h = hashlib.sha256()
     for step in (1, 5, 1):
         eng.rotate_vector_inplace(a, step, gk)
@@ -37,7 +40,12 @@ if mode == "limbs":
         eng.mod_switch_to_inplace(b, a.limbs)
         b.scale = a.scale
         h.update(a.download().tobytes())
-    print(json.dumps({"sha256": h.hexdigest(), "limbs": a.limbs}))
+    # hoisted rotations (one decomposition, two automorphisms) at the current level and at the top
+    for ct in (a, eng.encrypt(pk, eng.encode(x, top, 2.0 ** 40))):
+        for o in eng.apply_galois_hoisted(ct, [bk.galois_elt_from_step(13, 1), bk.galois_elt_from_step(13, 5)], gk):
+            h.update(o.download().tobytes())
+    on, key_bytes, n_keys = eng.hybrid_info()
+    print(json.dumps({"sha256": h.hexdigest(), "limbs": a.limbs, "level_key_bytes": key_bytes, "level_keys": n_keys}))
     eng.close()
 else:
     from b200ckks.app import App

@@ -2,6 +2,7 @@
 
 * programmatic dependent launch ($B200CKKS_NO_PDL): identical limbs, bit for bit, on both key-switching paths - PDL
   only moves WHEN a kernel is set up, every kernel still waits for its predecessors before touching memory;
+* seed-compressed level keys ($B200CKKS_COMPRESS_KEYS): identical limbs at half the resident key bytes;
 * one-pass leaves of the polynomial evaluation trees ($B200CKKS_TERMWISE_LEAVES restores the reference's
   multiply_const + rescale + reduced-error add per term): same output level, same values within the bootstrapping /
   ReLU tolerance, and the rescale count the fusion exists to cut."""
@@ -19,7 +20,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 def child(args, **env):
     e = dict(os.environ, B200CKKS_SEED="11")
-    for k in ("B200CKKS_NO_PDL", "B200CKKS_TERMWISE_LEAVES", "B200CKKS_HYBRID_KS", "B200CKKS_ENCRYPT_CONSTANTS"):
+    for k in ("B200CKKS_NO_PDL", "B200CKKS_TERMWISE_LEAVES", "B200CKKS_HYBRID_KS", "B200CKKS_ENCRYPT_CONSTANTS",
+              "B200CKKS_COMPRESS_KEYS"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, os.path.join(HERE, "switches_child.py"), *args], env=e, capture_output=True, text=True,
@@ -34,6 +36,17 @@ def test_programmatic_dependent_launch_is_bit_identical(path):
     with_pdl = child(args)
     without = child(args, B200CKKS_NO_PDL="1")
     assert with_pdl == without
+
+
+def test_seed_compressed_keys_are_bit_identical_at_half_the_bytes():
+    """level keys keep only their non-uniform halves resident; the uniform halves are regenerated
+    from their public ChaCha8 key each time a key is used.  Same seeds -> the regenerated words are the words keygen
+    used, so every rotation / relinearization (hybrid levels, SEAL-shaped top level, hoisted) is identical bit for bit."""
+    plain = child(["limbs", "hybrid"])
+    packed = child(["limbs", "hybrid"], B200CKKS_COMPRESS_KEYS="1")
+    assert packed["sha256"] == plain["sha256"] and packed["limbs"] == plain["limbs"]
+    assert packed["level_keys"] == plain["level_keys"] > 0
+    assert packed["level_key_bytes"] * 2 == plain["level_key_bytes"]
 
 
 def test_one_pass_tree_leaves_match_the_termwise_sequence():

@@ -14,7 +14,9 @@ from b200ckks.app import App
 
 cudart = ctypes.CDLL("libcudart.so")
 BITS = [51] + [46] * 16 + [51] * 14 + [51]
-s = App().session(16, BITS, hamming_weight=192, rotation_steps=list(range(1, 40)) + [1024 * k for k in range(1, 32)])
+s = App().session(16, BITS, hamming_weight=192)
+from b200ckks import synthetic
+net = s.resnet(20, synthetic.random_weights(20, seed=0))  # declares the rotation keys of the network
 rng = np.random.default_rng(3)
 x = rng.uniform(-0.9, 0.9, s.slots)
 t = rng.uniform(-0.25, 0.25, (16, 32, 32))
