@@ -374,11 +374,13 @@ def run_engine(args):
         # DRAM bytes of this kernel from an `ncu --set full` capture.  ncu over the ~94k launches of an image is
         # impractical, so the capture is the same kernel inside an l = 31 key switch (its dominant caller here); the
         # algorithmic bytes of THAT launch are given beside it (traffic / traffic_algorithmic_bytes = re-read factor).
-        traffic, traffic_algo = None, None
+        traffic, traffic_algo, traffic_src = None, None, None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             traffic = tj.get(f"{dom}_resnet20", tj.get(f"{dom}_l31"))
-            traffic_algo = tj.get(f"{dom}_l31_algorithmic")
+            traffic_algo = tj.get(f"{dom}_resnet20_algorithmic", tj.get(f"{dom}_l31_algorithmic"))
+            traffic_src = tj.get(f"{dom}_resnet20_source", "profiles/r1_ncu_full_keyswitch_l31.md (one launch of this kernel in an "
+                                                           "l=31 key-switch chunk)")
         except Exception:
             pass
         d = kernels[dom]
@@ -388,7 +390,7 @@ def run_engine(args):
                                             "other": "k_hyb_conv (basis conversion) and samplers"}[dom],
                 "achieved": d["algorithmic_GBps"], "peak": peak, "unit": "GB/s", "frac": d["frac_of_hbm_peak"], "traffic": traffic,
                 "traffic_algorithmic_bytes": traffic_algo,
-                "traffic_source": "profiles/r1_ncu_full_keyswitch_l31.md (one launch of this kernel in an l=31 key-switch chunk)",
+                "traffic_source": traffic_src,
                 "peak_source": which, "launches_per_step": d["launches"], "ms_per_launch": round(d["ms"] / d["launches"], 5),
                 "kernel_share_of_step": round(d["ms"] / prof_ms, 4),
                 "algorithmic_bytes_per_launch": int(d["limb_polys"] * ALGO_BYTES_PER_UNIT[dom] / d["launches"]),
