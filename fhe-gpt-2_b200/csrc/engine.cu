@@ -261,10 +261,12 @@ namespace bk
         tables.itw = d_itw;
         tables.primes = d_primes;
         tables.log_n = log_n;
-        tables.wide = 1;
-        for (uint64_t q : primes)
-            if ((q >> 57) || !(q >> 32))
-                tables.wide = 0; // the unreduced forward butterflies need 66 q < 2^64 (and reduce with barrett64_r32)
+        {
+            size_t ok = 0;
+            for (uint64_t q : primes)
+                ok += !(q >> 57) && (q >> 32); // the unreduced forward butterflies need 66 q < 2^64 (and barrett64_r32)
+            tables.wide = ok == primes.size() ? 1 : ok ? 2 : 0;
+        }
         if (std::getenv("B200CKKS_CLASSIC_NTT"))
             tables.wide = 0;
     }
@@ -500,13 +502,17 @@ namespace bk
             return;
         ProfScope ps(c, s, TAG_FWD_COLS, jobs);
         dim3 grid(32, jobs);
-        if (c.tables.wide)
+        if (c.tables.wide == 1)
         {
-            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, true, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, 1, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
+        }
+        else if (c.tables.wide == 2)
+        {
+            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, 2, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
         }
         else
         {
-            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, false, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
+            BK_DISPATCH_LOGR(c.log_n, launch_pdl(k_fwd_cols<LOGR, Load, 0, 8>, grid, 8 * ((1 << LOGR) / 16), 0, s, ld, out, c.tables));
         }
         c.count();
     }
@@ -518,10 +524,12 @@ namespace bk
         const unsigned threads = block_pass_threads(c, jobs);
         dim3 grid((unsigned)(c.n / (16 * threads)), jobs);
         ProfScope ps(c, s, TAG_FWD_BLOCKS, jobs);
-        if (c.tables.wide)
-            launch_pdl(k_fwd_blocks<Store, true>, grid, threads, threads * 128, s, in, st, c.tables);
+        if (c.tables.wide == 1)
+            launch_pdl(k_fwd_blocks<Store, 1>, grid, threads, threads * 128, s, in, st, c.tables);
+        else if (c.tables.wide == 2)
+            launch_pdl(k_fwd_blocks<Store, 2>, grid, threads, threads * 128, s, in, st, c.tables);
         else
-            launch_pdl(k_fwd_blocks<Store, false>, grid, threads, threads * 128, s, in, st, c.tables);
+            launch_pdl(k_fwd_blocks<Store, 0>, grid, threads, threads * 128, s, in, st, c.tables);
         c.count();
     }
     template <class Load>

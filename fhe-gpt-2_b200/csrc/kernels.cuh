@@ -226,42 +226,48 @@ struct StModDown
         const u64 *b = p == 0 ? base0 : base1;
         u64 *out = dst + (size_t)job * n + base + t;
         const ulonglong2 f = __ldg(inv + i);
-        int src[16];
-        if (p == 0 && perm)
-        {
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                src[k] = (int)__ldg(perm + base + t + 16 * k);
-        }
-        else
-        {
-#pragma unroll
-            for (int k = 0; k < 16; k++)
-                src[k] = base + t + 16 * k;
-        }
-        u64 r[16], add[16];
-#pragma unroll
-        for (int k = 0; k < 16; k++)
-            r[k] = __ldg(a + 16 * k);
         if (b)
-        {
             b += (size_t)i * n;
+        // two batches of 8 coefficients: enough loads in flight to cover the latency, few enough registers not to spill
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                add[k] = __ldg(b + src[k]);
-        }
-        else
+        for (int h = 0; h < 16; h += 8)
         {
+            int src[8];
+            if (p == 0 && perm)
+            {
 #pragma unroll
-            for (int k = 0; k < 16; k++)
-                add[k] = 0;
-        }
+                for (int k = 0; k < 8; k++)
+                    src[k] = (int)__ldg(perm + base + t + 16 * (h + k));
+            }
+            else
+            {
 #pragma unroll
-        for (int k = 0; k < 16; k++)
-        {
-            u64 d = r[k] + 2 * pd.two_q - s[swz(t + 16 * k)]; // transform value in [0,4q)
-            u64 v = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
-            out[16 * k] = addmod(v, add[k], pd.q);
+                for (int k = 0; k < 8; k++)
+                    src[k] = base + t + 16 * (h + k);
+            }
+            u64 r[8], add[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                r[k] = __ldg(a + 16 * (h + k));
+            if (b)
+            {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    add[k] = __ldg(b + src[k]);
+            }
+            else
+            {
+#pragma unroll
+                for (int k = 0; k < 8; k++)
+                    add[k] = 0;
+            }
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+            {
+                u64 d = r[k] + 2 * pd.two_q - s[swz(t + 16 * (h + k))]; // transform value in [0,4q)
+                u64 v = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+                out[16 * (h + k)] = addmod(v, add[k], pd.q);
+            }
         }
     }
 };

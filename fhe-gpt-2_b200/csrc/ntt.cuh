@@ -28,7 +28,8 @@ struct NttTables
     const ulonglong2 *itw; // [n_primes][N] inverse, same indexing
     const PrimeDev *primes;
     int log_n;
-    int wide; // every modulus lies in (2^32, 2^57): forward transforms may use the unreduced butterflies below
+    int wide; // forward transforms use the unreduced butterflies below: 1 = for every modulus (all in (2^32, 2^57)),
+              // 2 = for the moduli in that range, lazy butterflies for the others, 0 = never
 };
 
 // ---- butterflies ---------------------------------------------------------------------------
@@ -46,6 +47,12 @@ __device__ __forceinline__ void gs_bfly(u64 &X, u64 &Y, ulonglong2 w, u64 q, u64
     u64 d = X + two_q - Y;
     X = s - (s >= two_q ? two_q : 0ull);
     Y = mul_shoup_lazy(d, w.x, w.y, q);
+}
+
+// moduli the unreduced butterflies (and barrett64_r32) apply to
+__device__ __forceinline__ bool wide_modulus(u64 q)
+{
+    return (q >> 57) == 0 && (q >> 32) != 0;
 }
 
 // Unreduced forward butterfly for moduli below 2^57.  Nothing is reduced between stages: with t in [0,4q)
@@ -167,7 +174,7 @@ __device__ __forceinline__ int cols_idx(int row)
 //          (must return a value < 4q of prime(job)).
 // Output: lazy values in [0,4q) at out[job*N + idx].
 // ============================================================================================
-template <int LOGR, class Load, bool WIDE = false, int COLS = 16>
+template <int LOGR, class Load, int WIDE = 0, int COLS = 16>
 __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out, NttTables T)
 {
     pdl_prologue();
@@ -194,7 +201,9 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = ld.load(job, (t + TR * k) * 256 + col, pd);
-    constexpr bool wide = WIDE; // host dispatch: T.wide (every modulus below 2^57)
+    // host dispatch on T.wide: 1 = every modulus lies in (2^32, 2^57); 2 = some do (the GPT-2 chain ends in a 60-bit
+    // special prime) and a launch may mix them, so the job's own modulus decides - uniform over the CTA
+    const bool wide = WIDE == 1 || (WIDE == 2 && wide_modulus(pd.q));
     const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
     if (wide)
         fwd_radix_wide<4>(x, tw, 1u, neg_q, four_q);
@@ -253,7 +262,7 @@ __global__ void __launch_bounds__(256) k_fwd_cols(Load ld, u64 *__restrict__ out
 //          or, with BATCH: void post_all(int job, int base, int t, const u64 *s, const PrimeDev&) for all 16
 //          coefficients base + t + 16 k of the thread at once (values at s[swz(t + 16 k)]).
 // ============================================================================================
-template <class Store, bool WIDE = false>
+template <class Store, int WIDE = 0>
 __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ in, Store st, NttTables T)
 {
     pdl_prologue();
@@ -276,7 +285,7 @@ __global__ void __launch_bounds__(256, 2) k_fwd_blocks(const u64 *__restrict__ i
 #pragma unroll
     for (int k = 0; k < 16; k++)
         x[k] = src[t + 16 * k];
-    constexpr bool wide = WIDE;
+    const bool wide = WIDE == 1 || (WIDE == 2 && wide_modulus(pd.q));
     const u64 neg_q = 0ull - pd.q, four_q = 2 * pd.two_q;
     if (wide)
         fwd_radix_wide<4>(x, tw, B, neg_q, four_q);

@@ -10,6 +10,8 @@ import numpy as np
 from b200ckks.app import App
 
 BITS = [51] + [46] * 16 + [51] * 14 + [51]
+if os.environ.get("BOOT_CHAIN") == "gpt2":  # the GPT-2 chain (gpt2/util.h:37-75): 60-bit special prime, mixed butterflies
+    BITS = [49] + [46] * 21 + [49] * 14 + [60]
 logns = [int(a) for a in sys.argv[1:]] or [14, 13, 12]
 s = App().session(16, BITS, hamming_weight=192)
 eng = s.engine()
