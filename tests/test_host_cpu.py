@@ -125,3 +125,37 @@ int main() {
     assert out[0].split() == ["e4e7f110", "15593bd1", "1fdd0f50", "c47120a3", "c7f4d1c7", "0368c033", "9aaa2204", "4e6cd4c3",
                               "466482d2", "09aa9f07", "05d7c214", "a2028bd9", "d19c12b5", "b94e16de", "e883d0cb", "4e3c50a2"]
     assert out[1] == "1"
+
+
+def test_every_kernel_waits_for_its_predecessors_before_touching_memory():
+    """Programmatic dependent launch (engine.h launch_pdl) lets a kernel be scheduled while its predecessor still runs;
+    that is only safe if EVERY kernel starts with pdl_prologue() (griddepcontrol.wait) and no launch bypasses
+    launch_pdl.  Static check over fhe-gpt-2_b200/csrc."""
+    import glob
+    import re
+
+    src_dir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "fhe-gpt-2_b200", "csrc")
+    kernels = 0
+    for path in glob.glob(os.path.join(src_dir, "*.cu")) + glob.glob(os.path.join(src_dir, "*.cuh")):
+        text = open(path).read()
+        assert "<<<" not in text, f"{path}: a triple-chevron launch bypasses launch_pdl"
+        for m in re.finditer(r"__global__", text):
+            pos = m.end()
+            while True:  # skip __launch_bounds__(...) / __cluster_dims__(...) up to the parameter list
+                par = text.index("(", pos)
+                name = re.search(r"(\w+)\s*$", text[:par]).group(1)
+                depth, q = 0, par
+                while True:
+                    depth += text[q] == "("
+                    depth -= text[q] == ")"
+                    if depth == 0:
+                        break
+                    q += 1
+                if name in ("__launch_bounds__", "__cluster_dims__"):
+                    pos = q + 1
+                    continue
+                break
+            body = text[text.index("{", q):][:120]
+            assert "pdl_prologue();" in body, f"{path}: kernel {name} does not begin with pdl_prologue()"
+            kernels += 1
+    assert kernels >= 30
