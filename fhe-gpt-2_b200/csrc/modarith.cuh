@@ -94,13 +94,33 @@ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q)
     return a >= b ? a - b : a + q - b;
 }
 
-// 128-bit accumulate of a 64x64 product: (hi:lo) += a*b
+// 128-bit accumulate of a 64x64 product: (hi:lo) += a*b, for (a >> 32) + (b >> 32) < 2^32 - true for every use in
+// the engine: b is a residue or a key / plaintext / table word below its modulus (< 2^60), a is a residue or an
+// unreduced NTT output (< 66 q with q < 2^57, or < 4 q with q < 2^60).  Written out in 32-bit halves because
+// `a * b` next to `__umul64hi(a, b)` compiles to FIVE wide multiplies and two narrow ones (the low product twice):
+// here it is the four wide multiplies of the schoolbook product - the two cross products share one 64-bit sum, which
+// cannot overflow under the precondition - and the multiplier pipe, which bounds the key-switch inner product and the
+// basis conversion, does a third less work per term (IMAD.WIDE issues at half the rate of IMAD, profiles/r2_ntt_lab.md).
 __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b)
 {
-    u64 pl = a * b;
-    u64 ph = __umul64hi(a, b);
-    asm("add.cc.u64 %0, %0, %2;\n\t"
-        "addc.u64 %1, %1, %3;"
+    asm("{\n\t"
+        ".reg .u32 a0, a1, b0, b1, l0, l1, m0, m1;\n\t"
+        ".reg .u64 p00, mid, t, plo, phi;\n\t"
+        "mov.b64 {a0, a1}, %2;\n\t"
+        "mov.b64 {b0, b1}, %3;\n\t"
+        "mul.wide.u32 p00, a0, b0;\n\t"
+        "mul.wide.u32 mid, a0, b1;\n\t"
+        "mad.wide.u32 mid, a1, b0, mid;\n\t"
+        "mov.b64 {l0, l1}, p00;\n\t"
+        "mov.b64 {m0, m1}, mid;\n\t"
+        "add.cc.u32 l1, l1, m0;\n\t"
+        "addc.u32 m1, m1, 0;\n\t"
+        "mov.b64 plo, {l0, l1};\n\t"
+        "mov.b64 t, {m1, 0};\n\t"
+        "mad.wide.u32 phi, a1, b1, t;\n\t"
+        "add.cc.u64 %0, %0, plo;\n\t"
+        "addc.u64 %1, %1, phi;\n\t"
+        "}"
         : "+l"(lo), "+l"(hi)
-        : "l"(pl), "l"(ph));
+        : "l"(a), "l"(b));
 }
