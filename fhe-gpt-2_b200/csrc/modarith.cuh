@@ -61,8 +61,8 @@ __device__ __forceinline__ u64 barrett64_r32(u64 x, const PrimeDev &p)
     return csub(r, p.q);
 }
 
-// (hi:lo) mod q, hi:lo < 2^128 arbitrary as long as q < 2^63 (here q < 2^61).
-__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
+// (hi:lo) mod q, hi:lo < 2^128 arbitrary as long as q < 2^63 (here q < 2^61): the reference's two-round quotient.
+__device__ __forceinline__ u64 barrett128_exact(u64 lo, u64 hi, const PrimeDev &p)
 {
     // floor(input * ratio / 2^128), two rounds as in uintarithsmallmod.h:167-204
     u64 carry = __umul64hi(lo, p.r0);
@@ -76,6 +76,29 @@ __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
     u64 c2 = u2hi + (s < t1 ? 1ull : 0ull);
     u64 quot = hi * p.r1 + t3 + c2;
     u64 r = lo - quot * p.q;
+    return csub(r, p.q);
+}
+
+// The same residue with 17 multiplier-pipe units instead of ~39 (a unit = one IMAD; IMAD.WIDE / IMAD.HI count two):
+// for q > 2^32 the high word r1 of floor(2^128 / q) fits in 32 bits, and the quotient only has to be close -
+//   quot = hi r1 + floor(lo r1 / 2^64) + (floor(hi r0 / 2^64) from three of its four partial products)
+// undershoots floor(x / q) by at most 5 (one from Barrett, two from dropped fractions, two from the dropped partial
+// product, none from dropping lo r0 / 2^128 beyond those), so x - quot q lies in [0, 6q) and three conditional
+// subtractions finish.  One of these per output coefficient is half the work of the basis conversion of hybrid key
+// switching (k_hyb_conv) and the tail of every inner product / plaintext-product sum.
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
+{
+    if (p.r1 >> 32) // moduli below 2^32 (test chains): uniform over the launch
+        return barrett128_exact(lo, hi, p);
+    const unsigned r1 = (unsigned)p.r1, r00 = (unsigned)p.r0, r01 = (unsigned)(p.r0 >> 32);
+    const unsigned l0 = (unsigned)lo, l1 = (unsigned)(lo >> 32), h0 = (unsigned)hi, h1 = (unsigned)(hi >> 32);
+    u64 quot = (u64)h0 * r1 + ((u64)(h1 * r1) << 32);                   // hi r1 mod 2^64
+    quot += ((u64)l1 * r1 + __umulhi(l0, r1)) >> 32;                    // floor(lo r1 / 2^64), exact
+    quot += (u64)h1 * r01 + __umulhi(h1, r00) + __umulhi(h0, r01);      // floor(hi r0 / 2^64) - {0, 1, 2}
+    u64 r = lo - quot * p.q;
+    const u64 four_q = 2 * p.two_q;
+    r = r >= four_q ? r - four_q : r;
+    r = r >= p.two_q ? r - p.two_q : r;
     return csub(r, p.q);
 }
 
