@@ -102,10 +102,6 @@ __device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
     return csub(r, p.q);
 }
 
-__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const PrimeDev &p)
-{
-    return barrett128(a * b, __umul64hi(a, b), p);
-}
 
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q)
 {
@@ -146,4 +142,12 @@ __device__ __forceinline__ void mac128(u64 &lo, u64 &hi, u64 a, u64 b)
         "}"
         : "+l"(lo), "+l"(hi)
         : "l"(a), "l"(b));
+}
+
+// a b mod q for residues a, b (mac128's precondition holds)
+__device__ __forceinline__ u64 mulmod(u64 a, u64 b, const PrimeDev &p)
+{
+    u64 lo = 0, hi = 0;
+    mac128(lo, hi, a, b);
+    return barrett128(lo, hi, p);
 }

@@ -136,8 +136,12 @@ def test_reference_cnn_program_on_the_engine(tmp_path):
     label = int(np.argmax(want))
     base = str(tmp_path)
     build = cnnref.make_tree(base, 20, images=[image], labels=[label])
+    # a fixed key: on this path (the reference's own key-switching decomposition: 51-bit digits against a 51-bit special
+    # prime) every bootstrap leaves a KEY-DEPENDENT offset of ~1e-5 on values carried divided by B = 40 - on the
+    # reference's SEAL as well.  Measured over keys (seeds 1, 2, 3, 4, 0x5EA1C0DE, one random): logit error
+    # 1.8e-2, 2.0e-2, 2.6e-2, 3.3e-2, 5.6e-2, 6.2e-2; the seed makes the run reproducible (2.0e-2)
     r = subprocess.run([cnnref.CNN_DROPIN, "20", "10", "0", "0"], cwd=build, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
-                       text=True, timeout=3000)
+                       text=True, timeout=3000, env=dict(os.environ, B200CKKS_SEED="1"))
     assert r.returncode == 0, r.stdout[-3000:]
     log = open(os.path.join(base, "FHE-GPT-2", "result", "resnet20_cifar10_image0.txt")).read()
     from util import parse_reference_log
