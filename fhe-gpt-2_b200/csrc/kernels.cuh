@@ -135,8 +135,8 @@ struct StPlain
 
 // Key-switch digits: keep the unreduced NTT output in place (the reference multiplies its lazy
 // values straight into the key, evaluator.cpp:2407-2436).  Range: [0,4q) from the lazy butterflies
-// (primes >= 2^57), [0,66q) from the unreduced "wide" butterflies (primes < 2^57, ntt.cuh).  Either way
-// the 128-bit sums of k_ks_mac hold: 61 * 4 * 2^120 < 2^128 and 61 * 66 * 2^114 < 2^128 (primes are
+// (primes >= 2^57), [0,70q) from the unreduced "wide" butterflies (primes < 2^57, ntt.cuh).  Either way
+// the 128-bit sums of k_ks_mac hold: 61 * 4 * 2^120 < 2^128 and 61 * 70 * 2^114 < 2^128 (primes are
 // limited to 60 bits at context creation).  job = iloc * l + J as in
 // LdKsDigit; the I == J job is skipped (its operand is the NTT-form input itself).
 struct StKsDigit
@@ -552,9 +552,20 @@ static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTable
             mac128(lx, hx, y[k].x, wk);
             mac128(ly, hy, y[k].y, wk);
         }
+        // the output feeds a forward NTT: where that transform runs the unreduced butterflies (wide modulus) it takes
+        // any representative below 6q (6q + 16 stages x 4q < 2^64 for q < 2^57) and the three conditional
+        // subtractions of the canonical reduction are skipped; elsewhere the value is brought to [0, q)
         ulonglong2 r;
-        r.x = barrett128(lx, hx, pd);
-        r.y = barrett128(ly, hy, pd);
+        if (T.wide && wide_modulus(pd.q))
+        {
+            r.x = barrett128_lazy6(lx, hx, pd);
+            r.y = barrett128_lazy6(ly, hy, pd);
+        }
+        else
+        {
+            r.x = barrett128(lx, hx, pd);
+            r.y = barrett128(ly, hy, pd);
+        }
         const size_t job = a.down ? (size_t)dd * a.h.l + t : (size_t)t * a.h.dnum + dd;
         *reinterpret_cast<ulonglong2 *>(a.out + job * n + i) = r;
     }

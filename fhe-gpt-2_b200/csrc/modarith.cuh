@@ -86,21 +86,28 @@ __device__ __forceinline__ u64 barrett128_exact(u64 lo, u64 hi, const PrimeDev &
 // product, none from dropping lo r0 / 2^128 beyond those), so x - quot q lies in [0, 6q) and three conditional
 // subtractions finish.  One of these per output coefficient is half the work of the basis conversion of hybrid key
 // switching (k_hyb_conv) and the tail of every inner product / plaintext-product sum.
-__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
+// x - quot q in [0, 6q) for q > 2^32 (see barrett128 below): for consumers that take a lazy representative
+__device__ __forceinline__ u64 barrett128_lazy6(u64 lo, u64 hi, const PrimeDev &p)
 {
-    if (p.r1 >> 32) // moduli below 2^32 (test chains): uniform over the launch
-        return barrett128_exact(lo, hi, p);
     const unsigned r1 = (unsigned)p.r1, r00 = (unsigned)p.r0, r01 = (unsigned)(p.r0 >> 32);
     const unsigned l0 = (unsigned)lo, l1 = (unsigned)(lo >> 32), h0 = (unsigned)hi, h1 = (unsigned)(hi >> 32);
     u64 quot = (u64)h0 * r1 + ((u64)(h1 * r1) << 32);                   // hi r1 mod 2^64
     quot += ((u64)l1 * r1 + __umulhi(l0, r1)) >> 32;                    // floor(lo r1 / 2^64), exact
     quot += (u64)h1 * r01 + __umulhi(h1, r00) + __umulhi(h0, r01);      // floor(hi r0 / 2^64) - {0, 1, 2}
-    u64 r = lo - quot * p.q;
+    return lo - quot * p.q;
+}
+
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const PrimeDev &p)
+{
+    if (p.r1 >> 32) // moduli below 2^32 (test chains): uniform over the launch
+        return barrett128_exact(lo, hi, p);
+    u64 r = barrett128_lazy6(lo, hi, p);
     const u64 four_q = 2 * p.two_q;
     r = r >= four_q ? r - four_q : r;
     r = r >= p.two_q ? r - p.two_q : r;
     return csub(r, p.q);
 }
+
 
 
 __device__ __forceinline__ u64 addmod(u64 a, u64 b, u64 q)
@@ -115,7 +122,7 @@ __device__ __forceinline__ u64 submod(u64 a, u64 b, u64 q)
 
 // 128-bit accumulate of a 64x64 product: (hi:lo) += a*b, for (a >> 32) + (b >> 32) < 2^32 - true for every use in
 // the engine: b is a residue or a key / plaintext / table word below its modulus (< 2^60), a is a residue or an
-// unreduced NTT output (< 66 q with q < 2^57, or < 4 q with q < 2^60).  Written out in 32-bit halves because
+// unreduced NTT output (< 70 q with q < 2^57, or < 4 q with q < 2^60).  Written out in 32-bit halves because
 // `a * b` next to `__umul64hi(a, b)` compiles to FIVE wide multiplies and two narrow ones (the low product twice):
 // here it is the four wide multiplies of the schoolbook product - the two cross products share one 64-bit sum, which
 // cannot overflow under the precondition - and the multiplier pipe, which bounds the key-switch inner product and the

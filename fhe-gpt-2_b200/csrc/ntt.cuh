@@ -57,7 +57,8 @@ __device__ __forceinline__ bool wide_modulus(u64 q)
 
 // Unreduced forward butterfly for moduli below 2^57.  Nothing is reduced between stages: with t in [0,4q)
 //   X' = X + t,   Y' = X + 4q - t,
-// both outputs grow by at most 4q per stage, so 16 stages starting below 2q stay below 66q < 2^64.  The Shoup
+// both outputs grow by at most 4q per stage, so 16 stages starting below 6q (loaders return values below 4q, the
+// basis conversion of hybrid key switching below 6q) stay below 70q < 2^64.  The Shoup
 // quotient is taken from three of the four 32x32 partial products (x1 w1 + hi(x1 w0) + hi(x0 w1)); it undershoots
 // floor(x ws / 2^64) by at most 2, hence t = x w - quot q lies in [0,4q) instead of [0,2q).  Residues mod q are
 // unaffected, and every value is brought back to [0,q) before it leaves the transform.
