@@ -419,6 +419,30 @@ def run_engine(args):
             int_roof["frac"] = int_roof[dom]["frac"]
         roof["int_roofline"] = int_roof
 
+    # ---- BASELINE config 4 beside it (rank 0, N = 1, default workload only): ResNet-110, 109 convolutions and 108
+    # bootstraps, same session and keys (the key plan covers it: same layer shapes, more of them), one image alone,
+    # random-init weights of the architecture (the fixture holds resnet20_new only) ------------------------------
+    resnet110 = None
+    if rank == 0 and world == 1 and args.layers == 20 and not args.no_resnet110:
+        try:
+            from b200ckks import synthetic
+
+            net110 = sess.resnet(110, synthetic.random_weights(110, seed=0))
+            img110 = image_of(0)
+            net110.infer(img110, trace=False)            # untimed: encodes and caches its 109 layers' plaintexts
+            ct110 = [net110.encrypt_image(img110) for _ in range(2)]
+            sess.sync()
+            eng.timer_begin()
+            out110 = [net110.infer_encrypted(c)[0] for c in ct110]
+            ms110 = eng.timer_end()
+            l110 = net110.decrypt_logits(out110[0])
+            resnet110 = {"seconds_per_image": round(ms110 * 1e-3 / len(ct110), 3), "images_in_flight": 1, "bootstraps": 108,
+                         "weights": "random-init weights of the architecture", "logits_finite": bool(np.isfinite(l110).all()),
+                         "reference": "./cnn 110 10 i i (BASELINE.json configs[3])"}
+            del net110, out110, ct110
+        except Exception as e:  # a key outside the plan, or memory: report it rather than lose the line
+            resnet110 = {"unavailable": str(e)[:200]}
+
     # ---- CPU baseline beside it (rank 0, N = 1 only; bounded sample) ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -461,7 +485,7 @@ def run_engine(args):
                     "h2d_bytes_per_step": (h2d1 - h2d0) // e2e_steps, "d2h_bytes_per_step": (d2h1 - d2h0) // e2e_steps,
                     "call": ("bka_resnet_infer_batch(net, images[n][3072] on the host, in_flight) -> logits[n][10] on the host" if K > 1
                              else "bka_resnet_infer(net, image[3072] on the host) -> logits[10] on the host")},
-            "exact": exact, "key_switch_us": ks_us,
+            "exact": exact, "key_switch_us": ks_us, "resnet110": resnet110,
             "gpu_launches": int(launches_tp), "clocks": clocks, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "ops_per_image": {k: v // args.steps for k, v in stats.items()},
             "keys": {"plan": plan_source, "plan_seconds": round(plan_s, 1), "generate_seconds": round(gen_s, 1),
@@ -689,6 +713,7 @@ def main():
                          "hybrid key switching (tolerance mode)")
     ap.add_argument("--in-flight", type=int, default=4, help="images in flight per GPU (a step = that many images per GPU)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-resnet110", action="store_true", help="skip the ResNet-110 leg (BASELINE config 4, one image alone)")
     ap.add_argument("--no-exact", action="store_true", help="skip the exact-mode child run and the key-switch timings")
     ap.add_argument("--compress-keys", action="store_true",
                     help="seed-compressed evaluation keys: the uniform half of every level key is regenerated from its public "
