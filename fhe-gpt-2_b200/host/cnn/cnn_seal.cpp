@@ -351,6 +351,18 @@ void multiplexed_parallel_batch_norm_seal(const TensorCipher &cnn_in, TensorCiph
                                           double epsilon, CKKSEncoder &encoder, Encryptor &encryptor, Evaluator &evaluator,
                                           double B, bool)
 {
+    multiplexed_parallel_batch_norm_named(cnn_in, cnn_out, bias, running_mean, running_var, weight, epsilon, encoder, encryptor,
+                                          evaluator, B, nullptr, 0);
+}
+
+// The same with a NAME for the shift vector (owner, index): a layer's shift is a parameter of the network, so on the
+// engine its encoding stays in HBM per (level, scale) instead of being rebuilt and encoded for every image.
+void multiplexed_parallel_batch_norm_named(const TensorCipher &cnn_in, TensorCipher &cnn_out, const vector<double> &bias,
+                                           const vector<double> &running_mean, const vector<double> &running_var,
+                                           const vector<double> &weight, double epsilon, CKKSEncoder &encoder,
+                                           Encryptor &encryptor, Evaluator &evaluator, double B, const void *owner,
+                                           std::uint64_t index)
+{
     const int ki = cnn_in.k(), hi = cnn_in.h(), wi = cnn_in.w(), ci = cnn_in.c(), ti = cnn_in.t(), pi = cnn_in.p(),
               logn = cnn_in.logn();
     if ((int)bias.size() != ci || (int)running_mean.size() != ci || (int)running_var.size() != ci || (int)weight.size() != ci)
@@ -367,22 +379,38 @@ void multiplexed_parallel_batch_norm_seal(const TensorCipher &cnn_in, TensorCiph
     // the convolution already multiplied by weight / sqrt(var + eps); what is left is the constant
     // (mean * weight / sqrt(var + eps) - bias) / B per channel, laid out like the tensor
     const long per_copy = n / pi, plane = (long)ki * ki * hi * wi, row = (long)ki * wi;
-    vector<double> g((std::size_t)n, 0.0);
-    for (long slot = 0; slot < n; slot++)
-    {
-        const long r = slot % per_copy;
-        if (r >= plane * ti)
-            continue;
-        const long ch = (long)ki * ki * (r / plane) + ki * (((r % plane) / row) % ki) + (r % row) % ki;
-        if (ch >= ci)
-            continue;
-        g[(std::size_t)slot] = (running_mean[(std::size_t)ch] * weight[(std::size_t)ch] /
-                                    std::sqrt(running_var[(std::size_t)ch] + epsilon) -
-                                bias[(std::size_t)ch]) /
-                               B;
-    }
+    vector<double> g;
+    auto shift = [&]() -> const vector<double> & {
+        g.assign((std::size_t)n, 0.0);
+        for (long slot = 0; slot < n; slot++)
+        {
+            const long r = slot % per_copy;
+            if (r >= plane * ti)
+                continue;
+            const long ch = (long)ki * ki * (r / plane) + ki * (((r % plane) / row) % ki) + (r % row) % ki;
+            if (ch >= ci)
+                continue;
+            g[(std::size_t)slot] = (running_mean[(std::size_t)ch] * weight[(std::size_t)ch] /
+                                        std::sqrt(running_var[(std::size_t)ch] + epsilon) -
+                                    bias[(std::size_t)ch]) /
+                                   B;
+        }
+        return g;
+    };
     Plaintext plain;
     Ciphertext cipher_g, temp = cnn_in.cipher();
+#ifdef B200CKKS_FACADE
+    if (owner && !encrypt_constants())
+    {
+        evaluator.sub_vector_inplace_cached(temp, owner, index, 2, shift);
+        cnn_out = TensorCipher(logn, ki, hi, wi, ci, ti, pi, temp);
+        return;
+    }
+#else
+    (void)owner;
+    (void)index;
+#endif
+    shift();
     if (encrypt_constants())
     { // the reference's sequence (cnn_seal.cpp:566-570): a fresh top-level encryption of g, walked down by the subtraction
         encoder.encode(g, temp.scale(), plain);

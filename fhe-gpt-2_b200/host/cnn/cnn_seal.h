@@ -73,6 +73,11 @@ void multiplexed_parallel_convolution_seal(const TensorCipher &cnn_in, TensorCip
                                            std::vector<double> constant_weight, double epsilon, seal::CKKSEncoder &encoder,
                                            seal::Encryptor &encryptor, seal::Evaluator &evaluator, seal::GaloisKeys &gal_keys,
                                            std::vector<seal::Ciphertext> &cipher_pool, bool end = false);
+void multiplexed_parallel_batch_norm_named(const TensorCipher &cnn_in, TensorCipher &cnn_out, const std::vector<double> &bias,
+                                           const std::vector<double> &running_mean, const std::vector<double> &running_var,
+                                           const std::vector<double> &weight, double epsilon, seal::CKKSEncoder &encoder,
+                                           seal::Encryptor &encryptor, seal::Evaluator &evaluator, double B, const void *owner,
+                                           std::uint64_t index);
 void multiplexed_parallel_batch_norm_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, std::vector<double> bias,
                                           std::vector<double> running_mean, std::vector<double> running_var,
                                           std::vector<double> weight, double epsilon, seal::CKKSEncoder &encoder,

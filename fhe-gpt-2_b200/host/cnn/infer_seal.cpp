@@ -230,6 +230,7 @@ ResNetCifar10::~ResNetCifar10()
     for (auto &p : conv_plans_)
         if (p)
             forget_named(evaluator_, p.get());
+    forget_named(evaluator_, this); // the batch-norm shifts cached under this object's name
     for (auto *b : boot_)
         delete b;
 }
@@ -340,9 +341,9 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
                      w_.bn_weight[(std::size_t)stage]);
     };
     auto bn = [&](int stage) {
-        multiplexed_parallel_batch_norm_seal(cnn, cnn, w_.bn_bias[(std::size_t)stage], w_.bn_running_mean[(std::size_t)stage],
-                                             w_.bn_running_var[(std::size_t)stage], w_.bn_weight[(std::size_t)stage], epsilon,
-                                             encoder_, encryptor_, evaluator_, B);
+        multiplexed_parallel_batch_norm_named(cnn, cnn, w_.bn_bias[(std::size_t)stage], w_.bn_running_mean[(std::size_t)stage],
+                                              w_.bn_running_var[(std::size_t)stage], w_.bn_weight[(std::size_t)stage], epsilon,
+                                              encoder_, encryptor_, evaluator_, B, this, (std::uint64_t)stage);
         log_op(1, cnn);
     };
     auto relu = [&]() {
@@ -396,9 +397,9 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
                 const std::size_t sc = (std::size_t)j - 1;
                 planned_conv(temp, layer_num_ - 1 + sc, co, 2, 1, w_.shortcut_weight[sc], w_.shortcut_bn_var[sc],
                              w_.shortcut_bn_weight[sc]);
-                multiplexed_parallel_batch_norm_seal(temp, temp, w_.shortcut_bn_bias[sc], w_.shortcut_bn_mean[sc],
-                                                     w_.shortcut_bn_var[sc], w_.shortcut_bn_weight[sc], epsilon, encoder_,
-                                                     encryptor_, evaluator_, B);
+                multiplexed_parallel_batch_norm_named(temp, temp, w_.shortcut_bn_bias[sc], w_.shortcut_bn_mean[sc],
+                                                      w_.shortcut_bn_var[sc], w_.shortcut_bn_weight[sc], epsilon, encoder_,
+                                                      encryptor_, evaluator_, B, this, (std::uint64_t)(1000 + sc));
                 log_op(1, temp);
             }
             else if (j >= 1 && k == 0)

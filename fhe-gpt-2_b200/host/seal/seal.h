@@ -1959,6 +1959,18 @@ namespace seal
                                                      variant, make, once);
             multiply_plain_inplace(encrypted, plain);
         }
+        // encrypted -= (named vector), encoded at the ciphertext's own level and scale (the batch-norm shift of a layer:
+        // a parameter of the network, encoded once instead of once per image).  Same residues as encode + sub_plain.
+        template <class Make>
+        void sub_vector_inplace_cached(
+            Ciphertext &encrypted, const void *owner, std::uint64_t index, std::uint64_t variant, Make &&make)
+        {
+            stats_.encode_vector++;
+            std::unique_ptr<Plaintext> once;
+            const Plaintext &plain = named_plaintext((int)encrypted.coeff_modulus_size(), encrypted.scale(), owner, index,
+                                                     variant, make, once);
+            sub_plain_inplace(encrypted, plain);
+        }
         // accumulator <- accumulator + encrypted * (named vector), the two calls
         //   multiply_vector_reduced_error(encrypted, v, tmp); add_inplace_reduced_error(accumulator, tmp)
         // of a BSGS / convolution-tap loop as one pass over the data (bk_multiply_plain_accumulate); an accumulator
