@@ -539,7 +539,7 @@ void averagepooling_seal_scale(const TensorCipher &cnn_in, TensorCipher &cnn_out
 }
 
 void matrix_multiplication_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, vector<double> matrix, vector<double> bias,
-                                int q, int r, Evaluator &evaluator, GaloisKeys &gal_keys)
+                                int q, int r, Evaluator &evaluator, GaloisKeys &gal_keys, const void *owner)
 {
     const int logn = cnn_in.logn();
     if ((int)matrix.size() != q * r)
@@ -555,6 +555,32 @@ void matrix_multiplication_seal(const TensorCipher &cnn_in, TensorCipher &cnn_ou
             W[(std::size_t)(i - j + r - 1)][(std::size_t)i] = matrix[(std::size_t)(i * r + j)];
 
     Ciphertext ct = cnn_in.cipher(), temp, sum;
+#ifdef B200CKKS_FACADE
+    if (owner && !encrypt_constants())
+    {
+        // all q + r - 1 rotations are rotations of ONE ciphertext (shared decomposition), the diagonals are parameters
+        // of the network (encoded once, kept in HBM), and the sum of products is one pass
+        vector<int> steps;
+        for (int s = 0; s < q + r - 1; s++)
+            steps.push_back(r - 1 - s);
+        vector<Ciphertext> rot;
+        rotated_copies(ct, steps, rot, evaluator, gal_keys);
+        vector<const Ciphertext *> terms;
+        vector<std::uint64_t> ids;
+        for (int s = 0; s < q + r - 1; s++)
+        {
+            terms.push_back(&rot[(std::size_t)s]);
+            ids.push_back((std::uint64_t)s);
+        }
+        multiply_vector_named_sum(evaluator, sum, terms, owner, ids, 3,
+                                  [&](std::uint64_t idx) -> const vector<double> & { return W[(std::size_t)idx]; });
+        evaluator.rescale_to_next_inplace(sum);
+        cnn_out = TensorCipher(logn, cnn_in.k(), cnn_in.h(), cnn_in.w(), cnn_in.c(), cnn_in.t(), cnn_in.p(), sum);
+        return;
+    }
+#else
+    (void)owner;
+#endif
     Accumulator acc{ evaluator, sum };
     for (int s = 0; s < q + r - 1; s++)
     {

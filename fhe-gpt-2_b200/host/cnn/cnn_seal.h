@@ -92,7 +92,8 @@ void multiplexed_parallel_downsampling_seal(const TensorCipher &cnn_in, TensorCi
 void averagepooling_seal_scale(const TensorCipher &cnn_in, TensorCipher &cnn_out, seal::Evaluator &evaluator,
                                seal::GaloisKeys &gal_keys, double B);
 void matrix_multiplication_seal(const TensorCipher &cnn_in, TensorCipher &cnn_out, std::vector<double> matrix,
-                                std::vector<double> bias, int q, int r, seal::Evaluator &evaluator, seal::GaloisKeys &gal_keys);
+                                std::vector<double> bias, int q, int r, seal::Evaluator &evaluator, seal::GaloisKeys &gal_keys,
+                                const void *owner = nullptr); // owner: name under which the diagonals are cached (engine)
 // rotate by `steps` (any sign) using only keys the network generates: steps 34..55 and 57..61 go through 33 first
 void memory_save_rotate(const seal::Ciphertext &cipher_in, seal::Ciphertext &cipher_out, int steps, seal::Evaluator &evaluator,
                         seal::GaloisKeys &gal_keys);

@@ -231,6 +231,7 @@ ResNetCifar10::~ResNetCifar10()
         if (p)
             forget_named(evaluator_, p.get());
     forget_named(evaluator_, this); // the batch-norm shifts cached under this object's name
+    forget_named(evaluator_, &w_.linear_weight);
     for (auto *b : boot_)
         delete b;
 }
@@ -415,7 +416,8 @@ TensorCipher ResNetCifar10::infer_encrypted(const TensorCipher &input, vector<Re
     }
     averagepooling_seal_scale(cnn, cnn, evaluator_, gal_keys_, B);
     log_op(6, cnn);
-    matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, variant_.classes, 64, evaluator_, gal_keys_);
+    matrix_multiplication_seal(cnn, cnn, w_.linear_weight, w_.linear_bias, variant_.classes, 64, evaluator_, gal_keys_,
+                               &w_.linear_weight);
     log_op(7, cnn);
     return cnn;
 }
