@@ -1117,7 +1117,8 @@ namespace bk
         return it == gk->keys.end() ? nullptr : it->second;
     }
 
-    static void apply_galois(Context &c, bk_ct_t a, uint32_t elt, bk_gkeys_t gk)
+    // dst == nullptr or dst == a: in place; otherwise `a` is left untouched and dst receives the result (no copy of `a`)
+    static void apply_galois(Context &c, bk_ct_t a, uint32_t elt, bk_gkeys_t gk, bk_ct_t dst = nullptr)
     {
         check_ct(&c, a, "encrypted");
         if (!gk || gk->ctx != &c)
@@ -1137,7 +1138,16 @@ namespace bk
         size_t words = (size_t)2 * l * c.n;
         u64 *out = alloc_words(c, words);
         key_switch(c, s, a->d + (size_t)l * c.n, perm, a->d, nullptr, out, l, key);
-        adopt(a, out, words, 2, l);
+        if (dst && dst != a)
+        {
+            if (dst->ctx != &c)
+                throw std::invalid_argument("destination is not valid for encryption parameters");
+            adopt(dst, out, words, 2, l);
+            dst->scale = a->scale;
+            dst->ntt = true;
+        }
+        else
+            adopt(a, out, words, 2, l);
     }
 
     static void rotate_internal(Context &c, bk_ct_t a, int steps, bk_gkeys_t gk)
@@ -2264,6 +2274,14 @@ extern "C"
     {
         BK_TRY
         apply_galois(*ctx, a, galois_elt, gk);
+        BK_END
+    }
+    bk_status bk_apply_galois(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk, bk_ct_t dst)
+    {
+        BK_TRY
+        if (!dst)
+            throw std::invalid_argument("destination is null");
+        apply_galois(*ctx, a, galois_elt, gk, dst);
         BK_END
     }
     bk_status bk_rotate_vector_inplace(bk_context_t ctx, bk_ct_t a, int steps, bk_gkeys_t gk)

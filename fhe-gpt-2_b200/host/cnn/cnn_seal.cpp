@@ -54,8 +54,14 @@ namespace
 
     void rotated_copy(const Ciphertext &src, Ciphertext &dst, int steps, Evaluator &evaluator, GaloisKeys &gal_keys)
     {
-        dst = src;
-        memory_save_rotate(dst, dst, steps, evaluator, gal_keys);
+        const long n = (long)src.poly_modulus_degree() / 2;
+        if (&dst == &src || ((steps % n) + n) % n == 0)
+        {
+            dst = src;
+            memory_save_rotate(dst, dst, steps, evaluator, gal_keys);
+        }
+        else
+            memory_save_rotate(src, dst, steps, evaluator, gal_keys); // rotates straight into dst
     }
 
     // dst[i] = src rotated by steps[i].  The reference rotates one by one (rotated_copy); on the engine the rotations
@@ -108,13 +114,13 @@ void memory_save_rotate(const Ciphertext &cipher_in, Ciphertext &cipher_out, int
     steps = (int)(((steps % n) + n) % n);
     if (steps == 0)
         return; // the reference leaves cipher_out untouched here; every caller passes the same object twice
-    Ciphertext temp = cipher_in;
+    Ciphertext temp;
     const int first = ((34 <= steps && steps <= 55) || (57 <= steps && steps <= 61)) ? 33 : 0;
     if (first == 0)
-        evaluator.rotate_vector_inplace(temp, steps, gal_keys);
+        evaluator.rotate_vector(cipher_in, steps, gal_keys, temp);
     else
     {
-        evaluator.rotate_vector_inplace(temp, first, gal_keys);
+        evaluator.rotate_vector(cipher_in, first, gal_keys, temp);
         evaluator.rotate_vector_inplace(temp, steps - first, gal_keys);
     }
     cipher_out = std::move(temp);

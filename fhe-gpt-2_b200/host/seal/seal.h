@@ -1689,8 +1689,26 @@ namespace seal
             const Ciphertext &encrypted, std::uint32_t galois_elt, const GaloisKeys &galois_keys, Ciphertext &destination,
             MemoryPoolHandle = {}) const
         {
-            destination = encrypted;
-            apply_galois_inplace(destination, galois_elt, galois_keys);
+            if (&destination == &encrypted)
+            {
+                apply_galois_inplace(destination, galois_elt, galois_keys);
+                return;
+            }
+            if (!galois_keys.handle())
+                throw std::invalid_argument("galois_keys is not valid for encryption parameters");
+            if (!galois_keys.has_key(galois_elt))
+                throw std::invalid_argument("Galois key not present");
+            need(encrypted, "encrypted");
+            galois_keys.ensure(galois_elt, (int)encrypted.coeff_modulus_size());
+            stats_.key_switch_rotate++;
+            stats_.hit(0, encrypted.coeff_modulus_size());
+            encrypted.push();
+            destination.bind(context_.impl());
+            {
+                std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
+                detail::check(bk_apply_galois(h(), encrypted.handle(), galois_elt, galois_keys.handle(), destination.handle()));
+            }
+            destination.pull();
         }
         void rotate_vector_inplace(
             Ciphertext &encrypted, int steps, const GaloisKeys &galois_keys, MemoryPoolHandle = {}) const
@@ -1731,6 +1749,14 @@ namespace seal
             const Ciphertext &encrypted, int steps, const GaloisKeys &galois_keys, Ciphertext &destination,
             MemoryPoolHandle = {}) const
         {
+            std::uint32_t elt = 0;
+            if (steps != 0 && galois_keys.handle())
+                detail::check(bk_galois_elt_from_step(context_.impl()->log_n, steps, &elt));
+            if (steps != 0 && &destination != &encrypted && galois_keys.handle() && galois_keys.has_key(elt))
+            { // one key switch from `encrypted` straight into `destination`: no copy first
+                apply_galois(encrypted, elt, galois_keys, destination);
+                return;
+            }
             destination = encrypted;
             rotate_vector_inplace(destination, steps, galois_keys);
         }
@@ -1742,8 +1768,7 @@ namespace seal
         inline void complex_conjugate(
             const Ciphertext &encrypted, const GaloisKeys &galois_keys, Ciphertext &destination, MemoryPoolHandle = {}) const
         {
-            destination = encrypted;
-            complex_conjugate_inplace(destination, galois_keys);
+            apply_galois(encrypted, (std::uint32_t)((2u << context_.impl()->log_n) - 1), galois_keys, destination);
         }
 
         // ---- fork: constants and vectors (evaluator.cpp:287-310, evaluator.h:1192-1213).  The scalar is

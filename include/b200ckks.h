@@ -209,7 +209,11 @@ bk_status bk_relinearize_inplace(bk_context_t ctx, bk_ct_t a, bk_kskey_t relin_k
 bk_status bk_rescale_to_next_inplace(bk_context_t ctx, bk_ct_t a);             /* :1118-1181,1378-1414; rns.cpp:737-808 */
 bk_status bk_mod_switch_to_next_inplace(bk_context_t ctx, bk_ct_t a);          /* :1183-1246 */
 bk_status bk_mod_switch_to_inplace(bk_context_t ctx, bk_ct_t a, int limbs);    /* :1326-1348 */
-bk_status bk_apply_galois_inplace(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk); /* :2120-2222 */
+bk_status bk_apply_galois_inplace(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk);
+/* out of place (Evaluator::apply_galois / rotate_vector / complex_conjugate with a destination, evaluator.h:1120-1180):
+ * `a` is read, dst receives the result - the reference copies `a` into the destination and works in place
+ * (evaluator.h:1131-1137); the key switch here writes a fresh buffer anyway, so the copy is not made */
+bk_status bk_apply_galois(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk, bk_ct_t dst); /* :2120-2222 */
 bk_status bk_rotate_vector_inplace(bk_context_t ctx, bk_ct_t a, int steps, bk_gkeys_t gk);         /* :2224-2279 */
 bk_status bk_complex_conjugate_inplace(bk_context_t ctx, bk_ct_t a, bk_gkeys_t gk);                /* evaluator.h:1321-1341 */
 /* Hoisted automorphisms (engine extension; the reference carries the idea as dead code, Bootstrapper.cpp:2088-2230,
