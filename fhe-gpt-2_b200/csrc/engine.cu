@@ -766,6 +766,85 @@ namespace bk
         P->d_ws = upload_sync(ws);
         P->d_psinv = upload_sync(psinv);
         P->d_keyfactor = upload_sync(keyfactor);
+        // rounding and exact-conversion constants of a division by D = the product of `dropped` onto `targets` limbs
+        auto rounding_tables = [&](const std::vector<int> &dropped, int targets, u64 *&d_half, double *&d_pinv, u64 *&d_negd, u64 *&d_addc) {
+            const int cnt = (int)dropped.size();
+            auto dmod = [&](uint64_t m) {
+                uint64_t r = 1 % m;
+                for (int b = 0; b < cnt; b++)
+                    r = bk::mulmod(r, q(dropped[(size_t)b]) % m, m);
+                return r;
+            };
+            // floor(D / 2) = (D - 1) / 2 mod an odd m
+            auto half_mod = [&](uint64_t m) { return bk::mulmod((dmod(m) + m - 1) % m, (m + 1) / 2, m); };
+            std::vector<u64> half((size_t)2 * cnt), negd((size_t)targets), addc((size_t)targets);
+            std::vector<double> pinv((size_t)cnt);
+            for (int a = 0; a < cnt; a++)
+            {
+                half[(size_t)a] = half[(size_t)cnt + a] = half_mod(q(dropped[(size_t)a]));
+                pinv[(size_t)a] = 1.0 / (double)q(dropped[(size_t)a]);
+            }
+            for (int i = 0; i < targets; i++)
+            {
+                negd[(size_t)i] = (q(i) - dmod(q(i))) % q(i);
+                addc[(size_t)i] = (q(i) - half_mod(q(i))) % q(i);
+            }
+            d_half = upload_sync(half);
+            d_pinv = upload_sync(pinv);
+            d_negd = upload_sync(negd);
+            d_addc = upload_sync(addc);
+        };
+        {
+            std::vector<int> dropped;
+            for (int a = 0; a < alpha; a++)
+                dropped.push_back(eprime(l + a));
+            rounding_tables(dropped, l, P->d_shalf, P->d_spinv, P->d_negd, P->d_addc);
+        }
+        if (alpha > 1 && alpha + 1 <= 17 && l >= 2)
+        {
+            // dropped basis of the merged ModDown + rescale: D_0 = q_{l-1}, D_{1+a} = special modulus a
+            const int da = alpha + 1, lo = l - 1;
+            auto dprime = [&](int a) { return a == 0 ? lo : eprime(l + a - 1); };
+            auto dropped_hat = [&](int skip, uint64_t m) {
+                uint64_t r = 1 % m;
+                for (int b = 0; b < da; b++)
+                    if (b != skip)
+                        r = bk::mulmod(r, q(dprime(b)) % m, m);
+                return r;
+            };
+            std::vector<ulonglong2> rpre((size_t)2 * da), dinv((size_t)lo), qlinv((size_t)lo);
+            std::vector<int> rprimes((size_t)2 * da);
+            std::vector<u64> rws((size_t)lo * da);
+            for (int p = 0; p < 2; p++)
+                for (int a = 0; a < da; a++)
+                {
+                    uint64_t m = q(dprime(a));
+                    uint64_t v = bk::invmod(dropped_hat(a, m), m);
+                    rpre[(size_t)p * da + a] = make_ulonglong2(v, bk::shoup(v, m));
+                    rprimes[(size_t)p * da + a] = dprime(a);
+                }
+            for (int i = 0; i < lo; i++)
+            {
+                for (int a = 0; a < da; a++)
+                    rws[(size_t)i * da + a] = dropped_hat(a, q(i));
+                uint64_t v = bk::invmod(dropped_hat(-1, q(i)), q(i));
+                dinv[(size_t)i] = make_ulonglong2(v, bk::shoup(v, q(i)));
+                uint64_t w = bk::invmod(q(lo) % q(i), q(i));
+                qlinv[(size_t)i] = make_ulonglong2(w, bk::shoup(w, q(i)));
+            }
+            uint64_t pm = special_hat(-1, q(lo));
+            P->r_pmod = make_ulonglong2(pm, bk::shoup(pm, q(lo)));
+            P->d_r_sprescale = upload_sync(rpre);
+            P->d_r_sprimes = upload_sync(rprimes);
+            P->d_r_ws = upload_sync(rws);
+            P->d_r_dinv = upload_sync(dinv);
+            P->d_r_qlinv = upload_sync(qlinv);
+            std::vector<int> dropped;
+            for (int a = 0; a < da; a++)
+                dropped.push_back(dprime(a));
+            rounding_tables(dropped, lo, P->d_r_shalf, P->d_r_spinv, P->d_r_negd, P->d_r_addc);
+            P->rescale_tables = true;
+        }
         BK_CUDA(cudaDeviceSynchronize()); // pageable uploads must have landed before any stream reads them
         std::lock_guard<std::mutex> g(c.mu);
         auto ins = c.hplans.emplace(l, P.get());
@@ -780,7 +859,13 @@ namespace bk
         ProfScope ps(c, s, TAG_OTHER, groups * a.nT);
         switch (ds)
         {
-#define BK_HYB_CONV_CASE(DS) case DS: launch_pdl(k_hyb_conv<DS>, grid, 128, 0, s, a, c.tables); break;
+#define BK_HYB_CONV_CASE(DS)                                                                                           \
+    case DS:                                                                                                           \
+        if (a.down)                                                                                                    \
+            launch_pdl(k_hyb_conv<DS, true>, grid, 128, 0, s, a, c.tables);                                            \
+        else                                                                                                           \
+            launch_pdl(k_hyb_conv<DS, false>, grid, 128, 0, s, a, c.tables);                                           \
+        break;
             BK_HYB_CONV_CASE(1) BK_HYB_CONV_CASE(2) BK_HYB_CONV_CASE(3) BK_HYB_CONV_CASE(4) BK_HYB_CONV_CASE(5)
             BK_HYB_CONV_CASE(6) BK_HYB_CONV_CASE(7) BK_HYB_CONV_CASE(8) BK_HYB_CONV_CASE(9) BK_HYB_CONV_CASE(10)
             BK_HYB_CONV_CASE(11) BK_HYB_CONV_CASE(12) BK_HYB_CONV_CASE(13) BK_HYB_CONV_CASE(14) BK_HYB_CONV_CASE(15)
@@ -807,7 +892,7 @@ namespace bk
         for (int e0 = 0; e0 < P.ne; e0 += chunk)
         {
             const int nE = std::min(chunk, P.ne - e0);
-            HybConvArgs cv{ y, P.d_w, conv, n, h, e0, nE, 0 };
+            HybConvArgs cv{ y, P.d_w, conv, n, h, e0, nE, 0, nullptr, nullptr, nullptr };
             launch_hyb_conv(c, s, cv, P.dnum, P.dsize);
             LdHybPlain ld{ conv, n, h, e0 };
             launch_fwd_cols(c, s, ld, inter, nE * P.dnum);
@@ -874,13 +959,36 @@ namespace bk
         const size_t n = c.n;
         LdInvSpecials ld{ acc, n, h };
         launch_inv_blocks(c, s, ld, inter, 2 * P.alpha);
-        StInvScaled st{ tl, n, P.d_sprescale, P.d_sprimes };
+        StInvScaledAdd st{ tl, n, P.d_sprescale, P.d_sprimes, P.d_shalf };
         launch_inv_cols(c, s, inter, st, 2 * P.alpha);
-        HybConvArgs cv{ tl, P.d_ws, conv, n, h, 0, P.l, 1 };
+        HybConvArgs cv{ tl, P.d_ws, conv, n, h, 0, P.l, 1, P.d_spinv, P.d_negd, P.d_addc };
         launch_hyb_conv(c, s, cv, 2, P.alpha);
         launch_fwd_cols(c, s, LdPlain{ conv, limb_map(P.l), n }, inter, 2 * P.l);
         StModDown st2{ acc, out, base0, base1, perm, P.d_psinv, n, P.l, P.ne };
         launch_fwd_blocks(c, s, inter, st2, 2 * P.l);
+    }
+
+    // The same ModDown with the rescale that follows a relinearization folded in: one division by D = q_{l-1} P_S
+    // instead of one by P_S and one by q_{l-1}.  With x = acc + P_S base over the extended basis (P_S base vanishes on
+    // the special limbs, so only limb l-1 of the dropped ones sees the base),
+    //   out_i = (x_i - [x]_D) D^-1 = (acc_i - conv_i) D^-1 + base_i q_{l-1}^-1   (mod q_i, i < l-1).
+    // Saves the 2l forward transforms of the intermediate result and the rescale's two inverse ones; the quotient is
+    // rounded to nearest and the basis conversion exact (HybridPlan::d_shalf), as in hyb_mod_down.
+    static void hyb_mod_down_rescale(Context &c, cudaStream_t s, const HybridPlan &P, const HybDims &h, const u64 *acc, u64 *conv, u64 *inter,
+                                     u64 *tl, u64 *out, const u64 *base0, const u64 *base1)
+    {
+        const size_t n = c.n;
+        const int da = P.alpha + 1, lo = P.l - 1;
+        LdInvDropped ld{ acc, base0, base1, n, h, P.r_pmod };
+        launch_inv_blocks(c, s, ld, inter, 2 * da);
+        StInvScaledAdd st{ tl, n, P.d_r_sprescale, P.d_r_sprimes, P.d_r_shalf };
+        launch_inv_cols(c, s, inter, st, 2 * da);
+        const HybDims hd{ lo, da, h.dsize, h.dnum, h.special_prime };
+        HybConvArgs cv{ tl, P.d_r_ws, conv, n, hd, 0, lo, 1, P.d_r_spinv, P.d_r_negd, P.d_r_addc };
+        launch_hyb_conv(c, s, cv, 2, da);
+        launch_fwd_cols(c, s, LdPlain{ conv, limb_map(lo), n }, inter, 2 * lo);
+        StModDownRescale st2{ acc, out, base0, base1, nullptr, P.d_r_dinv, n, lo, P.ne, P.d_r_qlinv };
+        launch_fwd_blocks(c, s, inter, st2, 2 * lo);
     }
 
     // polynomial-1 pointer and digit strides of a SEAL-shaped key for k_ks_mac; a seed-compressed level key gets its
@@ -903,18 +1011,19 @@ namespace bk
     }
 
     // Same contract as key_switch below; the key is the level-l hybrid key of `key`'s recipe.
+    // rescale: out is [2][l-1][N] and receives the result divided by q_{l-1} as well (perm must be null).
     static void key_switch_hybrid(Context &c, cudaStream_t s, const u64 *target, const uint32_t *perm, const u64 *base0,
-                                  const u64 *base1, u64 *out, int l, bk_kskey_t key)
+                                  const u64 *base1, u64 *out, int l, bk_kskey_t key, bool rescale = false)
     {
         const HybridPlan &P = hybrid_plan(c, l);
         bk_hybkey_s *hk = hybrid_key(c, key, l);
         const size_t n = c.n;
         const HybDims h{ l, P.alpha, P.dsize, P.dnum, c.n_primes - 1 };
         Scratch y(s, (size_t)l * n);
-        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha + 2 }) * n);
         Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
         Scratch acc(s, (size_t)2 * P.ne * n);
-        Scratch tl(s, (size_t)2 * P.alpha * n);
+        Scratch tl(s, (size_t)(2 * P.alpha + 2) * n);
         {
             LdInvPlain ld{ target, limb_map(l), n, perm };
             launch_inv_blocks(c, s, ld, inter.p, l);
@@ -922,7 +1031,14 @@ namespace bk
             launch_inv_cols(c, s, inter.p, st, l);
         }
         hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, target, 1, &perm, &hk, acc.p, 0);
-        hyb_mod_down(c, s, P, h, acc.p, conv.p, inter.p, tl.p, out, base0, base1, perm);
+        if (rescale)
+        {
+            if (perm || !base0 || !base1 || !P.rescale_tables)
+                throw std::logic_error("merged ModDown and rescale: relinearization at a hybrid level only");
+            hyb_mod_down_rescale(c, s, P, h, acc.p, conv.p, inter.p, tl.p, out, base0, base1);
+        }
+        else
+            hyb_mod_down(c, s, P, h, acc.p, conv.p, inter.p, tl.p, out, base0, base1, perm);
     }
 
     static void key_switch_hoisted_hybrid(Context &c, cudaStream_t s, const bk_ct_s *in, int count, const uint32_t *const *perms,
@@ -1294,21 +1410,22 @@ struct LinCombArgs
 {
     const u64 *src[LINCOMB_TERMS];
     int limbs_in[LINCOMB_TERMS];
+    int size_in[LINCOMB_TERMS]; // polynomials of each source (2, or 3 for an unrelinearized product)
     int terms;
     ulonglong2 c[LINCOMB_TERMS][62];
 };
 __global__ void __launch_bounds__(256) k_scalar_lincomb(u64 *__restrict__ dst, const __grid_constant__ LinCombArgs a,
                                                         const __grid_constant__ ScalarPack addc, const PrimeDev *primes,
-                                                        int log_n, int limbs)
+                                                        int log_n, int limbs, int polys)
 {
     pdl_prologue();
     const size_t n = size_t(1) << log_n;
     const size_t per_poly = (size_t)limbs * n;
-    const size_t total = per_poly; // two polynomials, two words per step
+    const size_t total = per_poly * polys / 2; // `polys` polynomials, two words per step
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
     {
         const size_t e = i * 2;
-        const int p = e >= per_poly;
+        const int p = (int)(e / per_poly);
         const size_t r = e - (size_t)p * per_poly;
         const int limb = (int)(r >> log_n);
         const size_t x = r & (n - 1);
@@ -1317,7 +1434,7 @@ __global__ void __launch_bounds__(256) k_scalar_lincomb(u64 *__restrict__ dst, c
 #pragma unroll
         for (int j = 0; j < LINCOMB_TERMS; j++)
         {
-            if (j < a.terms)
+            if (j < a.terms && p < a.size_in[j])
             {
                 const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2 *>(a.src[j] + ((size_t)p * a.limbs_in[j] + limb) * n + x));
                 const u64 f = a.c[j][limb].x;
@@ -2211,6 +2328,50 @@ extern "C"
         BK_END
     }
 
+    bk_status bk_relinearize_rescale_inplace(bk_context_t ctx, bk_ct_t a, bk_kskey_t relin_key)
+    {
+        BK_TRY
+        // relinearize_inplace followed by rescale_to_next_inplace (evaluator.cpp:1061-1116, 1378-1414).  With hybrid
+        // key switching at a level that has idle primes the two divisions (ModDown by P_S, rescale by q_{l-1}) are
+        // one (hyb_mod_down_rescale): same value up to one rounding instead of two, limbs
+        // differ - tolerance mode, like hybrid key switching itself.  Everywhere else: the two calls in sequence.
+        Context &c = *ctx;
+        check_ct(ctx, a, "encrypted");
+        if (!relin_key || relin_key->ctx != ctx)
+            throw std::invalid_argument("relin_keys is not valid for encryption parameters");
+        if (a->size != 2 && a->size != 3)
+            throw std::invalid_argument("not enough relinearization keys");
+        if (!a->ntt)
+            throw std::invalid_argument("CKKS encrypted must be in NTT form");
+        if (a->limbs < 2)
+            throw std::invalid_argument("end of modulus switching chain reached");
+        const int l = a->limbs;
+        static const bool merged = [] {
+            const char *e = std::getenv("B200CKKS_MERGED_RESCALE");
+            return !e || std::atoi(e) != 0;
+        }();
+        if (merged && a->size == 3 && relin_key->recipe && hybrid_plan(c, l).alpha > 1 && hybrid_plan(c, l).rescale_tables)
+        {
+            const size_t per_poly = (size_t)l * c.n;
+            const size_t words = (size_t)2 * (l - 1) * c.n;
+            u64 *out = alloc_words(c, words);
+            key_switch_hybrid(c, c.stream(), a->d + 2 * per_poly, nullptr, a->d, a->d + per_poly, out, l, relin_key, true);
+            adopt(a, out, words, 2, l - 1);
+            a->scale = a->scale / (double)c.primes[(size_t)(l - 1)];
+            return BK_OK;
+        }
+        if (a->size == 3)
+        {
+            const size_t per_poly = (size_t)l * c.n;
+            const size_t words = 2 * per_poly;
+            u64 *out = alloc_words(c, words);
+            key_switch(c, c.stream(), a->d + 2 * per_poly, nullptr, a->d, a->d + per_poly, out, l, relin_key);
+            adopt(a, out, words, 2, l);
+        }
+        rescale_core(c, a);
+        BK_END
+    }
+
     bk_status bk_rescale_to_next_inplace(bk_context_t ctx, bk_ct_t a)
     {
         BK_TRY
@@ -2714,15 +2875,16 @@ extern "C"
         Context &c = *ctx;
         if (!cts || !values || count < 1 || count > LINCOMB_TERMS)
             throw std::invalid_argument("between 1 and 8 terms are supported");
-        int limbs = 1 << 30;
+        int limbs = 1 << 30, polys = 2;
         for (int j = 0; j < count; j++)
         {
             check_ct(ctx, cts[j], "encrypted");
-            if (!cts[j]->ntt || cts[j]->size != 2)
-                throw std::invalid_argument("encrypted must be of size 2 and in NTT form");
+            if (!cts[j]->ntt || (cts[j]->size != 2 && cts[j]->size != 3))
+                throw std::invalid_argument("encrypted must be of size 2 or 3 and in NTT form");
             if (cts[j] == dst)
                 throw std::invalid_argument("destination must not be one of the sources");
             limbs = std::min(limbs, cts[j]->limbs);
+            polys = std::max(polys, cts[j]->size);
         }
         if (!c.scale_in_bounds(target_scale, limbs))
             throw std::invalid_argument("scale out of bounds");
@@ -2732,13 +2894,15 @@ extern "C"
         {
             a.src[j] = cts[j]->d;
             a.limbs_in[j] = cts[j]->limbs;
+            a.size_in[j] = cts[j]->size;
             scalar_residues(c, values[j], target_scale / cts[j]->scale, limbs, a.c[j]);
         }
         ScalarPack addc{};
         scalar_residues(c, constant, target_scale, limbs, addc.c);
-        ensure_ct(dst, 2, limbs, false);
+        ensure_ct(dst, polys, limbs, false);
         ProfScope ps_ew(c, c.stream(), TAG_ELEMENTWISE, 2 * limbs * count);
-        launch_pdl(k_scalar_lincomb, c.ew_grid((size_t)limbs * c.n), 256, 0, c.stream(), dst->d, a, addc, c.d_primes, c.log_n, limbs);
+        launch_pdl(k_scalar_lincomb, c.ew_grid((size_t)limbs * c.n * polys / 2), 256, 0, c.stream(), dst->d, a, addc, c.d_primes, c.log_n,
+                   limbs, polys);
         c.count();
         dst->scale = target_scale;
         dst->ntt = true;

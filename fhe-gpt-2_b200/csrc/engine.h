@@ -150,6 +150,29 @@ namespace bk
         u64 *d_ws = nullptr;               // [l][alpha] (P_S / p_a) mod q_i
         ulonglong2 *d_psinv = nullptr;     // [l] {P_S^-1 mod q_i, shoup}
         u64 *d_keyfactor = nullptr;        // [dnum][ne] P_S mod q_e on the digit's own limbs, 0 elsewhere
+        // the division by D (= P_S here) rounds to nearest and the basis conversion is exact: floor(D/2) joins the
+        // dropped residues before the conversion, the multiple u D by which the fast conversion overshoots is found
+        // from the fractional parts sum_a y_a / p_a in double precision and taken off again (k_hyb_conv<DS, true>).
+        // Without it every coefficient carries the same negative offset of a few units, and a constant polynomial
+        // times s(X) is ~2N/pi ~ 4e4 times larger in the slots whose root of unity lies next to 1 than random
+        // rounding noise of the same size (measured: 1e-6 instead of 3e-9 on a rescaled product).
+        u64 *d_shalf = nullptr;            // [2 alpha] floor(D/2) mod p_a, both polynomials
+        double *d_spinv = nullptr;         // [alpha] 1 / p_a
+        u64 *d_negd = nullptr;             // [l] -D mod q_i
+        u64 *d_addc = nullptr;             // [l] -floor(D/2) mod q_i
+        // ModDown and rescale as ONE division by D = q_{l-1} * P_S (relinearization followed by a rescale): the dropped
+        // basis is {q_{l-1}} + the alpha special moduli, the target limbs are 0 .. l-2.  Present when alpha + 1 <= 17.
+        bool rescale_tables = false;
+        ulonglong2 *d_r_sprescale = nullptr; // [2 (alpha+1)] {(D / p_a)^-1 mod p_a, shoup}, both polynomials
+        int *d_r_sprimes = nullptr;          // [2 (alpha+1)] prime index of each dropped limb (q_{l-1} first)
+        u64 *d_r_ws = nullptr;               // [l-1][alpha+1] (D / p_a) mod q_i
+        ulonglong2 *d_r_dinv = nullptr;      // [l-1] {D^-1 mod q_i, shoup}
+        ulonglong2 *d_r_qlinv = nullptr;     // [l-1] {q_{l-1}^-1 mod q_i, shoup}: the factor of the base ciphertext
+        ulonglong2 r_pmod{ 0, 0 };           // {P_S mod q_{l-1}, shoup}: the base joins the dropped limb l-1 times P_S
+        u64 *d_r_shalf = nullptr;            // as d_shalf .. d_addc for D = q_{l-1} P_S
+        double *d_r_spinv = nullptr;
+        u64 *d_r_negd = nullptr;
+        u64 *d_r_addc = nullptr;
         HybridPlan() = default;
         HybridPlan(const HybridPlan &) = delete;
         HybridPlan &operator=(const HybridPlan &) = delete;
@@ -163,6 +186,19 @@ namespace bk
             cudaFree(d_ws);
             cudaFree(d_psinv);
             cudaFree(d_keyfactor);
+            cudaFree(d_r_sprescale);
+            cudaFree(d_r_sprimes);
+            cudaFree(d_r_ws);
+            cudaFree(d_r_dinv);
+            cudaFree(d_r_qlinv);
+            cudaFree(d_shalf);
+            cudaFree(d_spinv);
+            cudaFree(d_negd);
+            cudaFree(d_addc);
+            cudaFree(d_r_shalf);
+            cudaFree(d_r_spinv);
+            cudaFree(d_r_negd);
+            cudaFree(d_r_addc);
         }
     };
 

@@ -197,7 +197,7 @@ struct StRescale
 // acc is in natural layout (written by k_ks_mac); register element (t,k) of a block is
 // coefficient 16t + k.  base_0 = c0 (optionally gathered through the Galois table), base_1 = c1
 // or nothing.
-struct StModDown
+template <bool SCALE_BASE> struct StModDownT
 {
     static constexpr bool RAW = false;
     static constexpr bool BATCH = true; // post_all: three dependent loads per coefficient, 16 coefficients in flight
@@ -211,6 +211,7 @@ struct StModDown
     size_t n;
     int l;
     int acc_limbs = 0;     // limbs per polynomial of acc; 0 = l + 1 (one special prime)
+    const ulonglong2 *base_scale = nullptr; // SCALE_BASE: [l] per-limb factor of the base (merged rescale: q_last^-1)
     __device__ __forceinline__ int prime(int job) const { return job % l; }
     __device__ __forceinline__ u64 pre(int, int, int, int, u64 v, const PrimeDev &) const { return v; }
     // Coefficients base + t + 16 k, k < 16, in the coalesced order of the store (acc, base and dst as full lines),
@@ -226,6 +227,9 @@ struct StModDown
         const u64 *b = p == 0 ? base0 : base1;
         u64 *out = dst + (size_t)job * n + base + t;
         const ulonglong2 f = __ldg(inv + i);
+        ulonglong2 g = make_ulonglong2(0, 0);
+        if (SCALE_BASE)
+            g = __ldg(base_scale + i);
         if (b)
             b += (size_t)i * n;
         // two batches of 8 coefficients: enough loads in flight to cover the latency, few enough registers not to spill
@@ -266,11 +270,15 @@ struct StModDown
             {
                 u64 d = r[k] + 2 * pd.two_q - s[swz(t + 16 * (h + k))]; // transform value in [0,4q)
                 u64 v = csub(mul_shoup_lazy(d, f.x, f.y, pd.q), pd.q);
+                if (SCALE_BASE)
+                    add[k] = csub(mul_shoup_lazy(add[k], g.x, g.y, pd.q), pd.q);
                 out[16 * (h + k)] = addmod(v, add[k], pd.q);
             }
         }
     }
 };
+using StModDown = StModDownT<false>;
+using StModDownRescale = StModDownT<true>; // hyb_mod_down_rescale (engine.cu)
 
 // ---------------------------------------------------------------- inverse block-pass loaders
 struct LdInvPlain
@@ -471,6 +479,23 @@ struct StInvScaled
     }
 };
 
+// the same after adding a per-job constant (floor(D/2) of a rounding division by D, HybridPlan::d_shalf)
+struct StInvScaledAdd
+{
+    u64 *dst;
+    size_t n;
+    const ulonglong2 *scale; // [jobs] {c, shoup(c)}
+    const int *primes;       // [jobs] prime index of each job
+    const u64 *add;          // [jobs]
+    __device__ __forceinline__ int prime(int job) const { return primes[job]; }
+    __device__ __forceinline__ void store(int job, int idx, u64 v, const PrimeDev &pd) const
+    {
+        v = addmod(csub(v, pd.q), add[job], pd.q);
+        ulonglong2 f = scale[job];
+        dst[(size_t)job * n + idx] = csub(mul_shoup_lazy(v, f.x, f.y, pd.q), pd.q);
+    }
+};
+
 // NTT block-pass store of the extended digits: job = eloc * dnum + d (extended limb e0 + eloc, digit d); the digit's own
 // limbs are skipped (their NTT form is the input itself)
 struct StHybDigit
@@ -505,6 +530,34 @@ struct LdInvSpecials
     __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
 };
 
+// the dropped limbs of a merged ModDown + rescale: job = p * (alpha + 1) + a; a = 0 is limb l-1 of the data basis, where
+// the base ciphertext joins the accumulator times P_S (P_S base is 0 on the special limbs), a >= 1 special limb a - 1
+struct LdInvDropped
+{
+    static constexpr bool TLAYOUT = false;
+    const u64 *acc;   // [2][ne][N]
+    const u64 *base0; // [l][N]
+    const u64 *base1; // [l][N]
+    size_t n;
+    HybDims h;
+    ulonglong2 pmod; // {P_S mod q_{l-1}, shoup}
+    __device__ __forceinline__ int prime(int job) const
+    {
+        const int a = job % (h.alpha + 1);
+        return a == 0 ? h.l - 1 : h.eprime(h.l + a - 1);
+    }
+    __device__ __forceinline__ u64 load(int job, int idx, const PrimeDev &pd) const
+    {
+        const int p = job / (h.alpha + 1), a = job % (h.alpha + 1);
+        if (a != 0)
+            return acc[((size_t)p * h.ne() + h.l + a - 1) * n + idx];
+        const u64 x = acc[((size_t)p * h.ne() + h.l - 1) * n + idx];
+        const u64 b = (p == 0 ? base0 : base1)[(size_t)(h.l - 1) * n + idx];
+        return addmod(x, csub(mul_shoup_lazy(b, pmod.x, pmod.y, pd.q), pd.q), pd.q);
+    }
+    __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }
+};
+
 // Basis conversion as its own kernel (the NTT column pass then loads plain words and keeps its register budget):
 // every thread keeps the DS source residues of two coefficients in registers and produces all targets of the chunk.
 //   digits  (down == 0): source group dd = digit d, targets t = extended limbs e0 .. e0 + nT - 1, out job = t * dnum + d
@@ -517,10 +570,14 @@ struct HybConvArgs
     size_t n;
     HybDims h;
     int e0, nT, down;
+    // ModDown only (k_hyb_conv<DS, true>): the conversion is made exact and the division rounds to nearest
+    const double *pinv; // [alpha] 1 / p_a
+    const u64 *negd;    // [l] -D mod q_i, D = product of the source moduli
+    const u64 *addc;    // [l] -floor(D/2) mod q_i (the source residues carry +floor(D/2), StInvScaledAdd)
 };
 
 constexpr int HYB_CONV_TARGETS = 8;
-template <int DS>
+template <int DS, bool DOWN>
 static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTables T)
 {
     pdl_prologue();
@@ -529,22 +586,48 @@ static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTable
     if (i >= n)
         return;
     const int dd = blockIdx.y;
-    const int first = a.down ? dd * a.h.alpha : dd * a.h.dsize;
-    const int cnt = a.down ? a.h.alpha : min(a.h.dsize, a.h.l - first);
+    const int first = DOWN ? dd * a.h.alpha : dd * a.h.dsize;
+    const int cnt = DOWN ? a.h.alpha : min(a.h.dsize, a.h.l - first);
     ulonglong2 y[DS];
 #pragma unroll
     for (int k = 0; k < DS; k++)
         y[k] = k < cnt ? *reinterpret_cast<const ulonglong2 *>(a.src + (size_t)(first + k) * n + i) : make_ulonglong2(0, 0);
+    // ModDown: sum_a y_a (D / p_a) = [x]_D + u D with u = floor(sum_a y_a / p_a) < alpha; u from the fractional parts
+    // in double precision (off by one only if the sum is within ~alpha 2^-52 of an integer: a one-unit error of the
+    // quotient with probability ~2^-48 per coefficient), u D is taken off again below
+    u64 ux = 0, uy = 0;
+    if (DOWN)
+    {
+        double fx = 0.0, fy = 0.0;
+#pragma unroll
+        for (int k = 0; k < DS; k++)
+            if (k < cnt)
+            {
+                const double pi = a.pinv[k];
+                fx = fma((double)y[k].x, pi, fx);
+                fy = fma((double)y[k].y, pi, fy);
+            }
+        ux = (u64)fx;
+        uy = (u64)fy;
+    }
     // blockIdx.z selects a slice of HYB_CONV_TARGETS targets, so that small digit counts still fill the machine
     const int t_begin = blockIdx.z * HYB_CONV_TARGETS, t_end = min(a.nT, t_begin + HYB_CONV_TARGETS);
     for (int t = t_begin; t < t_end; t++)
     {
         const int e = a.e0 + t;
-        if (!a.down && a.h.own(e, dd))
+        if (!DOWN && a.h.own(e, dd))
             continue;
-        const PrimeDev pd = T.primes[a.down ? e : a.h.eprime(e)];
-        const u64 *wv = a.down ? a.w + (size_t)e * a.h.alpha : a.w + ((size_t)e * a.h.dnum + dd) * a.h.dsize;
+        const PrimeDev pd = T.primes[DOWN ? e : a.h.eprime(e)];
+        const u64 *wv = DOWN ? a.w + (size_t)e * a.h.alpha : a.w + ((size_t)e * a.h.dnum + dd) * a.h.dsize;
         u64 lx = 0, hx = 0, ly = 0, hy = 0;
+        if (DOWN)
+        {
+            // - u D - floor(D/2): the converted value is [x + floor(D/2)]_D - floor(D/2) exactly (mod q_e)
+            const u64 nd = a.negd[e], ac = a.addc[e];
+            lx = ly = ac;
+            mac128(lx, hx, ux, nd);
+            mac128(ly, hy, uy, nd);
+        }
 #pragma unroll
         for (int k = 0; k < DS; k++)
         {
@@ -566,7 +649,7 @@ static __global__ void __launch_bounds__(128) k_hyb_conv(HybConvArgs a, NttTable
             r.x = barrett128(lx, hx, pd);
             r.y = barrett128(ly, hy, pd);
         }
-        const size_t job = a.down ? (size_t)dd * a.h.l + t : (size_t)t * a.h.dnum + dd;
+        const size_t job = DOWN ? (size_t)dd * a.h.l + t : (size_t)t * a.h.dnum + dd;
         *reinterpret_cast<ulonglong2 *>(a.out + job * n + i) = r;
     }
 }

@@ -42,8 +42,7 @@ void ModularReducer::double_angle_formula(Ciphertext &cipher)
 void ModularReducer::double_angle_formula_scaled(Ciphertext &cipher, double scale_coeff)
 {
     evaluator.square_inplace(cipher);
-    evaluator.relinearize_inplace(cipher, relin_keys);
-    evaluator.rescale_to_next_inplace(cipher);
+    relinearize_then_rescale(evaluator, cipher, relin_keys);
     evaluator.double_inplace(cipher);
     evaluator.add_const(cipher, -scale_coeff, cipher);
 }

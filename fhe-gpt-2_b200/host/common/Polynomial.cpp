@@ -1,5 +1,6 @@
 // common/Polynomial.cpp - see Polynomial.h.
 #include "common/Polynomial.h"
+#include <algorithm>
 #include <cmath>
 #include <stdexcept>
 
@@ -203,8 +204,7 @@ namespace boot
         {
             Ciphertext squared, top;
             evaluator.square(cipher, squared);
-            evaluator.relinearize_inplace(squared, relin_keys);
-            evaluator.rescale_to_next_inplace(squared);
+            relinearize_then_rescale(evaluator, squared, relin_keys);
             if (deg == 2)
             {
                 evaluator.multiply_const_inplace(squared, c(2));
@@ -245,13 +245,24 @@ namespace boot
             if (!Tdiff)
             {
                 evaluator.square(Ta, out);
-                evaluator.relinearize_inplace(out, relin_keys);
-                evaluator.rescale_to_next_inplace(out);
+                relinearize_then_rescale(evaluator, out, relin_keys);
                 evaluator.double_inplace(out);
                 evaluator.add_const(out, -1.0, out);
             }
             else
             {
+#ifdef B200CKKS_FACADE
+                if (merged_rescale() && Tdiff->coeff_modulus_size() >= std::min(Ta.coeff_modulus_size(), Tb.coeff_modulus_size()))
+                {
+                    // 2 Ta Tb - T|a-b| on the unrelinearized product, then one relinearization and rescale
+                    Ciphertext product, sum;
+                    evaluator.multiply_reduced_error_unrelinearized(Ta, Tb, product);
+                    evaluator.scalar_linear_combination({ &product, Tdiff }, { 2.0, -1.0 }, 0.0, product.scale(), sum);
+                    evaluator.relinearize_rescale_inplace(sum, relin_keys);
+                    out = std::move(sum);
+                    return;
+                }
+#endif
                 evaluator.multiply_reduced_error(Ta, Tb, relin_keys, out);
 #ifdef B200CKKS_FACADE
                 if (fused_leaves() && Tdiff->coeff_modulus_size() >= out.coeff_modulus_size())
@@ -305,8 +316,7 @@ namespace boot
         for (long i = 1; i < m; i++)
         {
             evaluator.square(giant[(std::size_t)(i - 1)], giant[(std::size_t)i]);
-            evaluator.relinearize_inplace(giant[(std::size_t)i], relin_keys);
-            evaluator.rescale_to_next_inplace(giant[(std::size_t)i]);
+            relinearize_then_rescale(evaluator, giant[(std::size_t)i], relin_keys);
             evaluator.double_inplace(giant[(std::size_t)i]);
             evaluator.add_const_inplace(giant[(std::size_t)i], -1.0);
         }
@@ -370,6 +380,19 @@ namespace boot
                     node[(std::size_t)i] = node[rem];
                 else
                 {
+#ifdef B200CKKS_FACADE
+                    if (merged_rescale() && node[rem].coeff_modulus_size() >=
+                                                std::min(node[quo].coeff_modulus_size(), giant[(std::size_t)gindex].coeff_modulus_size()))
+                    {
+                        // quotient * giant + remainder on the unrelinearized product, one relinearization and rescale
+                        Ciphertext product, sum;
+                        evaluator.multiply_reduced_error_unrelinearized(node[quo], giant[(std::size_t)gindex], product);
+                        evaluator.scalar_linear_combination({ &product, &node[rem] }, { 1.0, 1.0 }, 0.0, product.scale(), sum);
+                        evaluator.relinearize_rescale_inplace(sum, relin_keys);
+                        node[(std::size_t)i] = std::move(sum);
+                        continue;
+                    }
+#endif
                     evaluator.multiply_reduced_error(node[quo], giant[(std::size_t)gindex], relin_keys, node[(std::size_t)i]);
 #ifdef B200CKKS_FACADE
                     if (fused_leaves() && node[rem].coeff_modulus_size() >= node[(std::size_t)i].coeff_modulus_size())

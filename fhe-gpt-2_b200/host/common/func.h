@@ -78,6 +78,36 @@ inline bool fused_leaves()
 #endif
 }
 
+// A ciphertext product of the reference ends with relinearize_inplace and, after whatever is added to it at the
+// product's scale, rescale_to_next_inplace (common/Polynomial.cpp:242-252, comp/SEALfunc.cpp:18-24,
+// ckks_bootstrapping/ModularReducer.cpp:43-46).  On the engine the pair is one call
+// (Evaluator::relinearize_rescale_inplace: one division by q_last P_S in tolerance mode, the two calls otherwise), and
+// in tolerance mode the additions move in front of the relinearization, which is linear: the product stays of size 3,
+// the linear combination runs on three polynomials, and the sum is relinearized and rescaled once.
+// $B200CKKS_MERGED_RESCALE=0 keeps the separate calls in the reference's order.
+inline bool merged_rescale()
+{
+#ifdef B200CKKS_FACADE
+    static const bool on = [] {
+        const char *e = std::getenv("B200CKKS_MERGED_RESCALE");
+        return fused_leaves() && (!e || std::atoi(e) != 0);
+    }();
+    return on;
+#else
+    return false;
+#endif
+}
+template <class Evaluator, class Ciphertext, class RelinKeys>
+inline void relinearize_then_rescale(Evaluator &evaluator, Ciphertext &cipher, RelinKeys &relin_keys)
+{
+#ifdef B200CKKS_FACADE
+    evaluator.relinearize_rescale_inplace(cipher, relin_keys);
+#else
+    evaluator.relinearize_inplace(cipher, relin_keys);
+    evaluator.rescale_to_next_inplace(cipher);
+#endif
+}
+
 // baby-step size minimising ceil(M/k) + k - 1 (first minimiser, k <= 3 sqrt(M))
 inline int giantstep(int M)
 {

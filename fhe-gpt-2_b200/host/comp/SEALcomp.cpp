@@ -76,6 +76,14 @@ void minimax_ReLU_seal(long comp_no, std::vector<int> deg, long alpha, std::vect
     }
     else
         evaluator.add_const(x, 0.5, sum);
+#ifdef B200CKKS_FACADE
+    if (merged_rescale())
+    {
+        evaluator.multiply_reduced_error_unrelinearized(sum, cipher_in, cipher_res);
+        evaluator.relinearize_rescale_inplace(cipher_res, relin_keys);
+        return;
+    }
+#endif
     evaluator.multiply_reduced_error(sum, cipher_in, relin_keys, cipher_res);
     evaluator.rescale_to_next_inplace(cipher_res);
 }

@@ -1,6 +1,7 @@
 // comp/SEALfunc.cpp - see SEALfunc.h.  Every ciphertext operation goes through seal::Evaluator, i.e. through
 // the C ABI into the CUDA engine; the code below only decides which operation comes next.
 #include "comp/SEALfunc.h"
+#include <algorithm>
 #include <cmath>
 #include <map>
 #include <memory>
@@ -42,6 +43,17 @@ namespace seal
                const Ciphertext &Tm, const Ciphertext &Tn, const Ciphertext &Tmminusn)
     {
         Ciphertext twice;
+#ifdef B200CKKS_FACADE
+        if (merged_rescale() && Tmminusn.size() != 0 &&
+            Tmminusn.coeff_modulus_size() >= std::min(Tm.coeff_modulus_size(), Tn.coeff_modulus_size()))
+        {
+            // 2 Tm Tn - T(m-n) on the unrelinearized product, then one relinearization and rescale (func.h)
+            evaluator.multiply_reduced_error_unrelinearized(Tm, Tn, twice);
+            evaluator.scalar_linear_combination({ &twice, &Tmminusn }, { 2.0, -1.0 }, 0.0, twice.scale(), Tmplusn);
+            evaluator.relinearize_rescale_inplace(Tmplusn, relin_keys);
+            return;
+        }
+#endif
         evaluator.multiply_reduced_error(Tm, Tn, relin_keys, twice);
 #ifdef B200CKKS_FACADE
         if (fused_leaves() && Tmminusn.size() != 0 && Tmminusn.coeff_modulus_size() >= twice.coeff_modulus_size())
@@ -157,11 +169,55 @@ namespace seal
                     continue;
                 long k = j;
                 Ciphertext &acc = part[j];
-                evaluator.multiply_reduced_error(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), relin_keys, acc);
-                for (k *= 2; tree.tree[(std::size_t)k] != 0; k *= 2)
+                bool folded = false;
+#ifdef B200CKKS_FACADE
+                if (merged_rescale())
                 {
-                    evaluator.multiply_reduced_error(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), relin_keys, term);
-                    evaluator.add_inplace_reduced_error(acc, term);
+                    // every product of the chain stays of size 3; if they (and the remainder) meet at one level, the
+                    // whole sum is ONE pass over three polynomials, ONE relinearization and ONE rescale
+                    std::vector<Ciphertext> products;
+                    products.emplace_back();
+                    evaluator.multiply_reduced_error_unrelinearized(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), products.back());
+                    for (k *= 2; tree.tree[(std::size_t)k] != 0; k *= 2)
+                    {
+                        products.emplace_back();
+                        evaluator.multiply_reduced_error_unrelinearized(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1),
+                                                                        products.back());
+                    }
+                    bool one_level = products.size() + 1 <= 8 &&
+                                     part.at(k).coeff_modulus_size() >= products[0].coeff_modulus_size();
+                    for (const Ciphertext &p : products)
+                        one_level = one_level && p.coeff_modulus_size() == products[0].coeff_modulus_size();
+                    if (one_level)
+                    {
+                        std::vector<const Ciphertext *> terms;
+                        for (const Ciphertext &p : products)
+                            terms.push_back(&p);
+                        terms.push_back(&part.at(k));
+                        Ciphertext sum;
+                        evaluator.scalar_linear_combination(terms, std::vector<double>(terms.size(), 1.0), 0.0,
+                                                            products[0].scale(), sum);
+                        evaluator.relinearize_rescale_inplace(sum, relin_keys);
+                        acc = std::move(sum);
+                        continue;
+                    }
+                    // levels differ: each product is relinearized and they are folded as the reference folds them
+                    for (Ciphertext &p : products)
+                        evaluator.relinearize_inplace(p, relin_keys);
+                    acc = std::move(products[0]);
+                    for (std::size_t i = 1; i < products.size(); i++)
+                        evaluator.add_inplace_reduced_error(acc, products[i]);
+                    folded = true;
+                }
+#endif
+                if (!folded)
+                {
+                    evaluator.multiply_reduced_error(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), relin_keys, acc);
+                    for (k *= 2; tree.tree[(std::size_t)k] != 0; k *= 2)
+                    {
+                        evaluator.multiply_reduced_error(basis(tree.tree[(std::size_t)k]), part.at(2 * k + 1), relin_keys, term);
+                        evaluator.add_inplace_reduced_error(acc, term);
+                    }
                 }
 #ifdef B200CKKS_FACADE
                 if (fused_leaves() && part.at(k).coeff_modulus_size() >= acc.coeff_modulus_size())

@@ -94,8 +94,7 @@ namespace gpt2
         for (int i = 0; i < iters; i++)
         {
             evaluator.square(output, square);
-            evaluator.relinearize_inplace(square, relin_keys);
-            evaluator.rescale_to_next_inplace(square);
+            relinearize_then_rescale(evaluator, square, relin_keys);
 
             evaluator.multiply_inplace_reduced_error(square, minus_half_x, relin_keys);
             evaluator.rescale_to_next_inplace(square);
@@ -145,8 +144,7 @@ namespace gpt2
         evaluator.sub_inplace_reduced_error(z, folded);
 
         evaluator.square(z, y);
-        evaluator.relinearize_inplace(y, relin_keys);
-        evaluator.rescale_to_next_inplace(y);
+        relinearize_then_rescale(evaluator, y, relin_keys);
         decrypt_and_print_and_max_round(y, decryptor, encoder, 1.0, 0);
 
         evaluator.multiply_vector_inplace_reduced_error(y, mask);

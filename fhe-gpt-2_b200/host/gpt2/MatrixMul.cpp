@@ -64,8 +64,7 @@ namespace gpt2
             for (int j = 0; j < rows; j++)
             {
                 evaluator.multiply(left_inputs[(std::size_t)j].cipher(), right_inputs[(std::size_t)j].cipher(), cipher);
-                evaluator.relinearize_inplace(cipher, relin_keys);
-                evaluator.rescale_to_next_inplace(cipher);
+                relinearize_then_rescale(evaluator, cipher, relin_keys);
                 evaluator.mod_switch_to_inplace(accumulators[(std::size_t)i], cipher.parms_id());
                 evaluator.add_inplace_reduced_error(accumulators[(std::size_t)i], cipher);
             }

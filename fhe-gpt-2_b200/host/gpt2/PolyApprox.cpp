@@ -19,8 +19,7 @@ namespace gpt2
         void double_angle(Ciphertext &cipher, Evaluator &evaluator, RelinKeys &relin_keys)
         {
             evaluator.square_inplace(cipher);
-            evaluator.relinearize_inplace(cipher, relin_keys);
-            evaluator.rescale_to_next_inplace(cipher);
+            relinearize_then_rescale(evaluator, cipher, relin_keys);
             evaluator.add_inplace(cipher, cipher);
             evaluator.add_const_inplace(cipher, -1.0);
         }
@@ -174,8 +173,7 @@ namespace gpt2
         evaluator.add_inplace_reduced_error(output, quotient);
 
         evaluator.square(input, quotient);
-        evaluator.relinearize_inplace(quotient, relin_keys);
-        evaluator.rescale_to_next_inplace(quotient);
+        relinearize_then_rescale(evaluator, quotient, relin_keys);
         evaluator.multiply_const_inplace(quotient, qq_2);
         evaluator.rescale_to_next_inplace(quotient);
 
@@ -227,8 +225,7 @@ namespace gpt2
         for (int i = 0; i < r; i++)
         {
             evaluator.square_inplace(output);
-            evaluator.relinearize_inplace(output, relin_keys);
-            evaluator.rescale_to_next_inplace(output);
+            relinearize_then_rescale(evaluator, output, relin_keys);
         }
     }
 

@@ -1542,6 +1542,20 @@ namespace seal
             destination = encrypted;
             relinearize_inplace(destination, relin_keys);
         }
+        // engine extension: relinearize_inplace followed by rescale_to_next_inplace in one call
+        // (bk_relinearize_rescale_inplace).  In tolerance mode - hybrid key switching at a level with idle primes -
+        // the two divisions become one; otherwise it IS the two calls.  Counted as one relinearization + one rescale.
+        void relinearize_rescale_inplace(Ciphertext &encrypted, const RelinKeys &relin_keys) const
+        {
+            if (encrypted.size() > 2)
+            {
+                stats_.key_switch_relin++;
+                stats_.hit(0, encrypted.coeff_modulus_size());
+            }
+            stats_.rescale++;
+            stats_.hit(1, encrypted.coeff_modulus_size());
+            run1(encrypted, [&] { return bk_relinearize_rescale_inplace(h(), encrypted.handle(), relin_keys.handle()); });
+        }
 
         // ---- modulus switching / rescaling (evaluator.cpp:1118-1414)
         void mod_switch_to_next_inplace(Ciphertext &encrypted, MemoryPoolHandle = {}) const
@@ -1883,6 +1897,22 @@ namespace seal
             }
             reduced_error(encrypted1, encrypted2, 2);
             relinearize_inplace(encrypted1, relin_keys);
+        }
+        // engine extension: multiply_reduced_error without its relinearization - a size-3 product.  Relinearization
+        // is linear, so whatever is added to the product before its rescale (scalar_linear_combination takes terms
+        // of size 2 and 3) can be added first and the sum relinearized and rescaled once
+        // (relinearize_rescale_inplace).
+        void multiply_reduced_error_unrelinearized(
+            const Ciphertext &encrypted1, const Ciphertext &encrypted2, Ciphertext &destination) const
+        {
+            if (&encrypted2 == &destination)
+                multiply_size3(destination, encrypted1);
+            else
+            {
+                if (&encrypted1 != &destination)
+                    destination = encrypted1;
+                multiply_size3(destination, encrypted2);
+            }
         }
         inline void multiply_reduced_error(
             const Ciphertext &encrypted1, const Ciphertext &encrypted2, const RelinKeys &relin_keys,
@@ -2250,6 +2280,16 @@ namespace seal
                 sub_inplace(a, b);
             else
                 multiply_inplace(a, b);
+        }
+        void multiply_size3(Ciphertext &encrypted1, const Ciphertext &encrypted2) const
+        {
+            if (encrypted1.coeff_modulus_size() == encrypted2.coeff_modulus_size())
+            {
+                encrypted1.scale() = encrypted2.scale();
+                multiply_inplace(encrypted1, encrypted2);
+            }
+            else
+                reduced_error(encrypted1, encrypted2, 2);
         }
         // the three near-identical bodies of evaluator.cpp:312-486; op: 0 add, 1 sub, 2 multiply
         void reduced_error(Ciphertext &encrypted1, const Ciphertext &encrypted2, int op) const

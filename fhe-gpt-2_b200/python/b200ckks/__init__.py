@@ -466,6 +466,11 @@ class Context:
     def relinearize_inplace(self, a, rk):
         _ck(_L.bk_relinearize_inplace(self.h, a.h, rk.h))
 
+    def relinearize_rescale_inplace(self, a, rk):
+        """relinearize_inplace + rescale_to_next_inplace as one call; one division by q_last * P_S in hybrid mode at a
+        level with idle primes (bk_relinearize_rescale_inplace), exactly the two calls elsewhere"""
+        _ck(_L.bk_relinearize_rescale_inplace(self.h, a.h, rk.h))
+
     def rescale_to_next_inplace(self, a):
         _ck(_L.bk_rescale_to_next_inplace(self.h, a.h))
 

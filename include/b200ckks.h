@@ -207,6 +207,11 @@ bk_status bk_multiply_inplace(bk_context_t ctx, bk_ct_t a, bk_ct_t b);         /
 bk_status bk_square_inplace(bk_context_t ctx, bk_ct_t a);                      /* ckks_square :1000-1059 */
 bk_status bk_relinearize_inplace(bk_context_t ctx, bk_ct_t a, bk_kskey_t relin_key); /* :1061-1116 + :2281-2525 */
 bk_status bk_rescale_to_next_inplace(bk_context_t ctx, bk_ct_t a);             /* :1118-1181,1378-1414; rns.cpp:737-808 */
+/* relinearize_inplace then rescale_to_next_inplace as one call (the pair every ciphertext product of the
+ * reference's polynomial evaluations ends with: common/Polynomial.cpp:242-252, comp/SEALfunc.cpp:18-24,
+ * ckks_bootstrapping/ModularReducer.cpp:43-46).  In tolerance mode (hybrid key switching, a level with idle primes)
+ * the ModDown by P_S and the division by q_last are one division by q_last * P_S; otherwise exactly the two calls. */
+bk_status bk_relinearize_rescale_inplace(bk_context_t ctx, bk_ct_t a, bk_kskey_t relin_key);
 bk_status bk_mod_switch_to_next_inplace(bk_context_t ctx, bk_ct_t a);          /* :1183-1246 */
 bk_status bk_mod_switch_to_inplace(bk_context_t ctx, bk_ct_t a, int limbs);    /* :1326-1348 */
 bk_status bk_apply_galois_inplace(bk_context_t ctx, bk_ct_t a, uint32_t galois_elt, bk_gkeys_t gk);

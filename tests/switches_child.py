@@ -63,6 +63,8 @@ else:
     relu_stats = sess.stats(reset=True)
     out = {"boot": sess.decrypt(boot).real.tolist()[:512], "boot_in": xb[:512].tolist(), "boot_limbs": boot.info()[1],
            "boot_rescales": boot_stats["rescale"], "relu": sess.decrypt(relu).real.tolist()[:1024], "relu_in": xr[:1024].tolist(),
-           "relu_limbs": relu.info()[1], "relu_rescales": relu_stats["rescale"]}
+           "relu_limbs": relu.info()[1], "relu_rescales": relu_stats["rescale"],
+           "boot_relins": boot_stats["key_switch_relin"], "relu_relins": relu_stats["key_switch_relin"],
+           "boot_scale": boot.info()[2], "relu_scale": relu.info()[2]}
     print(json.dumps(out))
     sess.close()

@@ -48,6 +48,22 @@ def run_levels(bk, log_n, bits, levels):
             eng.relinearize_inplace(m, rk)
             eng.rescale_to_next_inplace(m)
             worst.setdefault("relinearize", []).append(np.abs(dec(m) - x * x).max())
+            # the same pair as one call: ModDown and rescale merged into one division by q_{l-1} P_S where the level
+            # has idle primes (elsewhere the two calls) - same level, same scale, same value
+            m2 = c.copy()
+            eng.multiply_inplace(m2, c)
+            eng.relinearize_rescale_inplace(m2, rk)
+            assert m2.info()[:2] == m.info()[:2] and abs(m2.info()[2] / m.info()[2] - 1) < 1e-12, (l, m2.info(), m.info())
+            worst.setdefault("relinearize+rescale merged", []).append(np.abs(dec(m2) - x * x).max())
+            worst.setdefault("merged vs two calls", []).append(np.abs(dec(m2) - dec(m)).max())
+            # linear follow-ups move in front of the relinearization: 2 x^2 - x on the size-3 product
+            p3 = c.copy()
+            eng.multiply_inplace(p3, c)
+            lc = eng.scalar_linear_combination([p3, c], [2.0, -1.0], 0.25, p3.info()[2])
+            assert lc.info()[0] == 3
+            eng.relinearize_rescale_inplace(lc, rk)
+            assert lc.info()[:2] == m.info()[:2]
+            worst.setdefault("size-3 combination", []).append(np.abs(dec(lc) - (2 * x * x - x + 0.25)).max())
     on, nbytes, keys = eng.hybrid_info()
     assert on and keys >= len(levels) and nbytes > 0
     eng.close()

@@ -5,7 +5,9 @@
 * seed-compressed level keys ($B200CKKS_COMPRESS_KEYS): identical limbs at half the resident key bytes;
 * one-pass leaves of the polynomial evaluation trees ($B200CKKS_TERMWISE_LEAVES restores the reference's
   multiply_const + rescale + reduced-error add per term): same output level, same values within the bootstrapping /
-  ReLU tolerance, and the rescale count the fusion exists to cut."""
+  ReLU tolerance, and the rescale count the fusion exists to cut;
+* relinearization and rescale as one division ($B200CKKS_MERGED_RESCALE=0 keeps the two calls and the reference's
+  order of additions): same levels and scales out, same values, three relinearizations fewer per ReLU."""
 import json
 import os
 import subprocess
@@ -21,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def child(args, **env):
     e = dict(os.environ, B200CKKS_SEED="11")
     for k in ("B200CKKS_NO_PDL", "B200CKKS_TERMWISE_LEAVES", "B200CKKS_HYBRID_KS", "B200CKKS_ENCRYPT_CONSTANTS",
-              "B200CKKS_COMPRESS_KEYS"):
+              "B200CKKS_COMPRESS_KEYS", "B200CKKS_MERGED_RESCALE"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, os.path.join(HERE, "switches_child.py"), *args], env=e, capture_output=True, text=True,
@@ -65,3 +67,28 @@ def test_one_pass_tree_leaves_match_the_termwise_sequence():
     want = np.maximum(xr, 0)
     er_f, er_t = np.abs(np.array(fused["relu"]) - want).max(), np.abs(np.array(term["relu"]) - want).max()
     assert er_f < 2.0 ** -13 and er_t < 2.0 ** -13, (er_f, er_t)  # the minimax ReLU's bound (alpha = 13)
+
+
+@pytest.mark.parametrize("hybrid", ["1", "0"])
+def test_merged_relinearize_and_rescale_match_the_two_calls(hybrid):
+    """Evaluator::relinearize_rescale_inplace (bk_relinearize_rescale_inplace: ModDown by P_S and division by q_last as
+    one rounding division in hybrid mode, the two calls otherwise) with the additions of a product moved in front of
+    its relinearization, against relinearize_inplace + rescale_to_next_inplace in the reference's order."""
+    merged = child(["leaves"], B200CKKS_HYBRID_KS=hybrid)
+    two = child(["leaves"], B200CKKS_HYBRID_KS=hybrid, B200CKKS_MERGED_RESCALE="0")
+    for k in ("boot_limbs", "relu_limbs", "boot_rescales", "relu_rescales"):
+        assert merged[k] == two[k], k
+    assert abs(merged["boot_scale"] / two["boot_scale"] - 1) < 1e-9 and abs(merged["relu_scale"] / two["relu_scale"] - 1) < 1e-9
+    # a chain of products T_g1 q_1 + T_g2 q_2 + r is relinearized once: 27 -> 24 per ReLU (one chain in each of the three
+    # polynomials); EvalMod has no such chain
+    assert (two["relu_relins"], merged["relu_relins"]) == (27, 24)
+    assert two["boot_relins"] == merged["boot_relins"] == 18
+    x = np.array(merged["boot_in"])
+    eb_m, eb_t = np.abs(np.array(merged["boot"]) - x).max(), np.abs(np.array(two["boot"]) - x).max()
+    assert eb_m < 1e-4 and eb_t < 1e-4, (eb_m, eb_t)
+    assert eb_m < 2 * eb_t + 1e-6, (eb_m, eb_t)                # no precision given up (same keys, same input)
+    xr = np.array(merged["relu_in"])
+    want = np.maximum(xr, 0)
+    er_m, er_t = np.abs(np.array(merged["relu"]) - want).max(), np.abs(np.array(two["relu"]) - want).max()
+    assert er_m < 2.0 ** -13 and er_t < 2.0 ** -13, (er_m, er_t)
+    assert np.abs(np.array(merged["relu"]) - np.array(two["relu"])).max() < 2.0 ** -13
