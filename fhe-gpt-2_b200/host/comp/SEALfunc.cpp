@@ -44,12 +44,16 @@ namespace seal
     {
         Ciphertext twice;
 #ifdef B200CKKS_FACADE
-        if (merged_rescale() && Tmminusn.size() != 0 &&
-            Tmminusn.coeff_modulus_size() >= std::min(Tm.coeff_modulus_size(), Tn.coeff_modulus_size()))
+        if (merged_rescale() && (Tmminusn.size() == 0 ||
+                                 Tmminusn.coeff_modulus_size() >= std::min(Tm.coeff_modulus_size(), Tn.coeff_modulus_size())))
         {
-            // 2 Tm Tn - T(m-n) on the unrelinearized product, then one relinearization and rescale (func.h)
+            // 2 Tm Tn - T(m-n) on the unrelinearized product, then one relinearization and rescale (func.h); T0 = 1 is
+            // the constant it is (geneT0T1) and joins at the product's scale
             evaluator.multiply_reduced_error_unrelinearized(Tm, Tn, twice);
-            evaluator.scalar_linear_combination({ &twice, &Tmminusn }, { 2.0, -1.0 }, 0.0, twice.scale(), Tmplusn);
+            if (Tmminusn.size() == 0)
+                evaluator.scalar_linear_combination({ &twice }, { 2.0 }, -1.0, twice.scale(), Tmplusn);
+            else
+                evaluator.scalar_linear_combination({ &twice, &Tmminusn }, { 2.0, -1.0 }, 0.0, twice.scale(), Tmplusn);
             evaluator.relinearize_rescale_inplace(Tmplusn, relin_keys);
             return;
         }
