@@ -800,7 +800,7 @@ namespace bk
                 dropped.push_back(eprime(l + a));
             rounding_tables(dropped, l, P->d_shalf, P->d_spinv, P->d_negd, P->d_addc);
         }
-        if (alpha > 1 && alpha + 1 <= 17 && l >= 2)
+        if (alpha + 1 <= 17 && l >= 2)
         {
             // dropped basis of the merged ModDown + rescale: D_0 = q_{l-1}, D_{1+a} = special modulus a
             const int da = alpha + 1, lo = l - 1;
@@ -1033,7 +1033,7 @@ namespace bk
         hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, target, 1, &perm, &hk, acc.p, 0);
         if (rescale)
         {
-            if (perm || !base0 || !base1 || !P.rescale_tables)
+            if (perm || !base0 || !P.rescale_tables)
                 throw std::logic_error("merged ModDown and rescale: relinearization at a hybrid level only");
             hyb_mod_down_rescale(c, s, P, h, acc.p, conv.p, inter.p, tl.p, out, base0, base1);
         }
@@ -2506,7 +2506,7 @@ extern "C"
     //   (bk_encode_ext at the ciphertext's level) or NULL where the group has no such term.  outs[g]: the giant step's
     //   ciphertext at the input's level, scale = ct scale * plaintext scale.
     bk_status bk_bsgs_inner_sums(bk_context_t ctx, bk_ct_t in, const uint32_t *elts, int n_baby, bk_gkeys_t gk,
-                                 const bk_pt_t *pts, int n_giant, bk_ct_t *outs)
+                                 const bk_pt_t *pts, int n_giant, bk_ct_t *outs, int rescale)
     {
         BK_TRY
         Context &c = *ctx;
@@ -2570,11 +2570,18 @@ extern "C"
         const u64 *c0 = in->d, *c1 = in->d + (size_t)l * n;
         const int count = (int)perms.size();
         Scratch y(s, (size_t)l * n);
-        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha }) * n);
+        Scratch inter(s, (size_t)std::max({ hyb_chunk(P) * P.dnum, 2 * l, 2 * P.alpha + 2 }) * n);
         Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
         Scratch acc(s, (size_t)std::max(count, 1) * 2 * ne * n);
-        Scratch tl(s, (size_t)2 * P.alpha * n);
+        Scratch tl(s, (size_t)(2 * P.alpha + 2) * n);
         Scratch sum(s, (size_t)2 * ne * n);
+        // rescale != 0: every inner sum leaves divided by q_{l-1} as well (l - 1 limbs) - the rescale that follows the
+        // transform moves in front of the giant-step rotations, which then run one level lower, and is one division
+        // with the ModDown (hyb_mod_down_rescale)
+        if (rescale && l < 2)
+            throw std::invalid_argument("end of modulus switching chain reached");
+        const bool merged = rescale && P.rescale_tables;
+        const int lo = rescale ? l - 1 : l;
         Scratch base0(s, (size_t)l * n), base1(s, (size_t)l * n);
         if (count > 0)
         {
@@ -2587,7 +2594,7 @@ extern "C"
         for (int g = 0; g < n_giant; g++)
         {
             const bk_pt_t *row = pts + (size_t)g * n_baby;
-            ensure_ct(outs[g], 2, l, false);
+            ensure_ct(outs[g], 2, merged ? lo : l, false);
             // (1) the key-switched halves, summed in the extended basis
             int ext_terms = 0;
             for (int k0 = 0; k0 < n_baby;)
@@ -2654,15 +2661,30 @@ extern "C"
                 launch_pdl(k_mul_plain_sum<false>, c.ew_grid((size_t)l * n / 2), 256, 0, s, base1.p, a, c.d_primes, c.log_n, l, 1, -1, 0);
                 c.count();
             }
-            if (ext_terms)
-                hyb_mod_down(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr, nullptr);
+            bool divided = false;
+            if (ext_terms && merged)
+            {
+                hyb_mod_down_rescale(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr);
+                divided = true;
+            }
             else
-            { // only the unrotated term: (c0 pt, c1 pt)
-                BK_CUDA(cudaMemcpyAsync(outs[g]->d, base0.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
-                BK_CUDA(cudaMemcpyAsync(outs[g]->d + (size_t)l * n, base1.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+            {
+                if (merged)
+                    ensure_ct(outs[g], 2, l, false);
+                if (ext_terms)
+                    hyb_mod_down(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr, nullptr);
+                else
+                { // only the unrotated term: (c0 pt, c1 pt)
+                    BK_CUDA(cudaMemcpyAsync(outs[g]->d, base0.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+                    BK_CUDA(cudaMemcpyAsync(outs[g]->d + (size_t)l * n, base1.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));
+                }
             }
             outs[g]->scale = new_scale;
             outs[g]->ntt = true;
+            if (divided)
+                outs[g]->scale = new_scale / (double)c.primes[(size_t)lo];
+            else if (rescale)
+                rescale_core(c, outs[g]);
         }
         BK_END
     }

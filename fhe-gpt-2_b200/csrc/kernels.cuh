@@ -537,7 +537,7 @@ struct LdInvDropped
     static constexpr bool TLAYOUT = false;
     const u64 *acc;   // [2][ne][N]
     const u64 *base0; // [l][N]
-    const u64 *base1; // [l][N]
+    const u64 *base1; // [l][N] or null
     size_t n;
     HybDims h;
     ulonglong2 pmod; // {P_S mod q_{l-1}, shoup}
@@ -552,7 +552,10 @@ struct LdInvDropped
         if (a != 0)
             return acc[((size_t)p * h.ne() + h.l + a - 1) * n + idx];
         const u64 x = acc[((size_t)p * h.ne() + h.l - 1) * n + idx];
-        const u64 b = (p == 0 ? base0 : base1)[(size_t)(h.l - 1) * n + idx];
+        const u64 *bp = p == 0 ? base0 : base1;
+        if (!bp)
+            return x;
+        const u64 b = bp[(size_t)(h.l - 1) * n + idx];
         return addmod(x, csub(mul_shoup_lazy(b, pmod.x, pmod.y, pd.q), pd.q), pd.q);
     }
     __device__ __forceinline__ u64 load_t(int, int, int) const { return 0; }

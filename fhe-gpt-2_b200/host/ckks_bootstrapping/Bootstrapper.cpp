@@ -405,9 +405,14 @@ int Bootstrapper::bsgs_width(int M, int limbs) const
 #endif
 }
 
+// rescale: the result is rescaled to the next level (the call every transform of the reference is followed by,
+// Bootstrapper.cpp:2399-2468).  With double-hoisted inner sums and $B200CKKS_EARLY_RESCALE (common/func.h:
+// early_rescale, off by default: it costs precision) the rescale moves in front of the giant-step rotations - it
+// commutes with them and with the sum - where it is part of each inner sum's division by the special modulus; the
+// giant steps then run one level lower.
 void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
                                          int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
-                                         std::uint64_t cache_variant)
+                                         std::uint64_t cache_variant, bool rescale)
 {
     const SignedPlan p(totlen, bsgs_width(2 * totlen + 1, (int)cipher.coeff_modulus_size()));
     const int N = (int)Nh;
@@ -441,7 +446,7 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
                                                      rotation(coeff_logn, N, -giant_of[g] * p.gs * basicstep, fftcoeff[(std::size_t)diag], rot);
                                                      return rot;
                                                  },
-                                                 giants))
+                                                 giants, rescale && early_rescale()))
             {
                 Ciphertext total, product;
                 bool total_started = false;
@@ -457,6 +462,8 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
                         accumulate(evaluator, total, total_started, giants[g]);
                 }
                 rtncipher = total;
+                if (rescale && !early_rescale())
+                    evaluator.rescale_to_next_inplace(rtncipher);
                 return;
             }
         }
@@ -500,11 +507,13 @@ void Bootstrapper::bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &ciph
             accumulate(evaluator, total, total_started, giantct);
     }
     rtncipher = total;
+    if (rescale)
+        evaluator.rescale_to_next_inplace(rtncipher);
 }
 
 void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Ciphertext &cipher, int totlen, int basicstep,
                                                  int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner,
-                                                 std::uint64_t cache_variant)
+                                                 std::uint64_t cache_variant, bool rescale)
 {
     const int gs = bsgs_width(totlen + 1, (int)cipher.coeff_modulus_size());
     const int giantlast = totlen / gs;
@@ -536,7 +545,7 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
                                                      rotation(coeff_logn, N, -(int)g * gs * basicstep, fftcoeff[(std::size_t)diag], rot);
                                                      return rot;
                                                  },
-                                                 giants))
+                                                 giants, rescale && early_rescale()))
             {
                 Ciphertext total, product;
                 bool total_started = false;
@@ -551,6 +560,8 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
                         accumulate(evaluator, total, total_started, giants[g]);
                 }
                 rtncipher = total;
+                if (rescale && !early_rescale())
+                    evaluator.rescale_to_next_inplace(rtncipher);
                 return;
             }
         }
@@ -593,6 +604,8 @@ void Bootstrapper::rotated_bsgs_linear_transform(Ciphertext &rtncipher, Cipherte
             accumulate(evaluator, total, total_started, giantct);
     }
     rtncipher = total;
+    if (rescale)
+        evaluator.rescale_to_next_inplace(rtncipher);
 }
 
 // SlotToCoeff: three transforms; the last one also carries the scale correction that makes the output scale
@@ -605,10 +618,8 @@ void Bootstrapper::sfl_common(Ciphertext &rtncipher, Ciphertext &cipher, bool fu
     const std::size_t u = (std::size_t)slot_index;
 
     Ciphertext tmpct, tmpct2;
-    bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], coeff_logn, fftcoeff1[u], &fftcoeff1[u]);
-    evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], coeff_logn, fftcoeff2[u], &fftcoeff2[u]);
-    evaluator.rescale_to_next_inplace(tmpct2);
+    bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], coeff_logn, fftcoeff1[u], &fftcoeff1[u], 0, true);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], coeff_logn, fftcoeff2[u], &fftcoeff2[u], 0, true);
 
     const auto &modulus = util::iter(context.first_context_data()->parms().coeff_modulus());
     auto curr_level = context.get_context_data(tmpct2.parms_id())->chain_index();
@@ -630,10 +641,9 @@ void Bootstrapper::sfl_common(Ciphertext &rtncipher, Ciphertext &cipher, bool fu
     }
 
     if (full)
-        rotated_bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant);
+        rotated_bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant, true);
     else
-        bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant);
-    evaluator.rescale_to_next_inplace(rtncipher);
+        bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], coeff_logn, scaled, &fftcoeff3[u], variant, true);
 }
 
 void Bootstrapper::sfl_3(Ciphertext &rtncipher, Ciphertext &cipher)
@@ -658,12 +668,9 @@ void Bootstrapper::sflinv_3(Ciphertext &rtncipher, Ciphertext &cipher)
     const Split s = split_encode(logn);
     const std::size_t u = (std::size_t)slot_index;
     Ciphertext tmpct, tmpct2;
-    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u]);
-    evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u]);
-    evaluator.rescale_to_next_inplace(tmpct2);
-    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn + 1, invfftcoeff3[u], &invfftcoeff3[u]);
-    evaluator.rescale_to_next_inplace(rtncipher);
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u], 0, true);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u], 0, true);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn + 1, invfftcoeff3[u], &invfftcoeff3[u], 0, true);
 }
 
 void Bootstrapper::sflinv_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
@@ -671,12 +678,9 @@ void Bootstrapper::sflinv_full_3(Ciphertext &rtncipher, Ciphertext &cipher)
     const Split s = split_encode(logn);
     const std::size_t u = (std::size_t)slot_index;
     Ciphertext tmpct, tmpct2;
-    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u]);
-    evaluator.rescale_to_next_inplace(tmpct);
-    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u]);
-    evaluator.rescale_to_next_inplace(tmpct2);
-    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn, invfftcoeff3[u], &invfftcoeff3[u]);
-    evaluator.rescale_to_next_inplace(rtncipher);
+    rotated_bsgs_linear_transform(tmpct, cipher, s.totlen[0], s.basicstep[0], (int)logn, invfftcoeff1[u], &invfftcoeff1[u], 0, true);
+    bsgs_linear_transform(tmpct2, tmpct, s.totlen[1], s.basicstep[1], (int)logn, invfftcoeff2[u], &invfftcoeff2[u], 0, true);
+    bsgs_linear_transform(rtncipher, tmpct2, s.totlen[2], s.basicstep[2], (int)logn, invfftcoeff3[u], &invfftcoeff3[u], 0, true);
 }
 
 // ------------------------------------------------------------------------------------ CoeffToSlot / SlotToCoeff

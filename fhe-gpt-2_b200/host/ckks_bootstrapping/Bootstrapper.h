@@ -89,10 +89,10 @@ public:
     // address of a Diagonals object that outlives the call, and a variant if its values were rescaled
     void bsgs_linear_transform(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher, int totlen, int basicstep,
                                int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner = nullptr,
-                               std::uint64_t cache_variant = 0);
+                               std::uint64_t cache_variant = 0, bool rescale = false);
     void rotated_bsgs_linear_transform(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher, int totlen, int basicstep,
                                        int coeff_logn, const Diagonals &fftcoeff, const void *cache_owner = nullptr,
-                                       std::uint64_t cache_variant = 0);
+                                       std::uint64_t cache_variant = 0, bool rescale = false);
 
     void sfl_3(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher);
     void sfl_full_3(seal::Ciphertext &rtncipher, seal::Ciphertext &cipher);

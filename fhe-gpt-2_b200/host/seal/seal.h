@@ -2128,8 +2128,11 @@ namespace seal
         bool bsgs_inner_sums_cached(
             const Ciphertext &encrypted, const std::vector<int> &baby_steps, const GaloisKeys &galois_keys,
             const std::vector<std::vector<std::pair<int, std::uint64_t>>> &groups, const void *owner, std::uint64_t variant,
-            MakeAt &&make_at, std::vector<Ciphertext> &giants)
+            MakeAt &&make_at, std::vector<Ciphertext> &giants, bool rescale = false)
         {
+            // rescale: giants[g] = rescale_to_next(that sum) - the one rescale after the transform, taken per inner sum
+            // as part of its division by the special modulus; the caller's giant-step rotations and final sum then run
+            // one level lower and no rescale follows (counted as the one rescale it replaces)
             int hybrid = 0;
             bk_context_hybrid(h(), &hybrid, nullptr, nullptr);
             if (!hybrid || !galois_keys.handle() || groups.empty() || baby_steps.empty())
@@ -2179,7 +2182,12 @@ namespace seal
             {
                 std::shared_lock<std::shared_mutex> rl(galois_keys.st_->mu);
                 detail::check(bk_bsgs_inner_sums(h(), encrypted.handle(), elts.data(), (int)nb, galois_keys.handle(), pts.data(),
-                                                 (int)ng, outs.data()));
+                                                 (int)ng, outs.data(), rescale ? 1 : 0));
+            }
+            if (rescale)
+            {
+                stats_.rescale++;
+                stats_.hit(1, (std::size_t)limbs);
             }
             for (auto &c : giants)
                 c.pull();

@@ -234,9 +234,11 @@ bk_status bk_apply_galois_hoisted(bk_context_t ctx, bk_ct_t in, const uint32_t *
  * bk_encode_ext) are multiplied there, and the division by P_S is done once per giant step instead of once per baby
  * rotation.  elts[k] = 1 means "no rotation"; NULL plaintexts are skipped.  Level-aware hybrid mode only
  * (BK_LOGIC_ERROR otherwise); tolerance mode: decrypted values equal the rotation-by-rotation sequence up to
- * key-switching noise. */
+ * key-switching noise.  rescale != 0: outs[g] is rescale_to_next of that sum - the rescale the reference applies after
+ * the whole transform (Bootstrapper.cpp:2018-2086 callers) commutes with the giant-step rotations and the final sum,
+ * so it is taken here as one division by q_last * P_S with the ModDown, and the giant steps run one level lower. */
 bk_status bk_bsgs_inner_sums(bk_context_t ctx, bk_ct_t in, const uint32_t *elts, int n_baby, bk_gkeys_t gk,
-                             const bk_pt_t *pts, int n_giant, bk_ct_t *outs);
+                             const bk_pt_t *pts, int n_giant, bk_ct_t *outs, int rescale);
 /* CKKSEncoder::encode at `limbs` limbs plus the special moduli the level-aware key switch uses at that level (the
  * operand format of bk_bsgs_inner_sums); usable as an ordinary plaintext of that level as well. */
 bk_status bk_encode_ext(bk_context_t ctx, const double *values, int n_values, int is_complex, int limbs, double scale,

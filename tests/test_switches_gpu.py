@@ -23,7 +23,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 def child(args, **env):
     e = dict(os.environ, B200CKKS_SEED="11")
     for k in ("B200CKKS_NO_PDL", "B200CKKS_TERMWISE_LEAVES", "B200CKKS_HYBRID_KS", "B200CKKS_ENCRYPT_CONSTANTS",
-              "B200CKKS_COMPRESS_KEYS", "B200CKKS_MERGED_RESCALE"):
+              "B200CKKS_COMPRESS_KEYS", "B200CKKS_MERGED_RESCALE", "B200CKKS_EARLY_RESCALE"):
         e.pop(k, None)
     e.update(env)
     r = subprocess.run([sys.executable, os.path.join(HERE, "switches_child.py"), *args], env=e, capture_output=True, text=True,
@@ -92,3 +92,16 @@ def test_merged_relinearize_and_rescale_match_the_two_calls(hybrid):
     er_m, er_t = np.abs(np.array(merged["relu"]) - want).max(), np.abs(np.array(two["relu"]) - want).max()
     assert er_m < 2.0 ** -13 and er_t < 2.0 ** -13, (er_m, er_t)
     assert np.abs(np.array(merged["relu"]) - np.array(two["relu"])).max() < 2.0 ** -13
+
+
+def test_early_rescale_of_double_hoisted_transforms():
+    """$B200CKKS_EARLY_RESCALE=1 (opt-in, common/func.h): the rescale after a linear transform is taken per inner sum,
+    merged with its division by the special modulus (bk_bsgs_inner_sums, rescale = 1), and the giant-step rotations run
+    one level lower.  Same level, scale and rescale count out; values within the bootstrapping tolerance."""
+    early = child(["leaves"], B200CKKS_HYBRID_KS="1", B200CKKS_EARLY_RESCALE="1")
+    late = child(["leaves"], B200CKKS_HYBRID_KS="1")
+    assert early["boot_limbs"] == late["boot_limbs"] and early["boot_rescales"] == late["boot_rescales"]
+    assert abs(early["boot_scale"] / late["boot_scale"] - 1) < 1e-9
+    x = np.array(early["boot_in"])
+    e_early, e_late = np.abs(np.array(early["boot"]) - x).max(), np.abs(np.array(late["boot"]) - x).max()
+    assert e_early < 1e-4 and e_late < 1e-4, (e_early, e_late)
