@@ -380,10 +380,14 @@ int Bootstrapper::bsgs_width(int M, int limbs) const
         const char *e = std::getenv("B200CKKS_BSGS_MAX_BABY");
         return e ? std::max(2, std::atoi(e)) : 32;
     }();
+    static const double baby_cost = [] {
+        const char *e = std::getenv("B200CKKS_BSGS_BABY_COST"); // per key limb-polynomial, in forward-NTT equivalents
+        return e ? std::atof(e) : 0.2;
+    }();
     int alpha = 1, dsize = 1;
     bk_context_hybrid_shape(context.handle(), limbs, &alpha, &dsize);
     const double dnum = (limbs + dsize - 1) / dsize, ne = limbs + alpha;
-    const double b = 0.2 * 2 * dnum * ne;
+    const double b = baby_cost * 2 * dnum * ne;
     const double m = 2.0 * alpha + 2.0 * alpha * limbs / 8.0 + 2.0 * limbs;
     const double g = dnum * ne + dnum * dsize * limbs / 8.0 + m + b;
     double best = 1e300;
