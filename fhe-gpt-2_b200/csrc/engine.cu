@@ -2574,7 +2574,6 @@ extern "C"
         Scratch conv(s, (size_t)std::max(hyb_chunk(P) * P.dnum, 2 * l) * n);
         Scratch acc(s, (size_t)std::max(count, 1) * 2 * ne * n);
         Scratch tl(s, (size_t)(2 * P.alpha + 2) * n);
-        Scratch sum(s, (size_t)2 * ne * n);
         // rescale != 0: every inner sum leaves divided by q_{l-1} as well (l - 1 limbs) - the rescale that follows the
         // transform moves in front of the giant-step rotations, which then run one level lower, and is one division
         // with the ModDown (hyb_mod_down_rescale)
@@ -2591,36 +2590,70 @@ extern "C"
             launch_inv_cols(c, s, inter.p, st, l);
             hyb_extend_and_mac(c, s, P, h, y.p, conv.p, inter.p, c1, count, perms.data(), hks.data(), acc.p, 1);
         }
+        // (1) the key-switched halves, summed in the extended basis: all giant steps multiply the same rotated
+        //     ciphertexts, so up to MUL_SUM_GROUPS of them share one pass over those (k_mul_plain_sum_multi)
+        const size_t sum_words = (size_t)2 * ne * n;
+        Scratch sums(s, (size_t)n_giant * sum_words);
+        std::vector<int> ext_terms_of((size_t)n_giant, 0);
+        for (int g0 = 0; g0 < n_giant; g0 += MUL_SUM_GROUPS)
+        {
+            const int ng = std::min(MUL_SUM_GROUPS, n_giant - g0);
+            bool first = true;
+            for (int k0 = 0; k0 < n_baby;)
+            {
+                MulSumMultiArgs a{};
+                a.count = 0;
+                int k = k0, ops = 0;
+                for (; k < n_baby && a.count < MUL_SUM_TERMS; k++)
+                {
+                    if (rot_of[(size_t)k] < 0)
+                        continue;
+                    bool used = false;
+                    for (int g = 0; g < ng; g++)
+                        if (pts[(size_t)(g0 + g) * n_baby + k])
+                        {
+                            a.pt[g][a.count] = pts[(size_t)(g0 + g) * n_baby + k]->d;
+                            ext_terms_of[(size_t)(g0 + g)]++;
+                            used = true;
+                            ops++;
+                        }
+                    if (used)
+                    {
+                        a.ct[a.count] = acc.p + (size_t)rot_of[(size_t)k] * 2 * ne * n;
+                        a.count++;
+                    }
+                }
+                k0 = k;
+                if (!a.count)
+                    continue;
+                const size_t total2 = sum_words / 2;
+                u64 *dst = sums.p + (size_t)g0 * sum_words;
+                ProfScope ps_ew(c, s, TAG_ELEMENTWISE, 2 * ne * ops);
+#define BK_MULTI(ACC, GG)                                                                                                  \
+    launch_pdl(k_mul_plain_sum_multi<ACC, GG>, c.ew_grid(total2), 256, 0, s, dst, sum_words, a, c.d_primes, c.log_n, ne, 2, ne - 1,  \
+               c.n_primes - 1)
+                switch (ng * 2 + (first ? 0 : 1))
+                {
+                case 2: BK_MULTI(false, 1); break;
+                case 3: BK_MULTI(true, 1); break;
+                case 4: BK_MULTI(false, 2); break;
+                case 5: BK_MULTI(true, 2); break;
+                case 6: BK_MULTI(false, 3); break;
+                case 7: BK_MULTI(true, 3); break;
+                case 8: BK_MULTI(false, 4); break;
+                default: BK_MULTI(true, 4); break;
+                }
+#undef BK_MULTI
+                c.count();
+                first = false;
+            }
+        }
         for (int g = 0; g < n_giant; g++)
         {
             const bk_pt_t *row = pts + (size_t)g * n_baby;
             ensure_ct(outs[g], 2, merged ? lo : l, false);
-            // (1) the key-switched halves, summed in the extended basis
-            int ext_terms = 0;
-            for (int k0 = 0; k0 < n_baby;)
-            {
-                MulSumArgs a{};
-                a.count = 0;
-                int k = k0;
-                for (; k < n_baby && a.count < MUL_SUM_TERMS; k++)
-                    if (row[k] && rot_of[(size_t)k] >= 0)
-                    {
-                        a.ct[a.count] = acc.p + (size_t)rot_of[(size_t)k] * 2 * ne * n;
-                        a.pt[a.count] = row[k]->d;
-                        a.count++;
-                    }
-                k0 = k;
-                if (!a.count)
-                    continue;
-                const size_t total2 = (size_t)2 * ne * n / 2;
-                ProfScope ps_ew(c, s, TAG_ELEMENTWISE, 2 * ne * a.count);
-                if (ext_terms == 0)
-                    launch_pdl(k_mul_plain_sum<false>, c.ew_grid(total2), 256, 0, s, sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
-                else
-                    launch_pdl(k_mul_plain_sum<true>, c.ew_grid(total2), 256, 0, s, sum.p, a, c.d_primes, c.log_n, ne, 2, ne - 1, c.n_primes - 1);
-                c.count();
-                ext_terms += a.count;
-            }
+            const int ext_terms = ext_terms_of[(size_t)g];
+            u64 *const sum_g = sums.p + (size_t)g * sum_words;
             // (2) the c0 halves: permutations of the input's c0 (and c1 for the unrotated term), in the ordinary basis
             int plain_terms = 0;
             const bk_pt_s *identity = nullptr;
@@ -2664,7 +2697,7 @@ extern "C"
             bool divided = false;
             if (ext_terms && merged)
             {
-                hyb_mod_down_rescale(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr);
+                hyb_mod_down_rescale(c, s, P, h, sum_g, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr);
                 divided = true;
             }
             else
@@ -2672,7 +2705,7 @@ extern "C"
                 if (merged)
                     ensure_ct(outs[g], 2, l, false);
                 if (ext_terms)
-                    hyb_mod_down(c, s, P, h, sum.p, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr, nullptr);
+                    hyb_mod_down(c, s, P, h, sum_g, conv.p, inter.p, tl.p, outs[g]->d, base0.p, identity ? base1.p : nullptr, nullptr);
                 else
                 { // only the unrotated term: (c0 pt, c1 pt)
                     BK_CUDA(cudaMemcpyAsync(outs[g]->d, base0.p, (size_t)l * n * sizeof(u64), cudaMemcpyDeviceToDevice, s));

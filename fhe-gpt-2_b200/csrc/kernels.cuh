@@ -1074,6 +1074,70 @@ __global__ void __launch_bounds__(256) k_mul_plain_sum(u64 *__restrict__ dst, Mu
     }
 }
 
+// The same for up to MUL_SUM_GROUPS sums over the SAME ciphertext operands with different plaintexts - the giant steps
+// of a double-hoisted BSGS transform, which all multiply the same rotated (extended-basis) ciphertexts: every
+// ciphertext word is read once for the whole group instead of once per giant step (k babies, G giants: (2 + G) k + 2 G
+// limb-polynomials per extended limb instead of G (3 k + 2)).  dst of sum g at dst + g * dst_stride; a null plaintext
+// means "no such term in that sum".
+constexpr int MUL_SUM_GROUPS = 4;
+struct MulSumMultiArgs
+{
+    const u64 *ct[MUL_SUM_TERMS];
+    const u64 *pt[MUL_SUM_GROUPS][MUL_SUM_TERMS];
+    int count;
+};
+template <bool ACCUMULATE, int G>
+__global__ void __launch_bounds__(256) k_mul_plain_sum_multi(u64 *__restrict__ dst, size_t dst_stride, const __grid_constant__ MulSumMultiArgs a,
+                                                             const PrimeDev *primes, int log_n, int limbs, int polys, int special_pos,
+                                                             int special_prime)
+{
+    pdl_prologue();
+    const size_t n = size_t(1) << log_n;
+    const size_t per_poly = (size_t)limbs * n;
+    const size_t total = (size_t)polys * per_poly / 2;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    {
+        const size_t e = i * 2, ep = e % per_poly;
+        const int limb = (int)(ep >> log_n);
+        const PrimeDev pd = primes[limb == special_pos ? special_prime : limb];
+        u64 lx[G], hx[G], ly[G], hy[G];
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            lx[g] = hx[g] = ly[g] = hy[g] = 0;
+            if (ACCUMULATE)
+            {
+                ulonglong2 vc = *reinterpret_cast<const ulonglong2 *>(dst + (size_t)g * dst_stride + e);
+                lx[g] = vc.x;
+                ly[g] = vc.y;
+            }
+        }
+        for (int t = 0; t < a.count; t++)
+        {
+            const ulonglong2 va = __ldcs(reinterpret_cast<const ulonglong2 *>(a.ct[t] + e));
+#pragma unroll
+            for (int g = 0; g < G; g++)
+            {
+                const u64 *p = a.pt[g][t];
+                if (p)
+                {
+                    const ulonglong2 vp = *reinterpret_cast<const ulonglong2 *>(p + ep);
+                    mac128(lx[g], hx[g], va.x, vp.x);
+                    mac128(ly[g], hy[g], va.y, vp.y);
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < G; g++)
+        {
+            ulonglong2 r;
+            r.x = barrett128(lx[g], hx[g], pd);
+            r.y = barrett128(ly[g], hy[g], pd);
+            *reinterpret_cast<ulonglong2 *>(dst + (size_t)g * dst_stride + e) = r;
+        }
+    }
+}
+
 // dst[limbs][N] (+)= sum_t src[.][perm_t[x]] * pt_t[.][x]: the part of a double-hoisted BSGS inner sum that needs no key
 // switch (the c0 halves of the rotated ciphertexts are plain permutations of the input's c0).  perm_t == null: identity.
 constexpr int GATHER_SUM_TERMS = 16;
