@@ -54,6 +54,49 @@ def bconv(res, src, dst):
     return [[sum(y[i][j] * ((qs // src[i]) % t) for i in range(len(src))) % t for j in range(N)] for t in dst]
 
 
+def bconv_rounding(res, src, dst):
+    """The engine's exact, rounding form of the conversion (HybridPlan::d_shalf / d_spinv / d_negd / d_addc,
+    k_hyb_conv<DS, true>): for x given by its residues modulo the moduli `src` (product D) returns
+    [x + floor(D/2)]_D - floor(D/2) modulo each dst - so that (x - that) / D = round(x / D).  floor(D/2) joins the source
+    residues first; the multiple u D by which the fast conversion overshoots is found from the fractional parts
+    sum_a y_a / p_a in double precision, as the kernel does, and taken off again."""
+    D = prod(src)
+    half = D // 2
+    y = [[((c + half) * pow(D // m, -1, m)) % m for c in r] for r, m in zip(res, src)]
+    out = []
+    u = [int(sum(float(y[a][j]) * (1.0 / src[a]) for a in range(len(src)))) for j in range(N)]
+    for t in dst:
+        out.append([(sum(y[a][j] * ((D // src[a]) % t) for a in range(len(src))) - u[j] * (D % t) - half) % t for j in range(N)])
+    return out
+
+
+def crt(res, mods):
+    """the integer in [0, prod(mods)) with the given residues, coefficient by coefficient"""
+    M = prod(mods)
+    return [sum(r[j] * (M // m) * pow(M // m, -1, m) for r, m in zip(res, mods)) % M for j in range(N)]
+
+
+def mod_down_rounded(acc_p, E, l, S):
+    """hyb_mod_down: round(x / P_S) on the limbs 0 .. l-1, x given over the extended basis E = q_0..q_{l-1} + S"""
+    PS = prod(S)
+    conv = bconv_rounding(acc_p[l:], S, E[:l])
+    return [[((acc_p[i][j] - conv[i][j]) * pow(PS % E[i], -1, E[i])) % E[i] for j in range(N)] for i in range(l)]
+
+
+def mod_down_rescale(acc_p, base_p, E, l, S):
+    """hyb_mod_down_rescale (relinearization followed by a rescale as ONE division): round((acc + P_S base) / D) with
+    D = q_{l-1} P_S on the limbs 0 .. l-2.  The dropped basis is q_{l-1} + S; P_S base vanishes on S, so only the dropped
+    limb l-1 sees the base (LdInvDropped); out_i = (acc_i - conv_i) D^-1 + base_i q_{l-1}^-1 (StModDownT<true>)."""
+    PS = prod(S)
+    ql = E[l - 1]
+    dropped = [ql] + list(S)
+    D = prod(dropped)
+    first = [(a + (PS % ql) * b) % ql for a, b in zip(acc_p[l - 1], base_p[l - 1])]
+    conv = bconv_rounding([first] + [list(r) for r in acc_p[l:]], dropped, E[: l - 1])
+    return [[((acc_p[i][j] - conv[i][j]) * pow(D % E[i], -1, E[i]) + base_p[i][j] * pow(ql % E[i], -1, E[i])) % E[i]
+             for j in range(N)] for i in range(l - 1)]
+
+
 class Toy:
     def __init__(self, L=6, seed=1):
         self.rng = random.Random(seed)
