@@ -128,6 +128,21 @@ def test_multiply_relinearize_rescale(small, limbs):
     assert_ct_equal(ea, ref, a, "rescale")
 
 
+@pytest.mark.parametrize("limbs", [5, 2])
+def test_relinearize_rescale_as_one_call_is_the_two_calls_on_the_exact_path(small, limbs):
+    """bk_relinearize_rescale_inplace outside hybrid mode: relinearize_inplace then rescale_to_next_inplace, limb for limb
+    what the reference's two calls give (evaluator.cpp:1061-1116, 1378-1414)."""
+    ref, eng, rk, gk = small
+    a, b = _pair(small, limbs, 7)
+    ea, eb = to_engine(eng, ref, a), to_engine(eng, ref, b)
+    ref.op("multiply", a, b)
+    eng.multiply_inplace(ea, eb)
+    ref.op("relinearize", a)
+    ref.op("rescale", a)
+    eng.relinearize_rescale_inplace(ea, rk)
+    assert_ct_equal(ea, ref, a, "relinearize + rescale in one call")
+
+
 def test_square_and_rescale_size3(small):
     ref, eng, rk, gk = small
     a, _ = _pair(small, 4, 3)
